@@ -1,0 +1,148 @@
+"""Shared-parameter multi-agent controller with the reference's API (marl/controllers/basic_controller.py:12-101).
+
+`select_actions` is ONE kernel launch (input assembly + fc1 + GRU step + fc2 + avail mask + epsilon-greedy with
+Philox), `forward` the same kernel without the selection tail.  The reference's hooks (`_build_inputs`,
+`_compute_agent_outputs`, `_build_agent`, `_get_input_shape`) are kept: a subclass that overrides the first two is
+served through them (dense-input kernel) instead of the fused path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch as th
+
+from .. import _native as nat
+from ..components.action_selectors import make_select_struct
+from ..exceptions import HiddenStateNotInitialized
+from ..modules.agents import REGISTRY as agent_REGISTRY
+from ..modules.agents.drqn_agent import DRQNAgentNetwork
+from .multi_agent_controller import MultiAgentController
+
+
+class BasicMAC(MultiAgentController):
+    def __init__(self, scheme, groups, args):
+        super().__init__(scheme, groups, args)
+        self._obs_dim = scheme["obs"]["vshape"] if isinstance(scheme["obs"]["vshape"], int) else scheme["obs"]["vshape"][0]
+
+    # ------------------------------------------------------------------ public API
+    def select_actions(self, ep_batch, t_ep, t_env, bs=slice(None), test_mode=False, u=None, e=None):
+        avail_actions = ep_batch["avail_actions"][:, t_ep]
+        if self._fusable() and isinstance(bs, slice) and bs == slice(None):
+            sel = self.action_selector
+            eps = sel._epsilon(t_env, test_mode)
+            B = ep_batch.batch_size
+            dev = avail_actions.device
+            actions = th.empty(B, self.n_agents, dtype=th.long, device=dev)
+            greedy = th.empty(B, self.n_agents, dtype=th.long, device=dev)
+            status = th.zeros(1, dtype=th.int32, device=dev) if sel.validate else None
+            s, keep = make_select_struct(avail_actions, eps, actions, greedy, status, u, e)
+            self._step(ep_batch, t_ep, s)
+            if status is not None and int(status.item()) != 0:
+                raise ValueError("Expected at least one available action per agent (Categorical probs are all zero)")
+            return actions, greedy
+        agent_outs = self.forward(ep_batch, t_ep, test_mode=test_mode)
+        return self.action_selector.select(agent_outs[bs], avail_actions[bs], t_env, test_mode, u=u, e=e)
+
+    def forward(self, ep_batch, t, test_mode=False):
+        if self._fusable():
+            return self._step(ep_batch, t, None)
+        agent_inputs = self._build_inputs(ep_batch, t)
+        if self.hidden_states is None:
+            raise HiddenStateNotInitialized()
+        agent_outs = self._compute_agent_outputs(agent_inputs)
+        return agent_outs.view(ep_batch.batch_size, self.n_agents, -1)
+
+    def init_hidden(self, batch_size):
+        self.hidden_states = self.agent.init_hidden().unsqueeze(0).expand(batch_size, self.n_agents, -1)
+
+    def update_trained_steps(self, update):
+        if isinstance(update, th.Tensor):   # device-side count: accumulate without a host sync
+            a = self.agent
+            if a._trained_steps_dev is None:
+                a._trained_steps_dev = th.zeros((), dtype=th.long, device=update.device)
+            a._trained_steps_dev += update.reshape(()).to(th.long)
+        else:
+            self.agent._trained_steps_host += int(update)
+
+    def parameters(self):
+        return self.agent.parameters()
+
+    def load_state(self, other_mac: "BasicMAC"):
+        self.agent.load_state_dict(other_mac.agent.state_dict())
+
+    def load_state_dict(self, agent):
+        self.agent.load_state_dict(agent)
+
+    def save_models(self, path, name):
+        th.save(self.agent.state_dict(), "{}/{}agent.th".format(path, name))
+
+    def load_models(self, path, name):
+        self.agent.load_state_dict(th.load("{}/{}agent.th".format(path, name), map_location=lambda storage, loc: storage))
+
+    # ------------------------------------------------------------------ hooks (kept for subclasses)
+    def _build_agent(self, input_shape):
+        return agent_REGISTRY[self.args.agent](input_shape, self.args)
+
+    def _build_inputs(self, batch, t):
+        """[obs_t | one-hot(a_{t-1}) | agent id], row order b-major (basic_controller.py:80-92).  Only used by
+        subclasses / the non-fused path; the kernels never materialise this tensor."""
+        bs = batch.batch_size
+        parts = [batch["obs"][:, t]]
+        if self.args.obs_last_action:
+            parts.append(th.zeros_like(batch["actions_onehot"][:, t]) if t == 0 else batch["actions_onehot"][:, t - 1])
+        if self.args.obs_agent_id:
+            parts.append(th.eye(self.n_agents, device=batch.device).unsqueeze(0).expand(bs, -1, -1))
+        return th.cat([x.reshape(bs * self.n_agents, -1) for x in parts], dim=1)
+
+    def _compute_agent_outputs(self, agent_inputs):
+        agent_outs, self.hidden_states = self.agent(agent_inputs, self.hidden_states)
+        return agent_outs
+
+    def _get_input_shape(self, scheme):
+        input_shape = scheme["obs"]["vshape"]
+        if self.args.obs_last_action:
+            input_shape += scheme["actions_onehot"]["vshape"][0]
+        if self.args.obs_agent_id:
+            input_shape += self.n_agents
+        return input_shape
+
+    # ------------------------------------------------------------------ fused path
+    def _fusable(self):
+        cls = type(self)
+        return (cls._build_inputs is BasicMAC._build_inputs and cls._compute_agent_outputs is BasicMAC._compute_agent_outputs
+                and isinstance(self.agent, DRQNAgentNetwork) and self.args.obs_last_action and self.args.obs_agent_id
+                and self.agent_output_type == "q")
+
+    def _step(self, ep_batch, t, select_struct):
+        if self.hidden_states is None:
+            raise HiddenStateNotInitialized()
+        obs = nat.require_cuda(ep_batch["obs"], "ep_batch")[:, t]
+        B, N, OBS = obs.shape
+        A = self.n_actions
+        if obs.stride(2) != 1 or obs.stride(1) != OBS:
+            obs = obs.contiguous()
+        last = None
+        if t > 0:
+            last = ep_batch["actions_onehot"][:, t - 1]
+            if last.stride(2) != 1 or last.stride(1) != A:
+                last = last.contiguous()
+        rows = B * N
+        h_in = self.hidden_states
+        if h_in.dim() == 3 and h_in.stride(0) == 0:   # fresh init_hidden(): zeros
+            h_ptr = None
+        else:
+            h_in = h_in.reshape(rows, nat.HID)
+            if not h_in.is_contiguous():
+                h_in = h_in.contiguous()
+            h_ptr = h_in
+        q = th.empty(B, N, A, dtype=th.float32, device=obs.device)
+        h_out = th.empty(rows, nat.HID, dtype=th.float32, device=obs.device)
+        flat = self.agent.flat_params()
+        with th.cuda.device(obs.device):
+            nat.check(nat.lib().mal_agent_step(
+                nat.ptr(flat), rows, N, OBS, A, 0, nat.ptr(obs), obs.stride(0), nat.ptr(last),
+                last.stride(0) if last is not None else 0, nat.ptr(h_ptr), nat.ptr(h_out), nat.ptr(q),
+                C.byref(select_struct) if select_struct is not None else None, nat.current_stream(obs.device)),
+                "mal_agent_step")
+        self.hidden_states = h_out
+        return q

@@ -1,0 +1,252 @@
+// K9: fused single-timestep agent forward + epsilon-greedy action selection.
+//
+// Reference: BasicMAC.select_actions / forward / _build_inputs (marl/controllers/basic_controller.py:29-54,80-92),
+// DRQNAgentNetwork.forward (marl/modules/agents/drqn_agent.py:29-35) and EpsilonGreedyActionSelector.select
+// (marl/components/action_selectors.py:44-62) -- ~25 ATen launches per env step in the reference, ONE here.
+//
+// Layout: a CTA owns AS_ROWS (= 8) agent rows; every weight row is streamed once per CTA straight from
+// L2 with lanes along k (coalesced), the 8 per-row partial dot products are folded with a 9-shuffle
+// multi-value butterfly, gate math and the argmax/selection run warp-per-row.
+#pragma once
+#include "mal_common.cuh"
+
+#define AS_ROWS 8
+#define AS_THREADS 256
+#define AS_WARPS (AS_THREADS / 32)
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, counter layout identical to curand_init(seed, subsequence, offset) as used by
+// ATen/native/cuda/DistributionTemplates.h (distribution_elementwise_grid_stride_kernel).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// The uniform in (0,1] that torch's grid-stride distribution kernel hands to element `li` of a tensor of
+// `numel` elements when the generator state is (seed, offset): thread idx = li % (256*grid), the (li / (256*grid))-th
+// 32-bit output of that thread's stream.
+__device__ __forceinline__ float torch_philox_uniform(uint64_t seed, uint64_t offset, uint32_t grid, uint64_t li) {
+    const uint64_t span = 256ull * grid;
+    const uint64_t idx = li % span, q = li / span;
+    const uint64_t ctr = offset / 4 + q / 4;
+    uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)idx, (uint32_t)(idx >> 32));
+    uint4 o = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t comp = (uint32_t)(q & 3);
+    uint32_t x = comp == 0 ? o.x : comp == 1 ? o.y : comp == 2 ? o.z : o.w;
+    return x * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f);   // _curand_uniform
+}
+__device__ __forceinline__ float torch_uniform01(float r) { return r == 1.0f ? 0.0f : r; }   // uniform_kernel
+__device__ __forceinline__ float torch_exponential1(float r) {                                 // transformation::exponential
+    const float eps_half = 1.1920928955078125e-07f / 2.0f;
+    float lg = (r >= 1.0f - eps_half) ? -eps_half : logf(r);
+    return -1.0f * lg;
+}
+
+struct SelectArgs {
+    const int32_t *avail;
+    int64_t avail_sb;
+    int32_t N;
+    float epsilon;
+    int32_t rng_mode;
+    const float *u, *e;
+    uint64_t seed, offset_u, offset_e;
+    uint32_t grid_u, grid_e;
+    int64_t *actions, *greedy;
+    int32_t *status;
+};
+
+// One warp selects for one row.  qv = this lane's Q-value (lane < A).
+__device__ __forceinline__ void select_row(const SelectArgs &s, int row, int A, int lane, float qv) {
+    const bool valid = lane < A;
+    const int av = valid ? s.avail[(int64_t)(row / s.N) * s.avail_sb + (int64_t)(row % s.N) * A + lane] : 0;
+    // greedy branch: masked_q[avail == 0] = -inf ; max(dim=2)[1]
+    float gv = (valid && av != 0) ? qv : -INFINITY;
+    int gi = lane;
+    warp_argmax(gv, gi);
+    // random branch: Categorical(avail.float()).sample() == argmax(p / Exp(1))
+    const float avf = (float)av;
+    const float tot = warp_sum(avf);
+    float ev;
+    if (s.rng_mode == 0) ev = valid ? s.e[(int64_t)row * A + lane] : 1.0f;
+    else ev = valid ? torch_exponential1(torch_philox_uniform(s.seed, s.offset_e, s.grid_e, (uint64_t)row * A + lane)) : 1.0f;
+    float rv = valid ? (avf / tot) / ev : -INFINITY;
+    int ri = lane;
+    warp_argmax(rv, ri);
+    if (lane == 0) {
+        float uu = (s.rng_mode == 0) ? s.u[row]
+                                     : torch_uniform01(torch_philox_uniform(s.seed, s.offset_u, s.grid_u, (uint64_t)row));
+        const long long pick_random = (uu < s.epsilon) ? 1 : 0;
+        s.actions[row] = pick_random * ri + (1 - pick_random) * gi;
+        s.greedy[row] = 1 - pick_random;
+        if (!(tot > 0.0f) && s.status) atomicExch(s.status, 1);
+    }
+}
+
+__global__ void __launch_bounds__(AS_THREADS) k_eps_greedy_select(const float *q, int64_t q_ld, int rows, int A,
+                                                                  SelectArgs s) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float qv = lane < A ? q[(int64_t)warp * q_ld + lane] : 0.0f;
+    select_row(s, warp, A, lane, qv);
+}
+
+// fold 8 per-lane partials across the warp: afterwards lane L holds the full sum of value index (L >> 2).
+__device__ __forceinline__ float warp_fold8(const float (&v)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float w[4], u[2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float send = b4 ? v[q] : v[q + 4];
+        float keep = b4 ? v[q + 4] : v[q];
+        w[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        float send = b3 ? w[q] : w[q + 2];
+        float keep = b3 ? w[q + 2] : w[q];
+        u[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float send = b2 ? u[0] : u[1];
+    float keep = b2 ? u[1] : u[0];
+    float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
+}
+
+struct AgentStepArgs {
+    const float *params;
+    int rows, N, OBS, A;
+    int dense;                                  // 1: obs is the full [rows, d_in] agent input (row stride obs_sb)
+    const float *obs; int64_t obs_sb;
+    const float *onehot; int64_t onehot_sb;     // NULL at t == 0
+    const float *h_in;                          // NULL -> zeros
+    float *h_out, *q;
+    int do_select;
+    SelectArgs sel;
+};
+
+__global__ void __launch_bounds__(AS_THREADS) k_agent_step(AgentStepArgs a) {
+    extern __shared__ float as_smem[];
+    const AgentLayout L = agent_layout(a.dense ? a.OBS : a.OBS + a.A + a.N, a.A);
+    const int Kin = a.dense ? a.OBS : a.OBS + a.A;
+    const int ldin = Kin + 1;
+    float *in_s = as_smem;                       // [8][ldin]
+    float *x_s = in_s + AS_ROWS * ldin;          // [8][64]
+    float *h_s = x_s + AS_ROWS * HID;            // [8][64]
+    float *g_s = h_s + AS_ROWS * HID;            // [8][384]  gi | gh
+    float *hn_s = g_s + AS_ROWS * 2 * G3;        // [8][64]
+    float *q_s = hn_s + AS_ROWS * HID;           // [8][32]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * AS_ROWS;
+    const float *P = a.params;
+
+    // ---- stage inputs (obs | last action one-hot) and previous hidden state
+    for (int idx = tid; idx < AS_ROWS * Kin; idx += AS_THREADS) {
+        int r = idx / Kin, k = idx - r * Kin, row = r0 + r;
+        float v = 0.0f;
+        if (row < a.rows) {
+            const int b = row / a.N, n = row - b * a.N;
+            if (a.dense) v = a.obs[(int64_t)row * a.obs_sb + k];
+            else if (k < a.OBS) v = a.obs[(int64_t)b * a.obs_sb + (int64_t)n * a.OBS + k];
+            else if (a.onehot) v = a.onehot[(int64_t)b * a.onehot_sb + (int64_t)n * a.A + (k - a.OBS)];
+        }
+        in_s[r * ldin + k] = v;
+    }
+    for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
+        int r = idx >> 6, row = r0 + r;
+        h_s[idx] = (a.h_in && row < a.rows) ? a.h_in[(int64_t)row * HID + (idx & 63)] : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- fc1 + relu (agent-id one-hot column folded in as a bias gather)
+    for (int j = warp; j < HID; j += AS_WARPS) {
+        const float *w = P + L.fc1_w + (int64_t)j * L.d_in;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = lane; k < Kin; k += 32) {
+            float wv = __ldg(w + k);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[r] = fmaf(wv, in_s[r * ldin + k], acc[r]);
+        }
+        float s = warp_fold8(acc, lane);
+        if ((lane & 3) == 0) {
+            int r = lane >> 2, row = r0 + r;
+            int n = row < a.rows ? row % a.N : 0;
+            s += __ldg(P + L.fc1_b + j) + (a.dense ? 0.0f : __ldg(w + Kin + n));
+            x_s[r * HID + j] = fmaxf(s, 0.0f);
+        }
+    }
+    __syncthreads();
+
+    // ---- gi = W_ih x + b_ih ; gh = W_hh h + b_hh   (384 weight rows of 64)
+    {
+        float xv[8][2], hv[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            xv[r][0] = x_s[r * HID + 2 * lane]; xv[r][1] = x_s[r * HID + 2 * lane + 1];
+            hv[r][0] = h_s[r * HID + 2 * lane]; hv[r][1] = h_s[r * HID + 2 * lane + 1];
+        }
+#pragma unroll 4
+        for (int jj = warp; jj < 2 * G3; jj += AS_WARPS) {
+            const bool hh = jj >= G3;
+            const int j = hh ? jj - G3 : jj;
+            const float2 wv = __ldg(reinterpret_cast<const float2 *>(P + (hh ? L.w_hh : L.w_ih) + (int64_t)j * HID) + lane);
+            float acc[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                acc[r] = hh ? fmaf(wv.y, hv[r][1], wv.x * hv[r][0]) : fmaf(wv.y, xv[r][1], wv.x * xv[r][0]);
+            float s = warp_fold8(acc, lane);
+            if ((lane & 3) == 0) g_s[(lane >> 2) * 2 * G3 + jj] = s + __ldg(P + (hh ? L.b_hh : L.b_ih) + j);
+        }
+    }
+    __syncthreads();
+
+    // ---- gate math: r,z,n ; h' = n + z (h - n)
+    for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
+        int r = idx >> 6, i = idx & 63, row = r0 + r;
+        const float *g = g_s + r * 2 * G3;
+        float rr = sigmoidf_acc(g[i] + g[G3 + i]);
+        float zz = sigmoidf_acc(g[HID + i] + g[G3 + HID + i]);
+        float nn = tanhf(g[2 * HID + i] + rr * g[G3 + 2 * HID + i]);
+        float hp = h_s[idx];
+        float hn = nn + zz * (hp - nn);
+        hn_s[idx] = hn;
+        if (row < a.rows) a.h_out[(int64_t)row * HID + i] = hn;
+    }
+    __syncthreads();
+
+    // ---- fc2
+    {
+        float hv[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { hv[r][0] = hn_s[r * HID + 2 * lane]; hv[r][1] = hn_s[r * HID + 2 * lane + 1]; }
+        for (int j = warp; j < a.A; j += AS_WARPS) {
+            const float2 wv = __ldg(reinterpret_cast<const float2 *>(P + L.fc2_w + (int64_t)j * HID) + lane);
+            float acc[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[r] = fmaf(wv.y, hv[r][1], wv.x * hv[r][0]);
+            float s = warp_fold8(acc, lane);
+            if ((lane & 3) == 0) {
+                int r = lane >> 2, row = r0 + r;
+                s += __ldg(P + L.fc2_b + j);
+                q_s[r * 32 + j] = s;
+                if (row < a.rows) a.q[(int64_t)row * a.A + j] = s;
+            }
+        }
+    }
+    if (!a.do_select) return;
+    __syncthreads();
+    // ---- epsilon-greedy selection: one warp per row
+    {
+        int row = r0 + warp;
+        if (row < a.rows) select_row(a.sel, row, a.A, lane, lane < a.A ? q_s[warp * 32 + lane] : 0.0f);
+    }
+}

@@ -1,0 +1,878 @@
+// K0-K8: the QLearner.train step (marl/learners/q_learner.py:34-131) as hand-written sm_100a kernels.
+//
+// Decomposition (cuDNN-RNN style, but fp32-exact and fused around the reference's glue ops):
+//   * everything that does NOT depend on h_{t-1} is hoisted out of the time loop into grouped panel GEMMs over
+//     all (t, b, n) rows at once:  x = relu(fc1 [obs | last action | agent id]),  gi = W_ih x + b_ih;
+//   * the serial part (gh = W_hh h, gate math) runs in a lean recurrence kernel that keeps W_hh in REGISTERS
+//     (one gate row per thread) and h in shared memory: 2 barriers per timestep, no weight traffic at all;
+//   * q = fc2 h, the chosen-action gather and the avail-masked (double-Q) target max are one warp-per-row epilogue;
+//   * the QMIX hypernetworks are two grouped panel GEMMs; abs/bmm/ELU/bmm + TD error + masked loss + the whole
+//     element-wise part of the mixer backward are ONE warp-per-(b,t) kernel;
+//   * BPTT mirrors the forward: a reverse recurrence with W_hh^T in registers emits d(gates); all weight
+//     gradients are split-M reductions (deterministic two-pass: per-chunk partials, then a flat gather);
+//   * clip_grad_norm_ + RMSprop are one pass over the flat parameter / gradient / square_avg buffers.
+#pragma once
+#include "mal_common.cuh"
+
+// =============================================================================================
+// row loaders shared by the panel GEMM and the split reduction
+// =============================================================================================
+struct BatchView {
+    int B, TT, T, N, A, OBS, S, R;
+    mal_field_t obs, onehot, state;
+};
+
+enum { A_DENSE = 0, A_AGENT_IN = 1, A_STATE = 2 };
+
+struct RowSrc {           // resolved per row
+    const float *p0;      // dense row / obs row / state row
+    const float *p1;      // last-action one-hot row (may be null)
+    int agent;
+};
+
+__device__ __forceinline__ RowSrc resolve_row(int kind, const BatchView &bv, const float *A, int64_t lda, int shift,
+                                              int64_t m) {
+    RowSrc r;
+    r.p1 = nullptr;
+    r.agent = 0;
+    if (kind == A_DENSE) {
+        r.p0 = A + (m - shift) * lda;   // shift = row shift (h_{t-1} pairing); callers guard m >= shift
+    } else if (kind == A_AGENT_IN) {
+        int t = (int)(m / bv.R), rr = (int)(m - (int64_t)t * bv.R);
+        int b = rr / bv.N, n = rr - b * bv.N;
+        r.agent = n;
+        r.p0 = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
+        r.p1 = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
+    } else {
+        int b = (int)(m / bv.T), t = (int)(m - (int64_t)b * bv.T);
+        r.p0 = field_ptr<float>(bv.state, b, t + shift);
+    }
+    return r;
+}
+
+// element k of the logical input row; for A_AGENT_IN: [obs | last-action one-hot | agent-id one-hot]
+__device__ __forceinline__ float row_elem(int kind, const BatchView &bv, const RowSrc &r, int k) {
+    if (kind != A_AGENT_IN) return r.p0[k];
+    if (k < bv.OBS) return r.p0[k];
+    k -= bv.OBS;
+    if (k < bv.A) return r.p1 ? r.p1[k] : 0.0f;
+    return (k - bv.A) == r.agent ? 1.0f : 0.0f;
+}
+
+// =============================================================================================
+// grouped panel GEMM:  Y[m, n] = epi( sum_k A[m,k] * W[n,k] )      (tile 64x64, 256 threads, 4x4 micro-tile)
+// =============================================================================================
+enum { EPI_BIAS = 0, EPI_RELU = 1, EPI_MASKPOS = 2, EPI_FC1 = 3 };
+
+struct LinProb {
+    int M, K, Nout;
+    int a_kind, shift;
+    const float *A; int64_t lda;
+    const float *W; int64_t ldw; int w_trans;     // w_trans: W(n,k) = W[k*ldw + n]
+    const float *bias;
+    int epi;
+    const float *aux; int64_t ld_aux;             // EPI_MASKPOS: multiply by (aux[m,n] > 0)
+    float *Y; int64_t ldy;
+};
+#define LIN_MAX_PROBS 8
+struct LinGroup {
+    int n;
+    LinProb p[LIN_MAX_PROBS];
+    BatchView bv;
+};
+
+#define LIN_TM 64
+#define LIN_TN 64
+#define LIN_KC 64
+#define LIN_LDW (LIN_KC + 4)
+
+__global__ void __launch_bounds__(256) k_linear_group(const __grid_constant__ LinGroup g) {
+    extern __shared__ __align__(16) float lin_smem[];
+    const LinProb &p = g.p[blockIdx.y];
+    const int64_t m0 = (int64_t)blockIdx.x * LIN_TM;
+    if (m0 >= p.M) return;
+    const int nkc = (p.K + LIN_KC - 1) / LIN_KC;
+    const int KA = nkc * LIN_KC + 4;
+    float *A_s = lin_smem;                 // [64][KA]
+    float *W_s = lin_smem + LIN_TM * KA;   // [64][68]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    // ---- stage the whole A row-panel once (zero padded)
+    for (int r = warp; r < LIN_TM; r += 8) {
+        const int64_t m = m0 + r;
+        float *dst = A_s + r * KA;
+        if (m < p.M) {
+            RowSrc rs = resolve_row(p.a_kind, g.bv, p.A, p.lda, p.shift, m);
+            for (int k = lane; k < nkc * LIN_KC; k += 32) dst[k] = k < p.K ? row_elem(p.a_kind, g.bv, rs, k) : 0.0f;
+        } else {
+            for (int k = lane; k < nkc * LIN_KC; k += 32) dst[k] = 0.0f;
+        }
+    }
+
+    for (int n0 = 0; n0 < p.Nout; n0 += LIN_TN) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        for (int kc = 0; kc < nkc; ++kc) {
+            const int k0 = kc * LIN_KC;
+            __syncthreads();   // previous W chunk fully consumed (and A panel staged on the first pass)
+#pragma unroll 4
+            for (int q = 0; q < (LIN_TN * LIN_KC) / 256; ++q) {
+                int idx = tid + 256 * q;
+                int j, kk;
+                if (!p.w_trans) { j = idx >> 6; kk = idx & 63; } else { j = idx & 63; kk = idx >> 6; }
+                int n = n0 + j, k = k0 + kk;
+                float v = 0.0f;
+                if (n < p.Nout && k < p.K) v = p.w_trans ? __ldg(p.W + (int64_t)k * p.ldw + n) : __ldg(p.W + (int64_t)n * p.ldw + k);
+                W_s[j * LIN_LDW + kk] = v;
+            }
+            __syncthreads();
+            const float *a_base = A_s + ty * KA + k0;
+            const float *w_base = W_s + tx * LIN_LDW;
+#pragma unroll 4
+            for (int k4 = 0; k4 < LIN_KC / 4; ++k4) {
+                float4 av[4], wv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4 *>(a_base + i * 16 * KA + 4 * k4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4 *>(w_base + j * 16 * LIN_LDW + 4 * k4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[i][j] = fmaf(av[i].x, wv[j].x, acc[i][j]);
+                        acc[i][j] = fmaf(av[i].y, wv[j].y, acc[i][j]);
+                        acc[i][j] = fmaf(av[i].z, wv[j].z, acc[i][j]);
+                        acc[i][j] = fmaf(av[i].w, wv[j].w, acc[i][j]);
+                    }
+            }
+        }
+        // ---- epilogue
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t m = m0 + ty + 16 * i;
+            if (m >= p.M) continue;
+            int agent = 0;
+            if (p.epi == EPI_FC1) agent = (int)((m % g.bv.R) % g.bv.N);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx + 16 * j;
+                if (n >= p.Nout) continue;
+                float v = acc[i][j];
+                if (p.bias) v += __ldg(p.bias + n);
+                if (p.epi == EPI_FC1) { v += __ldg(p.W + (int64_t)n * p.ldw + p.K + agent); v = fmaxf(v, 0.0f); }
+                else if (p.epi == EPI_RELU) v = fmaxf(v, 0.0f);
+                else if (p.epi == EPI_MASKPOS) v = (p.aux[m * p.ld_aux + n] > 0.0f) ? v : 0.0f;
+                p.Y[m * p.ldy + n] = v;
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// grouped split-M reduction:  part[c][n][k] = sum_{m in chunk c} dY[m,n] * A[m,k] ;  partB[c][n] = sum dY[m,n]
+// =============================================================================================
+struct RedProb {
+    int64_t M0, M;            // rows [M0, M)
+    int K, Nout;
+    const float *dY; int64_t ldy;
+    int a_kind, shift;
+    const float *A; int64_t lda;
+    float *partW, *partB;     // [n_chunks][Nout][K], [n_chunks][Nout] (partB may be null)
+    int n_chunks; int64_t rows_per_chunk;
+    int tile0, n_ktiles;      // first tile id of this problem, number of k tiles
+};
+#define RED_MAX_PROBS 12
+struct RedGroup {
+    int n;
+    RedProb p[RED_MAX_PROBS];
+    BatchView bv;
+};
+#define RED_MR 32
+#define RED_LD 68
+
+__global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ RedGroup g) {
+    __shared__ __align__(16) float dY_s[RED_MR * RED_LD];
+    __shared__ __align__(16) float A_s[RED_MR * RED_LD];
+    int pi = 0;
+    while (pi + 1 < g.n && (int)blockIdx.y >= g.p[pi + 1].tile0) ++pi;
+    const RedProb &p = g.p[pi];
+    const int chunk = blockIdx.x;
+    if (chunk >= p.n_chunks) return;
+    const int tile = blockIdx.y - p.tile0;
+    const int nt = tile / p.n_ktiles, kt = tile - nt * p.n_ktiles;
+    const int n0 = nt * 64, k0 = kt * 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int64_t mb = p.M0 + (int64_t)chunk * p.rows_per_chunk;
+    int64_t me = mb + p.rows_per_chunk;
+    if (me > p.M) me = p.M;
+
+    float acc[4][4];
+    float bsum[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    for (int64_t mm = mb; mm < me; mm += RED_MR) {
+        __syncthreads();
+        for (int r = warp; r < RED_MR; r += 8) {
+            const int64_t m = mm + r;
+            const bool ok = m < me;
+            const bool ok_a = ok && (p.a_kind != A_DENSE || m >= p.shift);
+            RowSrc rs;
+            rs.p0 = rs.p1 = nullptr; rs.agent = 0;
+            if (ok_a) rs = resolve_row(p.a_kind, g.bv, p.A, p.lda, p.shift, m);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                dY_s[r * RED_LD + c] = (ok && n0 + c < p.Nout) ? p.dY[m * p.ldy + n0 + c] : 0.0f;
+                A_s[r * RED_LD + c] = (ok_a && k0 + c < p.K) ? row_elem(p.a_kind, g.bv, rs, k0 + c) : 0.0f;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < RED_MR; ++r) {
+            const float4 d = *reinterpret_cast<const float4 *>(dY_s + r * RED_LD + 4 * ty);
+            const float4 a = *reinterpret_cast<const float4 *>(A_s + r * RED_LD + 4 * tx);
+            const float dv[4] = {d.x, d.y, d.z, d.w}, avv[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bsum[i] += dv[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], avv[j], acc[i][j]);
+            }
+        }
+    }
+    float *pw = p.partW + (int64_t)chunk * p.Nout * p.K;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + 4 * ty + i;
+        if (n >= p.Nout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + 4 * tx + j;
+            if (k < p.K) pw[(int64_t)n * p.K + k] = acc[i][j];
+        }
+        if (p.partB && kt == 0 && tx == 0) p.partB[(int64_t)chunk * p.Nout + n] = bsum[i];
+    }
+}
+
+// =============================================================================================
+// mask, mask.sum()          q_learner.py:40-42,98,112
+// =============================================================================================
+__global__ void __launch_bounds__(1024) k_mask_prep(mal_field_t filled, mal_field_t terminated, int B, int T,
+                                                    float *mask, float *scalars) {
+    __shared__ float s_sum[32];
+    __shared__ int s_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float sum = 0.0f;
+    int cnt = 0;
+    for (int idx = tid; idx < B * T; idx += blockDim.x) {
+        int b = idx / T, t = idx - b * T;
+        float m = (float)(*field_ptr<long long>(filled, b, t));
+        if (t > 0) m = m * (1.0f - (float)(*field_ptr<unsigned char>(terminated, b, t - 1)));
+        mask[idx] = m;
+        sum += m;
+        cnt += (m != 0.0f);
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        int c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += s_sum[w]; c += s_cnt[w]; }
+        scalars[MAL_SC_MASK_SUM] = s;
+        reinterpret_cast<int *>(scalars)[MAL_SC_MASK_COUNT] = c;
+    }
+}
+
+// =============================================================================================
+// GRU recurrence, forward.  grid (ceil(R/RT), nets), 192 threads: thread j owns gate row j of W_hh.
+// =============================================================================================
+struct GruFwdArgs {
+    const float *params[2];    // online, target (flat agent buffers)
+    const float *gi[2];        // [TT*R,192]
+    float *hout[2];            // [TT*R,64]
+    float *gates;              // [TT*R,256] online only: r|z|n|ghn
+    int TT, R, d_in, n_actions;
+};
+
+template <int RT>
+__global__ void __launch_bounds__(192) k_gru_fwd(GruFwdArgs a) {
+    constexpr int ITEMS = RT * HID;
+    constexpr int IPT = (ITEMS + 191) / 192;
+    __shared__ __align__(16) float h_s[RT * HID];
+    __shared__ float gh_s[RT * G3];
+    const int tid = threadIdx.x, net = blockIdx.y;
+    const int r0 = blockIdx.x * RT;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const float *P = a.params[net];
+    const float *gi = a.gi[net];
+    float *hout = a.hout[net];
+    float *gates = net == 0 ? a.gates : nullptr;
+
+    float w[HID];
+    {
+        const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)tid * HID);
+#pragma unroll
+        for (int k4 = 0; k4 < HID / 4; ++k4) {
+            float4 v = __ldg(wr + k4);
+            w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
+        }
+    }
+    const float bj = __ldg(P + L.b_hh + tid);
+    for (int idx = tid; idx < ITEMS; idx += 192) h_s[idx] = 0.0f;   // init_hidden: zeros
+
+    float g_r[IPT], g_z[IPT], g_n[IPT];
+    auto prefetch = [&](int t) {
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            int item = tid + 192 * q;
+            int r = item >> 6, i = item & 63, row = r0 + r;
+            if (item < ITEMS && row < a.R && t < a.TT) {
+                const float *gp = gi + ((int64_t)t * a.R + row) * G3;
+                g_r[q] = __ldg(gp + i); g_z[q] = __ldg(gp + HID + i); g_n[q] = __ldg(gp + 2 * HID + i);
+            } else { g_r[q] = g_z[q] = g_n[q] = 0.0f; }
+        }
+    };
+    prefetch(0);
+    __syncthreads();
+
+    for (int t = 0; t < a.TT; ++t) {
+        // phase 1: gh[r][j] = b_hh[j] + W_hh[j,:] . h[r,:]
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            float acc0 = bj, acc1 = 0.0f;
+            const float4 *hp = reinterpret_cast<const float4 *>(h_s + r * HID);
+#pragma unroll
+            for (int k4 = 0; k4 < HID / 4; ++k4) {
+                float4 hv = hp[k4];
+                acc0 = fmaf(w[4 * k4], hv.x, acc0);
+                acc1 = fmaf(w[4 * k4 + 1], hv.y, acc1);
+                acc0 = fmaf(w[4 * k4 + 2], hv.z, acc0);
+                acc1 = fmaf(w[4 * k4 + 3], hv.w, acc1);
+            }
+            gh_s[r * G3 + tid] = acc0 + acc1;
+        }
+        __syncthreads();
+        // phase 2: gate math per (row, hidden unit)
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            int item = tid + 192 * q;
+            if (item < ITEMS) {
+                int r = item >> 6, i = item & 63, row = r0 + r;
+                const float *gh = gh_s + r * G3;
+                float ghn = gh[2 * HID + i];
+                float rr = sigmoidf_acc(g_r[q] + gh[i]);
+                float zz = sigmoidf_acc(g_z[q] + gh[HID + i]);
+                float nn = tanhf(g_n[q] + rr * ghn);
+                float hp = h_s[item];
+                float hn = nn + zz * (hp - nn);
+                h_s[item] = hn;
+                if (row < a.R) {
+                    const int64_t m = (int64_t)t * a.R + row;
+                    hout[m * HID + i] = hn;
+                    if (gates) {
+                        float *gp = gates + m * 4 * HID;
+                        gp[i] = rr; gp[HID + i] = zz; gp[2 * HID + i] = nn; gp[3 * HID + i] = ghn;
+                    }
+                }
+            }
+        }
+        prefetch(t + 1);
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// q = fc2 h for both nets, chosen-action gather, avail-masked (double-Q) target max.   q_learner.py:52-78
+// one warp per (t, row); lane = action
+// =============================================================================================
+struct HeadArgs {
+    const float *params[2];
+    const float *hout[2];
+    int B, TT, N, A, R, d_in, double_q;
+    mal_field_t actions, avail;
+    float *mac_out, *target_mac_out;   // [B,TT,N,A] or null
+    float *chosen, *target_max;        // [B,T,N]
+    int *argmax;                       // [B,T,N]
+};
+
+__global__ void __launch_bounds__(256) k_q_head(HeadArgs a) {
+    __shared__ float w2_s[2][MAL_MAX_ACTIONS * (HID + 1)];
+    __shared__ float b2_s[2][MAL_MAX_ACTIONS];
+    __shared__ float hs[8][2][HID];
+    const AgentLayout L = agent_layout(a.d_in, a.A);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int idx = tid; idx < 2 * a.A * HID; idx += 256) {
+        int net = idx / (a.A * HID), rem = idx - net * a.A * HID;
+        int j = rem >> 6, k = rem & 63;
+        w2_s[net][j * (HID + 1) + k] = __ldg(a.params[net] + L.fc2_w + rem);
+    }
+    if (tid < 2 * a.A) { int net = tid / a.A, j = tid - net * a.A; b2_s[net][j] = __ldg(a.params[net] + L.fc2_b + j); }
+    __syncthreads();
+    const int T = a.TT - 1;
+    const int64_t total = (int64_t)a.TT * a.R;
+    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
+        const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
+        const int b = row / a.N, n = row - b * a.N;
+        __syncwarp();
+        hs[warp][0][lane] = a.hout[0][m * HID + lane];
+        hs[warp][0][lane + 32] = a.hout[0][m * HID + lane + 32];
+        hs[warp][1][lane] = a.hout[1][m * HID + lane];
+        hs[warp][1][lane + 32] = a.hout[1][m * HID + lane + 32];
+        __syncwarp();
+        float qo = 0.0f, qt = 0.0f;
+        if (lane < a.A) {
+            float o0 = b2_s[0][lane], o1 = 0.0f, t0 = b2_s[1][lane], t1 = 0.0f;
+            const float *wo = w2_s[0] + lane * (HID + 1), *wt = w2_s[1] + lane * (HID + 1);
+#pragma unroll 8
+            for (int k = 0; k < HID; k += 2) {
+                o0 = fmaf(wo[k], hs[warp][0][k], o0);
+                o1 = fmaf(wo[k + 1], hs[warp][0][k + 1], o1);
+                t0 = fmaf(wt[k], hs[warp][1][k], t0);
+                t1 = fmaf(wt[k + 1], hs[warp][1][k + 1], t1);
+            }
+            qo = o0 + o1;
+            qt = t0 + t1;
+            const int64_t o = (((int64_t)b * a.TT + t) * a.N + n) * a.A + lane;
+            if (a.mac_out) a.mac_out[o] = qo;
+            if (a.target_mac_out) a.target_mac_out[o] = qt;
+        }
+        if (t < T) {   // chosen_action_qvals = gather(mac_out[:, :-1], 3, actions)
+            const int act = (int)(field_ptr<long long>(a.actions, b, t)[n]);
+            float c = __shfl_sync(0xffffffffu, qo, act & 31);
+            if (lane == 0) a.chosen[((int64_t)b * T + t) * a.N + n] = c;
+        }
+        if (t >= 1) {  // targets use step t's Q for transition t-1
+            const int av = lane < a.A ? field_ptr<int>(a.avail, b, t)[(int64_t)n * a.A + lane] : 0;
+            const bool valid = lane < a.A;
+            float mt = valid ? (av == 0 ? -9999999.0f : qt) : -INFINITY;
+            float sel = a.double_q ? (valid ? (av == 0 ? -9999999.0f : qo) : -INFINITY) : mt;
+            int si = lane;
+            warp_argmax(sel, si);
+            float tm = __shfl_sync(0xffffffffu, mt, si);
+            if (lane == 0) {
+                const int64_t o = ((int64_t)b * T + (t - 1)) * a.N + n;
+                a.target_max[o] = tm;
+                a.argmax[o] = si;
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// mixer (VDN / QMIX) + TD target + masked L2 loss + element-wise part of the mixer backward.
+// One warp per (b,t); lane = embed index e.                      qmix.py:41-59, vdn.py:9-10, q_learner.py:81-98
+// =============================================================================================
+struct MixArgs {
+    int mixer, B, T, N, E, HE, S;
+    const float *y1[2], *a2[2];        // online, target
+    const float *mparams[2];
+    const float *chosen, *target_max;  // [B*T,N]
+    const float *mask;                 // [B*T]
+    mal_field_t reward, terminated;
+    float gamma;
+    const float *scalars;              // mask sum
+    float *q_tot, *target_q_tot, *targets, *td;
+    float *d_a2, *d_y1, *d_chosen;     // backward seeds
+    float *part_stats;                 // [gridDim.x][4]   sum mtd^2, sum |mtd|, sum q_tot*m, sum targets*m
+    float *part_v2;                    // [gridDim.x][E+1] d V.2.weight | d V.2.bias
+};
+
+__device__ __forceinline__ float qmix_row(const MixArgs &a, int net, int64_t m, const float *q, int lane,
+                                          float *pre_out, float *hidden_out, float *wf_out, float *v1_out) {
+    const MixerLayout ML = mixer_layout(a.mixer, a.S, a.N, a.E, a.HE);
+    const int two = (ML.layers == 2);
+    const int ld1 = two ? 2 * a.HE + 2 * a.E : 2 * a.E;
+    const int ld2 = a.E * a.N + a.E;
+    const float *y1 = a.y1[net] + m * ld1 + (two ? 2 * a.HE : 0);   // -> [b1 | v1]
+    const float *a2 = a.a2[net] + m * ld2;
+    const bool act = lane < a.E;
+    float pre = act ? y1[lane] : 0.0f;
+    for (int n = 0; n < a.N; ++n) {
+        float w1 = act ? fabsf(a2[n * a.E + lane]) : 0.0f;
+        pre = fmaf(q[n], w1, pre);
+    }
+    float hidden = pre > 0.0f ? pre : expm1f(pre);
+    float wf = act ? fabsf(a2[a.N * a.E + lane]) : 0.0f;
+    float v1 = act ? y1[a.E + lane] : 0.0f;
+    float v2w = act ? __ldg(a.mparams[net] + ML.v2_w + lane) : 0.0f;
+    float y = warp_sum(act ? fmaf(hidden, wf, v1 * v2w) : 0.0f) + __ldg(a.mparams[net] + ML.v2_b);
+    *pre_out = pre; *hidden_out = hidden; *wf_out = wf; *v1_out = v1;
+    return y;
+}
+
+__global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
+    __shared__ float s_stats[8][4];
+    __shared__ float s_v2[8][MAL_MAX_EMBED + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t total = (int64_t)a.B * a.T;
+    const float msum = a.scalars[MAL_SC_MASK_SUM];
+    const MixerLayout ML = mixer_layout(a.mixer, a.S, a.N, a.E, a.HE);
+    const int two = (ML.layers == 2);
+    const int ld1 = two ? 2 * a.HE + 2 * a.E : 2 * a.E;
+    const int ld2 = a.E * a.N + a.E;
+    float st0 = 0, st1 = 0, st2 = 0, st3 = 0, dv2w = 0, dv2b = 0;
+    float q[MAL_MAX_ACTIONS];   // N <= 32 agents per team
+
+    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
+        const int b = (int)(m / a.T), t = (int)(m - (int64_t)b * a.T);
+        float y, ty, pre = 0, hidden = 0, wf = 0, v1 = 0;
+        if (a.mixer == MAL_MIXER_VDN) {
+            float s0 = 0, s1 = 0;
+            for (int n = 0; n < a.N; ++n) { s0 += a.chosen[m * a.N + n]; s1 += a.target_max[m * a.N + n]; }
+            y = s0; ty = s1;
+        } else {
+            float d0, d1, d2, d3;
+            for (int n = 0; n < a.N; ++n) q[n] = a.target_max[m * a.N + n];
+            ty = qmix_row(a, 1, m, q, lane, &d0, &d1, &d2, &d3);
+            for (int n = 0; n < a.N; ++n) q[n] = a.chosen[m * a.N + n];
+            y = qmix_row(a, 0, m, q, lane, &pre, &hidden, &wf, &v1);
+        }
+        const float rew = *field_ptr<float>(a.reward, b, t);
+        const float term = (float)(*field_ptr<unsigned char>(a.terminated, b, t));
+        const float mk = a.mask[m];
+        const float target = rew + a.gamma * (1.0f - term) * ty;
+        const float tdv = y - target;
+        const float mtd = tdv * mk;
+        const float gseed = 2.0f * mtd * mk / msum;   // d loss / d q_tot
+        if (lane == 0) {
+            a.q_tot[m] = y; a.target_q_tot[m] = ty; a.targets[m] = target; a.td[m] = tdv;
+            st0 += mtd * mtd; st1 += fabsf(mtd); st2 += y * mk; st3 += target * mk;
+        }
+        if (a.mixer == MAL_MIXER_VDN) {
+            if (lane < a.N) a.d_chosen[m * a.N + lane] = gseed;
+            continue;
+        }
+        // ---- element-wise mixer backward
+        const bool act = lane < a.E;
+        const float *a2 = a.a2[0] + m * ld2;
+        float *da2 = a.d_a2 + m * ld2;
+        float *dy1 = a.d_y1 + m * ld1 + (two ? 2 * a.HE : 0);
+        const float dhidden = gseed * wf;
+        const float dwf = gseed * hidden;
+        const float dpre = dhidden * (pre > 0.0f ? 1.0f : expf(pre));
+        if (act) {
+            const float af = a2[a.N * a.E + lane];
+            da2[a.N * a.E + lane] = dwf * (af > 0.0f ? 1.0f : (af < 0.0f ? -1.0f : 0.0f));
+            dy1[lane] = dpre;                                                              // d hyper_b_1 out
+            const float v2w = __ldg(a.mparams[0] + ML.v2_w + lane);
+            dy1[a.E + lane] = v1 > 0.0f ? gseed * v2w : 0.0f;                               // d V.0 pre-activation
+            dv2w += gseed * v1;
+        }
+        if (lane == 0) dv2b += gseed;
+        for (int n = 0; n < a.N; ++n) {
+            const float a1 = act ? a2[n * a.E + lane] : 0.0f;
+            const float dq = warp_sum(act ? dpre * fabsf(a1) : 0.0f);
+            if (lane == 0) a.d_chosen[m * a.N + n] = dq;
+            if (act) da2[n * a.E + lane] = q[n] * dpre * (a1 > 0.0f ? 1.0f : (a1 < 0.0f ? -1.0f : 0.0f));
+        }
+    }
+    // ---- deterministic block partials
+    if (lane == 0) { s_stats[warp][0] = st0; s_stats[warp][1] = st1; s_stats[warp][2] = st2; s_stats[warp][3] = st3; }
+    if (a.mixer != MAL_MIXER_VDN) {
+        if (lane < a.E) s_v2[warp][lane] = dv2w;
+        if (lane == 0) s_v2[warp][a.E] = dv2b;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        float s = 0;
+        for (int w = 0; w < 8; ++w) s += s_stats[w][tid];
+        a.part_stats[blockIdx.x * 4 + tid] = s;
+    }
+    if (a.mixer != MAL_MIXER_VDN && tid <= a.E) {
+        float s = 0;
+        for (int w = 0; w < 8; ++w) s += s_v2[w][tid];
+        a.part_v2[(int64_t)blockIdx.x * (a.E + 1) + tid] = s;
+    }
+}
+
+// stand-alone mixer forward (QMixer.forward / VDNMixer.forward called outside the learner)
+__global__ void __launch_bounds__(256) k_mix_fwd(MixArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)a.B * a.T;
+    float q[MAL_MAX_ACTIONS];
+    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
+        float y;
+        if (a.mixer == MAL_MIXER_VDN) {
+            y = 0.0f;
+            for (int n = 0; n < a.N; ++n) y += a.chosen[m * a.N + n];
+        } else {
+            float d0, d1, d2, d3;
+            for (int n = 0; n < a.N; ++n) q[n] = a.chosen[m * a.N + n];
+            y = qmix_row(a, 0, m, q, lane, &d0, &d1, &d2, &d3);
+        }
+        if (lane == 0) a.q_tot[m] = y;
+    }
+}
+
+// loss / logging scalars from the block partials (q_learner.py:98,117-124)
+__global__ void k_stats_finalize(const float *part_stats, int nblk, int n_agents, float *scalars) {
+    if (threadIdx.x < 4) {
+        float s = 0;
+        for (int i = 0; i < nblk; ++i) s += part_stats[i * 4 + threadIdx.x];
+        const float msum = scalars[MAL_SC_MASK_SUM];
+        if (threadIdx.x == 0) scalars[MAL_SC_LOSS] = s / msum;
+        if (threadIdx.x == 1) scalars[MAL_SC_TD_ABS] = s / msum;
+        if (threadIdx.x == 2) scalars[MAL_SC_Q_TAKEN] = s / (msum * n_agents);
+        if (threadIdx.x == 3) scalars[MAL_SC_TARGET] = s / (msum * n_agents);
+    }
+}
+
+// =============================================================================================
+// GRU recurrence, backward (BPTT).  grid ceil(R/RT), 192 threads: thread (g,k) owns W_hh[g*64 + :, k].
+// =============================================================================================
+struct GruBwdArgs {
+    const float *params;       // online agent
+    const float *hout;         // [TT*R,64]
+    const float *gates;        // [TT*R,256]
+    const float *d_chosen;     // [B,T,N]
+    mal_field_t actions;
+    float *d_g;                // [TT*R,256]: d gi_r | d gi_z | d gi_n | d gh_n
+    int TT, R, N, d_in, n_actions;
+};
+
+template <int RT>
+__global__ void __launch_bounds__(192) k_gru_bwd(GruBwdArgs a) {
+    constexpr int ITEMS = RT * HID;
+    constexpr int IPT = (ITEMS + 191) / 192;
+    __shared__ __align__(16) float dgh_s[RT * G3];
+    __shared__ float part_s[RT * G3];          // [r][g][k]
+    __shared__ float w2_s[MAL_MAX_ACTIONS * HID];
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * RT;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const int T = a.TT - 1;
+    const int g = tid >> 6, k = tid & 63;
+
+    float wT[HID];   // W_hh[g*64 + j][k], j = 0..63
+#pragma unroll
+    for (int j = 0; j < HID; ++j) wT[j] = __ldg(a.params + L.w_hh + (int64_t)(g * HID + j) * HID + k);
+    for (int idx = tid; idx < a.n_actions * HID; idx += 192) w2_s[idx] = __ldg(a.params + L.fc2_w + idx);
+    for (int idx = tid; idx < RT * G3; idx += 192) part_s[idx] = 0.0f;
+
+    float carry[IPT];
+    float n_r[IPT], n_z[IPT], n_n[IPT], n_ghn[IPT], n_hp[IPT], n_dc[IPT];
+    int n_act[IPT];
+    auto prefetch = [&](int t) {
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            int item = tid + 192 * q;
+            int r = item >> 6, i = item & 63, row = r0 + r;
+            n_r[q] = n_z[q] = n_n[q] = n_ghn[q] = n_hp[q] = n_dc[q] = 0.0f;
+            n_act[q] = 0;
+            if (item < ITEMS && row < a.R && t >= 0) {
+                const int64_t m = (int64_t)t * a.R + row;
+                const float *gp = a.gates + m * 4 * HID;
+                n_r[q] = gp[i]; n_z[q] = gp[HID + i]; n_n[q] = gp[2 * HID + i]; n_ghn[q] = gp[3 * HID + i];
+                if (t > 0) n_hp[q] = a.hout[(m - a.R) * HID + i];
+                if (t < T) {
+                    int b = row / a.N, n = row - b * a.N;
+                    n_dc[q] = a.d_chosen[((int64_t)b * T + t) * a.N + n];
+                    n_act[q] = (int)(field_ptr<long long>(a.actions, b, t)[n]);
+                }
+            }
+        }
+    };
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) carry[q] = 0.0f;
+    prefetch(a.TT - 1);
+    __syncthreads();
+
+    for (int t = a.TT - 1; t >= 0; --t) {
+        // phase A: d h_t -> d gates
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            int item = tid + 192 * q;
+            if (item < ITEMS) {
+                int r = item >> 6, i = item & 63, row = r0 + r;
+                const float *ps = part_s + r * G3;
+                float dh = carry[q] + ps[i] + ps[HID + i] + ps[2 * HID + i] + n_dc[q] * w2_s[n_act[q] * HID + i];
+                const float rr = n_r[q], zz = n_z[q], nn = n_n[q];
+                float dn = dh * (1.0f - zz);
+                float dz = dh * (n_hp[q] - nn);
+                float dnp = dn * (1.0f - nn * nn);
+                float dzp = dz * zz * (1.0f - zz);
+                float drp = dnp * n_ghn[q] * rr * (1.0f - rr);
+                float dghn = dnp * rr;
+                carry[q] = dh * zz;
+                dgh_s[r * G3 + i] = drp; dgh_s[r * G3 + HID + i] = dzp; dgh_s[r * G3 + 2 * HID + i] = dghn;
+                if (row < a.R) {
+                    float *dp = a.d_g + ((int64_t)t * a.R + row) * 4 * HID;
+                    dp[i] = drp; dp[HID + i] = dzp; dp[2 * HID + i] = dnp; dp[3 * HID + i] = dghn;
+                }
+            }
+        }
+        prefetch(t - 1);
+        __syncthreads();
+        // phase B: part[r][g][k] = sum_j dgh[r][g*64+j] * W_hh[g*64+j][k]
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const float4 *dp = reinterpret_cast<const float4 *>(dgh_s + r * G3 + g * HID);
+            float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+            for (int j4 = 0; j4 < HID / 4; ++j4) {
+                float4 d = dp[j4];
+                acc0 = fmaf(wT[4 * j4], d.x, acc0);
+                acc1 = fmaf(wT[4 * j4 + 1], d.y, acc1);
+                acc0 = fmaf(wT[4 * j4 + 2], d.z, acc0);
+                acc1 = fmaf(wT[4 * j4 + 3], d.w, acc1);
+            }
+            part_s[r * G3 + tid] = acc0 + acc1;
+        }
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// fc2 gradients (sparse in the action index).  block 256 = 4 groups x 64 hidden units; per-block partials.
+// =============================================================================================
+struct Fc2GradArgs {
+    const float *hout, *d_chosen;
+    mal_field_t actions;
+    int B, T, N, A, R;
+    float *part;     // [gridDim.x][A*64 + A]
+    int64_t items_per_block;
+};
+
+__global__ void __launch_bounds__(256) k_fc2_grad(Fc2GradArgs a) {
+    __shared__ float acc_s[4][MAL_MAX_ACTIONS][HID];
+    __shared__ float accb_s[4][MAL_MAX_ACTIONS];
+    const int tid = threadIdx.x, grp = tid >> 6, i = tid & 63;
+    for (int j = 0; j < a.A; ++j) acc_s[grp][j][i] = 0.0f;
+    if (i < a.A) accb_s[grp][i] = 0.0f;
+    __syncthreads();
+    const int64_t total = (int64_t)a.T * a.R;
+    const int64_t beg = (int64_t)blockIdx.x * a.items_per_block;
+    int64_t end = beg + a.items_per_block;
+    if (end > total) end = total;
+    for (int64_t m = beg + grp; m < end; m += 4) {
+        const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
+        const int b = row / a.N, n = row - b * a.N;
+        const float d = a.d_chosen[((int64_t)b * a.T + t) * a.N + n];
+        const int act = (int)(field_ptr<long long>(a.actions, b, t)[n]);
+        acc_s[grp][act][i] += d * a.hout[m * HID + i];
+        if (i == 0) accb_s[grp][act] += d;
+    }
+    __syncthreads();
+    float *out = a.part + (int64_t)blockIdx.x * (a.A * HID + a.A);
+    for (int idx = tid; idx < a.A * HID; idx += 256) {
+        int j = idx >> 6, ii = idx & 63;
+        out[idx] = acc_s[0][j][ii] + acc_s[1][j][ii] + acc_s[2][j][ii] + acc_s[3][j][ii];
+    }
+    if (tid < a.A) out[a.A * HID + tid] = accb_s[0][tid] + accb_s[1][tid] + accb_s[2][tid] + accb_s[3][tid];
+}
+
+// =============================================================================================
+// gather per-chunk partials into the flat gradient (fixed summation order) + per-block sum of squares
+// =============================================================================================
+struct GradSeg {
+    int64_t grad_off;
+    int count;
+    const float *part;
+    int n_chunks;
+    int64_t chunk_stride;
+};
+#define GRAD_MAX_SEGS 32
+struct GradReduceArgs {
+    int n;
+    GradSeg s[GRAD_MAX_SEGS];
+    int64_t total;
+    float *grad;
+    float *norm_part;   // [gridDim.x]
+};
+
+__global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ GradReduceArgs a) {
+    __shared__ float s_sq[8];
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    float v = 0.0f;
+    if (p < a.total) {
+        int si = 0;
+        while (si + 1 < a.n && p >= a.s[si + 1].grad_off) ++si;
+        const GradSeg &s = a.s[si];
+        const int64_t off = p - s.grad_off;
+        if (off < s.count) {
+            const float *src = s.part + off;
+            for (int c = 0; c < s.n_chunks; ++c) v += src[(int64_t)c * s.chunk_stride];
+        }
+        a.grad[p] = v;
+    }
+    float sq = warp_sum(v * v);
+    if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0;
+        for (int w = 0; w < 8; ++w) s += s_sq[w];
+        a.norm_part[blockIdx.x] = s;
+    }
+}
+
+// sum of squares of an arbitrary flat gradient (used when mal_clip_rmsprop is called stand-alone)
+__global__ void __launch_bounds__(256) k_sumsq(const float *g, int64_t n, float *norm_part) {
+    __shared__ float s_sq[8];
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    float v = p < n ? g[p] : 0.0f;
+    float sq = warp_sum(v * v);
+    if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0;
+        for (int w = 0; w < 8; ++w) s += s_sq[w];
+        norm_part[blockIdx.x] = s;
+    }
+}
+
+// =============================================================================================
+// clip_grad_norm_ (q_learner.py:104) + RMSprop.step (learner.py:25-31), one pass over the flat buffers
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer,
+                                                      float *grad, float *sq, const float *norm_part, int n_part,
+                                                      float lr, float alpha, float eps, float clip, float *scalars) {
+    __shared__ float s_red[8];
+    __shared__ float s_coef;
+    // every block recomputes the global norm from the per-block partials in the same fixed order
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n_part; i += 256) s += norm_part[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_red[w];
+        const float norm = sqrtf(tot);
+        float coef = clip / (norm + 1e-6f);
+        s_coef = coef < 1.0f ? coef : 1.0f;
+        if (blockIdx.x == 0) scalars[MAL_SC_GRAD_NORM] = norm;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n_agent + n_mixer) return;
+    float *param = p < n_agent ? agent + p : mixer + (p - n_agent);
+    const float gv = grad[p] * coef;
+    grad[p] = gv;   // clip_grad_norm_ scales .grad in place
+    const float v = alpha * sq[p] + (1.0f - alpha) * gv * gv;
+    sq[p] = v;
+    *param = *param - lr * gv / (sqrtf(v) + eps);
+}
+
+__global__ void __launch_bounds__(256) k_copy_f32(float *dst, const float *src, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t n4 = n / 4;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        for (int64_t j = i; j < n4; j += (int64_t)gridDim.x * 256)
+            reinterpret_cast<float4 *>(dst)[j] = reinterpret_cast<const float4 *>(src)[j];
+        for (int64_t j = n4 * 4 + i; j < n; j += (int64_t)gridDim.x * 256) dst[j] = src[j];
+    } else {
+        for (int64_t j = i; j < n; j += (int64_t)gridDim.x * 256) dst[j] = src[j];
+    }
+}

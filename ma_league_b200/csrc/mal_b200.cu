@@ -1,0 +1,692 @@
+// libmal_b200.so -- C ABI (include/mal_b200.h) over the sm_100a kernels.  Host side: argument checks,
+// workspace planning and launches only.  No allocation, no synchronisation, no CPU fallback.
+#include <stdarg.h>
+#include <string.h>
+#include "mal_common.cuh"
+#include "replay.cuh"
+#include "actsel.cuh"
+#include "learner.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void mal_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *mal_last_error(void) { return g_err; }
+extern "C" int mal_version(void) { return MAL_ABI_VERSION; }
+
+extern "C" int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions) { return agent_layout(d_in, n_actions).total; }
+extern "C" int64_t mal_mixer_param_count(int32_t mixer, int32_t S, int32_t N, int32_t E, int32_t HE) {
+    return mixer_layout(mixer, S, N, E, HE).total;
+}
+
+static int device_sm_count(int *sms, int *threads_per_sm) {
+    static thread_local int c_dev = -1, c_sms = 0, c_tps = 0;
+    int dev = 0;
+    MAL_CUDA(cudaGetDevice(&dev));
+    if (dev != c_dev) {
+        MAL_CUDA(cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev));
+        MAL_CUDA(cudaDeviceGetAttribute(&c_tps, cudaDevAttrMaxThreadsPerMultiProcessor, dev));
+        c_dev = dev;
+    }
+    *sms = c_sms;
+    *threads_per_sm = c_tps;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// replay
+// ---------------------------------------------------------------------------------------------
+extern "C" int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst_ids, const void *src,
+                               int64_t src_stride, const int64_t *src_ids, int32_t n, int64_t bytes, void *stream) {
+    if (n <= 0 || bytes <= 0) return 0;
+    MAL_REQUIRE(dst && src, "mal_record_copy: null buffer");
+    MAL_REQUIRE((bytes % 16) == 0 && (dst_stride % 16) == 0 && (src_stride % 16) == 0 &&
+                    (((uintptr_t)dst | (uintptr_t)src) & 15) == 0,
+                "mal_record_copy: records must be 16-byte aligned multiples of 16 bytes");
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    RecordCopyArgs a;
+    a.dst = (uint8_t *)dst; a.src = (const uint8_t *)src;
+    a.dst_stride = dst_stride; a.src_stride = src_stride;
+    a.dst_ids = dst_ids; a.src_ids = src_ids;
+    a.n = n; a.bytes = bytes;
+    a.tiles_per_rec = (int32_t)ceil_div64(bytes, RC_TILE);
+    a.n_tiles = (int64_t)a.tiles_per_rec * n;
+    const size_t smem = (size_t)RC_STAGES * RC_TILE;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        MAL_CUDA(cudaFuncSetAttribute(k_record_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int64_t grid = a.n_tiles < (int64_t)sms * 3 ? a.n_tiles : (int64_t)sms * 3;   // 3 x 64 KB rings per SM
+    k_record_copy_tma<<<(unsigned)grid, 32, smem, (cudaStream_t)stream>>>(a);
+    MAL_LAUNCH_CHECK("k_record_copy_tma");
+    return 0;
+}
+
+extern "C" int mal_max_t_filled(const int64_t *filled, int64_t sb, int64_t st, int32_t B, int32_t TT, int32_t *out,
+                                void *stream) {
+    MAL_REQUIRE(filled && out && B > 0 && TT > 0, "mal_max_t_filled: bad arguments");
+    k_max_t_filled<<<1, 256, 0, (cudaStream_t)stream>>>(filled, sb, st, B, TT, out);
+    MAL_LAUNCH_CHECK("k_max_t_filled");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// act-select
+// ---------------------------------------------------------------------------------------------
+static int fill_select(const mal_select_t *sel, int rows, int N, int A, SelectArgs *s) {
+    MAL_REQUIRE(sel->avail && sel->actions && sel->greedy, "select: avail/actions/greedy must be set");
+    MAL_REQUIRE(sel->rng_mode == 0 || sel->rng_mode == 1, "select: rng_mode must be 0 (injected) or 1 (philox)");
+    if (sel->rng_mode == 0) MAL_REQUIRE(sel->u && sel->e, "select: rng_mode 0 needs u and e");
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    s->avail = sel->avail; s->avail_sb = sel->avail_sb; s->N = N; s->epsilon = sel->epsilon; s->rng_mode = sel->rng_mode;
+    s->u = sel->u; s->e = sel->e; s->seed = sel->seed;
+    s->actions = sel->actions; s->greedy = sel->greedy; s->status = sel->status;
+    // torch's calc_execution_policy (ATen/native/cuda/DistributionTemplates.h): block 256, grid capped at
+    // SMs * (maxThreadsPerSM / 256); each op advances the generator by ((numel-1)/(256*grid*4)+1)*4.
+    const uint64_t cap = (uint64_t)sms * (uint64_t)(tps / 256);
+    uint64_t n_u = (uint64_t)rows, n_e = (uint64_t)rows * (uint64_t)A;
+    uint64_t g_u = (n_u + 255) / 256; if (g_u > cap) g_u = cap;
+    uint64_t g_e = (n_e + 255) / 256; if (g_e > cap) g_e = cap;
+    s->grid_u = (uint32_t)g_u; s->grid_e = (uint32_t)g_e;
+    s->offset_u = sel->offset;
+    s->offset_e = sel->offset + ((n_u - 1) / (256 * g_u * 4) + 1) * 4;
+    return 0;
+}
+
+// total generator advance (in 32-bit outputs) of one select over rows x A, for the caller to apply to torch's generator
+extern "C" int mal_select_philox_advance(int32_t rows, int32_t n_actions, uint64_t *advance) {
+    MAL_REQUIRE(rows > 0 && n_actions > 0 && advance, "mal_select_philox_advance: bad arguments");
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    const uint64_t cap = (uint64_t)sms * (uint64_t)(tps / 256);
+    uint64_t n_u = (uint64_t)rows, n_e = (uint64_t)rows * (uint64_t)n_actions;
+    uint64_t g_u = (n_u + 255) / 256; if (g_u > cap) g_u = cap;
+    uint64_t g_e = (n_e + 255) / 256; if (g_e > cap) g_e = cap;
+    *advance = ((n_u - 1) / (256 * g_u * 4) + 1) * 4 + ((n_e - 1) / (256 * g_e * 4) + 1) * 4;
+    return 0;
+}
+
+extern "C" int mal_eps_greedy_select(const float *q, int64_t q_ld, int32_t rows, int32_t n_agents, int32_t n_actions,
+                                     const mal_select_t *sel, void *stream) {
+    MAL_REQUIRE(q && sel && rows > 0 && n_agents > 0, "mal_eps_greedy_select: bad arguments");
+    MAL_REQUIRE(n_actions >= 1 && n_actions <= MAL_MAX_ACTIONS, "n_actions must be in [1, %d]", MAL_MAX_ACTIONS);
+    SelectArgs s;
+    if (int rc = fill_select(sel, rows, n_agents, n_actions, &s)) return rc;
+    const int warps_per_block = AS_THREADS / 32;
+    k_eps_greedy_select<<<(rows + warps_per_block - 1) / warps_per_block, AS_THREADS, 0, (cudaStream_t)stream>>>(
+        q, q_ld, rows, n_actions, s);
+    MAL_LAUNCH_CHECK("k_eps_greedy_select");
+    return 0;
+}
+
+extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t obs_dim, int32_t n_actions,
+                              int32_t dense_input, const float *obs, int64_t obs_sb, const float *last_onehot,
+                              int64_t onehot_sb, const float *h_in, float *h_out, float *q, const mal_select_t *sel,
+                              void *stream) {
+    MAL_REQUIRE(agent && obs && h_out && q && rows > 0, "mal_agent_step: bad arguments");
+    MAL_REQUIRE(n_actions >= 1 && n_actions <= MAL_MAX_ACTIONS, "n_actions must be in [1, %d]", MAL_MAX_ACTIONS);
+    MAL_REQUIRE(n_agents >= 1 && obs_dim >= 1, "mal_agent_step: bad dims");
+    AgentStepArgs a;
+    a.params = agent; a.rows = rows; a.N = n_agents; a.OBS = obs_dim; a.A = n_actions;
+    a.dense = dense_input ? 1 : 0;
+    a.obs = obs; a.obs_sb = obs_sb; a.onehot = dense_input ? nullptr : last_onehot; a.onehot_sb = onehot_sb;
+    a.h_in = h_in; a.h_out = h_out; a.q = q; a.do_select = sel ? 1 : 0;
+    memset(&a.sel, 0, sizeof(a.sel));
+    if (sel) if (int rc = fill_select(sel, rows, n_agents, n_actions, &a.sel)) return rc;
+    const int Kin = dense_input ? obs_dim : obs_dim + n_actions;
+    const size_t smem = sizeof(float) * (size_t)(AS_ROWS * (Kin + 1) + AS_ROWS * HID * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
+    MAL_REQUIRE(smem <= 200 * 1024, "mal_agent_step: obs_dim too large for the shared-memory staging");
+    if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_agent_step<<<(rows + AS_ROWS - 1) / AS_ROWS, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
+    MAL_LAUNCH_CHECK("k_agent_step");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// learner: planning
+// ---------------------------------------------------------------------------------------------
+struct Dims {
+    int B, TT, T, N, A, OBS, S, R, E, HE, d_in, mixer, two;
+    int64_t M1, BT;
+    int ld1, ld2;
+};
+
+static int get_dims(const mal_batch_t *b, const mal_learner_cfg_t *c, Dims *d) {
+    MAL_REQUIRE(b && c, "null batch/cfg");
+    MAL_REQUIRE(b->B >= 1 && b->TT >= 2 && b->N >= 1 && b->OBS >= 1 && b->S >= 1, "bad batch dims (need TT >= 2)");
+    MAL_REQUIRE(b->A >= 1 && b->A <= MAL_MAX_ACTIONS, "n_actions must be in [1, %d]", MAL_MAX_ACTIONS);
+    MAL_REQUIRE(b->N <= MAL_MAX_ACTIONS, "n_agents must be <= %d", MAL_MAX_ACTIONS);
+    MAL_REQUIRE(c->mixer == MAL_MIXER_VDN || c->mixer == MAL_MIXER_QMIX2 || c->mixer == MAL_MIXER_QMIX1,
+                "Mixer %d not recognised.", c->mixer);
+    d->B = b->B; d->TT = b->TT; d->T = b->TT - 1; d->N = b->N; d->A = b->A; d->OBS = b->OBS; d->S = b->S;
+    d->R = b->B * b->N; d->d_in = b->OBS + b->A + b->N; d->mixer = c->mixer;
+    d->E = c->embed; d->HE = c->hyper_embed; d->two = (c->mixer == MAL_MIXER_QMIX2);
+    if (c->mixer != MAL_MIXER_VDN) {
+        MAL_REQUIRE(d->E >= 1 && d->E <= MAL_MAX_EMBED, "mixing_embed_dim must be in [1, %d]", MAL_MAX_EMBED);
+        if (d->two) MAL_REQUIRE(d->HE >= 1, "hypernet_embed must be >= 1");
+    } else { d->E = 0; d->HE = 0; }
+    d->M1 = (int64_t)d->TT * d->R;
+    d->BT = (int64_t)d->B * d->T;
+    d->ld1 = d->mixer == MAL_MIXER_VDN ? 0 : (d->two ? 2 * d->HE + 2 * d->E : 2 * d->E);
+    d->ld2 = d->mixer == MAL_MIXER_VDN ? 0 : d->E * d->N + d->E;
+    return 0;
+}
+
+static void chunking(int64_t M, int max_chunks, int *n_chunks, int64_t *rows_per_chunk) {
+    int64_t nc = ceil_div64(M, 256);
+    if (nc < 1) nc = 1;
+    if (nc > max_chunks) nc = max_chunks;
+    int64_t rpc = align_up64(ceil_div64(M, nc), RED_MR);
+    nc = ceil_div64(M, rpc);
+    *n_chunks = (int)nc;
+    *rows_per_chunk = rpc;
+}
+
+// offsets (in floats) inside the partials scratch
+struct PartLayout {
+    int nc_a; int64_t rpc_a;        // agent reductions over M1 rows
+    int nc_m; int64_t rpc_m;        // mixer reductions over BT rows
+    int nblk_fc2; int64_t ipb_fc2;
+    int nblk_mix;
+    int nblk_norm;
+    int64_t wih_w, wih_b, whha_w, whha_b, whhb_w, whhb_b, fc1_w, fc1_b, fc2;
+    int64_t m_l2a_w, m_l2a_b, m_l2b_w, m_l2b_b, m_l1_w, m_l1_b;   // mixer: layer-2 (w1b, wfb), layer-1 block
+    int64_t mix_stats, mix_v2, norm;
+    int64_t total;
+};
+
+static PartLayout part_layout(const Dims &d, int sms) {
+    PartLayout p;
+    memset(&p, 0, sizeof(p));
+    chunking(d.M1, 192, &p.nc_a, &p.rpc_a);
+    chunking(d.BT, 128, &p.nc_m, &p.rpc_m);
+    const int64_t TR = (int64_t)d.T * d.R;
+    int64_t nb = ceil_div64(TR, 512); if (nb < 1) nb = 1; if (nb > 128) nb = 128;
+    p.nblk_fc2 = (int)nb; p.ipb_fc2 = ceil_div64(TR, nb);
+    int64_t nm = ceil_div64(d.BT, 8); if (nm > (int64_t)sms * 4) nm = (int64_t)sms * 4; if (nm < 1) nm = 1;
+    p.nblk_mix = (int)nm;
+    const int64_t P = agent_layout(d.d_in, d.A).total + mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
+    p.nblk_norm = (int)ceil_div64(P, 256);
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += align_up64(n, 64); return r; };
+    p.wih_w = take((int64_t)p.nc_a * G3 * HID);   p.wih_b = take((int64_t)p.nc_a * G3);
+    p.whha_w = take((int64_t)p.nc_a * 128 * HID); p.whha_b = take((int64_t)p.nc_a * 128);
+    p.whhb_w = take((int64_t)p.nc_a * 64 * HID);  p.whhb_b = take((int64_t)p.nc_a * 64);
+    p.fc1_w = take((int64_t)p.nc_a * HID * d.d_in); p.fc1_b = take((int64_t)p.nc_a * HID);
+    p.fc2 = take((int64_t)p.nblk_fc2 * (d.A * HID + d.A));
+    if (d.mixer != MAL_MIXER_VDN) {
+        const int K2 = d.two ? d.HE : d.S;
+        p.m_l2a_w = take((int64_t)p.nc_m * d.E * d.N * K2); p.m_l2a_b = take((int64_t)p.nc_m * d.E * d.N);
+        p.m_l2b_w = take((int64_t)p.nc_m * d.E * K2);       p.m_l2b_b = take((int64_t)p.nc_m * d.E);
+        p.m_l1_w = take((int64_t)p.nc_m * d.ld1 * d.S);     p.m_l1_b = take((int64_t)p.nc_m * d.ld1);
+        p.mix_v2 = take((int64_t)p.nblk_mix * (d.E + 1));
+    }
+    p.mix_stats = take((int64_t)p.nblk_mix * 4);
+    p.norm = take(p.nblk_norm);
+    p.total = o;
+    return p;
+}
+
+extern "C" int mal_learner_plan(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, mal_plan_t *plan) {
+    Dims d;
+    if (int rc = get_dims(batch, cfg, &d)) return rc;
+    MAL_REQUIRE(plan, "null plan");
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) { sms = 148; }   // planning also works without a device (CPU-side tests)
+    memset(plan, 0, sizeof(*plan));
+    int64_t o = 0;
+    auto take = [&](int64_t n_elems, int64_t elem) { int64_t r = o; o += align_up64(n_elems * elem, 256); return r; };
+    plan->n_agent_params = agent_layout(d.d_in, d.A).total;
+    plan->n_mixer_params = mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
+    plan->scalars = take(64, 4);
+    plan->x_on = take(d.M1 * HID, 4);   plan->x_tg = take(d.M1 * HID, 4);
+    plan->gi_on = take(d.M1 * G3, 4);   plan->gi_tg = take(d.M1 * G3, 4);
+    plan->h_on = take(d.M1 * HID, 4);   plan->h_tg = take(d.M1 * HID, 4);
+    plan->gates = take(d.M1 * 4 * HID, 4);
+    const int64_t nq = cfg->save_q ? (int64_t)d.B * d.TT * d.N * d.A : 0;
+    plan->mac_out = take(nq, 4);        plan->target_mac_out = take(nq, 4);
+    plan->chosen = take(d.BT * d.N, 4); plan->target_max = take(d.BT * d.N, 4);
+    plan->argmax = take(d.BT * d.N, 4);
+    plan->mask = take(d.BT, 4);
+    plan->y1_on = take(d.BT * d.ld1, 4); plan->y1_tg = take(d.BT * d.ld1, 4);
+    plan->a2_on = take(d.BT * d.ld2, 4); plan->a2_tg = take(d.BT * d.ld2, 4);
+    plan->q_tot = take(d.BT, 4); plan->target_q_tot = take(d.BT, 4);
+    plan->targets = take(d.BT, 4); plan->td = take(d.BT, 4);
+    plan->d_a2 = take(d.BT * d.ld2, 4); plan->d_y1 = take(d.BT * d.ld1, 4);
+    plan->d_chosen = take(d.BT * d.N, 4);
+    plan->d_g = take(d.M1 * 4 * HID, 4);
+    plan->d_x = take(d.M1 * HID, 4);
+    PartLayout pl = part_layout(d, sms);
+    plan->partials_bytes = pl.total * 4;
+    plan->partials = take(pl.total, 4);
+    plan->total_bytes = o;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// learner: launches
+// ---------------------------------------------------------------------------------------------
+static BatchView make_view(const mal_batch_t *b, const Dims &d) {
+    BatchView v;
+    v.B = d.B; v.TT = d.TT; v.T = d.T; v.N = d.N; v.A = d.A; v.OBS = d.OBS; v.S = d.S; v.R = d.R;
+    v.obs = b->obs; v.onehot = b->onehot; v.state = b->state;
+    return v;
+}
+
+static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st) {
+    const int nkc = (maxK + LIN_KC - 1) / LIN_KC;
+    const size_t smem = sizeof(float) * ((size_t)LIN_TM * (nkc * LIN_KC + 4) + (size_t)LIN_TN * LIN_LDW);
+    MAL_REQUIRE(smem <= 220 * 1024, "inner dimension %d too large for the panel GEMM", maxK);
+    static thread_local size_t attr = 48 * 1024;
+    if (smem > attr) {
+        MAL_CUDA(cudaFuncSetAttribute(k_linear_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid((unsigned)ceil_div64(maxM, LIN_TM), g.n);
+    k_linear_group<<<grid, 256, smem, st>>>(g);
+    MAL_LAUNCH_CHECK("k_linear_group");
+    return 0;
+}
+
+static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const float *A, int64_t lda, const float *W,
+                   int64_t ldw, int w_trans, const float *bias, int epi, const float *aux, int64_t ld_aux, float *Y,
+                   int64_t ldy) {
+    LinProb p;
+    p.M = (int)M; p.K = K; p.Nout = Nout; p.a_kind = a_kind; p.shift = shift; p.A = A; p.lda = lda;
+    p.W = W; p.ldw = ldw; p.w_trans = w_trans; p.bias = bias; p.epi = epi; p.aux = aux; p.ld_aux = ld_aux;
+    p.Y = Y; p.ldy = ldy;
+    return p;
+}
+
+template <int RT>
+static void launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st) {
+    dim3 grid((a.R + RT - 1) / RT, nets);
+    k_gru_fwd<RT><<<grid, 192, 0, st>>>(a);
+}
+template <int RT>
+static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st) {
+    k_gru_bwd<RT><<<(a.R + RT - 1) / RT, 192, 0, st>>>(a);
+}
+static int pick_rt(int64_t chains, int sms) {
+    // smallest rows-per-CTA that still fits every chain in ~2 co-resident CTAs per SM; larger problems queue in waves
+    if (chains <= (int64_t)sms * 2 * 2) return 2;
+    if (chains <= (int64_t)sms * 2 * 4) return 4;
+    return 8;
+}
+
+extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
+                                   const float *agent, const float *target_agent, const float *mixer,
+                                   const float *target_mixer, void *workspace, void *stream) {
+    Dims d;
+    if (int rc = get_dims(batch, cfg, &d)) return rc;
+    MAL_REQUIRE(plan && workspace && agent && target_agent, "mal_learner_forward: null argument");
+    MAL_REQUIRE(d.mixer == MAL_MIXER_VDN || (mixer && target_mixer), "mal_learner_forward: mixer parameters missing");
+    MAL_REQUIRE(d.M1 * 4 * HID < (int64_t)1 << 40, "problem too large");
+    MAL_REQUIRE(d.M1 < 2147483647LL && d.BT < 2147483647LL, "row count overflows int32");
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)workspace;
+    auto F = [&](int64_t off) { return reinterpret_cast<float *>(ws + off); };
+    const AgentLayout AL = agent_layout(d.d_in, d.A);
+    const MixerLayout ML = mixer_layout(d.mixer, d.S, d.N, d.E, d.HE);
+    const BatchView bv = make_view(batch, d);
+    float *scalars = F(plan->scalars);
+    const PartLayout pl = part_layout(d, sms);
+    float *parts = F(plan->partials);
+    const float *ap[2] = {agent, target_agent};
+    const float *mp[2] = {mixer, target_mixer};
+    float *x[2] = {F(plan->x_on), F(plan->x_tg)}, *gi[2] = {F(plan->gi_on), F(plan->gi_tg)};
+    float *hh[2] = {F(plan->h_on), F(plan->h_tg)};
+    float *y1[2] = {F(plan->y1_on), F(plan->y1_tg)}, *a2[2] = {F(plan->a2_on), F(plan->a2_tg)};
+
+    // mask and mask.sum()                                                   q_learner.py:40-42
+    k_mask_prep<<<1, 1024, 0, st>>>(batch->filled, batch->terminated, d.B, d.T, F(plan->mask), scalars);
+    MAL_LAUNCH_CHECK("k_mask_prep");
+
+    // x = relu(fc1([obs | last action | agent id]))  for every (t,b,n), both nets   basic_controller.py:80-92
+    {
+        LinGroup g; g.n = 2; g.bv = bv;
+        for (int net = 0; net < 2; ++net)
+            g.p[net] = lin(d.M1, d.OBS + d.A, HID, A_AGENT_IN, 0, nullptr, 0, ap[net] + AL.fc1_w, d.d_in, 0,
+                           ap[net] + AL.fc1_b, EPI_FC1, nullptr, 0, x[net], HID);
+        if (int rc = launch_linear(g, d.M1, d.OBS + d.A, st)) return rc;
+    }
+    // gi = W_ih x + b_ih
+    {
+        LinGroup g; g.n = 2; g.bv = bv;
+        for (int net = 0; net < 2; ++net)
+            g.p[net] = lin(d.M1, HID, G3, A_DENSE, 0, x[net], HID, ap[net] + AL.w_ih, HID, 0, ap[net] + AL.b_ih,
+                           EPI_BIAS, nullptr, 0, gi[net], G3);
+        if (int rc = launch_linear(g, d.M1, HID, st)) return rc;
+    }
+    // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
+    {
+        GruFwdArgs a;
+        for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
+        a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
+        switch (pick_rt((int64_t)d.R * 2, sms)) {
+            case 2: launch_gru_fwd<2>(a, 2, st); break;
+            case 4: launch_gru_fwd<4>(a, 2, st); break;
+            default: launch_gru_fwd<8>(a, 2, st); break;
+        }
+        MAL_LAUNCH_CHECK("k_gru_fwd");
+    }
+    // q, chosen-action gather, masked double-Q target max                   q_learner.py:52-78
+    {
+        HeadArgs a;
+        for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.hout[net] = hh[net]; }
+        a.B = d.B; a.TT = d.TT; a.N = d.N; a.A = d.A; a.R = d.R; a.d_in = d.d_in; a.double_q = cfg->double_q;
+        a.actions = batch->actions; a.avail = batch->avail;
+        a.mac_out = cfg->save_q ? F(plan->mac_out) : nullptr;
+        a.target_mac_out = cfg->save_q ? F(plan->target_mac_out) : nullptr;
+        a.chosen = F(plan->chosen); a.target_max = F(plan->target_max);
+        a.argmax = reinterpret_cast<int *>(ws + plan->argmax);
+        int64_t grid = ceil_div64(d.M1, 8); if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+        k_q_head<<<(unsigned)grid, 256, 0, st>>>(a);
+        MAL_LAUNCH_CHECK("k_q_head");
+    }
+    // mixer hypernetworks                                                   qmix.py:41-59
+    if (d.mixer == MAL_MIXER_QMIX2) {
+        LinGroup g; g.n = 8; g.bv = bv;
+        for (int net = 0; net < 2; ++net) {
+            const float *P = mp[net];
+            g.p[net * 4 + 0] = lin(d.BT, d.S, d.HE, A_STATE, net, nullptr, 0, P + ML.w1a_w, d.S, 0, P + ML.w1a_b, EPI_RELU, nullptr, 0, y1[net], d.ld1);
+            g.p[net * 4 + 1] = lin(d.BT, d.S, d.HE, A_STATE, net, nullptr, 0, P + ML.wfa_w, d.S, 0, P + ML.wfa_b, EPI_RELU, nullptr, 0, y1[net] + d.HE, d.ld1);
+            g.p[net * 4 + 2] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.b1_w, d.S, 0, P + ML.b1_b, EPI_BIAS, nullptr, 0, y1[net] + 2 * d.HE, d.ld1);
+            g.p[net * 4 + 3] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.v0_w, d.S, 0, P + ML.v0_b, EPI_RELU, nullptr, 0, y1[net] + 2 * d.HE + d.E, d.ld1);
+        }
+        if (int rc = launch_linear(g, d.BT, d.S, st)) return rc;
+        LinGroup h; h.n = 4; h.bv = bv;
+        for (int net = 0; net < 2; ++net) {
+            const float *P = mp[net];
+            h.p[net * 2 + 0] = lin(d.BT, d.HE, d.E * d.N, A_DENSE, 0, y1[net], d.ld1, P + ML.w1b_w, d.HE, 0, P + ML.w1b_b, EPI_BIAS, nullptr, 0, a2[net], d.ld2);
+            h.p[net * 2 + 1] = lin(d.BT, d.HE, d.E, A_DENSE, 0, y1[net] + d.HE, d.ld1, P + ML.wfb_w, d.HE, 0, P + ML.wfb_b, EPI_BIAS, nullptr, 0, a2[net] + d.E * d.N, d.ld2);
+        }
+        if (int rc = launch_linear(h, d.BT, d.HE, st)) return rc;
+    } else if (d.mixer == MAL_MIXER_QMIX1) {
+        LinGroup g; g.n = 8; g.bv = bv;
+        for (int net = 0; net < 2; ++net) {
+            const float *P = mp[net];
+            g.p[net * 4 + 0] = lin(d.BT, d.S, d.E * d.N, A_STATE, net, nullptr, 0, P + ML.w1b_w, d.S, 0, P + ML.w1b_b, EPI_BIAS, nullptr, 0, a2[net], d.ld2);
+            g.p[net * 4 + 1] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.wfb_w, d.S, 0, P + ML.wfb_b, EPI_BIAS, nullptr, 0, a2[net] + d.E * d.N, d.ld2);
+            g.p[net * 4 + 2] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.b1_w, d.S, 0, P + ML.b1_b, EPI_BIAS, nullptr, 0, y1[net], d.ld1);
+            g.p[net * 4 + 3] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.v0_w, d.S, 0, P + ML.v0_b, EPI_RELU, nullptr, 0, y1[net] + d.E, d.ld1);
+        }
+        if (int rc = launch_linear(g, d.BT, d.S, st)) return rc;
+    }
+    // mixing + TD error + masked loss + element-wise mixer backward          q_learner.py:81-98
+    {
+        MixArgs a;
+        a.mixer = d.mixer; a.B = d.B; a.T = d.T; a.N = d.N; a.E = d.E; a.HE = d.HE; a.S = d.S;
+        for (int net = 0; net < 2; ++net) { a.y1[net] = y1[net]; a.a2[net] = a2[net]; a.mparams[net] = mp[net]; }
+        a.chosen = F(plan->chosen); a.target_max = F(plan->target_max); a.mask = F(plan->mask);
+        a.reward = batch->reward; a.terminated = batch->terminated; a.gamma = cfg->gamma; a.scalars = scalars;
+        a.q_tot = F(plan->q_tot); a.target_q_tot = F(plan->target_q_tot); a.targets = F(plan->targets); a.td = F(plan->td);
+        a.d_a2 = F(plan->d_a2); a.d_y1 = F(plan->d_y1); a.d_chosen = F(plan->d_chosen);
+        a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
+        k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a);
+        MAL_LAUNCH_CHECK("k_mix_td");
+        k_stats_finalize<<<1, 32, 0, st>>>(parts + pl.mix_stats, pl.nblk_mix, d.N, scalars);
+        MAL_LAUNCH_CHECK("k_stats_finalize");
+    }
+    return 0;
+}
+
+extern "C" int mal_mixer_forward(int32_t mixer, int32_t B, int32_t T, int32_t N, int32_t S, int32_t E, int32_t HE,
+                                 const float *params, const float *agent_qs, const float *states, int64_t state_sb,
+                                 int64_t state_st, float *scratch, float *q_tot, void *stream) {
+    MAL_REQUIRE(agent_qs && q_tot && B > 0 && T > 0 && N > 0 && N <= MAL_MAX_ACTIONS, "mal_mixer_forward: bad arguments");
+    MAL_REQUIRE(mixer == MAL_MIXER_VDN || mixer == MAL_MIXER_QMIX2 || mixer == MAL_MIXER_QMIX1, "Mixer %d not recognised.", mixer);
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    MixArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mixer = mixer; a.B = B; a.T = T; a.N = N; a.E = E; a.HE = HE; a.S = S;
+    a.chosen = agent_qs; a.q_tot = q_tot;
+    const int64_t BT = (int64_t)B * T;
+    if (mixer != MAL_MIXER_VDN) {
+        MAL_REQUIRE(params && states && scratch && S > 0, "mal_mixer_forward: params/states/scratch missing");
+        MAL_REQUIRE(E >= 1 && E <= MAL_MAX_EMBED, "mixing_embed_dim must be in [1, %d]", MAL_MAX_EMBED);
+        const MixerLayout ML = mixer_layout(mixer, S, N, E, HE);
+        const int two = mixer == MAL_MIXER_QMIX2;
+        const int ld1 = two ? 2 * HE + 2 * E : 2 * E, ld2 = E * N + E;
+        float *y1 = scratch, *a2 = scratch + BT * ld1;   // scratch: BT * (ld1 + ld2) floats
+        BatchView bv;
+        memset(&bv, 0, sizeof(bv));
+        bv.B = B; bv.T = T; bv.TT = T; bv.N = N; bv.S = S; bv.R = B * N;
+        bv.state.ptr = states; bv.state.sb = state_sb; bv.state.st = state_st;
+        LinGroup g; g.bv = bv;
+        if (two) {
+            g.n = 4;
+            g.p[0] = lin(BT, S, HE, A_STATE, 0, nullptr, 0, params + ML.w1a_w, S, 0, params + ML.w1a_b, EPI_RELU, nullptr, 0, y1, ld1);
+            g.p[1] = lin(BT, S, HE, A_STATE, 0, nullptr, 0, params + ML.wfa_w, S, 0, params + ML.wfa_b, EPI_RELU, nullptr, 0, y1 + HE, ld1);
+            g.p[2] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.b1_w, S, 0, params + ML.b1_b, EPI_BIAS, nullptr, 0, y1 + 2 * HE, ld1);
+            g.p[3] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.v0_w, S, 0, params + ML.v0_b, EPI_RELU, nullptr, 0, y1 + 2 * HE + E, ld1);
+            if (int rc = launch_linear(g, BT, S, st)) return rc;
+            LinGroup h; h.bv = bv; h.n = 2;
+            h.p[0] = lin(BT, HE, E * N, A_DENSE, 0, y1, ld1, params + ML.w1b_w, HE, 0, params + ML.w1b_b, EPI_BIAS, nullptr, 0, a2, ld2);
+            h.p[1] = lin(BT, HE, E, A_DENSE, 0, y1 + HE, ld1, params + ML.wfb_w, HE, 0, params + ML.wfb_b, EPI_BIAS, nullptr, 0, a2 + E * N, ld2);
+            if (int rc = launch_linear(h, BT, HE, st)) return rc;
+        } else {
+            g.n = 4;
+            g.p[0] = lin(BT, S, E * N, A_STATE, 0, nullptr, 0, params + ML.w1b_w, S, 0, params + ML.w1b_b, EPI_BIAS, nullptr, 0, a2, ld2);
+            g.p[1] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.wfb_w, S, 0, params + ML.wfb_b, EPI_BIAS, nullptr, 0, a2 + E * N, ld2);
+            g.p[2] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.b1_w, S, 0, params + ML.b1_b, EPI_BIAS, nullptr, 0, y1, ld1);
+            g.p[3] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.v0_w, S, 0, params + ML.v0_b, EPI_RELU, nullptr, 0, y1 + E, ld1);
+            if (int rc = launch_linear(g, BT, S, st)) return rc;
+        }
+        a.y1[0] = y1; a.a2[0] = a2; a.mparams[0] = params;
+    }
+    int64_t grid = ceil_div64(BT, 8); if (grid > (int64_t)sms * 4) grid = (int64_t)sms * 4;
+    k_mix_fwd<<<(unsigned)grid, 256, 0, st>>>(a);
+    MAL_LAUNCH_CHECK("k_mix_fwd");
+    return 0;
+}
+
+static RedProb red(int64_t M, int K, int Nout, const float *dY, int64_t ldy, int a_kind, int shift, const float *A,
+                   int64_t lda, float *partW, float *partB, int n_chunks, int64_t rpc) {
+    RedProb p;
+    p.M0 = 0; p.M = M; p.K = K; p.Nout = Nout; p.dY = dY; p.ldy = ldy; p.a_kind = a_kind; p.shift = shift;
+    p.A = A; p.lda = lda; p.partW = partW; p.partB = partB; p.n_chunks = n_chunks; p.rows_per_chunk = rpc;
+    p.tile0 = 0; p.n_ktiles = (K + 63) / 64;
+    return p;
+}
+
+static int launch_reduce(RedGroup &g, cudaStream_t st) {
+    int tiles = 0, maxc = 0;
+    for (int i = 0; i < g.n; ++i) {
+        g.p[i].tile0 = tiles;
+        tiles += ((g.p[i].Nout + 63) / 64) * g.p[i].n_ktiles;
+        if (g.p[i].n_chunks > maxc) maxc = g.p[i].n_chunks;
+    }
+    dim3 grid(maxc, tiles);
+    k_reduce_group<<<grid, 256, 0, st>>>(g);
+    MAL_LAUNCH_CHECK("k_reduce_group");
+    return 0;
+}
+
+extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
+                                    const float *agent, const float *mixer, void *workspace, float *grad, void *stream) {
+    Dims d;
+    if (int rc = get_dims(batch, cfg, &d)) return rc;
+    MAL_REQUIRE(plan && workspace && agent && grad, "mal_learner_backward: null argument");
+    MAL_REQUIRE(d.mixer == MAL_MIXER_VDN || mixer, "mal_learner_backward: mixer parameters missing");
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)workspace;
+    auto F = [&](int64_t off) { return reinterpret_cast<float *>(ws + off); };
+    const AgentLayout AL = agent_layout(d.d_in, d.A);
+    const MixerLayout ML = mixer_layout(d.mixer, d.S, d.N, d.E, d.HE);
+    const BatchView bv = make_view(batch, d);
+    const PartLayout pl = part_layout(d, sms);
+    float *parts = F(plan->partials);
+    float *d_g = F(plan->d_g), *d_x = F(plan->d_x), *d_a2 = F(plan->d_a2), *d_y1 = F(plan->d_y1);
+    float *y1 = F(plan->y1_on);
+
+    // ---- mixer: hypernet backward
+    if (d.mixer == MAL_MIXER_QMIX2) {
+        LinGroup g; g.n = 2; g.bv = bv;   // d h1 = (d a1 . W12) * (h1 > 0) ; d hf = (d af . Wf2) * (hf > 0)
+        g.p[0] = lin(d.BT, d.E * d.N, d.HE, A_DENSE, 0, d_a2, d.ld2, mixer + ML.w1b_w, d.HE, 1, nullptr, EPI_MASKPOS, y1, d.ld1, d_y1, d.ld1);
+        g.p[1] = lin(d.BT, d.E, d.HE, A_DENSE, 0, d_a2 + d.E * d.N, d.ld2, mixer + ML.wfb_w, d.HE, 1, nullptr, EPI_MASKPOS, y1 + d.HE, d.ld1, d_y1 + d.HE, d.ld1);
+        if (int rc = launch_linear(g, d.BT, d.E * d.N, st)) return rc;
+        RedGroup r; r.n = 3; r.bv = bv;
+        r.p[0] = red(d.BT, d.HE, d.E * d.N, d_a2, d.ld2, A_DENSE, 0, y1, d.ld1, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m, pl.rpc_m);
+        r.p[1] = red(d.BT, d.HE, d.E, d_a2 + d.E * d.N, d.ld2, A_DENSE, 0, y1 + d.HE, d.ld1, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m, pl.rpc_m);
+        r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m, pl.rpc_m);
+        if (int rc = launch_reduce(r, st)) return rc;
+    } else if (d.mixer == MAL_MIXER_QMIX1) {
+        RedGroup r; r.n = 3; r.bv = bv;
+        r.p[0] = red(d.BT, d.S, d.E * d.N, d_a2, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m, pl.rpc_m);
+        r.p[1] = red(d.BT, d.S, d.E, d_a2 + d.E * d.N, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m, pl.rpc_m);
+        r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m, pl.rpc_m);
+        if (int rc = launch_reduce(r, st)) return rc;
+    }
+
+    // ---- agent: BPTT recurrence
+    {
+        GruBwdArgs a;
+        a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.d_chosen = F(plan->d_chosen);
+        a.actions = batch->actions; a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.N = d.N; a.d_in = d.d_in; a.n_actions = d.A;
+        switch (pick_rt((int64_t)d.R, sms)) {
+            case 2: launch_gru_bwd<2>(a, st); break;
+            case 4: launch_gru_bwd<4>(a, st); break;
+            default: launch_gru_bwd<8>(a, st); break;
+        }
+        MAL_LAUNCH_CHECK("k_gru_bwd");
+    }
+    // d x = (d gi . W_ih) * (x > 0)
+    {
+        LinGroup g; g.n = 1; g.bv = bv;
+        g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, agent + AL.w_ih, HID, 1, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);
+        if (int rc = launch_linear(g, d.M1, G3, st)) return rc;
+    }
+    // weight gradients of the agent
+    {
+        RedGroup r; r.n = 4; r.bv = bv;
+        r.p[0] = red(d.M1, HID, G3, d_g, 4 * HID, A_DENSE, 0, F(plan->x_on), HID, parts + pl.wih_w, parts + pl.wih_b, pl.nc_a, pl.rpc_a);
+        // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)
+        r.p[1] = red(d.M1, HID, 128, d_g, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whha_w, parts + pl.whha_b, pl.nc_a, pl.rpc_a);
+        r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
+        r.p[3] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_a, pl.rpc_a);
+        if (int rc = launch_reduce(r, st)) return rc;
+        Fc2GradArgs f;
+        f.hout = F(plan->h_on); f.d_chosen = F(plan->d_chosen); f.actions = batch->actions;
+        f.B = d.B; f.T = d.T; f.N = d.N; f.A = d.A; f.R = d.R; f.part = parts + pl.fc2; f.items_per_block = pl.ipb_fc2;
+        k_fc2_grad<<<pl.nblk_fc2, 256, 0, st>>>(f);
+        MAL_LAUNCH_CHECK("k_fc2_grad");
+    }
+    // ---- gather partials into the flat gradient (state_dict order) + sum of squares
+    {
+        GradReduceArgs a;
+        memset(&a, 0, sizeof(a));
+        int n = 0;
+        auto seg = [&](int64_t off, int64_t count, const float *part, int n_chunks, int64_t stride) {
+            a.s[n].grad_off = off; a.s[n].count = (int)count; a.s[n].part = part; a.s[n].n_chunks = n_chunks;
+            a.s[n].chunk_stride = stride; ++n;
+        };
+        const int fc2n = d.A * HID + d.A;
+        seg(AL.fc1_w, (int64_t)HID * d.d_in, parts + pl.fc1_w, pl.nc_a, (int64_t)HID * d.d_in);
+        seg(AL.fc1_b, HID, parts + pl.fc1_b, pl.nc_a, HID);
+        seg(AL.w_ih, (int64_t)G3 * HID, parts + pl.wih_w, pl.nc_a, (int64_t)G3 * HID);
+        seg(AL.w_hh, 128 * HID, parts + pl.whha_w, pl.nc_a, 128 * HID);
+        seg(AL.w_hh + 128 * HID, 64 * HID, parts + pl.whhb_w, pl.nc_a, 64 * HID);
+        seg(AL.b_ih, G3, parts + pl.wih_b, pl.nc_a, G3);
+        seg(AL.b_hh, 128, parts + pl.whha_b, pl.nc_a, 128);
+        seg(AL.b_hh + 128, 64, parts + pl.whhb_b, pl.nc_a, 64);
+        seg(AL.fc2_w, (int64_t)d.A * HID, parts + pl.fc2, pl.nblk_fc2, fc2n);
+        seg(AL.fc2_b, d.A, parts + pl.fc2 + d.A * HID, pl.nblk_fc2, fc2n);
+        const int64_t o = AL.total;
+        if (d.mixer != MAL_MIXER_VDN) {
+            const int K2 = d.two ? d.HE : d.S;
+            const int64_t l1w = (int64_t)d.ld1 * d.S;
+            const int b1row = d.two ? 2 * d.HE : 0;
+            if (d.two) {
+                seg(o + ML.w1a_w, (int64_t)d.HE * d.S, parts + pl.m_l1_w, pl.nc_m, l1w);
+                seg(o + ML.w1a_b, d.HE, parts + pl.m_l1_b, pl.nc_m, d.ld1);
+            }
+            seg(o + ML.w1b_w, (int64_t)d.E * d.N * K2, parts + pl.m_l2a_w, pl.nc_m, (int64_t)d.E * d.N * K2);
+            seg(o + ML.w1b_b, d.E * d.N, parts + pl.m_l2a_b, pl.nc_m, d.E * d.N);
+            if (d.two) {
+                seg(o + ML.wfa_w, (int64_t)d.HE * d.S, parts + pl.m_l1_w + (int64_t)d.HE * d.S, pl.nc_m, l1w);
+                seg(o + ML.wfa_b, d.HE, parts + pl.m_l1_b + d.HE, pl.nc_m, d.ld1);
+            }
+            seg(o + ML.wfb_w, (int64_t)d.E * K2, parts + pl.m_l2b_w, pl.nc_m, (int64_t)d.E * K2);
+            seg(o + ML.wfb_b, d.E, parts + pl.m_l2b_b, pl.nc_m, d.E);
+            seg(o + ML.b1_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)b1row * d.S, pl.nc_m, l1w);
+            seg(o + ML.b1_b, d.E, parts + pl.m_l1_b + b1row, pl.nc_m, d.ld1);
+            seg(o + ML.v0_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)(b1row + d.E) * d.S, pl.nc_m, l1w);
+            seg(o + ML.v0_b, d.E, parts + pl.m_l1_b + b1row + d.E, pl.nc_m, d.ld1);
+            seg(o + ML.v2_w, d.E, parts + pl.mix_v2, pl.nblk_mix, d.E + 1);
+            seg(o + ML.v2_b, 1, parts + pl.mix_v2 + d.E, pl.nblk_mix, d.E + 1);
+        }
+        a.n = n;
+        a.total = AL.total + ML.total;
+        a.grad = grad;
+        a.norm_part = parts + pl.norm;
+        k_grad_reduce<<<pl.nblk_norm, 256, 0, st>>>(a);
+        MAL_LAUNCH_CHECK("k_grad_reduce");
+    }
+    return 0;
+}
+
+static int launch_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
+                               float *sq, const float *norm_part, int n_part, float lr, float alpha, float eps,
+                               float clip, float *scalars, cudaStream_t st) {
+    const int64_t P = n_agent + n_mixer;
+    k_clip_rmsprop<<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
+                                                                n_part, lr, alpha, eps, clip, scalars);
+    MAL_LAUNCH_CHECK("k_clip_rmsprop");
+    return 0;
+}
+
+extern "C" int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
+                                float *square_avg, float lr, float alpha, float eps, float clip, float *scalars,
+                                float *scratch, void *stream) {
+    MAL_REQUIRE(agent && grad && square_avg && scalars && scratch && n_agent > 0 && n_mixer >= 0,
+                "mal_clip_rmsprop: bad arguments (scratch needs ceil(P/256) floats)");
+    MAL_REQUIRE(n_mixer == 0 || mixer, "mal_clip_rmsprop: mixer buffer missing");
+    const int64_t P = n_agent + n_mixer;
+    const int nb = (int)ceil_div64(P, 256);
+    k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch);
+    MAL_LAUNCH_CHECK("k_sumsq");
+    return launch_clip_rmsprop(agent, n_agent, mixer, n_mixer, grad, square_avg, scratch, nb, lr, alpha, eps, clip,
+                               scalars, (cudaStream_t)stream);
+}
+
+extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
+                                float *agent, const float *target_agent, float *mixer, const float *target_mixer,
+                                void *workspace, float *grad, float *square_avg, void *stream) {
+    MAL_REQUIRE(square_avg, "mal_learner_step: square_avg missing");
+    if (int rc = mal_learner_forward(batch, cfg, plan, agent, target_agent, mixer, target_mixer, workspace, stream)) return rc;
+    if (int rc = mal_learner_backward(batch, cfg, plan, agent, mixer, workspace, grad, stream)) return rc;
+    Dims d;
+    if (int rc = get_dims(batch, cfg, &d)) return rc;
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    const PartLayout pl = part_layout(d, sms);
+    uint8_t *ws = (uint8_t *)workspace;
+    float *parts = reinterpret_cast<float *>(ws + plan->partials);
+    float *scalars = reinterpret_cast<float *>(ws + plan->scalars);
+    return launch_clip_rmsprop(agent, plan->n_agent_params, mixer, plan->n_mixer_params, grad, square_avg,
+                               parts + pl.norm, pl.nblk_norm, cfg->lr, cfg->alpha, cfg->eps, cfg->clip, scalars,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int mal_copy_f32(float *dst, const float *src, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    MAL_REQUIRE(dst && src, "mal_copy_f32: null buffer");
+    int64_t grid = ceil_div64(n, 1024); if (grid > 1184) grid = 1184; if (grid < 1) grid = 1;
+    k_copy_f32<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    MAL_LAUNCH_CHECK("k_copy_f32");
+    return 0;
+}

@@ -1,0 +1,133 @@
+// Common device/host helpers for libmal_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/mal_b200.h"
+
+#define HID MAL_HID          // rnn_hidden_dim
+#define G3 (3 * MAL_HID)     // GRU gate rows (r|z|n)
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+void mal_set_error(const char *fmt, ...);
+
+#define MAL_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            mal_set_error(__VA_ARGS__);        \
+            return 1;                          \
+        }                                      \
+    } while (0)
+
+#define MAL_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            mal_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 2;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+#define MAL_LAUNCH_CHECK(name)                                                             \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            mal_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));        \
+            return 3;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t align_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
+
+// ---------------------------------------------------------------------------------------------
+// parameter layouts (offsets in floats inside the flat state_dict-ordered buffers)
+// ---------------------------------------------------------------------------------------------
+struct AgentLayout {   // drqn_agent.py:21-23
+    int d_in, n_actions;
+    int64_t fc1_w, fc1_b, w_ih, w_hh, b_ih, b_hh, fc2_w, fc2_b, total;
+};
+__host__ __device__ inline AgentLayout agent_layout(int d_in, int n_actions) {
+    AgentLayout L;
+    L.d_in = d_in; L.n_actions = n_actions;
+    int64_t o = 0;
+    L.fc1_w = o; o += (int64_t)HID * d_in;
+    L.fc1_b = o; o += HID;
+    L.w_ih = o;  o += (int64_t)G3 * HID;
+    L.w_hh = o;  o += (int64_t)G3 * HID;
+    L.b_ih = o;  o += G3;
+    L.b_hh = o;  o += G3;
+    L.fc2_w = o; o += (int64_t)n_actions * HID;
+    L.fc2_b = o; o += n_actions;
+    L.total = o;
+    return L;
+}
+
+struct MixerLayout {   // qmix.py:16-39 (layers == 2: Linear-ReLU-Linear hypernets; == 1: single Linear)
+    int S, N, E, HE, layers;
+    int64_t w1a_w, w1a_b, w1b_w, w1b_b;   // hyper_w_1.{0,2}  (layers==1: only w1b = hyper_w_1, K = S)
+    int64_t wfa_w, wfa_b, wfb_w, wfb_b;   // hyper_w_final.{0,2}
+    int64_t b1_w, b1_b, v0_w, v0_b, v2_w, v2_b, total;
+};
+__host__ __device__ inline MixerLayout mixer_layout(int mixer, int S, int N, int E, int HE) {
+    MixerLayout L;
+    L.S = S; L.N = N; L.E = E; L.HE = HE; L.layers = (mixer == MAL_MIXER_QMIX2) ? 2 : 1;
+    int64_t o = 0;
+    if (mixer == MAL_MIXER_VDN) { L.total = 0; L.layers = 0; return L; }
+    if (L.layers == 2) {
+        L.w1a_w = o; o += (int64_t)HE * S;  L.w1a_b = o; o += HE;
+        L.w1b_w = o; o += (int64_t)E * N * HE; L.w1b_b = o; o += E * N;
+        L.wfa_w = o; o += (int64_t)HE * S;  L.wfa_b = o; o += HE;
+        L.wfb_w = o; o += (int64_t)E * HE;  L.wfb_b = o; o += E;
+    } else {
+        L.w1a_w = L.w1a_b = -1;
+        L.w1b_w = o; o += (int64_t)E * N * S; L.w1b_b = o; o += E * N;
+        L.wfa_w = L.wfa_b = -1;
+        L.wfb_w = o; o += (int64_t)E * S;   L.wfb_b = o; o += E;
+    }
+    L.b1_w = o; o += (int64_t)E * S; L.b1_b = o; o += E;
+    L.v0_w = o; o += (int64_t)E * S; L.v0_b = o; o += E;
+    L.v2_w = o; o += E;              L.v2_b = o; o += 1;
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// torch.max / argmax ordering: NaN beats everything, ties resolve to the lowest index.
+__device__ __forceinline__ bool arg_better(float av, int ai, float bv, int bi) {
+    bool an = (av != av), bn = (bv != bv);
+    if (an || bn) {
+        if (an && bn) return ai < bi;
+        return an;
+    }
+    if (av > bv) return true;
+    if (av < bv) return false;
+    return ai < bi;
+}
+
+__device__ __forceinline__ void warp_argmax(float &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (arg_better(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ const T *field_ptr(const mal_field_t &f, int64_t b, int64_t t) {
+    return reinterpret_cast<const T *>(f.ptr) + b * f.sb + t * f.st;
+}

@@ -1,0 +1,203 @@
+"""Q-learning learner for VDN / QMIX with the reference's API (marl/learners/q_learner.py:11-147).
+
+`train()` is one call into libmal_b200 (`mal_learner_step`): online + target RNN unroll, chosen-Q gather, masked
+double-Q target max, mixers, TD loss, full backward (mixer + BPTT), clip_grad_norm_ and RMSprop.  Nothing is read
+back to the host except on log steps (the reference syncs every step through `.item()`, q_learner.py:113).
+"""
+import copy
+import ctypes as C
+
+import torch as th
+
+from .. import _native as nat
+from ..flat import ensure_flat, flat_views
+from ..modules.mixers.qmix import QMixer
+from ..modules.mixers.vdn import VDNMixer
+from .learner import Learner
+
+
+class QLearner(Learner):
+    def __init__(self, mac, scheme, logger, args, name=None):
+        super().__init__(mac, scheme, logger, args, name)
+        self.last_target_update_episode = 0
+        self.mixer = None
+        if args.mixer is not None:
+            if args.mixer == "vdn":
+                self.mixer = VDNMixer()
+            elif args.mixer == "qmix":
+                self.mixer = QMixer(args)
+            else:
+                raise ValueError("Mixer {} not recognised.".format(args.mixer))
+            self.target_mixer = copy.deepcopy(self.mixer)
+        else:
+            raise ValueError("mixer=None (IQL) is broken in the reference (q_learner.py:32) and not supported")
+        self.target_mac = copy.deepcopy(mac)
+        self._ws = None
+        self._ws_key = None
+        self._plan = nat.Plan()
+        self._grad = None
+        self.save_q = False      # tests: also materialise mac_out / target_mac_out
+
+    def parameters(self):
+        return list(self.mac.parameters()) + list(self.mixer.parameters())
+
+    # ------------------------------------------------------------------ ABI marshalling
+    def _mixer_kind(self):
+        return self.mixer.mal_kind if isinstance(self.mixer, QMixer) else nat.MIXER_VDN
+
+    def _cfg(self):
+        a = self.args
+        qm = isinstance(self.mixer, QMixer)
+        return nat.LearnerCfg(self._mixer_kind(), int(bool(a.double_q)), self.mixer.embed_dim if qm else 0,
+                              self.mixer.hypernet_embed if qm else 0, a.gamma, a.lr, a.optim_alpha, a.optim_eps,
+                              a.grad_norm_clip, int(self.save_q))
+
+    def _batch_struct(self, batch):
+        obs = nat.require_cuda(batch["obs"], "batch")
+        B, TT, N, OBS = obs.shape
+        A = self.args.n_actions
+        state = batch["state"]
+        S = state.shape[-1]
+        b = nat.Batch(B, TT, N, A, OBS, S)
+        b.obs = nat.field_of(obs, N * OBS)
+        b.onehot = nat.field_of(batch["actions_onehot"], N * A)
+        b.actions = nat.field_of(batch["actions"], N)
+        b.avail = nat.field_of(batch["avail_actions"], N * A)
+        b.state = nat.field_of(state, S)
+        b.reward = nat.field_of(batch["reward"], 1)
+        b.terminated = nat.field_of(batch["terminated"], 1)
+        b.filled = nat.field_of(batch["filled"], 1)
+        for key, dt in (("obs", th.float32), ("actions_onehot", th.float32), ("actions", th.long),
+                        ("avail_actions", th.int32), ("state", th.float32), ("reward", th.float32),
+                        ("terminated", th.uint8), ("filled", th.long)):
+            if batch[key].dtype != dt:
+                raise nat.MalError("scheme field %s must be %s (ma_experiment.py:99-118)" % (key, dt))
+        return b
+
+    def _prepare(self, batch):
+        """Flat buffers, plan and workspace for this batch shape."""
+        dev = batch["obs"].device
+        bs = self._batch_struct(batch)
+        cfg = self._cfg()
+        key = (bs.B, bs.TT, bs.N, bs.A, bs.OBS, bs.S, cfg.mixer, cfg.save_q, str(dev))
+        if key != self._ws_key:
+            nat.check(nat.lib().mal_learner_plan(C.byref(bs), C.byref(cfg), C.byref(self._plan)), "mal_learner_plan")
+            if self._ws is None or self._ws.numel() < self._plan.total_bytes or self._ws.device != dev:
+                self._ws = th.empty(self._plan.total_bytes, dtype=th.uint8, device=dev)
+            self._ws_key = key
+        flats = dict(agent=ensure_flat(self.mac.agent), tagent=ensure_flat(self.target_mac.agent),
+                     mixer=ensure_flat(self.mixer), tmixer=ensure_flat(self.target_mixer))
+        n_total = self._plan.n_agent_params + self._plan.n_mixer_params
+        if flats["agent"].numel() != self._plan.n_agent_params or \
+                (flats["mixer"].numel() if flats["mixer"] is not None else 0) != self._plan.n_mixer_params:
+            raise nat.MalError("parameter count mismatch between the modules and the kernel layout")
+        if self._grad is None or self._grad.numel() != n_total or self._grad.device != dev:
+            self._grad = th.zeros(n_total, dtype=th.float32, device=dev)
+        return bs, cfg, flats
+
+    def _ws_f32(self, offset, numel):
+        return self._ws[offset:offset + 4 * numel].view(th.float32)
+
+    def scalars(self):
+        return self._ws_f32(self._plan.scalars, 64)
+
+    # ------------------------------------------------------------------ training
+    def train(self, batch, t_env: int, episode_num: int):
+        bs, cfg, f = self._prepare(batch)
+        if self.optimiser is None:
+            raise nat.MalError("call build_optimizer() before train() (ma_experiment.py:61)")
+        dev = batch["obs"].device
+        with th.cuda.device(dev):
+            nat.check(nat.lib().mal_learner_step(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
+                                                 nat.ptr(f["tagent"]), nat.ptr(f["mixer"]), nat.ptr(f["tmixer"]),
+                                                 nat.ptr(self._ws), nat.ptr(self._grad),
+                                                 nat.ptr(self.optimiser.flat_sq), nat.current_stream(dev)),
+                      "mal_learner_step")
+        self.optimiser._steps += 1
+        for p, g in zip(self.parameters(), flat_views(self._grad, self.parameters())):
+            p.grad = g                                  # clipped gradients, as clip_grad_norm_ leaves them
+
+        if (episode_num - self.last_target_update_episode) / self.args.target_update_interval >= 1.0:
+            self.update_targets()
+            self.last_target_update_episode = episode_num
+
+        sc = self.scalars()
+        self.mac.update_trained_steps(sc[nat.SC_MASK_COUNT:nat.SC_MASK_COUNT + 1].view(th.int32))
+
+        if t_env - self.log_stats_t >= self.args.learner_log_interval:
+            h = sc[:8].cpu()                            # the only device->host sync of the step
+            self.logger.log_stat(self.name + "loss", float(h[nat.SC_LOSS]), t_env)
+            self.logger.log_stat(self.name + "grad_norm", h[nat.SC_GRAD_NORM].numpy(), t_env)
+            self.logger.log_stat(self.name + "td_error_abs", float(h[nat.SC_TD_ABS]), t_env)
+            self.logger.log_stat(self.name + "q_taken_mean", float(h[nat.SC_Q_TAKEN]), t_env)
+            self.logger.log_stat(self.name + "target_mean", float(h[nat.SC_TARGET]), t_env)
+            self.log_stats_t = t_env
+
+    def forward_only(self, batch):
+        """Forward half of train() (q_learner.py:36-98); intermediates stay in the workspace (tests, debugging)."""
+        bs, cfg, f = self._prepare(batch)
+        dev = batch["obs"].device
+        with th.cuda.device(dev):
+            nat.check(nat.lib().mal_learner_forward(C.byref(bs), C.byref(cfg), C.byref(self._plan),
+                                                    nat.ptr(f["agent"]), nat.ptr(f["tagent"]), nat.ptr(f["mixer"]),
+                                                    nat.ptr(f["tmixer"]), nat.ptr(self._ws), nat.current_stream(dev)),
+                      "mal_learner_forward")
+        return bs, cfg, f
+
+    def forward_backward(self, batch):
+        """forward + loss.backward() without the optimiser step; returns the flat unclipped gradient."""
+        bs, cfg, f = self.forward_only(batch)
+        dev = batch["obs"].device
+        with th.cuda.device(dev):
+            nat.check(nat.lib().mal_learner_backward(C.byref(bs), C.byref(cfg), C.byref(self._plan),
+                                                     nat.ptr(f["agent"]), nat.ptr(f["mixer"]), nat.ptr(self._ws),
+                                                     nat.ptr(self._grad), nat.current_stream(dev)),
+                      "mal_learner_backward")
+        return self._grad
+
+    def intermediates(self, batch):
+        """Views of the workspace arrays produced by the last forward for `batch`'s shape."""
+        p = self._plan
+        B, TT = batch.batch_size, batch.max_seq_length
+        N, A, T = self.args.n_agents, self.args.n_actions, TT - 1
+        out = dict(chosen=self._ws_f32(p.chosen, B * T * N).view(B, T, N),
+                   target_max=self._ws_f32(p.target_max, B * T * N).view(B, T, N),
+                   argmax=self._ws[p.argmax:p.argmax + 4 * B * T * N].view(th.int32).view(B, T, N),
+                   mask=self._ws_f32(p.mask, B * T).view(B, T, 1),
+                   q_tot=self._ws_f32(p.q_tot, B * T).view(B, T, 1),
+                   target_q_tot=self._ws_f32(p.target_q_tot, B * T).view(B, T, 1),
+                   targets=self._ws_f32(p.targets, B * T).view(B, T, 1),
+                   td=self._ws_f32(p.td, B * T).view(B, T, 1),
+                   hout=self._ws_f32(p.h_on, TT * B * N * nat.HID).view(TT, B * N, nat.HID),
+                   scalars=self.scalars())
+        if self.save_q:
+            out["mac_out"] = self._ws_f32(p.mac_out, B * TT * N * A).view(B, TT, N, A)
+            out["target_mac_out"] = self._ws_f32(p.target_mac_out, B * TT * N * A).view(B, TT, N, A)
+        return out
+
+    def update_targets(self):
+        """q_learner.py:127-131: online -> target copy (one flat device copy per network)."""
+        pairs = [(ensure_flat(self.target_mac.agent), ensure_flat(self.mac.agent)),
+                 (ensure_flat(self.target_mixer), ensure_flat(self.mixer))]
+        for dst, src in pairs:
+            if dst is None:
+                continue
+            with th.cuda.device(dst.device):
+                nat.check(nat.lib().mal_copy_f32(nat.ptr(dst), nat.ptr(src), src.numel(),
+                                                 nat.current_stream(dst.device)), "mal_copy_f32")
+        self.logger.info("Updated {0}target network.".format(self.name))
+
+    def save_models(self, path, name=None):
+        self.mac.save_models(path, name=self.name)
+        if self.mixer is not None:
+            th.save(self.mixer.state_dict(), "{}/{}mixer.th".format(path, self.name))
+        th.save(self.optimiser.state_dict(), "{}/{}opt.th".format(path, self.name))
+
+    def load_models(self, path):
+        self.mac.load_models(path, self.name)
+        self.target_mac.load_models(path, self.name)   # "not quite right", as in q_learner.py:141-142
+        if self.mixer is not None:
+            self.mixer.load_state_dict(
+                th.load("{}/{}mixer.th".format(path, self.name), map_location=lambda storage, loc: storage))
+        self.optimiser.load_state_dict(
+            th.load("{}/{}opt.th".format(path, self.name), map_location=lambda storage, loc: storage))
