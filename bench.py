@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's metric: QMIX train transitions/sec (B=32, T=200) + act-select.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  A "step" is one QLearner.train() on one sampled batch of synthetic episodes
+(SURVEY.md 8d).  `value` = transitions/s with the batch resident in HBM; `e2e` = the same through the public API
+with the batch in pinned HOST memory (H2D copy of the step's inputs + D2H read of the loss inside the timed region).
+Multi-GPU = league sharding: every rank owns an independent learner + replay buffer (weak scaling, no collective
+on the data path); timing is max-over-ranks of CUDA-event time.
+`--impl reference` times the reference's CPU implementation (oracle/torch_port.py, the same ATen op sequence;
+/root/reference itself is pure Python and does not exist on the GPU box) on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch as th   # noqa: E402
+
+METRIC = "qmix_train_transitions_per_sec"
+UNIT = "transitions/s"
+T_STEPS = 200   # transitions per episode (201 stored steps)
+
+
+def workload_dims(name):
+    from ma_league_b200.synthetic import CONFIGS, dims
+    c = CONFIGS[name]
+    d = dims(c["N"])
+    d.update(B=c["B"], mixer=c["mixer"], TT=T_STEPS + 1)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic bytes
+def kernel_bytes(d, mixer):
+    """Algorithmic bytes per launch of each learner kernel (DESIGN.md 'kernels'); M1 = TT*B*N rows, BT = B*T."""
+    B, TT, N, A, OBS, S = d["B"], d["TT"], d["N"], d["A"], d["OBS"], d["S"]
+    T, R = TT - 1, B * N
+    M1, BT, D = TT * R, B * T, OBS + A + N
+    E, HE = 32, 64
+    ld1, ld2 = 2 * HE + 2 * E, E * N + E
+    f = 4
+    out = {
+        "k_linear_group:fc1": M1 * (OBS + A) * f + 2 * M1 * 64 * f,
+        "k_linear_group:w_ih": 2 * M1 * (64 + 192) * f,
+        "k_gru_fwd": M1 * (2 * 192 + 2 * 64 + 256) * f,
+        "k_q_head": M1 * (2 * 64 * f + A * 4 + 8) + 3 * BT * N * f,
+        "k_gru_bwd": M1 * (256 + 64 + 256) * f + BT * N * 12,
+        "k_linear_group:dx": M1 * (192 + 64 + 64) * f,
+        "k_reduce_group:agent": M1 * (256 + 64 + 64 + 64 + (OBS + A)) * f,
+        "k_fc2_grad": T * R * (64 * f + 12),
+        "k_mask_prep": BT * (8 + 1 + 4),
+    }
+    if mixer == "qmix":
+        out.update({
+            "k_linear_group:mixer_l1": 2 * BT * (S + ld1) * f,
+            "k_linear_group:mixer_l2": 2 * BT * (2 * HE + ld2) * f,
+            "k_mix_td": BT * (2 * (ld1 - 2 * HE + ld2) + ld2 + 2 * E + 3 * N + 12) * f,
+            "k_linear_group:mixer_bwd_dh": BT * (ld2 + 2 * HE + 2 * HE) * f,
+            "k_reduce_group:mixer": BT * (ld2 + 2 * HE + ld1 + S) * f,
+        })
+    else:
+        out["k_mix_td"] = BT * (3 * N + 12) * f
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a, rank, world, device):
+    import ma_league_b200 as M
+    from ma_league_b200 import _native as nat
+    from ma_league_b200.synthetic import make_args, make_scheme, synth_episode_data, fill_episode_batch
+    nat.build()
+    lib = nat.lib()
+    d = workload_dims(a.workload)
+    N, A, OBS, S, B, TT = d["N"], d["A"], d["OBS"], d["S"], d["B"], d["TT"]
+    th.manual_seed(1000 + rank)
+    np.random.seed(1000 + rank)
+    args = make_args(N, A, S, mixer=d["mixer"], double_q=True, device=device, batch_size=B, buffer_size=a.buffer_size)
+    scheme, groups, pre = make_scheme(N, A, OBS, S)
+    buf = M.ReplayBuffer(scheme, groups, a.buffer_size, TT, preprocess=pre, device=device)
+    mac = M.mac_REGISTRY[args.mac](buf.scheme, groups, args)
+
+    class Log:
+        def log_stat(self, *x): pass
+        def info(self, *x): pass
+    learner = M.learner_REGISTRY[args.learner](mac, buf.scheme, Log(), args, name="home")
+    learner.build_optimizer()
+
+    # device-resident replay buffer pre-filled with synthetic episodes (every rank its own matchup data)
+    gen = th.Generator().manual_seed(7 + rank)
+    chunk = 256
+    for s0 in range(0, a.buffer_size, chunk):
+        n = min(chunk, a.buffer_size - s0)
+        data, lens = synth_episode_data(n, TT, N, A, OBS, S, gen, var_len=True, device=device)
+        lens[0] = TT - 1
+        eb = fill_episode_batch(M.EpisodeBatch(scheme, groups, n, TT, preprocess=pre, device=device), data, lens)
+        buf.insert_episode_batch(eb)
+
+    # NB pre-sampled batches whose total size exceeds L2 (126 MB): inputs come from HBM on every step
+    rb = buf._layout.record_bytes
+    nb = max(4, -(-160 * 2 ** 20 // (B * rb)))
+    batches = []
+    for _ in range(nb):
+        smp = buf.sample(B)
+        smp._storage.view(B, rb)[0].copy_(buf._storage.view(a.buffer_size, rb)[0])   # one full-length episode
+        mt = int(smp.max_t_filled())
+        assert mt == TT, mt
+        batches.append(smp[:, :mt])
+    transitions = B * (TT - 1)
+
+    def dist_max(x):
+        if world > 1:
+            t = th.tensor([x], dtype=th.float64, device=device)
+            th.distributed.all_reduce(t, op=th.distributed.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def barrier():
+        if world > 1:
+            th.distributed.barrier()
+        th.cuda.synchronize(device)
+
+    # ---------------- value: batch resident in HBM
+    for i in range(a.warmup):
+        learner.train(batches[i % nb], t_env=i, episode_num=0)
+    barrier()
+    launches0 = lib.mal_launch_count()
+    sampler = ClockSampler(th.cuda.current_device() if world == 1 else int(os.environ.get("LOCAL_RANK", 0)))
+    evs = [(th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(a.steps):
+        evs[i][0].record()
+        learner.train(batches[i % nb], t_env=i, episode_num=0)
+        evs[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = lib.mal_launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    dev_ms = dist_max(dev_ms)
+    wall = dist_max(wall)
+    ms_per_step = dev_ms / a.steps
+    value = world * transitions / (ms_per_step * 1e-3)
+
+    # ---------------- per-kernel profile (same steps again, CUDA events around every launch)
+    nat.profile_begin()
+    for i in range(a.steps):
+        learner.train(batches[i % nb], t_env=i, episode_num=0)
+    prof = nat.profile_end()
+    kb = kernel_bytes(d, d["mixer"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650"
+    kern = []
+    tot_ms = sum(ms for _, ms in prof.values())
+    for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per = ms / n
+        byts = kb.get(name)
+        kern.append({"kernel": name, "launches_per_step": n / a.steps, "us": round(per * 1e3, 2),
+                     "share": round(ms / tot_ms, 4),
+                     "gbs": round(byts / (per * 1e-3) / 1e9, 1) if byts else None})
+    top = kern[0]
+    roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(top["gbs"] / peak, 4) if top["gbs"] else None, "traffic": None,
+                "peak_source": peak_src, "us_per_launch": top["us"],
+                "note": "B=32 step is latency-bound (201-step serial chain, 6400 transitions); see DESIGN.md"}
+
+    # ---------------- e2e: batch in pinned host memory, H2D + train + D2H every step
+    # fresh packed samples (B whole records each) staged in pinned host memory
+    parents = []
+    for i in range(nb):
+        smp = buf.sample(B)
+        smp._storage.view(B, rb)[0].copy_(buf._storage.view(a.buffer_size, rb)[0])
+        parents.append(smp)
+    pinned = [p_._storage.cpu().pin_memory() for p_ in parents]
+    stage = [M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=device) for _ in range(2)]
+    out_host = th.empty(8, dtype=th.float32).pin_memory()
+    copy_stream = th.cuda.Stream(device=device)
+    ready = [th.cuda.Event(), th.cuda.Event()]
+    consumed = [th.cuda.Event(), th.cuda.Event()]
+
+    def prefetch(i):
+        slot = i % 2
+        with th.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            stage[slot]._storage.copy_(pinned[i % nb], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_steps(k, t0):
+        prefetch(t0)
+        for i in range(t0, t0 + k):
+            slot = i % 2
+            if i + 1 < t0 + k:
+                prefetch(i + 1)
+            th.cuda.current_stream(device).wait_event(ready[slot])
+            learner.train(stage[slot], t_env=i, episode_num=0)
+            consumed[slot].record()
+            out_host.copy_(learner.scalars()[:8], non_blocking=True)
+            th.cuda.current_stream(device).synchronize()      # the step's loss is on the host
+        return float(out_host[1])
+
+    for c in consumed:
+        c.record()
+    e2e_steps(max(a.warmup, 3), 0)
+    barrier()
+    t0 = time.perf_counter()
+    last_loss = e2e_steps(a.steps, 100)
+    barrier()
+    e2e_s = dist_max(time.perf_counter() - t0)
+    e2e = {"value": world * transitions * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * rb,
+           "d2h_bytes_per_step": 32, "ms_per_step": e2e_s / a.steps * 1e3,
+           "how": "pinned host batch -> double-buffered H2D on a copy stream -> QLearner.train -> loss D2H + sync"}
+    assert np.isfinite(last_loss)
+
+    # ---------------- second headline metric: act-select agent-steps/s, and replay sample GB/s
+    extra = {}
+    for bs in (1, B):
+        eb = M.EpisodeBatch(scheme, groups, bs, TT, preprocess=pre, device=device)
+        eb._storage.copy_(buf._storage[:bs * rb])
+        mac.init_hidden(bs)
+        mac.action_selector.validate = False
+        for i in range(10):
+            mac.select_actions(eb, t_ep=1 + i % 100, t_env=i)
+        th.cuda.synchronize(device)
+        reps = 200
+        s_, e_ = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        s_.record()
+        for i in range(reps):
+            mac.select_actions(eb, t_ep=1 + i % 100, t_env=i)
+        e_.record()
+        th.cuda.synchronize(device)
+        extra["act_select_agent_steps_per_s_bs%d" % bs] = round(bs * N * reps / (s_.elapsed_time(e_) * 1e-3), 1)
+    s_, e_ = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    ids = [th.as_tensor(np.random.choice(a.buffer_size, B, replace=False), device=device) for _ in range(20)]
+    for i in ids[:3]:
+        buf[i]
+    th.cuda.synchronize(device)
+    s_.record()
+    for i in ids:
+        buf[i]
+    e_.record()
+    th.cuda.synchronize(device)
+    us = s_.elapsed_time(e_) / len(ids) * 1e3
+    extra["replay_sample"] = {"us": round(us, 2), "gbs": round(2 * B * rb / (us * 1e-6) / 1e9, 1),
+                              "frac_of_hbm_peak": round(2 * B * rb / (us * 1e-6) / 1e9 / peak, 4),
+                              "bytes": 2 * B * rb}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: QMIX (2-layer hypernet, double-Q), B=%d, T=%d, N=%d, A=%d, OBS=%d, S=%d, "
+                                   "H=64, one independent league matchup per GPU" % (a.workload, B, TT - 1, N, A, OBS, S),
+                       "transitions_per_step": transitions, "parallelism": "league-sharded x%d (no collective)" % world,
+                       "l2": "inputs rotate over %d sampled batches (%.0f MB) > 126 MB L2" % (nb, nb * B * rb / 2 ** 20),
+                       "replay_buffer_episodes": a.buffer_size},
+            "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / a.steps,
+            "wall_ms_per_step": wall / a.steps * 1e3, "clocks": clocks, "roofline": roofline, "kernels": kern}
+    line.update(extra)
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(a, bounded_s=None):
+    """The reference's CPU path (torch port, all host threads).  Returns (value, ms_per_step, steps, cores, sample)."""
+    from oracle import np_oracle as O, torch_port as TP
+    from ma_league_b200.synthetic import synth_episode_data
+    d = workload_dims(a.workload)
+    N, A, OBS, S, B, TT = d["N"], d["A"], d["OBS"], d["S"], d["B"], d["TT"]
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    ap = O.init_params(O.agent_param_shapes(OBS + A + N, A), rng)
+    mp = O.init_params(O.qmix_param_shapes(S, N), rng) if d["mixer"] == "qmix" else None
+    L = TP.TorchPortLearner(ap, ap, mp, mp, mixer=d["mixer"], double_q=True, gamma=0.99, lr=5e-4, alpha=0.99, eps=1e-5,
+                            clip=10)
+    gen = th.Generator().manual_seed(0)
+    data, lens = synth_episode_data(B, TT, N, A, OBS, S, gen, var_len=False)
+    data["actions_onehot"] = th.from_numpy(O.onehot(data["actions"].numpy(), A))
+    data["filled"] = th.ones(B, TT, 1, dtype=th.long)
+    warm, steps = a.warmup, a.steps
+    if bounded_s is not None:
+        warm, steps = 2, 1000
+    for _ in range(warm):
+        L.train(data)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        L.train(data)
+        done += 1
+        if bounded_s is not None and time.perf_counter() - t0 > bounded_s:
+            break
+    el = time.perf_counter() - t0
+    return B * (TT - 1) * done / el, el / done * 1e3, done, cores, \
+        "%d full train steps (B=%d, T=%d) of oracle/torch_port.py on %d host threads" % (done, B, TT - 1, cores)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="qmix_5v5_b32")
+    ap.add_argument("--buffer-size", dest="buffer_size", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        d = workload_dims(a.workload)
+        v, ms, done, cores, sample = run_reference(a)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+                          "steps": done, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "%s: QMIX, B=%d, T=%d, N=%d on host CPU" % (a.workload, d["B"], d["TT"] - 1, d["N"])},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if not th.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    th.cuda.set_device(local)
+    device = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        th.distributed.init_process_group("nccl", device_id=th.device(device))
+    line = run_ours(a, rank, world, device)
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            v, ms, done, cores, sample = run_reference(a, bounded_s=12.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "ms_per_step": ms}
+        print(json.dumps(line))
+    if world > 1:
+        th.distributed.barrier()
+        th.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

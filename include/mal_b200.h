@@ -96,6 +96,13 @@ enum {
 int mal_version(void);
 const char *mal_last_error(void);
 
+/* Accounting: number of kernels this library has launched so far (process-wide), and an opt-in profiler that
+ * brackets every launch with CUDA events on the launching stream.  mal_profile_end synchronises and writes one
+ * text line per kernel name: "<name> <launches> <total_ms>\n". */
+uint64_t mal_launch_count(void);
+int mal_profile_begin(void);
+int mal_profile_end(char *out, int64_t out_len);
+
 /* Parameter counts in state_dict order (drqn_agent.py:21-23, qmix.py:16-39). */
 int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions);
 int64_t mal_mixer_param_count(int32_t mixer, int32_t state_dim, int32_t n_agents, int32_t embed, int32_t hyper_embed);

@@ -62,6 +62,9 @@ class Select(C.Structure):
 _PROTOS = {
     "mal_version": (C.c_int, []),
     "mal_last_error": (C.c_char_p, []),
+    "mal_launch_count": (C.c_uint64, []),
+    "mal_profile_begin": (C.c_int, []),
+    "mal_profile_end": (C.c_int, [C.c_char_p, C.c_int64]),
     "mal_agent_param_count": (C.c_int64, [C.c_int32, C.c_int32]),
     "mal_mixer_param_count": (C.c_int64, [C.c_int32] * 5),
     "mal_learner_plan": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan)]),
@@ -127,6 +130,21 @@ def lib():
             raise MalError("libmal_b200.so ABI %d != expected %d; rebuild" % (L.mal_version(), ABI_VERSION))
         _lib = L
     return _lib
+
+
+def profile_begin():
+    check(lib().mal_profile_begin(), "mal_profile_begin")
+
+
+def profile_end():
+    """{kernel name: (launches, total_ms)} for everything launched since profile_begin()."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().mal_profile_end(buf, len(buf)), "mal_profile_end")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def check(rc: int, what: str = ""):

@@ -18,6 +18,76 @@ void mal_set_error(const char *fmt, ...) {
 extern "C" const char *mal_last_error(void) { return g_err; }
 extern "C" int mal_version(void) { return MAL_ABI_VERSION; }
 
+// ---------------------------------------------------------------------------------------------
+// launch accounting + opt-in per-kernel timing (CUDA events on the launching stream; bench.py's roofline leg)
+// ---------------------------------------------------------------------------------------------
+#define PROF_MAX 8192
+static uint64_t g_launches = 0;
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[PROF_MAX][2];
+static const char *g_prof_name[PROF_MAX];
+static bool g_prof_created = false;
+
+struct ProfScope {
+    int slot;
+    cudaStream_t st;
+    ProfScope(const char *name, cudaStream_t stream) : slot(-1), st(stream) {
+        ++g_launches;
+        if (g_prof_on && g_prof_n < PROF_MAX) {
+            slot = g_prof_n++;
+            g_prof_name[slot] = name;
+            cudaEventRecord(g_prof_ev[slot][0], st);
+        }
+    }
+    ~ProfScope() {
+        if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st);
+    }
+};
+
+extern "C" uint64_t mal_launch_count(void) { return g_launches; }
+
+extern "C" int mal_profile_begin(void) {
+    if (!g_prof_created) {
+        for (int i = 0; i < PROF_MAX; ++i) {
+            MAL_CUDA(cudaEventCreate(&g_prof_ev[i][0]));
+            MAL_CUDA(cudaEventCreate(&g_prof_ev[i][1]));
+        }
+        g_prof_created = true;
+    }
+    g_prof_n = 0;
+    g_prof_on = true;
+    return 0;
+}
+
+// Synchronises, then writes one line per kernel name: "<name> <launches> <total_ms>\n".
+extern "C" int mal_profile_end(char *out, int64_t out_len) {
+    g_prof_on = false;
+    MAL_REQUIRE(out && out_len > 0, "mal_profile_end: bad buffer");
+    MAL_CUDA(cudaDeviceSynchronize());
+    const char *names[256];
+    int counts[256];
+    double totals[256];
+    int nn = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        float ms = 0.f;
+        MAL_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[i][0], g_prof_ev[i][1]));
+        int j = 0;
+        for (; j < nn; ++j) if (strcmp(names[j], g_prof_name[i]) == 0) break;
+        if (j == nn) { if (nn == 256) continue; names[nn] = g_prof_name[i]; counts[nn] = 0; totals[nn] = 0; ++nn; }
+        counts[j] += 1; totals[j] += ms;
+    }
+    int64_t pos = 0;
+    out[0] = 0;
+    for (int j = 0; j < nn; ++j) {
+        int w = snprintf(out + pos, (size_t)(out_len - pos), "%s %d %.6f\n", names[j], counts[j], totals[j]);
+        if (w < 0 || pos + w >= out_len) break;
+        pos += w;
+    }
+    g_prof_n = 0;
+    return 0;
+}
+
 extern "C" int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions) { return agent_layout(d_in, n_actions).total; }
 extern "C" int64_t mal_mixer_param_count(int32_t mixer, int32_t S, int32_t N, int32_t E, int32_t HE) {
     return mixer_layout(mixer, S, N, E, HE).total;
@@ -63,7 +133,7 @@ extern "C" int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst
         attr_set = true;
     }
     int64_t grid = a.n_tiles < (int64_t)sms * 3 ? a.n_tiles : (int64_t)sms * 3;   // 3 x 64 KB rings per SM
-    k_record_copy_tma<<<(unsigned)grid, 32, smem, (cudaStream_t)stream>>>(a);
+    { ProfScope _ps("k_record_copy_tma", (cudaStream_t)stream); k_record_copy_tma<<<(unsigned)grid, 32, smem, (cudaStream_t)stream>>>(a); }
     MAL_LAUNCH_CHECK("k_record_copy_tma");
     return 0;
 }
@@ -71,7 +141,7 @@ extern "C" int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst
 extern "C" int mal_max_t_filled(const int64_t *filled, int64_t sb, int64_t st, int32_t B, int32_t TT, int32_t *out,
                                 void *stream) {
     MAL_REQUIRE(filled && out && B > 0 && TT > 0, "mal_max_t_filled: bad arguments");
-    k_max_t_filled<<<1, 256, 0, (cudaStream_t)stream>>>(filled, sb, st, B, TT, out);
+    { ProfScope _ps("k_max_t_filled", (cudaStream_t)stream); k_max_t_filled<<<1, 256, 0, (cudaStream_t)stream>>>(filled, sb, st, B, TT, out); }
     MAL_LAUNCH_CHECK("k_max_t_filled");
     return 0;
 }
@@ -120,8 +190,8 @@ extern "C" int mal_eps_greedy_select(const float *q, int64_t q_ld, int32_t rows,
     SelectArgs s;
     if (int rc = fill_select(sel, rows, n_agents, n_actions, &s)) return rc;
     const int warps_per_block = AS_THREADS / 32;
-    k_eps_greedy_select<<<(rows + warps_per_block - 1) / warps_per_block, AS_THREADS, 0, (cudaStream_t)stream>>>(
-        q, q_ld, rows, n_actions, s);
+    { ProfScope _ps("k_eps_greedy_select", (cudaStream_t)stream); k_eps_greedy_select<<<(rows + warps_per_block - 1) / warps_per_block, AS_THREADS, 0, (cudaStream_t)stream>>>(
+        q, q_ld, rows, n_actions, s); }
     MAL_LAUNCH_CHECK("k_eps_greedy_select");
     return 0;
 }
@@ -144,7 +214,7 @@ extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents
     const size_t smem = sizeof(float) * (size_t)(AS_ROWS * (Kin + 1) + AS_ROWS * HID * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
     MAL_REQUIRE(smem <= 200 * 1024, "mal_agent_step: obs_dim too large for the shared-memory staging");
     if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_agent_step<<<(rows + AS_ROWS - 1) / AS_ROWS, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
+    { ProfScope _ps("k_agent_step", (cudaStream_t)stream); k_agent_step<<<(rows + AS_ROWS - 1) / AS_ROWS, AS_THREADS, smem, (cudaStream_t)stream>>>(a); }
     MAL_LAUNCH_CHECK("k_agent_step");
     return 0;
 }
@@ -280,7 +350,7 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
     return v;
 }
 
-static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st) {
+static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st, const char *tag) {
     const int nkc = (maxK + LIN_KC - 1) / LIN_KC;
     const size_t smem = sizeof(float) * ((size_t)LIN_TM * (nkc * LIN_KC + 4) + (size_t)LIN_TN * LIN_LDW);
     MAL_REQUIRE(smem <= 220 * 1024, "inner dimension %d too large for the panel GEMM", maxK);
@@ -290,7 +360,7 @@ static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st) {
         attr = smem;
     }
     dim3 grid((unsigned)ceil_div64(maxM, LIN_TM), g.n);
-    k_linear_group<<<grid, 256, smem, st>>>(g);
+    { ProfScope _ps(tag, st); k_linear_group<<<grid, 256, smem, st>>>(g); }
     MAL_LAUNCH_CHECK("k_linear_group");
     return 0;
 }
@@ -308,10 +378,12 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
 template <int RT>
 static void launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st) {
     dim3 grid((a.R + RT - 1) / RT, nets);
+    ProfScope _ps("k_gru_fwd", st);
     k_gru_fwd<RT><<<grid, 192, 0, st>>>(a);
 }
 template <int RT>
 static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st) {
+    ProfScope _ps("k_gru_bwd", st);
     k_gru_bwd<RT><<<(a.R + RT - 1) / RT, 192, 0, st>>>(a);
 }
 static int pick_rt(int64_t chains, int sms) {
@@ -348,7 +420,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     float *y1[2] = {F(plan->y1_on), F(plan->y1_tg)}, *a2[2] = {F(plan->a2_on), F(plan->a2_tg)};
 
     // mask and mask.sum()                                                   q_learner.py:40-42
-    k_mask_prep<<<1, 1024, 0, st>>>(batch->filled, batch->terminated, d.B, d.T, F(plan->mask), scalars);
+    { ProfScope _ps("k_mask_prep", st); k_mask_prep<<<1, 1024, 0, st>>>(batch->filled, batch->terminated, d.B, d.T, F(plan->mask), scalars); }
     MAL_LAUNCH_CHECK("k_mask_prep");
 
     // x = relu(fc1([obs | last action | agent id]))  for every (t,b,n), both nets   basic_controller.py:80-92
@@ -357,7 +429,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net)
             g.p[net] = lin(d.M1, d.OBS + d.A, HID, A_AGENT_IN, 0, nullptr, 0, ap[net] + AL.fc1_w, d.d_in, 0,
                            ap[net] + AL.fc1_b, EPI_FC1, nullptr, 0, x[net], HID);
-        if (int rc = launch_linear(g, d.M1, d.OBS + d.A, st)) return rc;
+        if (int rc = launch_linear(g, d.M1, d.OBS + d.A, st, "k_linear_group:fc1")) return rc;
     }
     // gi = W_ih x + b_ih
     {
@@ -365,7 +437,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net)
             g.p[net] = lin(d.M1, HID, G3, A_DENSE, 0, x[net], HID, ap[net] + AL.w_ih, HID, 0, ap[net] + AL.b_ih,
                            EPI_BIAS, nullptr, 0, gi[net], G3);
-        if (int rc = launch_linear(g, d.M1, HID, st)) return rc;
+        if (int rc = launch_linear(g, d.M1, HID, st, "k_linear_group:w_ih")) return rc;
     }
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
     {
@@ -390,7 +462,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.chosen = F(plan->chosen); a.target_max = F(plan->target_max);
         a.argmax = reinterpret_cast<int *>(ws + plan->argmax);
         int64_t grid = ceil_div64(d.M1, 8); if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-        k_q_head<<<(unsigned)grid, 256, 0, st>>>(a);
+        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)grid, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_q_head");
     }
     // mixer hypernetworks                                                   qmix.py:41-59
@@ -403,14 +475,14 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             g.p[net * 4 + 2] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.b1_w, d.S, 0, P + ML.b1_b, EPI_BIAS, nullptr, 0, y1[net] + 2 * d.HE, d.ld1);
             g.p[net * 4 + 3] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.v0_w, d.S, 0, P + ML.v0_b, EPI_RELU, nullptr, 0, y1[net] + 2 * d.HE + d.E, d.ld1);
         }
-        if (int rc = launch_linear(g, d.BT, d.S, st)) return rc;
+        if (int rc = launch_linear(g, d.BT, d.S, st, "k_linear_group:mixer_l1")) return rc;
         LinGroup h; h.n = 4; h.bv = bv;
         for (int net = 0; net < 2; ++net) {
             const float *P = mp[net];
             h.p[net * 2 + 0] = lin(d.BT, d.HE, d.E * d.N, A_DENSE, 0, y1[net], d.ld1, P + ML.w1b_w, d.HE, 0, P + ML.w1b_b, EPI_BIAS, nullptr, 0, a2[net], d.ld2);
             h.p[net * 2 + 1] = lin(d.BT, d.HE, d.E, A_DENSE, 0, y1[net] + d.HE, d.ld1, P + ML.wfb_w, d.HE, 0, P + ML.wfb_b, EPI_BIAS, nullptr, 0, a2[net] + d.E * d.N, d.ld2);
         }
-        if (int rc = launch_linear(h, d.BT, d.HE, st)) return rc;
+        if (int rc = launch_linear(h, d.BT, d.HE, st, "k_linear_group:mixer_l2")) return rc;
     } else if (d.mixer == MAL_MIXER_QMIX1) {
         LinGroup g; g.n = 8; g.bv = bv;
         for (int net = 0; net < 2; ++net) {
@@ -420,7 +492,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             g.p[net * 4 + 2] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.b1_w, d.S, 0, P + ML.b1_b, EPI_BIAS, nullptr, 0, y1[net], d.ld1);
             g.p[net * 4 + 3] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.v0_w, d.S, 0, P + ML.v0_b, EPI_RELU, nullptr, 0, y1[net] + d.E, d.ld1);
         }
-        if (int rc = launch_linear(g, d.BT, d.S, st)) return rc;
+        if (int rc = launch_linear(g, d.BT, d.S, st, "k_linear_group:mixer_l1")) return rc;
     }
     // mixing + TD error + masked loss + element-wise mixer backward          q_learner.py:81-98
     {
@@ -432,9 +504,9 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.q_tot = F(plan->q_tot); a.target_q_tot = F(plan->target_q_tot); a.targets = F(plan->targets); a.td = F(plan->td);
         a.d_a2 = F(plan->d_a2); a.d_y1 = F(plan->d_y1); a.d_chosen = F(plan->d_chosen);
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
-        k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a);
+        { ProfScope _ps("k_mix_td", st); k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_mix_td");
-        k_stats_finalize<<<1, 32, 0, st>>>(parts + pl.mix_stats, pl.nblk_mix, d.N, scalars);
+        { ProfScope _ps("k_stats_finalize", st); k_stats_finalize<<<1, 32, 0, st>>>(parts + pl.mix_stats, pl.nblk_mix, d.N, scalars); }
         MAL_LAUNCH_CHECK("k_stats_finalize");
     }
     return 0;
@@ -471,23 +543,23 @@ extern "C" int mal_mixer_forward(int32_t mixer, int32_t B, int32_t T, int32_t N,
             g.p[1] = lin(BT, S, HE, A_STATE, 0, nullptr, 0, params + ML.wfa_w, S, 0, params + ML.wfa_b, EPI_RELU, nullptr, 0, y1 + HE, ld1);
             g.p[2] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.b1_w, S, 0, params + ML.b1_b, EPI_BIAS, nullptr, 0, y1 + 2 * HE, ld1);
             g.p[3] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.v0_w, S, 0, params + ML.v0_b, EPI_RELU, nullptr, 0, y1 + 2 * HE + E, ld1);
-            if (int rc = launch_linear(g, BT, S, st)) return rc;
+            if (int rc = launch_linear(g, BT, S, st, "k_linear_group:mixer_fwd_l1")) return rc;
             LinGroup h; h.bv = bv; h.n = 2;
             h.p[0] = lin(BT, HE, E * N, A_DENSE, 0, y1, ld1, params + ML.w1b_w, HE, 0, params + ML.w1b_b, EPI_BIAS, nullptr, 0, a2, ld2);
             h.p[1] = lin(BT, HE, E, A_DENSE, 0, y1 + HE, ld1, params + ML.wfb_w, HE, 0, params + ML.wfb_b, EPI_BIAS, nullptr, 0, a2 + E * N, ld2);
-            if (int rc = launch_linear(h, BT, HE, st)) return rc;
+            if (int rc = launch_linear(h, BT, HE, st, "k_linear_group:mixer_fwd_l2")) return rc;
         } else {
             g.n = 4;
             g.p[0] = lin(BT, S, E * N, A_STATE, 0, nullptr, 0, params + ML.w1b_w, S, 0, params + ML.w1b_b, EPI_BIAS, nullptr, 0, a2, ld2);
             g.p[1] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.wfb_w, S, 0, params + ML.wfb_b, EPI_BIAS, nullptr, 0, a2 + E * N, ld2);
             g.p[2] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.b1_w, S, 0, params + ML.b1_b, EPI_BIAS, nullptr, 0, y1, ld1);
             g.p[3] = lin(BT, S, E, A_STATE, 0, nullptr, 0, params + ML.v0_w, S, 0, params + ML.v0_b, EPI_RELU, nullptr, 0, y1 + E, ld1);
-            if (int rc = launch_linear(g, BT, S, st)) return rc;
+            if (int rc = launch_linear(g, BT, S, st, "k_linear_group:mixer_fwd_l1")) return rc;
         }
         a.y1[0] = y1; a.a2[0] = a2; a.mparams[0] = params;
     }
     int64_t grid = ceil_div64(BT, 8); if (grid > (int64_t)sms * 4) grid = (int64_t)sms * 4;
-    k_mix_fwd<<<(unsigned)grid, 256, 0, st>>>(a);
+    { ProfScope _ps("k_mix_fwd", st); k_mix_fwd<<<(unsigned)grid, 256, 0, st>>>(a); }
     MAL_LAUNCH_CHECK("k_mix_fwd");
     return 0;
 }
@@ -501,7 +573,7 @@ static RedProb red(int64_t M, int K, int Nout, const float *dY, int64_t ldy, int
     return p;
 }
 
-static int launch_reduce(RedGroup &g, cudaStream_t st) {
+static int launch_reduce(RedGroup &g, cudaStream_t st, const char *tag) {
     int tiles = 0, maxc = 0;
     for (int i = 0; i < g.n; ++i) {
         g.p[i].tile0 = tiles;
@@ -509,7 +581,7 @@ static int launch_reduce(RedGroup &g, cudaStream_t st) {
         if (g.p[i].n_chunks > maxc) maxc = g.p[i].n_chunks;
     }
     dim3 grid(maxc, tiles);
-    k_reduce_group<<<grid, 256, 0, st>>>(g);
+    { ProfScope _ps(tag, st); k_reduce_group<<<grid, 256, 0, st>>>(g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
     return 0;
 }
@@ -538,18 +610,18 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         LinGroup g; g.n = 2; g.bv = bv;   // d h1 = (d a1 . W12) * (h1 > 0) ; d hf = (d af . Wf2) * (hf > 0)
         g.p[0] = lin(d.BT, d.E * d.N, d.HE, A_DENSE, 0, d_a2, d.ld2, mixer + ML.w1b_w, d.HE, 1, nullptr, EPI_MASKPOS, y1, d.ld1, d_y1, d.ld1);
         g.p[1] = lin(d.BT, d.E, d.HE, A_DENSE, 0, d_a2 + d.E * d.N, d.ld2, mixer + ML.wfb_w, d.HE, 1, nullptr, EPI_MASKPOS, y1 + d.HE, d.ld1, d_y1 + d.HE, d.ld1);
-        if (int rc = launch_linear(g, d.BT, d.E * d.N, st)) return rc;
+        if (int rc = launch_linear(g, d.BT, d.E * d.N, st, "k_linear_group:mixer_bwd_dh")) return rc;
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.BT, d.HE, d.E * d.N, d_a2, d.ld2, A_DENSE, 0, y1, d.ld1, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m, pl.rpc_m);
         r.p[1] = red(d.BT, d.HE, d.E, d_a2 + d.E * d.N, d.ld2, A_DENSE, 0, y1 + d.HE, d.ld1, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m, pl.rpc_m);
         r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m, pl.rpc_m);
-        if (int rc = launch_reduce(r, st)) return rc;
+        if (int rc = launch_reduce(r, st, "k_reduce_group:mixer")) return rc;
     } else if (d.mixer == MAL_MIXER_QMIX1) {
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.BT, d.S, d.E * d.N, d_a2, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m, pl.rpc_m);
         r.p[1] = red(d.BT, d.S, d.E, d_a2 + d.E * d.N, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m, pl.rpc_m);
         r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m, pl.rpc_m);
-        if (int rc = launch_reduce(r, st)) return rc;
+        if (int rc = launch_reduce(r, st, "k_reduce_group:mixer")) return rc;
     }
 
     // ---- agent: BPTT recurrence
@@ -568,7 +640,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     {
         LinGroup g; g.n = 1; g.bv = bv;
         g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, agent + AL.w_ih, HID, 1, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);
-        if (int rc = launch_linear(g, d.M1, G3, st)) return rc;
+        if (int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx")) return rc;
     }
     // weight gradients of the agent
     {
@@ -578,11 +650,11 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         r.p[1] = red(d.M1, HID, 128, d_g, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whha_w, parts + pl.whha_b, pl.nc_a, pl.rpc_a);
         r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
         r.p[3] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_a, pl.rpc_a);
-        if (int rc = launch_reduce(r, st)) return rc;
+        if (int rc = launch_reduce(r, st, "k_reduce_group:agent")) return rc;
         Fc2GradArgs f;
         f.hout = F(plan->h_on); f.d_chosen = F(plan->d_chosen); f.actions = batch->actions;
         f.B = d.B; f.T = d.T; f.N = d.N; f.A = d.A; f.R = d.R; f.part = parts + pl.fc2; f.items_per_block = pl.ipb_fc2;
-        k_fc2_grad<<<pl.nblk_fc2, 256, 0, st>>>(f);
+        { ProfScope _ps("k_fc2_grad", st); k_fc2_grad<<<pl.nblk_fc2, 256, 0, st>>>(f); }
         MAL_LAUNCH_CHECK("k_fc2_grad");
     }
     // ---- gather partials into the flat gradient (state_dict order) + sum of squares
@@ -633,7 +705,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         a.total = AL.total + ML.total;
         a.grad = grad;
         a.norm_part = parts + pl.norm;
-        k_grad_reduce<<<pl.nblk_norm, 256, 0, st>>>(a);
+        { ProfScope _ps("k_grad_reduce", st); k_grad_reduce<<<pl.nblk_norm, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_grad_reduce");
     }
     return 0;
@@ -643,8 +715,8 @@ static int launch_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int6
                                float *sq, const float *norm_part, int n_part, float lr, float alpha, float eps,
                                float clip, float *scalars, cudaStream_t st) {
     const int64_t P = n_agent + n_mixer;
-    k_clip_rmsprop<<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
-                                                                n_part, lr, alpha, eps, clip, scalars);
+    { ProfScope _ps("k_clip_rmsprop", st); k_clip_rmsprop<<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
+                                                                n_part, lr, alpha, eps, clip, scalars); }
     MAL_LAUNCH_CHECK("k_clip_rmsprop");
     return 0;
 }
@@ -657,7 +729,7 @@ extern "C" int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int
     MAL_REQUIRE(n_mixer == 0 || mixer, "mal_clip_rmsprop: mixer buffer missing");
     const int64_t P = n_agent + n_mixer;
     const int nb = (int)ceil_div64(P, 256);
-    k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch);
+    { ProfScope _ps("k_sumsq", (cudaStream_t)stream); k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch); }
     MAL_LAUNCH_CHECK("k_sumsq");
     return launch_clip_rmsprop(agent, n_agent, mixer, n_mixer, grad, square_avg, scratch, nb, lr, alpha, eps, clip,
                                scalars, (cudaStream_t)stream);
@@ -686,7 +758,7 @@ extern "C" int mal_copy_f32(float *dst, const float *src, int64_t n, void *strea
     if (n <= 0) return 0;
     MAL_REQUIRE(dst && src, "mal_copy_f32: null buffer");
     int64_t grid = ceil_div64(n, 1024); if (grid > 1184) grid = 1184; if (grid < 1) grid = 1;
-    k_copy_f32<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    { ProfScope _ps("k_copy_f32", (cudaStream_t)stream); k_copy_f32<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(dst, src, n); }
     MAL_LAUNCH_CHECK("k_copy_f32");
     return 0;
 }

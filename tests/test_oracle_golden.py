@@ -126,3 +126,26 @@ def test_ring_buffer_indices():
 def test_onehot():
     a = np.array([[[2], [0]]])
     assert np.array_equal(O.onehot(a, 3), np.array([[[0, 0, 1], [1, 0, 0]]], np.float32))
+
+
+# ---- oracle/torch_port.py: the CPU port used as the baseline arm issues the reference's op sequence
+@pytest.mark.parametrize("case", LEARNER_CASES)
+def test_torch_port_two_steps_match_reference(case):
+    import torch as th
+    from oracle import torch_port as TP
+    g = load_golden(case)
+    B, TT, N, A, OBS, S, is_qmix, double_q, layers, steps = [int(x) for x in g["meta"]]
+    gamma, lr, alpha, eps, clip = [float(x) for x in g["hyper"]]
+    L = TP.TorchPortLearner(sub(g, "agent0."), sub(g, "tagent0."), sub(g, "mixer0."), sub(g, "tmixer0."),
+                            mixer="qmix" if is_qmix else "vdn", double_q=bool(double_q), gamma=gamma, lr=lr,
+                            alpha=alpha, eps=eps, clip=clip)
+    batch = {k: th.from_numpy(v.copy()) for k, v in sub(g, "batch.").items()}
+    for i in range(steps):
+        out = L.train(batch)
+        if i == 0:
+            assert abs(out["loss"] - g["stat.loss"]) <= 1e-6 * abs(g["stat.loss"])
+            assert abs(out["grad_norm"] - float(g["grad_norm"])) <= 1e-6 * float(g["grad_norm"])
+    for k, v in L.ap.items():
+        assert np.array_equal(v.detach().numpy(), g["agentK." + k]), k      # same ops -> bit-identical on this host
+    for k, v in L.mp.items():
+        assert np.array_equal(v.detach().numpy(), g["mixerK." + k]), k
