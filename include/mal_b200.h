@@ -82,6 +82,7 @@ typedef struct mal_plan {
     int64_t d_chosen;                 /* f32 [B,T,N] */
     int64_t d_g;                      /* f32 [TT*R,256]  d(gi_r)|d(gi_z)|d(gi_n)|d(gh_n) */
     int64_t d_x;                      /* f32 [TT*R,64] */
+    int64_t dh_head;                  /* f32 [TT*R,64]  d_chosen * fc2.weight[a_t] (rows of t < T) */
     int64_t partials;                 /* f32 scratch for split reductions */
     int64_t partials_bytes;
     int64_t scalars;                  /* f32 [64]: see MAL_SC_* */
@@ -161,6 +162,16 @@ int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t o
                    void *stream);
 /* dense_input != 0: `obs` is the already assembled agent input [rows, obs_dim] with row stride obs_sb
  * (DRQNAgentNetwork.forward(inputs, hidden_state), drqn_agent.py:29-35); obs_dim is then the full input width. */
+
+/* Library options.  "tensor_cores": 1 (default) runs the batched projections on tcgen05 (3xTF32, fp32-accurate),
+ * 0 on the fp32 FFMA panel GEMM. */
+int mal_set_option(const char *name, int value);
+
+/* Unit-test hook: Y = epi(A W^T + bias) on dense operands through the learner's own GEMM kernels
+ * (epi 0 = bias, 1 = ReLU, 2 = multiply by (aux > 0); w_trans: W(n,k) = W[k*ldw + n]). */
+int mal_debug_linear(int32_t M, int32_t K, int32_t Nout, const float *A, int64_t lda, const float *W, int64_t ldw,
+                     int32_t w_trans, const float *bias, int32_t epi, const float *aux, int64_t ld_aux, float *Y,
+                     int64_t ldy, int32_t use_tc, void *stream);
 
 /* QMixer.forward / VDNMixer.forward outside the learner, qmix.py:41-59 / vdn.py:9-10.
  * agent_qs [B*T,N] contiguous, states [B,T,S] with strides in elements, scratch >= B*T*(2*HE+2*E + E*N+E)

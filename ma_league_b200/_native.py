@@ -46,7 +46,7 @@ class LearnerCfg(C.Structure):
 _PLAN_FIELDS = ["total_bytes", "n_agent_params", "n_mixer_params", "x_on", "x_tg", "gi_on", "gi_tg", "h_on", "h_tg",
                 "gates", "mac_out", "target_mac_out", "chosen", "target_max", "argmax", "mask", "y1_on", "y1_tg",
                 "a2_on", "a2_tg", "q_tot", "target_q_tot", "targets", "td", "d_a2", "d_y1", "d_chosen", "d_g", "d_x",
-                "partials", "partials_bytes", "scalars"]
+                "dh_head", "partials", "partials_bytes", "scalars"]
 
 
 class Plan(C.Structure):
@@ -65,6 +65,10 @@ _PROTOS = {
     "mal_launch_count": (C.c_uint64, []),
     "mal_profile_begin": (C.c_int, []),
     "mal_profile_end": (C.c_int, [C.c_char_p, C.c_int64]),
+    "mal_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "mal_debug_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                   C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                   C.c_int32, C.c_void_p]),
     "mal_agent_param_count": (C.c_int64, [C.c_int32, C.c_int32]),
     "mal_mixer_param_count": (C.c_int64, [C.c_int32] * 5),
     "mal_learner_plan": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan)]),

@@ -19,7 +19,7 @@
 // =============================================================================================
 struct BatchView {
     int B, TT, T, N, A, OBS, S, R;
-    mal_field_t obs, onehot, state;
+    mal_field_t obs, onehot, state, actions;
 };
 
 enum { A_DENSE = 0, A_AGENT_IN = 1, A_STATE = 2 };
@@ -179,6 +179,7 @@ struct RedProb {
     int64_t M0, M;            // rows [M0, M)
     int K, Nout;
     const float *dY; int64_t ldy;
+    int dy_kind;              // 0: dense dY[m*ldy + n];  1: one-hot(action[m]) * d_chosen[m]  (fc2 / gather backward)
     int a_kind, shift;
     const float *A; int64_t lda;
     float *partW, *partB;     // [n_chunks][Nout][K], [n_chunks][Nout] (partB may be null)
@@ -227,10 +228,19 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
             RowSrc rs;
             rs.p0 = rs.p1 = nullptr; rs.agent = 0;
             if (ok_a) rs = resolve_row(p.a_kind, g.bv, p.A, p.lda, p.shift, m);
+            float dsel = 0.0f;
+            int asel = -1;
+            if (p.dy_kind == 1 && ok) {   // row m = t*R + b*N + n of the [T*R] transition rows
+                const int t = (int)(m / g.bv.R), rr = (int)(m - (int64_t)t * g.bv.R);
+                const int b = rr / g.bv.N, n = rr - b * g.bv.N;
+                dsel = p.dY[((int64_t)b * g.bv.T + t) * g.bv.N + n];
+                asel = (int)(field_ptr<long long>(g.bv.actions, b, t)[n]);
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = lane + 32 * h;
-                dY_s[r * RED_LD + c] = (ok && n0 + c < p.Nout) ? p.dY[m * p.ldy + n0 + c] : 0.0f;
+                if (p.dy_kind == 1) dY_s[r * RED_LD + c] = (n0 + c == asel) ? dsel : 0.0f;
+                else dY_s[r * RED_LD + c] = (ok && n0 + c < p.Nout) ? p.dY[m * p.ldy + n0 + c] : 0.0f;
                 A_s[r * RED_LD + c] = (ok_a && k0 + c < p.K) ? row_elem(p.a_kind, g.bv, rs, k0 + c) : 0.0f;
             }
         }
@@ -263,39 +273,9 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
 }
 
 // =============================================================================================
-// mask, mask.sum()          q_learner.py:40-42,98,112
-// =============================================================================================
-__global__ void __launch_bounds__(1024) k_mask_prep(mal_field_t filled, mal_field_t terminated, int B, int T,
-                                                    float *mask, float *scalars) {
-    __shared__ float s_sum[32];
-    __shared__ int s_cnt[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float sum = 0.0f;
-    int cnt = 0;
-    for (int idx = tid; idx < B * T; idx += blockDim.x) {
-        int b = idx / T, t = idx - b * T;
-        float m = (float)(*field_ptr<long long>(filled, b, t));
-        if (t > 0) m = m * (1.0f - (float)(*field_ptr<unsigned char>(terminated, b, t - 1)));
-        mask[idx] = m;
-        sum += m;
-        cnt += (m != 0.0f);
-    }
-    sum = warp_sum(sum);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
-    __syncthreads();
-    if (tid == 0) {
-        float s = 0.0f;
-        int c = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += s_sum[w]; c += s_cnt[w]; }
-        scalars[MAL_SC_MASK_SUM] = s;
-        reinterpret_cast<int *>(scalars)[MAL_SC_MASK_COUNT] = c;
-    }
-}
-
-// =============================================================================================
-// GRU recurrence, forward.  grid (ceil(R/RT), nets), 192 threads: thread j owns gate row j of W_hh.
+// GRU recurrence, forward.  grid (ceil(R/RT), nets), 192 threads: thread j owns gate row j of W_hh (64 registers).
+// The per-step input-gate rows gi[t] (RT x 192 floats, contiguous) are fed by the bulk-copy engine (cp.async.bulk)
+// into a DEPTH-deep shared-memory ring several timesteps ahead, so no global-memory latency sits on the serial chain.
 // =============================================================================================
 struct GruFwdArgs {
     const float *params[2];    // online, target (flat agent buffers)
@@ -306,11 +286,14 @@ struct GruFwdArgs {
 };
 
 template <int RT>
-__global__ void __launch_bounds__(192) k_gru_fwd(GruFwdArgs a) {
+__global__ void __launch_bounds__(192, 1) k_gru_fwd(GruFwdArgs a) {
     constexpr int ITEMS = RT * HID;
     constexpr int IPT = (ITEMS + 191) / 192;
+    constexpr int DEPTH = RT >= 8 ? 4 : 8;
+    __shared__ __align__(128) float gi_s[DEPTH][RT * G3];
     __shared__ __align__(16) float h_s[RT * HID];
     __shared__ float gh_s[RT * G3];
+    __shared__ __align__(8) uint64_t bars[DEPTH];
     const int tid = threadIdx.x, net = blockIdx.y;
     const int r0 = blockIdx.x * RT;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
@@ -318,6 +301,25 @@ __global__ void __launch_bounds__(192) k_gru_fwd(GruFwdArgs a) {
     const float *gi = a.gi[net];
     float *hout = a.hout[net];
     float *gates = net == 0 ? a.gates : nullptr;
+    const int nrows = (a.R - r0) < RT ? (a.R - r0) : RT;
+    const uint32_t bytes = (uint32_t)nrows * G3 * 4;
+
+    for (int idx = tid; idx < DEPTH * RT * G3; idx += 192) (&gi_s[0][0])[idx] = 0.0f;   // rows past R stay zero
+    for (int idx = tid; idx < ITEMS; idx += 192) h_s[idx] = 0.0f;                       // init_hidden: zeros
+    if (tid == 0) {
+        for (int s = 0; s < DEPTH; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int s = t % DEPTH;
+        mbar_expect_tx(&bars[s], bytes);
+        bulk_g2s(gi_s[s], gi + ((int64_t)t * a.R + r0) * G3, bytes, &bars[s]);
+    };
+    if (tid == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int t = 0; t < DEPTH && t < a.TT; ++t) issue(t);
+    }
 
     float w[HID];
     {
@@ -329,51 +331,41 @@ __global__ void __launch_bounds__(192) k_gru_fwd(GruFwdArgs a) {
         }
     }
     const float bj = __ldg(P + L.b_hh + tid);
-    for (int idx = tid; idx < ITEMS; idx += 192) h_s[idx] = 0.0f;   // init_hidden: zeros
-
-    float g_r[IPT], g_z[IPT], g_n[IPT];
-    auto prefetch = [&](int t) {
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            int item = tid + 192 * q;
-            int r = item >> 6, i = item & 63, row = r0 + r;
-            if (item < ITEMS && row < a.R && t < a.TT) {
-                const float *gp = gi + ((int64_t)t * a.R + row) * G3;
-                g_r[q] = __ldg(gp + i); g_z[q] = __ldg(gp + HID + i); g_n[q] = __ldg(gp + 2 * HID + i);
-            } else { g_r[q] = g_z[q] = g_n[q] = 0.0f; }
-        }
-    };
-    prefetch(0);
-    __syncthreads();
 
     for (int t = 0; t < a.TT; ++t) {
-        // phase 1: gh[r][j] = b_hh[j] + W_hh[j,:] . h[r,:]
+        // phase 1: gh[r][j] = b_hh[j] + W_hh[j,:] . h[r,:]   (whole h row pulled into registers first: 16 LDS.128 in
+        // flight, then 4 independent FFMA chains -- the serial chain must not wait on shared-memory latency)
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
-            float acc0 = bj, acc1 = 0.0f;
+            float4 hv[HID / 4];
             const float4 *hp = reinterpret_cast<const float4 *>(h_s + r * HID);
 #pragma unroll
+            for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = hp[k4];
+            float acc0 = bj, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+#pragma unroll
             for (int k4 = 0; k4 < HID / 4; ++k4) {
-                float4 hv = hp[k4];
-                acc0 = fmaf(w[4 * k4], hv.x, acc0);
-                acc1 = fmaf(w[4 * k4 + 1], hv.y, acc1);
-                acc0 = fmaf(w[4 * k4 + 2], hv.z, acc0);
-                acc1 = fmaf(w[4 * k4 + 3], hv.w, acc1);
+                acc0 = fmaf(w[4 * k4], hv[k4].x, acc0);
+                acc1 = fmaf(w[4 * k4 + 1], hv[k4].y, acc1);
+                acc2 = fmaf(w[4 * k4 + 2], hv[k4].z, acc2);
+                acc3 = fmaf(w[4 * k4 + 3], hv[k4].w, acc3);
             }
-            gh_s[r * G3 + tid] = acc0 + acc1;
+            gh_s[r * G3 + tid] = (acc0 + acc1) + (acc2 + acc3);
         }
         __syncthreads();
-        // phase 2: gate math per (row, hidden unit)
+        // phase 2: gate math per (row, hidden unit); gi[t] has been staged by the copy engine
+        const int slot = t % DEPTH;
+        mbar_wait(&bars[slot], (uint32_t)((t / DEPTH) & 1));
 #pragma unroll
         for (int q = 0; q < IPT; ++q) {
             int item = tid + 192 * q;
             if (item < ITEMS) {
                 int r = item >> 6, i = item & 63, row = r0 + r;
                 const float *gh = gh_s + r * G3;
+                const float *gq = gi_s[slot] + r * G3;
                 float ghn = gh[2 * HID + i];
-                float rr = sigmoidf_acc(g_r[q] + gh[i]);
-                float zz = sigmoidf_acc(g_z[q] + gh[HID + i]);
-                float nn = tanhf(g_n[q] + rr * ghn);
+                float rr = sigmoidf_acc(gq[i] + gh[i]);
+                float zz = sigmoidf_acc(gq[HID + i] + gh[HID + i]);
+                float nn = tanhf(gq[2 * HID + i] + rr * ghn);
                 float hp = h_s[item];
                 float hn = nn + zz * (hp - nn);
                 h_s[item] = hn;
@@ -387,8 +379,8 @@ __global__ void __launch_bounds__(192) k_gru_fwd(GruFwdArgs a) {
                 }
             }
         }
-        prefetch(t + 1);
         __syncthreads();
+        if (tid == 0 && t + DEPTH < a.TT) issue(t + DEPTH);   // slot t%DEPTH is free again
     }
 }
 
@@ -470,21 +462,25 @@ __global__ void __launch_bounds__(256) k_q_head(HeadArgs a) {
 }
 
 // =============================================================================================
-// mixer (VDN / QMIX) + TD target + masked L2 loss + element-wise part of the mixer backward.
-// One warp per (b,t); lane = embed index e.                      qmix.py:41-59, vdn.py:9-10, q_learner.py:81-98
+// mask + mixer (VDN / QMIX) + TD target + masked L2 loss + element-wise part of the mixer backward + the
+// fc2/gather backward injection d h_t += d_chosen * W2[a_t].   One warp per (b,t); lane = embed index.
+//                                            q_learner.py:40-42,81-98, qmix.py:41-59, vdn.py:9-10
+// All seeds are UN-normalised (without the 1/mask.sum() factor); k_grad_reduce applies it once at the end.
 // =============================================================================================
+#define MIX_NSTAT 6   // sum mtd^2, sum |mtd|, sum q_tot*m, sum targets*m, sum m, count(m != 0)
 struct MixArgs {
-    int mixer, B, T, N, E, HE, S;
+    int mixer, B, T, N, E, HE, S, R, A, d_in;
     const float *y1[2], *a2[2];        // online, target
     const float *mparams[2];
+    const float *agent;                // online agent parameters (fc2.weight for the dh injection)
     const float *chosen, *target_max;  // [B*T,N]
-    const float *mask;                 // [B*T]
-    mal_field_t reward, terminated;
+    mal_field_t reward, terminated, filled, actions;
     float gamma;
-    const float *scalars;              // mask sum
+    float *mask;                       // [B*T] out
     float *q_tot, *target_q_tot, *targets, *td;
-    float *d_a2, *d_y1, *d_chosen;     // backward seeds
-    float *part_stats;                 // [gridDim.x][4]   sum mtd^2, sum |mtd|, sum q_tot*m, sum targets*m
+    float *d_a2, *d_y1, *d_chosen;     // backward seeds (un-normalised)
+    float *dh_head;                    // [TT*R,64]: rows of t < T
+    float *part_stats;                 // [gridDim.x][MIX_NSTAT]
     float *part_v2;                    // [gridDim.x][E+1] d V.2.weight | d V.2.bias
 };
 
@@ -512,16 +508,17 @@ __device__ __forceinline__ float qmix_row(const MixArgs &a, int net, int64_t m, 
 }
 
 __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
-    __shared__ float s_stats[8][4];
+    __shared__ float s_stats[8][MIX_NSTAT];
     __shared__ float s_v2[8][MAL_MAX_EMBED + 1];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = (int64_t)a.B * a.T;
-    const float msum = a.scalars[MAL_SC_MASK_SUM];
     const MixerLayout ML = mixer_layout(a.mixer, a.S, a.N, a.E, a.HE);
+    const AgentLayout AL = agent_layout(a.d_in, a.A);
     const int two = (ML.layers == 2);
     const int ld1 = two ? 2 * a.HE + 2 * a.E : 2 * a.E;
     const int ld2 = a.E * a.N + a.E;
-    float st0 = 0, st1 = 0, st2 = 0, st3 = 0, dv2w = 0, dv2b = 0;
+    float st[MIX_NSTAT] = {0, 0, 0, 0, 0, 0};
+    float dv2w = 0, dv2b = 0;
     float q[MAL_MAX_ACTIONS];   // N <= 32 agents per team
 
     for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
@@ -538,56 +535,70 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
             for (int n = 0; n < a.N; ++n) q[n] = a.chosen[m * a.N + n];
             y = qmix_row(a, 0, m, q, lane, &pre, &hidden, &wf, &v1);
         }
+        // mask = filled[:, :-1]; mask[:, 1:] *= 1 - terminated[:, :-1]
+        float mk = (float)(*field_ptr<long long>(a.filled, b, t));
+        if (t > 0) mk = mk * (1.0f - (float)(*field_ptr<unsigned char>(a.terminated, b, t - 1)));
         const float rew = *field_ptr<float>(a.reward, b, t);
         const float term = (float)(*field_ptr<unsigned char>(a.terminated, b, t));
-        const float mk = a.mask[m];
         const float target = rew + a.gamma * (1.0f - term) * ty;
         const float tdv = y - target;
         const float mtd = tdv * mk;
-        const float gseed = 2.0f * mtd * mk / msum;   // d loss / d q_tot
+        const float gseed = 2.0f * mtd * mk;   // (d loss / d q_tot) * mask.sum()
         if (lane == 0) {
+            a.mask[m] = mk;
             a.q_tot[m] = y; a.target_q_tot[m] = ty; a.targets[m] = target; a.td[m] = tdv;
-            st0 += mtd * mtd; st1 += fabsf(mtd); st2 += y * mk; st3 += target * mk;
+            st[0] += mtd * mtd; st[1] += fabsf(mtd); st[2] += y * mk; st[3] += target * mk;
+            st[4] += mk; st[5] += (mk != 0.0f) ? 1.0f : 0.0f;
         }
-        if (a.mixer == MAL_MIXER_VDN) {
-            if (lane < a.N) a.d_chosen[m * a.N + lane] = gseed;
-            continue;
-        }
-        // ---- element-wise mixer backward
+        float *da2 = nullptr, *dy1 = nullptr;
+        const float *a2 = nullptr;
+        float dpre = 0.0f;
         const bool act = lane < a.E;
-        const float *a2 = a.a2[0] + m * ld2;
-        float *da2 = a.d_a2 + m * ld2;
-        float *dy1 = a.d_y1 + m * ld1 + (two ? 2 * a.HE : 0);
-        const float dhidden = gseed * wf;
-        const float dwf = gseed * hidden;
-        const float dpre = dhidden * (pre > 0.0f ? 1.0f : expf(pre));
-        if (act) {
-            const float af = a2[a.N * a.E + lane];
-            da2[a.N * a.E + lane] = dwf * (af > 0.0f ? 1.0f : (af < 0.0f ? -1.0f : 0.0f));
-            dy1[lane] = dpre;                                                              // d hyper_b_1 out
-            const float v2w = __ldg(a.mparams[0] + ML.v2_w + lane);
-            dy1[a.E + lane] = v1 > 0.0f ? gseed * v2w : 0.0f;                               // d V.0 pre-activation
-            dv2w += gseed * v1;
+        if (a.mixer != MAL_MIXER_VDN) {   // element-wise mixer backward
+            a2 = a.a2[0] + m * ld2;
+            da2 = a.d_a2 + m * ld2;
+            dy1 = a.d_y1 + m * ld1 + (two ? 2 * a.HE : 0);
+            const float dhidden = gseed * wf;
+            const float dwf = gseed * hidden;
+            dpre = dhidden * (pre > 0.0f ? 1.0f : expf(pre));
+            if (act) {
+                const float af = a2[a.N * a.E + lane];
+                da2[a.N * a.E + lane] = dwf * (af > 0.0f ? 1.0f : (af < 0.0f ? -1.0f : 0.0f));
+                dy1[lane] = dpre;                                                          // d hyper_b_1 out
+                const float v2w = __ldg(a.mparams[0] + ML.v2_w + lane);
+                dy1[a.E + lane] = v1 > 0.0f ? gseed * v2w : 0.0f;                           // d V.0 pre-activation
+                dv2w += gseed * v1;
+            }
+            if (lane == 0) dv2b += gseed;
         }
-        if (lane == 0) dv2b += gseed;
         for (int n = 0; n < a.N; ++n) {
-            const float a1 = act ? a2[n * a.E + lane] : 0.0f;
-            const float dq = warp_sum(act ? dpre * fabsf(a1) : 0.0f);
+            float dq = gseed;   // VDN: d q_tot / d q_n = 1
+            if (a.mixer != MAL_MIXER_VDN) {
+                const float a1 = act ? a2[n * a.E + lane] : 0.0f;
+                dq = warp_sum(act ? dpre * fabsf(a1) : 0.0f);
+                if (act) da2[n * a.E + lane] = q[n] * dpre * (a1 > 0.0f ? 1.0f : (a1 < 0.0f ? -1.0f : 0.0f));
+            }
             if (lane == 0) a.d_chosen[m * a.N + n] = dq;
-            if (act) da2[n * a.E + lane] = q[n] * dpre * (a1 > 0.0f ? 1.0f : (a1 < 0.0f ? -1.0f : 0.0f));
+            // gather + fc2 backward: d h_t[row] += dq * fc2.weight[a_t, :]
+            const int actn = (int)(field_ptr<long long>(a.actions, b, t)[n]);
+            const float *w2 = a.agent + AL.fc2_w + (int64_t)actn * HID;
+            float *dh = a.dh_head + ((int64_t)t * a.R + (int64_t)b * a.N + n) * HID;
+            dh[lane] = dq * __ldg(w2 + lane);
+            dh[lane + 32] = dq * __ldg(w2 + lane + 32);
         }
     }
     // ---- deterministic block partials
-    if (lane == 0) { s_stats[warp][0] = st0; s_stats[warp][1] = st1; s_stats[warp][2] = st2; s_stats[warp][3] = st3; }
+    if (lane == 0)
+        for (int k = 0; k < MIX_NSTAT; ++k) s_stats[warp][k] = st[k];
     if (a.mixer != MAL_MIXER_VDN) {
         if (lane < a.E) s_v2[warp][lane] = dv2w;
         if (lane == 0) s_v2[warp][a.E] = dv2b;
     }
     __syncthreads();
-    if (tid < 4) {
+    if (tid < MIX_NSTAT) {
         float s = 0;
         for (int w = 0; w < 8; ++w) s += s_stats[w][tid];
-        a.part_stats[blockIdx.x * 4 + tid] = s;
+        a.part_stats[blockIdx.x * MIX_NSTAT + tid] = s;
     }
     if (a.mixer != MAL_MIXER_VDN && tid <= a.E) {
         float s = 0;
@@ -615,165 +626,146 @@ __global__ void __launch_bounds__(256) k_mix_fwd(MixArgs a) {
     }
 }
 
-// loss / logging scalars from the block partials (q_learner.py:98,117-124)
-__global__ void k_stats_finalize(const float *part_stats, int nblk, int n_agents, float *scalars) {
-    if (threadIdx.x < 4) {
-        float s = 0;
-        for (int i = 0; i < nblk; ++i) s += part_stats[i * 4 + threadIdx.x];
-        const float msum = scalars[MAL_SC_MASK_SUM];
-        if (threadIdx.x == 0) scalars[MAL_SC_LOSS] = s / msum;
-        if (threadIdx.x == 1) scalars[MAL_SC_TD_ABS] = s / msum;
-        if (threadIdx.x == 2) scalars[MAL_SC_Q_TAKEN] = s / (msum * n_agents);
-        if (threadIdx.x == 3) scalars[MAL_SC_TARGET] = s / (msum * n_agents);
+// mask.sum(), loss and the logging scalars from the block partials (q_learner.py:98,112,117-124); one warp per stat
+__global__ void __launch_bounds__(32 * MIX_NSTAT) k_stats_finalize(const float *part_stats, int nblk, int n_agents,
+                                                                   float *scalars) {
+    __shared__ float s[MIX_NSTAT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float v = 0.0f;
+    for (int i = lane; i < nblk; i += 32) v += part_stats[i * MIX_NSTAT + warp];
+    v = warp_sum(v);
+    if (lane == 0) s[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float msum = s[4];
+        scalars[MAL_SC_MASK_SUM] = msum;
+        scalars[MAL_SC_LOSS] = s[0] / msum;
+        scalars[MAL_SC_TD_ABS] = s[1] / msum;
+        scalars[MAL_SC_Q_TAKEN] = s[2] / (msum * n_agents);
+        scalars[MAL_SC_TARGET] = s[3] / (msum * n_agents);
+        reinterpret_cast<int *>(scalars)[MAL_SC_MASK_COUNT] = (int)(s[5] + 0.5f);
     }
 }
 
 // =============================================================================================
 // GRU recurrence, backward (BPTT).  grid ceil(R/RT), 192 threads: thread (g,k) owns W_hh[g*64 + :, k].
+// Saved gates, h_{t-1} and the fc2/gather injection of step t arrive through a cp.async.bulk ring.
 // =============================================================================================
 struct GruBwdArgs {
     const float *params;       // online agent
     const float *hout;         // [TT*R,64]
     const float *gates;        // [TT*R,256]
-    const float *d_chosen;     // [B,T,N]
-    mal_field_t actions;
+    const float *dh_head;      // [TT*R,64] (rows of t < TT-1 are valid)
     float *d_g;                // [TT*R,256]: d gi_r | d gi_z | d gi_n | d gh_n
-    int TT, R, N, d_in, n_actions;
+    int TT, R, d_in, n_actions;
 };
 
 template <int RT>
-__global__ void __launch_bounds__(192) k_gru_bwd(GruBwdArgs a) {
+__global__ void __launch_bounds__(192, 1) k_gru_bwd(GruBwdArgs a) {
     constexpr int ITEMS = RT * HID;
     constexpr int IPT = (ITEMS + 191) / 192;
+    constexpr int DEPTH = 16 / RT;
+    constexpr int SLOT = RT * (4 * HID + HID + HID);   // gates | h_prev | dh_head, floats
+    __shared__ __align__(128) float ring[DEPTH][SLOT];
     __shared__ __align__(16) float dgh_s[RT * G3];
     __shared__ float part_s[RT * G3];          // [r][g][k]
-    __shared__ float w2_s[MAL_MAX_ACTIONS * HID];
+    __shared__ __align__(8) uint64_t bars[DEPTH];
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * RT;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
     const int T = a.TT - 1;
     const int g = tid >> 6, k = tid & 63;
+    const int nrows = (a.R - r0) < RT ? (a.R - r0) : RT;
+
+    for (int idx = tid; idx < DEPTH * SLOT; idx += 192) (&ring[0][0])[idx] = 0.0f;
+    for (int idx = tid; idx < RT * G3; idx += 192) part_s[idx] = 0.0f;
+    if (tid == 0) {
+        for (int s = 0; s < DEPTH; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // step index i counts down: i = 0 is t = TT-1
+    auto issue = [&](int i) {
+        const int t = a.TT - 1 - i;
+        const int s = i % DEPTH;
+        const int64_t m = (int64_t)t * a.R + r0;
+        uint32_t bytes = (uint32_t)nrows * 4 * HID * 4;
+        if (t > 0) bytes += (uint32_t)nrows * HID * 4;
+        if (t < T) bytes += (uint32_t)nrows * HID * 4;
+        mbar_expect_tx(&bars[s], bytes);
+        bulk_g2s(ring[s], a.gates + m * 4 * HID, (uint32_t)nrows * 4 * HID * 4, &bars[s]);
+        if (t > 0) bulk_g2s(ring[s] + RT * 4 * HID, a.hout + (m - a.R) * HID, (uint32_t)nrows * HID * 4, &bars[s]);
+        if (t < T) bulk_g2s(ring[s] + RT * 5 * HID, a.dh_head + m * HID, (uint32_t)nrows * HID * 4, &bars[s]);
+    };
+    if (tid == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int i = 0; i < DEPTH && i < a.TT; ++i) issue(i);
+    }
 
     float wT[HID];   // W_hh[g*64 + j][k], j = 0..63
 #pragma unroll
     for (int j = 0; j < HID; ++j) wT[j] = __ldg(a.params + L.w_hh + (int64_t)(g * HID + j) * HID + k);
-    for (int idx = tid; idx < a.n_actions * HID; idx += 192) w2_s[idx] = __ldg(a.params + L.fc2_w + idx);
-    for (int idx = tid; idx < RT * G3; idx += 192) part_s[idx] = 0.0f;
-
     float carry[IPT];
-    float n_r[IPT], n_z[IPT], n_n[IPT], n_ghn[IPT], n_hp[IPT], n_dc[IPT];
-    int n_act[IPT];
-    auto prefetch = [&](int t) {
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            int item = tid + 192 * q;
-            int r = item >> 6, i = item & 63, row = r0 + r;
-            n_r[q] = n_z[q] = n_n[q] = n_ghn[q] = n_hp[q] = n_dc[q] = 0.0f;
-            n_act[q] = 0;
-            if (item < ITEMS && row < a.R && t >= 0) {
-                const int64_t m = (int64_t)t * a.R + row;
-                const float *gp = a.gates + m * 4 * HID;
-                n_r[q] = gp[i]; n_z[q] = gp[HID + i]; n_n[q] = gp[2 * HID + i]; n_ghn[q] = gp[3 * HID + i];
-                if (t > 0) n_hp[q] = a.hout[(m - a.R) * HID + i];
-                if (t < T) {
-                    int b = row / a.N, n = row - b * a.N;
-                    n_dc[q] = a.d_chosen[((int64_t)b * T + t) * a.N + n];
-                    n_act[q] = (int)(field_ptr<long long>(a.actions, b, t)[n]);
-                }
-            }
-        }
-    };
 #pragma unroll
     for (int q = 0; q < IPT; ++q) carry[q] = 0.0f;
-    prefetch(a.TT - 1);
-    __syncthreads();
 
-    for (int t = a.TT - 1; t >= 0; --t) {
+    for (int i = 0; i < a.TT; ++i) {
+        const int t = a.TT - 1 - i;
+        const int slot = i % DEPTH;
+        mbar_wait(&bars[slot], (uint32_t)((i / DEPTH) & 1));
+        const float *sg = ring[slot];
         // phase A: d h_t -> d gates
 #pragma unroll
         for (int q = 0; q < IPT; ++q) {
             int item = tid + 192 * q;
             if (item < ITEMS) {
-                int r = item >> 6, i = item & 63, row = r0 + r;
+                int r = item >> 6, ii = item & 63, row = r0 + r;
                 const float *ps = part_s + r * G3;
-                float dh = carry[q] + ps[i] + ps[HID + i] + ps[2 * HID + i] + n_dc[q] * w2_s[n_act[q] * HID + i];
-                const float rr = n_r[q], zz = n_z[q], nn = n_n[q];
+                const float *gp = sg + r * 4 * HID;
+                const float hp = t > 0 ? sg[RT * 4 * HID + r * HID + ii] : 0.0f;
+                const float dhh = t < T ? sg[RT * 5 * HID + r * HID + ii] : 0.0f;
+                float dh = carry[q] + ps[ii] + ps[HID + ii] + ps[2 * HID + ii] + dhh;
+                const float rr = gp[ii], zz = gp[HID + ii], nn = gp[2 * HID + ii], ghn = gp[3 * HID + ii];
                 float dn = dh * (1.0f - zz);
-                float dz = dh * (n_hp[q] - nn);
+                float dz = dh * (hp - nn);
                 float dnp = dn * (1.0f - nn * nn);
                 float dzp = dz * zz * (1.0f - zz);
-                float drp = dnp * n_ghn[q] * rr * (1.0f - rr);
+                float drp = dnp * ghn * rr * (1.0f - rr);
                 float dghn = dnp * rr;
                 carry[q] = dh * zz;
-                dgh_s[r * G3 + i] = drp; dgh_s[r * G3 + HID + i] = dzp; dgh_s[r * G3 + 2 * HID + i] = dghn;
+                dgh_s[r * G3 + ii] = drp; dgh_s[r * G3 + HID + ii] = dzp; dgh_s[r * G3 + 2 * HID + ii] = dghn;
                 if (row < a.R) {
                     float *dp = a.d_g + ((int64_t)t * a.R + row) * 4 * HID;
-                    dp[i] = drp; dp[HID + i] = dzp; dp[2 * HID + i] = dnp; dp[3 * HID + i] = dghn;
+                    dp[ii] = drp; dp[HID + ii] = dzp; dp[2 * HID + ii] = dnp; dp[3 * HID + ii] = dghn;
                 }
             }
         }
-        prefetch(t - 1);
         __syncthreads();
+        if (tid == 0 && i + DEPTH < a.TT) issue(i + DEPTH);   // every thread is past its reads of this slot
         // phase B: part[r][g][k] = sum_j dgh[r][g*64+j] * W_hh[g*64+j][k]
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             const float4 *dp = reinterpret_cast<const float4 *>(dgh_s + r * G3 + g * HID);
-            float acc0 = 0.0f, acc1 = 0.0f;
+            float4 dv[HID / 4];
+#pragma unroll
+            for (int j4 = 0; j4 < HID / 4; ++j4) dv[j4] = dp[j4];
+            float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
 #pragma unroll
             for (int j4 = 0; j4 < HID / 4; ++j4) {
-                float4 d = dp[j4];
-                acc0 = fmaf(wT[4 * j4], d.x, acc0);
-                acc1 = fmaf(wT[4 * j4 + 1], d.y, acc1);
-                acc0 = fmaf(wT[4 * j4 + 2], d.z, acc0);
-                acc1 = fmaf(wT[4 * j4 + 3], d.w, acc1);
+                acc0 = fmaf(wT[4 * j4], dv[j4].x, acc0);
+                acc1 = fmaf(wT[4 * j4 + 1], dv[j4].y, acc1);
+                acc2 = fmaf(wT[4 * j4 + 2], dv[j4].z, acc2);
+                acc3 = fmaf(wT[4 * j4 + 3], dv[j4].w, acc3);
             }
-            part_s[r * G3 + tid] = acc0 + acc1;
+            part_s[r * G3 + tid] = (acc0 + acc1) + (acc2 + acc3);
         }
         __syncthreads();
     }
 }
 
 // =============================================================================================
-// fc2 gradients (sparse in the action index).  block 256 = 4 groups x 64 hidden units; per-block partials.
-// =============================================================================================
-struct Fc2GradArgs {
-    const float *hout, *d_chosen;
-    mal_field_t actions;
-    int B, T, N, A, R;
-    float *part;     // [gridDim.x][A*64 + A]
-    int64_t items_per_block;
-};
-
-__global__ void __launch_bounds__(256) k_fc2_grad(Fc2GradArgs a) {
-    __shared__ float acc_s[4][MAL_MAX_ACTIONS][HID];
-    __shared__ float accb_s[4][MAL_MAX_ACTIONS];
-    const int tid = threadIdx.x, grp = tid >> 6, i = tid & 63;
-    for (int j = 0; j < a.A; ++j) acc_s[grp][j][i] = 0.0f;
-    if (i < a.A) accb_s[grp][i] = 0.0f;
-    __syncthreads();
-    const int64_t total = (int64_t)a.T * a.R;
-    const int64_t beg = (int64_t)blockIdx.x * a.items_per_block;
-    int64_t end = beg + a.items_per_block;
-    if (end > total) end = total;
-    for (int64_t m = beg + grp; m < end; m += 4) {
-        const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
-        const int b = row / a.N, n = row - b * a.N;
-        const float d = a.d_chosen[((int64_t)b * a.T + t) * a.N + n];
-        const int act = (int)(field_ptr<long long>(a.actions, b, t)[n]);
-        acc_s[grp][act][i] += d * a.hout[m * HID + i];
-        if (i == 0) accb_s[grp][act] += d;
-    }
-    __syncthreads();
-    float *out = a.part + (int64_t)blockIdx.x * (a.A * HID + a.A);
-    for (int idx = tid; idx < a.A * HID; idx += 256) {
-        int j = idx >> 6, ii = idx & 63;
-        out[idx] = acc_s[0][j][ii] + acc_s[1][j][ii] + acc_s[2][j][ii] + acc_s[3][j][ii];
-    }
-    if (tid < a.A) out[a.A * HID + tid] = accb_s[0][tid] + accb_s[1][tid] + accb_s[2][tid] + accb_s[3][tid];
-}
-
-// =============================================================================================
-// gather per-chunk partials into the flat gradient (fixed summation order) + per-block sum of squares
+// gather per-chunk partials into the flat gradient (fixed summation order), apply 1/mask.sum(),
+// per-block sum of squares for the global norm
 // =============================================================================================
 struct GradSeg {
     int64_t grad_off;
@@ -788,12 +780,14 @@ struct GradReduceArgs {
     GradSeg s[GRAD_MAX_SEGS];
     int64_t total;
     float *grad;
-    float *norm_part;   // [gridDim.x]
+    float *norm_part;        // [gridDim.x]
+    const float *scalars;    // mask sum
 };
 
 __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ GradReduceArgs a) {
     __shared__ float s_sq[8];
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const float inv = 1.0f / a.scalars[MAL_SC_MASK_SUM];
     float v = 0.0f;
     if (p < a.total) {
         int si = 0;
@@ -802,7 +796,16 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ Gra
         const int64_t off = p - s.grad_off;
         if (off < s.count) {
             const float *src = s.part + off;
-            for (int c = 0; c < s.n_chunks; ++c) v += src[(int64_t)c * s.chunk_stride];
+            float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+            int c = 0;
+            for (; c + 4 <= s.n_chunks; c += 4) {
+                v0 += src[(int64_t)c * s.chunk_stride];
+                v1 += src[(int64_t)(c + 1) * s.chunk_stride];
+                v2 += src[(int64_t)(c + 2) * s.chunk_stride];
+                v3 += src[(int64_t)(c + 3) * s.chunk_stride];
+            }
+            for (; c < s.n_chunks; ++c) v0 += src[(int64_t)c * s.chunk_stride];
+            v = ((v0 + v1) + (v2 + v3)) * inv;
         }
         a.grad[p] = v;
     }

@@ -6,6 +6,7 @@
 #include "replay.cuh"
 #include "actsel.cuh"
 #include "learner.cuh"
+#include "tc_gemm.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -249,10 +250,12 @@ static int get_dims(const mal_batch_t *b, const mal_learner_cfg_t *c, Dims *d) {
     return 0;
 }
 
-static void chunking(int64_t M, int max_chunks, int *n_chunks, int64_t *rows_per_chunk) {
-    int64_t nc = ceil_div64(M, 256);
+// split an M-row reduction into chunks so that chunks * tiles gives ~2 CTAs per SM (>= 128 rows per chunk, <= 64 chunks)
+static void chunking(int64_t M, int tiles, int sms, int *n_chunks, int64_t *rows_per_chunk) {
+    int64_t nc = ceil_div64((int64_t)2 * sms, tiles > 0 ? tiles : 1);
+    if (nc > 64) nc = 64;
+    if (nc > ceil_div64(M, 128)) nc = ceil_div64(M, 128);
     if (nc < 1) nc = 1;
-    if (nc > max_chunks) nc = max_chunks;
     int64_t rpc = align_up64(ceil_div64(M, nc), RED_MR);
     nc = ceil_div64(M, rpc);
     *n_chunks = (int)nc;
@@ -261,25 +264,28 @@ static void chunking(int64_t M, int max_chunks, int *n_chunks, int64_t *rows_per
 
 // offsets (in floats) inside the partials scratch
 struct PartLayout {
-    int nc_a; int64_t rpc_a;        // agent reductions over M1 rows
+    int nc_a; int64_t rpc_a;        // agent reductions over M1 rows (fc2: over T*R rows with the same chunk size)
+    int nc_a2;
     int nc_m; int64_t rpc_m;        // mixer reductions over BT rows
-    int nblk_fc2; int64_t ipb_fc2;
     int nblk_mix;
     int nblk_norm;
-    int64_t wih_w, wih_b, whha_w, whha_b, whhb_w, whhb_b, fc1_w, fc1_b, fc2;
+    int64_t wih_w, wih_b, whha_w, whha_b, whhb_w, whhb_b, fc1_w, fc1_b, fc2_w, fc2_b;
     int64_t m_l2a_w, m_l2a_b, m_l2b_w, m_l2b_b, m_l1_w, m_l1_b;   // mixer: layer-2 (w1b, wfb), layer-1 block
     int64_t mix_stats, mix_v2, norm;
     int64_t total;
 };
 
+static int tiles_of(int Nout, int K) { return ((Nout + 63) / 64) * ((K + 63) / 64); }
+
 static PartLayout part_layout(const Dims &d, int sms) {
     PartLayout p;
     memset(&p, 0, sizeof(p));
-    chunking(d.M1, 192, &p.nc_a, &p.rpc_a);
-    chunking(d.BT, 128, &p.nc_m, &p.rpc_m);
-    const int64_t TR = (int64_t)d.T * d.R;
-    int64_t nb = ceil_div64(TR, 512); if (nb < 1) nb = 1; if (nb > 128) nb = 128;
-    p.nblk_fc2 = (int)nb; p.ipb_fc2 = ceil_div64(TR, nb);
+    const int tiles_a = tiles_of(G3, HID) + tiles_of(128, HID) + tiles_of(64, HID) + tiles_of(HID, d.d_in) + tiles_of(d.A, HID);
+    chunking(d.M1, tiles_a, sms, &p.nc_a, &p.rpc_a);
+    p.nc_a2 = (int)ceil_div64((int64_t)d.T * d.R, p.rpc_a);
+    const int K2 = d.two ? d.HE : d.S;
+    const int tiles_m = d.mixer == MAL_MIXER_VDN ? 1 : tiles_of(d.E * d.N, K2) + tiles_of(d.E, K2) + tiles_of(d.ld1, d.S);
+    chunking(d.BT, tiles_m, sms, &p.nc_m, &p.rpc_m);
     int64_t nm = ceil_div64(d.BT, 8); if (nm > (int64_t)sms * 4) nm = (int64_t)sms * 4; if (nm < 1) nm = 1;
     p.nblk_mix = (int)nm;
     const int64_t P = agent_layout(d.d_in, d.A).total + mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
@@ -290,15 +296,14 @@ static PartLayout part_layout(const Dims &d, int sms) {
     p.whha_w = take((int64_t)p.nc_a * 128 * HID); p.whha_b = take((int64_t)p.nc_a * 128);
     p.whhb_w = take((int64_t)p.nc_a * 64 * HID);  p.whhb_b = take((int64_t)p.nc_a * 64);
     p.fc1_w = take((int64_t)p.nc_a * HID * d.d_in); p.fc1_b = take((int64_t)p.nc_a * HID);
-    p.fc2 = take((int64_t)p.nblk_fc2 * (d.A * HID + d.A));
+    p.fc2_w = take((int64_t)p.nc_a2 * d.A * HID);   p.fc2_b = take((int64_t)p.nc_a2 * d.A);
     if (d.mixer != MAL_MIXER_VDN) {
-        const int K2 = d.two ? d.HE : d.S;
         p.m_l2a_w = take((int64_t)p.nc_m * d.E * d.N * K2); p.m_l2a_b = take((int64_t)p.nc_m * d.E * d.N);
         p.m_l2b_w = take((int64_t)p.nc_m * d.E * K2);       p.m_l2b_b = take((int64_t)p.nc_m * d.E);
         p.m_l1_w = take((int64_t)p.nc_m * d.ld1 * d.S);     p.m_l1_b = take((int64_t)p.nc_m * d.ld1);
         p.mix_v2 = take((int64_t)p.nblk_mix * (d.E + 1));
     }
-    p.mix_stats = take((int64_t)p.nblk_mix * 4);
+    p.mix_stats = take((int64_t)p.nblk_mix * MIX_NSTAT);
     p.norm = take(p.nblk_norm);
     p.total = o;
     return p;
@@ -333,6 +338,7 @@ extern "C" int mal_learner_plan(const mal_batch_t *batch, const mal_learner_cfg_
     plan->d_chosen = take(d.BT * d.N, 4);
     plan->d_g = take(d.M1 * 4 * HID, 4);
     plan->d_x = take(d.M1 * HID, 4);
+    plan->dh_head = take(d.M1 * HID, 4);
     PartLayout pl = part_layout(d, sms);
     plan->partials_bytes = pl.total * 4;
     plan->partials = take(pl.total, 4);
@@ -346,11 +352,37 @@ extern "C" int mal_learner_plan(const mal_batch_t *batch, const mal_learner_cfg_
 static BatchView make_view(const mal_batch_t *b, const Dims &d) {
     BatchView v;
     v.B = d.B; v.TT = d.TT; v.T = d.T; v.N = d.N; v.A = d.A; v.OBS = d.OBS; v.S = d.S; v.R = d.R;
-    v.obs = b->obs; v.onehot = b->onehot; v.state = b->state;
+    v.obs = b->obs; v.onehot = b->onehot; v.state = b->state; v.actions = b->actions;
     return v;
 }
 
+static int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
+extern "C" int mal_set_option(const char *name, int value) {
+    MAL_REQUIRE(name, "mal_set_option: null name");
+    if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
+    mal_set_error("mal_set_option: unknown option %s", name);
+    return 1;
+}
+
+static int launch_linear_tc(LinGroup &g, int64_t maxM, cudaStream_t st, const char *tag) {
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    const size_t smem = 4 * (size_t)TC_SLAB_A + 4 * (size_t)TC_NMAX * 128 + 1024;
+    static thread_local bool attr = false;
+    if (!attr) {
+        MAL_CUDA(cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int64_t tiles = ceil_div64(maxM, TC_M);
+    int64_t per = sms / g.n; if (per < 1) per = 1;          // persistent: ~one CTA per SM over all problems
+    dim3 grid((unsigned)(tiles < per ? tiles : per), g.n);
+    { ProfScope _ps(tag, st); k_linear_tc<<<grid, TC_THREADS, smem, st>>>(g); }
+    MAL_LAUNCH_CHECK("k_linear_tc");
+    return 0;
+}
+
 static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st, const char *tag) {
+    if (g_use_tc) return launch_linear_tc(g, maxM, st, tag);
     const int nkc = (maxK + LIN_KC - 1) / LIN_KC;
     const size_t smem = sizeof(float) * ((size_t)LIN_TM * (nkc * LIN_KC + 4) + (size_t)LIN_TN * LIN_LDW);
     MAL_REQUIRE(smem <= 220 * 1024, "inner dimension %d too large for the panel GEMM", maxK);
@@ -418,10 +450,6 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     float *x[2] = {F(plan->x_on), F(plan->x_tg)}, *gi[2] = {F(plan->gi_on), F(plan->gi_tg)};
     float *hh[2] = {F(plan->h_on), F(plan->h_tg)};
     float *y1[2] = {F(plan->y1_on), F(plan->y1_tg)}, *a2[2] = {F(plan->a2_on), F(plan->a2_tg)};
-
-    // mask and mask.sum()                                                   q_learner.py:40-42
-    { ProfScope _ps("k_mask_prep", st); k_mask_prep<<<1, 1024, 0, st>>>(batch->filled, batch->terminated, d.B, d.T, F(plan->mask), scalars); }
-    MAL_LAUNCH_CHECK("k_mask_prep");
 
     // x = relu(fc1([obs | last action | agent id]))  for every (t,b,n), both nets   basic_controller.py:80-92
     {
@@ -497,19 +525,39 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     // mixing + TD error + masked loss + element-wise mixer backward          q_learner.py:81-98
     {
         MixArgs a;
+        memset(&a, 0, sizeof(a));
         a.mixer = d.mixer; a.B = d.B; a.T = d.T; a.N = d.N; a.E = d.E; a.HE = d.HE; a.S = d.S;
+        a.R = d.R; a.A = d.A; a.d_in = d.d_in; a.agent = agent;
         for (int net = 0; net < 2; ++net) { a.y1[net] = y1[net]; a.a2[net] = a2[net]; a.mparams[net] = mp[net]; }
         a.chosen = F(plan->chosen); a.target_max = F(plan->target_max); a.mask = F(plan->mask);
-        a.reward = batch->reward; a.terminated = batch->terminated; a.gamma = cfg->gamma; a.scalars = scalars;
+        a.reward = batch->reward; a.terminated = batch->terminated; a.filled = batch->filled; a.actions = batch->actions;
+        a.gamma = cfg->gamma; a.dh_head = F(plan->dh_head);
         a.q_tot = F(plan->q_tot); a.target_q_tot = F(plan->target_q_tot); a.targets = F(plan->targets); a.td = F(plan->td);
         a.d_a2 = F(plan->d_a2); a.d_y1 = F(plan->d_y1); a.d_chosen = F(plan->d_chosen);
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
         { ProfScope _ps("k_mix_td", st); k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_mix_td");
-        { ProfScope _ps("k_stats_finalize", st); k_stats_finalize<<<1, 32, 0, st>>>(parts + pl.mix_stats, pl.nblk_mix, d.N, scalars); }
+        { ProfScope _ps("k_stats_finalize", st); k_stats_finalize<<<1, 32 * MIX_NSTAT, 0, st>>>(parts + pl.mix_stats, pl.nblk_mix, d.N, scalars); }
         MAL_LAUNCH_CHECK("k_stats_finalize");
     }
     return 0;
+}
+
+// Y = epi(A W^T + bias) on dense row-major operands through the same kernels the learner uses (unit tests).
+extern "C" int mal_debug_linear(int32_t M, int32_t K, int32_t Nout, const float *A, int64_t lda, const float *W,
+                                int64_t ldw, int32_t w_trans, const float *bias, int32_t epi, const float *aux,
+                                int64_t ld_aux, float *Y, int64_t ldy, int32_t use_tc, void *stream) {
+    MAL_REQUIRE(A && W && Y && M > 0 && K > 0 && Nout > 0, "mal_debug_linear: bad arguments");
+    MAL_REQUIRE(epi == EPI_BIAS || epi == EPI_RELU || epi == EPI_MASKPOS, "mal_debug_linear: unsupported epilogue");
+    LinGroup g;
+    memset(&g, 0, sizeof(g));
+    g.n = 1;
+    g.p[0] = lin(M, K, Nout, A_DENSE, 0, A, lda, W, ldw, w_trans, bias, epi, aux, ld_aux, Y, ldy);
+    const int saved = g_use_tc;
+    g_use_tc = use_tc;
+    int rc = launch_linear(g, M, K, (cudaStream_t)stream, use_tc ? "k_linear_tc:debug" : "k_linear_group:debug");
+    g_use_tc = saved;
+    return rc;
 }
 
 extern "C" int mal_mixer_forward(int32_t mixer, int32_t B, int32_t T, int32_t N, int32_t S, int32_t E, int32_t HE,
@@ -567,7 +615,7 @@ extern "C" int mal_mixer_forward(int32_t mixer, int32_t B, int32_t T, int32_t N,
 static RedProb red(int64_t M, int K, int Nout, const float *dY, int64_t ldy, int a_kind, int shift, const float *A,
                    int64_t lda, float *partW, float *partB, int n_chunks, int64_t rpc) {
     RedProb p;
-    p.M0 = 0; p.M = M; p.K = K; p.Nout = Nout; p.dY = dY; p.ldy = ldy; p.a_kind = a_kind; p.shift = shift;
+    p.M0 = 0; p.M = M; p.K = K; p.Nout = Nout; p.dY = dY; p.ldy = ldy; p.dy_kind = 0; p.a_kind = a_kind; p.shift = shift;
     p.A = A; p.lda = lda; p.partW = partW; p.partB = partB; p.n_chunks = n_chunks; p.rows_per_chunk = rpc;
     p.tile0 = 0; p.n_ktiles = (K + 63) / 64;
     return p;
@@ -627,8 +675,8 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     // ---- agent: BPTT recurrence
     {
         GruBwdArgs a;
-        a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.d_chosen = F(plan->d_chosen);
-        a.actions = batch->actions; a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.N = d.N; a.d_in = d.d_in; a.n_actions = d.A;
+        a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
+        a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         switch (pick_rt((int64_t)d.R, sms)) {
             case 2: launch_gru_bwd<2>(a, st); break;
             case 4: launch_gru_bwd<4>(a, st); break;
@@ -644,18 +692,16 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
     // weight gradients of the agent
     {
-        RedGroup r; r.n = 4; r.bv = bv;
+        RedGroup r; r.n = 5; r.bv = bv;
         r.p[0] = red(d.M1, HID, G3, d_g, 4 * HID, A_DENSE, 0, F(plan->x_on), HID, parts + pl.wih_w, parts + pl.wih_b, pl.nc_a, pl.rpc_a);
         // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)
         r.p[1] = red(d.M1, HID, 128, d_g, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whha_w, parts + pl.whha_b, pl.nc_a, pl.rpc_a);
         r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
         r.p[3] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_a, pl.rpc_a);
+        // fc2: dY = one-hot(action) * d_chosen over the T*R transition rows, A = h_t
+        r.p[4] = red((int64_t)d.T * d.R, HID, d.A, F(plan->d_chosen), 0, A_DENSE, 0, F(plan->h_on), HID, parts + pl.fc2_w, parts + pl.fc2_b, pl.nc_a2, pl.rpc_a);
+        r.p[4].dy_kind = 1;
         if (int rc = launch_reduce(r, st, "k_reduce_group:agent")) return rc;
-        Fc2GradArgs f;
-        f.hout = F(plan->h_on); f.d_chosen = F(plan->d_chosen); f.actions = batch->actions;
-        f.B = d.B; f.T = d.T; f.N = d.N; f.A = d.A; f.R = d.R; f.part = parts + pl.fc2; f.items_per_block = pl.ipb_fc2;
-        { ProfScope _ps("k_fc2_grad", st); k_fc2_grad<<<pl.nblk_fc2, 256, 0, st>>>(f); }
-        MAL_LAUNCH_CHECK("k_fc2_grad");
     }
     // ---- gather partials into the flat gradient (state_dict order) + sum of squares
     {
@@ -666,7 +712,6 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
             a.s[n].grad_off = off; a.s[n].count = (int)count; a.s[n].part = part; a.s[n].n_chunks = n_chunks;
             a.s[n].chunk_stride = stride; ++n;
         };
-        const int fc2n = d.A * HID + d.A;
         seg(AL.fc1_w, (int64_t)HID * d.d_in, parts + pl.fc1_w, pl.nc_a, (int64_t)HID * d.d_in);
         seg(AL.fc1_b, HID, parts + pl.fc1_b, pl.nc_a, HID);
         seg(AL.w_ih, (int64_t)G3 * HID, parts + pl.wih_w, pl.nc_a, (int64_t)G3 * HID);
@@ -675,8 +720,8 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         seg(AL.b_ih, G3, parts + pl.wih_b, pl.nc_a, G3);
         seg(AL.b_hh, 128, parts + pl.whha_b, pl.nc_a, 128);
         seg(AL.b_hh + 128, 64, parts + pl.whhb_b, pl.nc_a, 64);
-        seg(AL.fc2_w, (int64_t)d.A * HID, parts + pl.fc2, pl.nblk_fc2, fc2n);
-        seg(AL.fc2_b, d.A, parts + pl.fc2 + d.A * HID, pl.nblk_fc2, fc2n);
+        seg(AL.fc2_w, (int64_t)d.A * HID, parts + pl.fc2_w, pl.nc_a2, (int64_t)d.A * HID);
+        seg(AL.fc2_b, d.A, parts + pl.fc2_b, pl.nc_a2, d.A);
         const int64_t o = AL.total;
         if (d.mixer != MAL_MIXER_VDN) {
             const int K2 = d.two ? d.HE : d.S;
@@ -705,6 +750,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         a.total = AL.total + ML.total;
         a.grad = grad;
         a.norm_part = parts + pl.norm;
+        a.scalars = F(plan->scalars);
         { ProfScope _ps("k_grad_reduce", st); k_grad_reduce<<<pl.nblk_norm, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_grad_reduce");
     }
