@@ -74,7 +74,7 @@ struct LinProb {
     const float *aux; int64_t ld_aux;             // EPI_MASKPOS: multiply by (aux[m,n] > 0)
     float *Y; int64_t ldy;
 };
-#define LIN_MAX_PROBS 8
+#define LIN_MAX_PROBS 12
 struct LinGroup {
     int n;
     LinProb p[LIN_MAX_PROBS];

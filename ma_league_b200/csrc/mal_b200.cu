@@ -364,21 +364,67 @@ extern "C" int mal_set_option(const char *name, int value) {
     return 1;
 }
 
-static int launch_linear_tc(LinGroup &g, int64_t maxM, cudaStream_t st, const char *tag) {
-    int sms, tps;
-    if (device_sm_count(&sms, &tps)) return 2;
-    const size_t smem = 4 * (size_t)TC_SLAB_A + 4 * (size_t)TC_NMAX * 128 + 1024;
+template <int AK, int EK>
+static int launch_tc_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag) {
     static thread_local bool attr = false;
     if (!attr) {
-        MAL_CUDA(cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MAL_CUDA(cudaFuncSetAttribute(k_linear_tc<AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         attr = true;
     }
-    int64_t tiles = ceil_div64(maxM, TC_M);
-    int64_t per = sms / g.n; if (per < 1) per = 1;          // persistent: ~one CTA per SM over all problems
-    dim3 grid((unsigned)(tiles < per ? tiles : per), g.n);
-    { ProfScope _ps(tag, st); k_linear_tc<<<grid, TC_THREADS, smem, st>>>(g); }
+    { ProfScope _ps(tag, st); k_linear_tc<AK, EK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g); }
     MAL_LAUNCH_CHECK("k_linear_tc");
     return 0;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, const char *tag) {
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    // split wide outputs into independent <= TC_NMAX-wide problems (each keeps its W slice resident in smem)
+    LinGroup g;
+    g.bv = g0.bv;
+    g.n = 0;
+    int pieces_total = 0;
+    for (int i = 0; i < g0.n; ++i) pieces_total += (g0.p[i].Nout + TC_NMAX - 1) / TC_NMAX;
+    const bool split = pieces_total <= LIN_MAX_PROBS;
+    for (int i = 0; i < g0.n; ++i) {
+        const LinProb &p = g0.p[i];
+        const int np = split ? (p.Nout + TC_NMAX - 1) / TC_NMAX : 1;
+        const int w = split ? ((((p.Nout + np - 1) / np) + 15) & ~15) : p.Nout;
+        for (int j = 0; j < np; ++j) {
+            LinProb q = p;
+            const int n_off = j * w;
+            q.Nout = (p.Nout - n_off) < w ? (p.Nout - n_off) : w;
+            q.W = p.w_trans ? p.W + n_off : p.W + (int64_t)n_off * p.ldw;
+            if (p.bias) q.bias = p.bias + n_off;
+            if (p.aux) q.aux = p.aux + n_off;
+            q.Y = p.Y + n_off;
+            g.p[g.n++] = q;
+        }
+    }
+    // kernel flavour: vectorised loaders need 16-byte aligned rows
+    bool dense = true, state = true;
+    int ek = -1;
+    for (int i = 0; i < g.n; ++i) {
+        const LinProb &p = g.p[i];
+        dense = dense && p.a_kind == A_DENSE && (p.lda & 3) == 0 && (p.K & 3) == 0 && aligned16(p.A);
+        state = state && p.a_kind == A_STATE && (p.K & 3) == 0 && (g.bv.state.sb & 3) == 0 && (g.bv.state.st & 3) == 0 &&
+                aligned16(g.bv.state.ptr);
+        const int e = (p.epi == EPI_BIAS || p.epi == EPI_RELU) ? TCE_BIAS_ACT : (p.epi == EPI_MASKPOS ? TCE_MASKPOS : TCE_FC1);
+        MAL_REQUIRE(ek < 0 || ek == e, "launch_linear_tc: mixed epilogue kinds in one group");
+        ek = e;
+    }
+    const int64_t tiles = ceil_div64(maxM, TC_M);
+    int64_t per = ceil_div64((int64_t)2 * sms, g.n); if (per < 1) per = 1;     // persistent: ~two CTAs per SM in total
+    dim3 grid((unsigned)(tiles < per ? tiles : per), g.n);
+    const int ak = dense ? TCA_VEC_DENSE : (state ? TCA_VEC_STATE : TCA_GENERIC);
+    if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid, st, tag);
+    if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid, st, tag);
+    if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid, st, tag);
+    if (ek == TCE_FC1) return launch_tc_inst<TCA_GENERIC, TCE_FC1>(g, grid, st, tag);
+    if (ek == TCE_MASKPOS) return launch_tc_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid, st, tag);
+    return launch_tc_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid, st, tag);
 }
 
 static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st, const char *tag) {

@@ -1,30 +1,38 @@
 // Tensor-core panel GEMM for the batched (rows x 64) GRU / hypernet projections:
 //     Y[m, n] = epi( sum_k A[m,k] * W[n,k] )         (same problem descriptors as k_linear_group)
 //
-// 5th-gen tensor cores (tcgen05.mma kind::tf32, SASS UTC*MMA) with the accumulator in TMEM.  Plain TF32 (10-bit
+// 5th-gen tensor cores (tcgen05.mma kind::tf32, SASS UTCHMMA) with the accumulators in TMEM.  Plain TF32 (10-bit
 // mantissa) misses the 1e-5 parity bar, so every operand is split in two TF32 pieces, x = hi + lo, and three MMAs
-// (hi*hi + lo*hi + hi*lo, fp32 accumulate) recover fp32-level accuracy ("3xTF32").
+// (hi*hi + lo*hi + hi*lo, fp32 accumulate) recover fp32-level accuracy ("3xTF32").  hi*hi accumulates in D1, the two
+// 2^-11-scaled correction products in a separate accumulator D2 (the tensor core adds into the accumulator with
+// truncation; keeping the small terms apart and summing D1 + D2 in fp32 in the epilogue keeps fp32-level accuracy:
+// measured 1.4e-7 relative at K = 64, the same as the FFMA kernel).
 //
-// One CTA = 128 threads owns 128-row M tiles (persistent loop).  Per (n-tile, 64-wide k-chunk):
-//   all threads : gather the A rows through the fused loaders, split hi/lo, store into the canonical K-major
-//                 SWIZZLE_128B shared-memory layout (8-row x 128-byte atoms, 16-byte chunks XOR-swizzled by row);
-//                 same for the W chunk;  fence.proxy.async + barrier
-//   thread 0    : 8 k-steps x 3 tcgen05.mma (M=128, N=n-tile, K=8) into TMEM, tcgen05.commit -> mbarrier;
-//                 hi*hi goes to accumulator D1, the two small correction products to a separate accumulator D2
-//                 (the tensor core adds into the accumulator with truncation; keeping the 2^-11-scaled terms apart
-//                 and summing D1 + D2 in fp32 in the epilogue keeps the result at fp32-level accuracy)
-//   all threads : wait, tcgen05.ld 32x32b (warp w <-> TMEM lanes 32w..32w+31 = tile rows), epilogue, vector stores
+// One CTA = 256 threads, persistent over 128-row M tiles; <= 80-wide N tiles (wider outputs are split into
+// independent problems on the host) so that two CTAs fit per SM and overlap each other's phases.
+// Per (m-tile, n-tile, 64-wide k-chunk):
+//   all threads : load the A rows (float4, coalesced) through the fused loaders, split hi/lo, STS.128 into the
+//                 canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunks XOR-ed with row&7);
+//                 the W chunk likewise (kept resident across m-tiles when there is only one);  fence.proxy.async
+//   thread 0    : 8 k-steps x 3 tcgen05.mma (M=128, N=n-tile, K=8), tcgen05.commit -> mbarrier
+//   all threads : wait, tcgen05.ld 32x32b (TMEM lane = tile row), bias / ReLU / ReLU-mask / fc1 epilogue, STG.128
 #pragma once
 #include "mal_common.cuh"
 #include "learner.cuh"
 
 #define TC_M 128
 #define TC_KC 64                  // k-chunk (floats) = two 128-byte swizzle slabs
-#define TC_NMAX 192               // widest n-tile (TMEM columns, smem budget)
+#define TC_NMAX 80                // widest n-tile
 #define TC_SLAB_A (TC_M * 128)    // bytes of one [128 rows x 32 floats] slab
+#define TC_SLAB_W (TC_NMAX * 128)
 #define TC_THREADS 256
 #define TC_WARPS (TC_THREADS / 32)
-#define TC_D2_COL 256             // TMEM column of the correction-term accumulator
+#define TC_TMEM_COLS 256
+#define TC_D2_COL 128             // TMEM column of the correction-term accumulator
+#define TC_SMEM_BYTES (4 * TC_SLAB_A + 4 * TC_SLAB_W)
+
+enum { TCA_VEC_DENSE = 0, TCA_VEC_STATE = 1, TCA_GENERIC = 2 };
+enum { TCE_BIAS_ACT = 0, TCE_MASKPOS = 1, TCE_FC1 = 2 };
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
     uint32_t r;
@@ -32,7 +40,7 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
     return r;
 }
 
-// byte offset of element (row r, k in [0,32)) inside one K-major SWIZZLE_128B slab of `rows` rows
+// byte offset of element (row r, k in [0,32)) inside one K-major SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t sw128_off(int r, int kk) {
     const uint32_t chunk = (uint32_t)(kk >> 2) ^ (uint32_t)(r & 7);
     return (uint32_t)r * 128u + chunk * 16u + (uint32_t)(kk & 3) * 4u;
@@ -60,8 +68,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -70,19 +77,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[32]) {   // fills r[0..15]
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tc(const __grid_constant__ LinGroup g) {
+// split a float4 into TF32 hi / lo pieces and store both with one STS.128 each
+__device__ __forceinline__ void split_store(uint8_t *hi_base, uint8_t *lo_base, uint32_t off, float4 v) {
+    uint4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - __uint_as_float(h.x)); l.y = tf32_rna(v.y - __uint_as_float(h.y));
+    l.z = tf32_rna(v.z - __uint_as_float(h.z)); l.w = tf32_rna(v.w - __uint_as_float(h.w));
+    *reinterpret_cast<uint4 *>(hi_base + off) = h;
+    *reinterpret_cast<uint4 *>(lo_base + off) = l;
+}
+
+template <int AK, int EK>
+__global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_constant__ LinGroup g) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
-    // carve: A_hi | A_lo (2 slabs each) | W_hi | W_lo (2 slabs of TC_NMAX rows each); every slab 1024-byte aligned
-    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
-    uint8_t *A_hi = base, *A_lo = base + 2 * TC_SLAB_A;
-    uint8_t *W_hi = base + 4 * TC_SLAB_A, *W_lo = W_hi + 2 * TC_NMAX * 128;
+    __shared__ float bias_s[TC_NMAX];
+    uint8_t *A_hi = tc_smem, *A_lo = tc_smem + 2 * TC_SLAB_A;
+    uint8_t *W_hi = tc_smem + 4 * TC_SLAB_A, *W_lo = W_hi + 2 * TC_SLAB_W;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const LinProb &p = g.p[blockIdx.y];
     const int n_mtiles = (p.M + TC_M - 1) / TC_M;
@@ -90,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tc(const __grid_consta
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"(512u));
+                     "r"((uint32_t)TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
@@ -103,86 +124,109 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tc(const __grid_consta
     const uint32_t tmem_base = tmem_base_s;
     uint32_t bar_phase = 0;
 
-    const int nkc = (p.K + TC_KC - 1) / TC_KC;
-    // n-tiles: equal widths, multiples of 16, at most TC_NMAX
-    const int n_ntiles = (p.Nout + TC_NMAX - 1) / TC_NMAX;
-    const int nt_w = (((p.Nout + n_ntiles - 1) / n_ntiles) + 15) & ~15;
+    const int K = p.K, M = p.M, Nout = p.Nout;
+    const int nkc = (K + TC_KC - 1) / TC_KC;
+    const int n_ntiles = (Nout + TC_NMAX - 1) / TC_NMAX;
+    const int nt_w = (((Nout + n_ntiles - 1) / n_ntiles) + 15) & ~15;
     int w_cached = -1;    // (n-tile * nkc + kc) currently staged in W_hi / W_lo
+    int bias_cached = -1;
+    const bool relu = (p.epi == EPI_RELU);
+    // vectorised staging map: thread -> float4 column c4 (16 per 64-wide chunk), rows r = tid/16 + 16*i
+    const int c4 = tid & 15, rbase = tid >> 4;
+    const uint32_t a_slab = (uint32_t)(c4 >> 3) * TC_SLAB_A, w_slab = (uint32_t)(c4 >> 3) * TC_SLAB_W;
 
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
         const int64_t m0 = (int64_t)mt * TC_M;
         for (int nt = 0; nt < n_ntiles; ++nt) {
             const int n0 = nt * nt_w;
-            const int nw = (p.Nout - n0) < nt_w ? (((p.Nout - n0) + 15) & ~15) : nt_w;   // MMA N (multiple of 16)
+            const int nw = (Nout - n0) < nt_w ? (((Nout - n0) + 15) & ~15) : nt_w;   // MMA N (multiple of 16)
+            if (bias_cached != nt) {
+                if (tid < TC_NMAX) bias_s[tid] = (p.bias && n0 + tid < Nout) ? __ldg(p.bias + n0 + tid) : 0.0f;
+                bias_cached = nt;    // made visible by the barrier below
+            }
             for (int kc = 0; kc < nkc; ++kc) {
                 const int k0 = kc * TC_KC;
-                // ---- stage the A chunk [128 x 64]: warp w handles rows w, w+8, ...; lanes along k (coalesced);
-                //      loads of 4 rows are issued back to back before any conversion (memory-level parallelism)
+                // ---------------- stage the A chunk [128 x 64]
                 if (nkc > 1 || nt == 0) {
+                    if (AK == TCA_GENERIC) {
+                        // lanes along k (coalesced scalar loads), 4 rows in flight per warp iteration
 #pragma unroll 1
-                    for (int rb = warp; rb < TC_M; rb += 4 * TC_WARPS) {
-                        float v0[4], v1[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int r = rb + u * TC_WARPS;
-                            const int64_t m = m0 + r;
-                            v0[u] = 0.0f; v1[u] = 0.0f;
-                            if (m < p.M) {
-                                RowSrc rs = resolve_row(p.a_kind, g.bv, p.A, p.lda, p.shift, m);
-                                if (k0 + lane < p.K) v0[u] = row_elem(p.a_kind, g.bv, rs, k0 + lane);
-                                if (k0 + 32 + lane < p.K) v1[u] = row_elem(p.a_kind, g.bv, rs, k0 + 32 + lane);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int r = rb + u * TC_WARPS;
-                            const uint32_t off = sw128_off(r, lane);
-                            const uint32_t h0 = tf32_rna(v0[u]), h1 = tf32_rna(v1[u]);
-                            *reinterpret_cast<uint32_t *>(A_hi + off) = h0;
-                            *reinterpret_cast<uint32_t *>(A_hi + TC_SLAB_A + off) = h1;
-                            *reinterpret_cast<uint32_t *>(A_lo + off) = tf32_rna(v0[u] - __uint_as_float(h0));
-                            *reinterpret_cast<uint32_t *>(A_lo + TC_SLAB_A + off) = tf32_rna(v1[u] - __uint_as_float(h1));
-                        }
-                    }
-                }
-                // ---- stage the W chunk [nw x 64] unless it is already resident
-                const int w_id = nt * nkc + kc;
-                if (w_id != w_cached) {
-                    const uint32_t slab_w = (uint32_t)TC_NMAX * 128u;
-                    if (!p.w_trans) {
-#pragma unroll 1
-                        for (int jb = warp; jb < nw; jb += 4 * TC_WARPS) {
+                        for (int rb = warp; rb < TC_M; rb += 4 * TC_WARPS) {
                             float v0[4], v1[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const int j = jb + u * TC_WARPS, n = n0 + j;
+                                const int64_t m = m0 + rb + u * TC_WARPS;
                                 v0[u] = 0.0f; v1[u] = 0.0f;
-                                if (j < nw && n < p.Nout) {
-                                    const float *wr = p.W + (int64_t)n * p.ldw;
-                                    if (k0 + lane < p.K) v0[u] = __ldg(wr + k0 + lane);
-                                    if (k0 + 32 + lane < p.K) v1[u] = __ldg(wr + k0 + 32 + lane);
+                                if (m < M) {
+                                    RowSrc rs = resolve_row(p.a_kind, g.bv, p.A, p.lda, p.shift, m);
+                                    if (k0 + lane < K) v0[u] = row_elem(p.a_kind, g.bv, rs, k0 + lane);
+                                    if (k0 + 32 + lane < K) v1[u] = row_elem(p.a_kind, g.bv, rs, k0 + 32 + lane);
                                 }
                             }
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const int j = jb + u * TC_WARPS;
-                                if (j < nw) {
-                                    const uint32_t off = sw128_off(j, lane);
-                                    const uint32_t h0 = tf32_rna(v0[u]), h1 = tf32_rna(v1[u]);
-                                    *reinterpret_cast<uint32_t *>(W_hi + off) = h0;
-                                    *reinterpret_cast<uint32_t *>(W_hi + slab_w + off) = h1;
-                                    *reinterpret_cast<uint32_t *>(W_lo + off) = tf32_rna(v0[u] - __uint_as_float(h0));
-                                    *reinterpret_cast<uint32_t *>(W_lo + slab_w + off) = tf32_rna(v1[u] - __uint_as_float(h1));
-                                }
+                                const uint32_t off = sw128_off(rb + u * TC_WARPS, lane);
+                                const uint32_t h0 = tf32_rna(v0[u]), h1 = tf32_rna(v1[u]);
+                                *reinterpret_cast<uint32_t *>(A_hi + off) = h0;
+                                *reinterpret_cast<uint32_t *>(A_hi + TC_SLAB_A + off) = h1;
+                                *reinterpret_cast<uint32_t *>(A_lo + off) = tf32_rna(v0[u] - __uint_as_float(h0));
+                                *reinterpret_cast<uint32_t *>(A_lo + TC_SLAB_A + off) = tf32_rna(v1[u] - __uint_as_float(h1));
                             }
                         }
-                    } else {   // W(n,k) = W[k*ldw + n]: lanes along n (coalesced), loop over k
+                    } else {
+                        float4 v[8];
+                        const int kcol = k0 + 4 * c4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int64_t m = m0 + rbase + 16 * i;
+                            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (m < M && kcol < K) {
+                                const float *rp;
+                                if (AK == TCA_VEC_DENSE) rp = p.A + m * p.lda;
+                                else {
+                                    const int b = (int)(m / g.bv.T), t = (int)(m - (int64_t)b * g.bv.T);
+                                    rp = field_ptr<float>(g.bv.state, b, t + p.shift);
+                                }
+                                v[i] = __ldg(reinterpret_cast<const float4 *>(rp + kcol));
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = rbase + 16 * i;
+                            split_store(A_hi, A_lo, a_slab + (uint32_t)r * 128u + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4), v[i]);
+                        }
+                    }
+                }
+                // ---------------- stage the W chunk [nw x 64] unless it is already resident
+                const int w_id = nt * nkc + kc;
+                if (w_id != w_cached) {
+                    if (!p.w_trans && (p.ldw & 3) == 0 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0)) {
+                        const int kcol = k0 + 4 * c4;
+#pragma unroll 1
+                        for (int j = rbase; j < nw; j += 16) {
+                            const int n = n0 + j;
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (n < Nout && kcol < K) v = __ldg(reinterpret_cast<const float4 *>(p.W + (int64_t)n * p.ldw + kcol));
+                            split_store(W_hi, W_lo, w_slab + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+                        }
+                    } else if (!p.w_trans) {
+                        for (int idx = tid; idx < nw * TC_KC; idx += TC_THREADS) {
+                            const int j = idx >> 6, kk = idx & 63;
+                            const int n = n0 + j, k = k0 + kk;
+                            float v = 0.0f;
+                            if (n < Nout && k < K) v = __ldg(p.W + (int64_t)n * p.ldw + k);
+                            const uint32_t off = (uint32_t)(kk >> 5) * TC_SLAB_W + sw128_off(j, kk & 31);
+                            const uint32_t h = tf32_rna(v);
+                            *reinterpret_cast<uint32_t *>(W_hi + off) = h;
+                            *reinterpret_cast<uint32_t *>(W_lo + off) = tf32_rna(v - __uint_as_float(h));
+                        }
+                    } else {   // W(n,k) = W[k*ldw + n]: lanes along n (coalesced)
                         for (int idx = tid; idx < nw * TC_KC; idx += TC_THREADS) {
                             const int kk = idx / nw, j = idx - kk * nw;
                             const int n = n0 + j, k = k0 + kk;
                             float v = 0.0f;
-                            if (n < p.Nout && k < p.K) v = __ldg(p.W + (int64_t)k * p.ldw + n);
-                            const uint32_t off = (uint32_t)(kk >> 5) * slab_w + sw128_off(j, kk & 31);
+                            if (n < Nout && k < K) v = __ldg(p.W + (int64_t)k * p.ldw + n);
+                            const uint32_t off = (uint32_t)(kk >> 5) * TC_SLAB_W + sw128_off(j, kk & 31);
                             const uint32_t h = tf32_rna(v);
                             *reinterpret_cast<uint32_t *>(W_hi + off) = h;
                             *reinterpret_cast<uint32_t *>(W_lo + off) = tf32_rna(v - __uint_as_float(h));
@@ -194,63 +238,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tc(const __grid_consta
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // ---- MMAs: D[128 x nw] (+)= A_chunk . W_chunk^T, three TF32 products per k-step
+                // ---------------- MMAs: D[128 x nw] (+)= A_chunk . W_chunk^T, three TF32 products per k-step
                 if (tid == 0) {
                     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nw >> 3) << 17) |
                                            ((uint32_t)(TC_M >> 4) << 24);
                     const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), w_hi = smem_u32(W_hi), w_lo = smem_u32(W_lo);
-                    const int ksteps = ((p.K - k0 < TC_KC ? p.K - k0 : TC_KC) + 7) / 8;
+                    const int ksteps = ((K - k0 < TC_KC ? K - k0 : TC_KC) + 7) / 8;
 #pragma unroll 1
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint32_t ao = (uint32_t)(ks >> 2) * TC_SLAB_A + (uint32_t)(ks & 3) * 32u;
-                        const uint32_t wo = (uint32_t)(ks >> 2) * (TC_NMAX * 128u) + (uint32_t)(ks & 3) * 32u;
+                        const uint32_t wo = (uint32_t)(ks >> 2) * TC_SLAB_W + (uint32_t)(ks & 3) * 32u;
                         const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
                         umma_tf32(tmem_base, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_hi + wo), idesc, first);
                         umma_tf32(tmem_base + TC_D2_COL, umma_desc_sw128(a_lo + ao), umma_desc_sw128(w_hi + wo), idesc, first);
                         umma_tf32(tmem_base + TC_D2_COL, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_lo + wo), idesc, 1u);
                     }
-                    // arrives on the mbarrier once every MMA issued so far has completed (implies fence::before_thread_sync)
+                    // arrives once every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      smem_u32(&mma_bar))
                                  : "memory");
                 }
-                mbar_wait(&mma_bar, bar_phase);   // smem chunks are free again, accumulator chunk is complete
+                mbar_wait(&mma_bar, bar_phase);   // smem chunks are free again, this chunk's products are in TMEM
                 bar_phase ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            // ---- epilogue: thread <-> row (TMEM lane = 32*(warp&3) + lane); warps 0-3 take the even 32-column
-            //      groups, warps 4-7 the odd ones
-            const int q = warp & 3;
-            const int64_t m = m0 + q * 32 + lane;
-            int agent = 0;
-            if (p.epi == EPI_FC1 && m < p.M) agent = (int)((m % g.bv.R) % g.bv.N);
-            for (int c0 = (warp >> 2) * 32; c0 < nw; c0 += 64) {
-                float v[32], v2[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TC_D2_COL + c0), v2);
-                if (m < p.M) {
-                    float *yrow = p.Y + m * p.ldy + n0 + c0;
-                    const bool vec = ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) && (n0 + c0 + 32 <= p.Nout);
+            // ---------------- epilogue: thread <-> row (TMEM lane 32*(warp&3)+lane); warps 0-3 take the even 16-column
+            //                  groups, warps 4-7 the odd ones
+            {
+                const int q = warp & 3;
+                const int64_t m = m0 + q * 32 + lane;
+                int agent = 0;
+                if (EK == TCE_FC1 && m < M) agent = (int)((m % g.bv.R) % g.bv.N);
+                const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c0 = (warp >> 2) * 16; c0 < nw; c0 += 32) {
+                    uint32_t d1[32], d2[32];
+                    tmem_ld16_nowait(tlane + (uint32_t)c0, d1);
+                    tmem_ld16_nowait(tlane + (uint32_t)(TC_D2_COL + c0), d2);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (m < M) {
+                        float x[16];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = n0 + c0 + i;
-                        if (n < p.Nout) {
-                            float x = v[i] + v2[i];
-                            if (p.bias) x += __ldg(p.bias + n);
-                            if (p.epi == EPI_FC1) { x += __ldg(p.W + (int64_t)n * p.ldw + p.K + agent); x = fmaxf(x, 0.0f); }
-                            else if (p.epi == EPI_RELU) x = fmaxf(x, 0.0f);
-                            else if (p.epi == EPI_MASKPOS) x = (p.aux[m * p.ld_aux + n] > 0.0f) ? x : 0.0f;
-                            v[i] = x;
+                        for (int i = 0; i < 16; ++i) {
+                            float s = (__uint_as_float(d1[i]) + __uint_as_float(d2[i])) + bias_s[c0 + i];
+                            if (EK == TCE_FC1) {
+                                const int n = n0 + c0 + i;
+                                if (n < Nout) s += __ldg(p.W + (int64_t)n * p.ldw + K + agent);
+                                s = fmaxf(s, 0.0f);
+                            } else if (EK == TCE_BIAS_ACT) {
+                                s = relu ? fmaxf(s, 0.0f) : s;
+                            }
+                            x[i] = s;
                         }
-                    }
-                    if (vec) {
+                        float *yrow = p.Y + m * p.ldy + n0 + c0;
+                        const bool full = (n0 + c0 + 16 <= Nout);
+                        if (EK == TCE_MASKPOS) {
+                            const float *arow = p.aux + m * p.ld_aux + n0 + c0;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4 *>(yrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
+                            for (int i = 0; i < 16; ++i)
+                                if (full || n0 + c0 + i < Nout) x[i] = (arow[i] > 0.0f) ? x[i] : 0.0f;
+                        }
+                        if (full && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0)) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (n0 + c0 + i < p.Nout) yrow[i] = v[i];
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4 *>(yrow + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + c0 + i < Nout) yrow[i] = x[i];
+                        }
                     }
                 }
             }
@@ -261,5 +317,5 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_linear_tc(const __grid_consta
         }
     }
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS));
 }
