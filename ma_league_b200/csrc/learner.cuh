@@ -192,8 +192,9 @@ struct RedGroup {
     RedProb p[RED_MAX_PROBS];
     BatchView bv;
 };
-#define RED_MR 32
+#define RED_MR 64
 #define RED_LD 68
+#define RED_EPT (RED_MR * 64 / 256)   // elements of each operand a thread stages per block (16)
 
 __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ RedGroup g) {
     __shared__ __align__(16) float dY_s[RED_MR * RED_LD];
@@ -219,10 +220,12 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-    for (int64_t mm = mb; mm < me; mm += RED_MR) {
-        __syncthreads();
-        for (int r = warp; r < RED_MR; r += 8) {
-            const int64_t m = mm + r;
+    // staging map: warp w owns rows w, w+8, ... (8 rows per block), lane owns columns lane and lane+32
+    float rdy[RED_EPT], ra[RED_EPT];
+    auto prefetch = [&](int64_t mm) {
+#pragma unroll
+        for (int u = 0; u < RED_MR / 8; ++u) {
+            const int64_t m = mm + warp + 8 * u;
             const bool ok = m < me;
             const bool ok_a = ok && (p.a_kind != A_DENSE || m >= p.shift);
             RowSrc rs;
@@ -239,17 +242,31 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = lane + 32 * h;
-                if (p.dy_kind == 1) dY_s[r * RED_LD + c] = (n0 + c == asel) ? dsel : 0.0f;
-                else dY_s[r * RED_LD + c] = (ok && n0 + c < p.Nout) ? p.dY[m * p.ldy + n0 + c] : 0.0f;
-                A_s[r * RED_LD + c] = (ok_a && k0 + c < p.K) ? row_elem(p.a_kind, g.bv, rs, k0 + c) : 0.0f;
+                float dv;
+                if (p.dy_kind == 1) dv = (n0 + c == asel) ? dsel : 0.0f;
+                else dv = (ok && n0 + c < p.Nout) ? p.dY[m * p.ldy + n0 + c] : 0.0f;
+                rdy[2 * u + h] = dv;
+                ra[2 * u + h] = (ok_a && k0 + c < p.K) ? row_elem(p.a_kind, g.bv, rs, k0 + c) : 0.0f;
             }
         }
+    };
+    if (mb < me) prefetch(mb);
+    for (int64_t mm = mb; mm < me; mm += RED_MR) {
+        __syncthreads();   // previous block fully consumed
+#pragma unroll
+        for (int u = 0; u < RED_MR / 8; ++u)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                dY_s[(warp + 8 * u) * RED_LD + lane + 32 * h] = rdy[2 * u + h];
+                A_s[(warp + 8 * u) * RED_LD + lane + 32 * h] = ra[2 * u + h];
+            }
         __syncthreads();
+        if (mm + RED_MR < me) prefetch(mm + RED_MR);   // next block's global loads fly while this one is reduced
 #pragma unroll 8
         for (int r = 0; r < RED_MR; ++r) {
             const float4 d = *reinterpret_cast<const float4 *>(dY_s + r * RED_LD + 4 * ty);
-            const float4 a = *reinterpret_cast<const float4 *>(A_s + r * RED_LD + 4 * tx);
-            const float dv[4] = {d.x, d.y, d.z, d.w}, avv[4] = {a.x, a.y, a.z, a.w};
+            const float4 av4 = *reinterpret_cast<const float4 *>(A_s + r * RED_LD + 4 * tx);
+            const float dv[4] = {d.x, d.y, d.z, d.w}, avv[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 bsum[i] += dv[i];
@@ -285,6 +302,8 @@ struct GruFwdArgs {
     int TT, R, d_in, n_actions;
 };
 
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+
 template <int RT>
 __global__ void __launch_bounds__(192, 1) k_gru_fwd(GruFwdArgs a) {
     constexpr int ITEMS = RT * HID;
@@ -292,9 +311,11 @@ __global__ void __launch_bounds__(192, 1) k_gru_fwd(GruFwdArgs a) {
     constexpr int DEPTH = RT >= 8 ? 4 : 8;
     __shared__ __align__(128) float gi_s[DEPTH][RT * G3];
     __shared__ __align__(16) float h_s[RT * HID];
-    __shared__ float gh_s[RT * G3];
+    __shared__ float rz_s[RT * 2 * HID];     // sigmoid(r), sigmoid(z) per row
+    __shared__ float ghn_s[RT * HID];        // W_hn h + b_hn per row
     __shared__ __align__(8) uint64_t bars[DEPTH];
     const int tid = threadIdx.x, net = blockIdx.y;
+    const int g = tid >> 6;                  // 0: reset gate rows, 1: update gate rows, 2: candidate rows
     const int r0 = blockIdx.x * RT;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
     const float *P = a.params[net];
@@ -333,8 +354,9 @@ __global__ void __launch_bounds__(192, 1) k_gru_fwd(GruFwdArgs a) {
     const float bj = __ldg(P + L.b_hh + tid);
 
     for (int t = 0; t < a.TT; ++t) {
-        // phase 1: gh[r][j] = b_hh[j] + W_hh[j,:] . h[r,:]   (whole h row pulled into registers first: 16 LDS.128 in
-        // flight, then 4 independent FFMA chains -- the serial chain must not wait on shared-memory latency)
+        const int slot = t % DEPTH;
+        // phase 1: gh[r][j] = b_hh[j] + W_hh[j,:] . h[r,:]; reset/update threads finish their gate right away
+        float acc[RT];
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             float4 hv[HID / 4];
@@ -349,25 +371,28 @@ __global__ void __launch_bounds__(192, 1) k_gru_fwd(GruFwdArgs a) {
                 acc2 = fmaf(w[4 * k4 + 2], hv[k4].z, acc2);
                 acc3 = fmaf(w[4 * k4 + 3], hv[k4].w, acc3);
             }
-            gh_s[r * G3 + tid] = (acc0 + acc1) + (acc2 + acc3);
+            acc[r] = (acc0 + acc1) + (acc2 + acc3);
+        }
+        mbar_wait(&bars[slot], (uint32_t)((t / DEPTH) & 1));   // gi[t] staged by the copy engine (long since)
+        if (g < 2) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) rz_s[r * 2 * HID + tid] = sigmoid_fast(gi_s[slot][r * G3 + tid] + acc[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) ghn_s[r * HID + (tid - 2 * HID)] = acc[r];
         }
         __syncthreads();
-        // phase 2: gate math per (row, hidden unit); gi[t] has been staged by the copy engine
-        const int slot = t % DEPTH;
-        mbar_wait(&bars[slot], (uint32_t)((t / DEPTH) & 1));
+        // phase 2: candidate + blend per (row, hidden unit)
 #pragma unroll
         for (int q = 0; q < IPT; ++q) {
-            int item = tid + 192 * q;
+            const int item = tid + 192 * q;
             if (item < ITEMS) {
-                int r = item >> 6, i = item & 63, row = r0 + r;
-                const float *gh = gh_s + r * G3;
-                const float *gq = gi_s[slot] + r * G3;
-                float ghn = gh[2 * HID + i];
-                float rr = sigmoidf_acc(gq[i] + gh[i]);
-                float zz = sigmoidf_acc(gq[HID + i] + gh[HID + i]);
-                float nn = tanhf(gq[2 * HID + i] + rr * ghn);
-                float hp = h_s[item];
-                float hn = nn + zz * (hp - nn);
+                const int r = item >> 6, i = item & 63, row = r0 + r;
+                const float rr = rz_s[r * 2 * HID + i], zz = rz_s[r * 2 * HID + HID + i];
+                const float ghn = ghn_s[item];
+                const float nn = tanhf(gi_s[slot][r * G3 + 2 * HID + i] + rr * ghn);
+                const float hp = h_s[item];
+                const float hn = nn + zz * (hp - nn);
                 h_s[item] = hn;
                 if (row < a.R) {
                     const int64_t m = (int64_t)t * a.R + row;
@@ -626,15 +651,28 @@ __global__ void __launch_bounds__(256) k_mix_fwd(MixArgs a) {
     }
 }
 
-// mask.sum(), loss and the logging scalars from the block partials (q_learner.py:98,112,117-124); one warp per stat
-__global__ void __launch_bounds__(32 * MIX_NSTAT) k_stats_finalize(const float *part_stats, int nblk, int n_agents,
-                                                                   float *scalars) {
+// mask.sum(), loss and the logging scalars from the block partials (q_learner.py:98,112,117-124): block 0, one warp
+// per statistic.  Blocks >= 1 fold the per-block d V.2 partials into one row (one warp per output, fixed order).
+__global__ void __launch_bounds__(256) k_stats_finalize(const float *part_stats, int nblk, int n_agents, float *scalars,
+                                                        const float *part_v2, int n_v2, float *v2_out) {
     __shared__ float s[MIX_NSTAT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float v = 0.0f;
-    for (int i = lane; i < nblk; i += 32) v += part_stats[i * MIX_NSTAT + warp];
-    v = warp_sum(v);
-    if (lane == 0) s[warp] = v;
+    if (blockIdx.x > 0) {
+        const int o = (blockIdx.x - 1) * 8 + warp;
+        if (o < n_v2) {
+            float v = 0.0f;
+            for (int i = lane; i < nblk; i += 32) v += part_v2[(int64_t)i * n_v2 + o];
+            v = warp_sum(v);
+            if (lane == 0) v2_out[o] = v;
+        }
+        return;
+    }
+    if (warp < MIX_NSTAT) {
+        float v = 0.0f;
+        for (int i = lane; i < nblk; i += 32) v += part_stats[i * MIX_NSTAT + warp];
+        v = warp_sum(v);
+        if (lane == 0) s[warp] = v;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         const float msum = s[4];

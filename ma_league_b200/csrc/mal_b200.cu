@@ -271,7 +271,7 @@ struct PartLayout {
     int nblk_norm;
     int64_t wih_w, wih_b, whha_w, whha_b, whhb_w, whhb_b, fc1_w, fc1_b, fc2_w, fc2_b;
     int64_t m_l2a_w, m_l2a_b, m_l2b_w, m_l2b_b, m_l1_w, m_l1_b;   // mixer: layer-2 (w1b, wfb), layer-1 block
-    int64_t mix_stats, mix_v2, norm;
+    int64_t mix_stats, mix_v2, mix_v2_sum, norm;
     int64_t total;
 };
 
@@ -302,6 +302,7 @@ static PartLayout part_layout(const Dims &d, int sms) {
         p.m_l2b_w = take((int64_t)p.nc_m * d.E * K2);       p.m_l2b_b = take((int64_t)p.nc_m * d.E);
         p.m_l1_w = take((int64_t)p.nc_m * d.ld1 * d.S);     p.m_l1_b = take((int64_t)p.nc_m * d.ld1);
         p.mix_v2 = take((int64_t)p.nblk_mix * (d.E + 1));
+        p.mix_v2_sum = take(d.E + 1);
     }
     p.mix_stats = take((int64_t)p.nblk_mix * MIX_NSTAT);
     p.norm = take(p.nblk_norm);
@@ -464,10 +465,12 @@ static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st) {
     ProfScope _ps("k_gru_bwd", st);
     k_gru_bwd<RT><<<(a.R + RT - 1) / RT, 192, 0, st>>>(a);
 }
-static int pick_rt(int64_t chains, int sms) {
-    // smallest rows-per-CTA that still fits every chain in ~2 co-resident CTAs per SM; larger problems queue in waves
-    if (chains <= (int64_t)sms * 2 * 2) return 2;
-    if (chains <= (int64_t)sms * 2 * 4) return 4;
+static int pick_rt(int rows, int nets, int sms) {
+    // smallest rows-per-CTA with at most one CTA per SM (the recurrences are latency-bound: a second CTA on an SM
+    // stretches every timestep); larger problems queue in waves of 8-row CTAs
+    const int cand[6] = {1, 2, 3, 4, 6, 8};
+    for (int i = 0; i < 6; ++i)
+        if ((int64_t)((rows + cand[i] - 1) / cand[i]) * nets <= sms) return cand[i];
     return 8;
 }
 
@@ -518,9 +521,12 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         GruFwdArgs a;
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        switch (pick_rt((int64_t)d.R * 2, sms)) {
+        switch (pick_rt(d.R, 2, sms)) {
+            case 1: launch_gru_fwd<1>(a, 2, st); break;
             case 2: launch_gru_fwd<2>(a, 2, st); break;
+            case 3: launch_gru_fwd<3>(a, 2, st); break;
             case 4: launch_gru_fwd<4>(a, 2, st); break;
+            case 6: launch_gru_fwd<6>(a, 2, st); break;
             default: launch_gru_fwd<8>(a, 2, st); break;
         }
         MAL_LAUNCH_CHECK("k_gru_fwd");
@@ -583,7 +589,9 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
         { ProfScope _ps("k_mix_td", st); k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_mix_td");
-        { ProfScope _ps("k_stats_finalize", st); k_stats_finalize<<<1, 32 * MIX_NSTAT, 0, st>>>(parts + pl.mix_stats, pl.nblk_mix, d.N, scalars); }
+        { ProfScope _ps("k_stats_finalize", st); k_stats_finalize<<<1 + (d.mixer != MAL_MIXER_VDN ? (d.E + 1 + 7) / 8 : 0), 256, 0, st>>>(
+                                                       parts + pl.mix_stats, pl.nblk_mix, d.N, scalars, parts + pl.mix_v2,
+                                                       d.E + 1, parts + pl.mix_v2_sum); }
         MAL_LAUNCH_CHECK("k_stats_finalize");
     }
     return 0;
@@ -723,10 +731,12 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        switch (pick_rt((int64_t)d.R, sms)) {
+        switch (pick_rt(d.R, 1, sms)) {
+            case 1: launch_gru_bwd<1>(a, st); break;
             case 2: launch_gru_bwd<2>(a, st); break;
             case 4: launch_gru_bwd<4>(a, st); break;
-            default: launch_gru_bwd<8>(a, st); break;
+            case 8: launch_gru_bwd<8>(a, st); break;
+            default: launch_gru_bwd<4>(a, st); break;   // 3 -> 4, 6 -> (two waves of) 4: ring depth is 16/RT
         }
         MAL_LAUNCH_CHECK("k_gru_bwd");
     }
@@ -789,8 +799,8 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
             seg(o + ML.b1_b, d.E, parts + pl.m_l1_b + b1row, pl.nc_m, d.ld1);
             seg(o + ML.v0_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)(b1row + d.E) * d.S, pl.nc_m, l1w);
             seg(o + ML.v0_b, d.E, parts + pl.m_l1_b + b1row + d.E, pl.nc_m, d.ld1);
-            seg(o + ML.v2_w, d.E, parts + pl.mix_v2, pl.nblk_mix, d.E + 1);
-            seg(o + ML.v2_b, 1, parts + pl.mix_v2 + d.E, pl.nblk_mix, d.E + 1);
+            seg(o + ML.v2_w, d.E, parts + pl.mix_v2_sum, 1, d.E + 1);
+            seg(o + ML.v2_b, 1, parts + pl.mix_v2_sum + d.E, 1, d.E + 1);
         }
         a.n = n;
         a.total = AL.total + ML.total;
