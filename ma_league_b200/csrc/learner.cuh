@@ -196,12 +196,16 @@ struct RedGroup {
 #define RED_LD 68
 #define RED_EPT (RED_MR * 64 / 256)   // elements of each operand a thread stages per block (16)
 
+// AK: loader of the A operand (A_DENSE / A_STATE / A_AGENT_IN); DK: dY kind (0 dense, 1 one-hot(action) * d_chosen).
+// Specialised so that each instance is straight-line code: all 32 staging loads of a thread issue back to back.
+template <int AK, int DK>
 __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ RedGroup g) {
     __shared__ __align__(16) float dY_s[RED_MR * RED_LD];
     __shared__ __align__(16) float A_s[RED_MR * RED_LD];
     int pi = 0;
     while (pi + 1 < g.n && (int)blockIdx.y >= g.p[pi + 1].tile0) ++pi;
-    const RedProb &p = g.p[pi];
+    const RedProb p = g.p[pi];          // copy the descriptor to registers once
+    const BatchView bv = g.bv;
     const int chunk = blockIdx.x;
     if (chunk >= p.n_chunks) return;
     const int tile = blockIdx.y - p.tile0;
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
     const int64_t mb = p.M0 + (int64_t)chunk * p.rows_per_chunk;
     int64_t me = mb + p.rows_per_chunk;
     if (me > p.M) me = p.M;
+    const bool want_bias = p.partB && kt == 0;
 
     float acc[4][4];
     float bsum[4] = {0, 0, 0, 0};
@@ -221,32 +226,59 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
     // staging map: warp w owns rows w, w+8, ... (8 rows per block), lane owns columns lane and lane+32
+    const int c0 = lane, c1 = lane + 32;
+    const bool n_ok0 = n0 + c0 < p.Nout, n_ok1 = n0 + c1 < p.Nout;
+    const bool k_ok0 = k0 + c0 < p.K, k_ok1 = k0 + c1 < p.K;
     float rdy[RED_EPT], ra[RED_EPT];
     auto prefetch = [&](int64_t mm) {
 #pragma unroll
         for (int u = 0; u < RED_MR / 8; ++u) {
             const int64_t m = mm + warp + 8 * u;
             const bool ok = m < me;
-            const bool ok_a = ok && (p.a_kind != A_DENSE || m >= p.shift);
-            RowSrc rs;
-            rs.p0 = rs.p1 = nullptr; rs.agent = 0;
-            if (ok_a) rs = resolve_row(p.a_kind, g.bv, p.A, p.lda, p.shift, m);
-            float dsel = 0.0f;
-            int asel = -1;
-            if (p.dy_kind == 1 && ok) {   // row m = t*R + b*N + n of the [T*R] transition rows
-                const int t = (int)(m / g.bv.R), rr = (int)(m - (int64_t)t * g.bv.R);
-                const int b = rr / g.bv.N, n = rr - b * g.bv.N;
-                dsel = p.dY[((int64_t)b * g.bv.T + t) * g.bv.N + n];
-                asel = (int)(field_ptr<long long>(g.bv.actions, b, t)[n]);
+            // ---- dY
+            if (DK == 0) {
+                const float *dyp = p.dY + m * p.ldy + n0;
+                rdy[2 * u] = (ok && n_ok0) ? __ldg(dyp + c0) : 0.0f;
+                rdy[2 * u + 1] = (ok && n_ok1) ? __ldg(dyp + c1) : 0.0f;
+            } else {   // row m = t*R + b*N + n of the [T*R] transition rows
+                const int t = (int)(m / bv.R), rr = (int)(m - (int64_t)t * bv.R);
+                const int b = rr / bv.N, n = rr - b * bv.N;
+                float dsel = 0.0f;
+                int asel = -1;
+                if (ok) {
+                    dsel = __ldg(p.dY + ((int64_t)b * bv.T + t) * bv.N + n);
+                    asel = (int)(field_ptr<long long>(bv.actions, b, t)[n]);
+                }
+                rdy[2 * u] = (n0 + c0 == asel) ? dsel : 0.0f;
+                rdy[2 * u + 1] = (n0 + c1 == asel) ? dsel : 0.0f;
             }
+            // ---- A
+            if (AK == A_DENSE) {
+                const bool oka = ok && m >= p.shift;
+                const float *ap = p.A + (m - p.shift) * p.lda + k0;
+                ra[2 * u] = (oka && k_ok0) ? __ldg(ap + c0) : 0.0f;
+                ra[2 * u + 1] = (oka && k_ok1) ? __ldg(ap + c1) : 0.0f;
+            } else if (AK == A_STATE) {
+                const int b = (int)(m / bv.T), t = (int)(m - (int64_t)b * bv.T);
+                const float *ap = field_ptr<float>(bv.state, b, t + p.shift) + k0;
+                ra[2 * u] = (ok && k_ok0) ? __ldg(ap + c0) : 0.0f;
+                ra[2 * u + 1] = (ok && k_ok1) ? __ldg(ap + c1) : 0.0f;
+            } else {   // [obs | last-action one-hot | agent-id one-hot]
+                const int t = (int)(m / bv.R), rr = (int)(m - (int64_t)t * bv.R);
+                const int b = rr / bv.N, n = rr - b * bv.N;
+                const float *po = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
+                const float *ph = field_ptr<float>(bv.onehot, b, t > 0 ? t - 1 : 0) + (int64_t)n * bv.A;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                float dv;
-                if (p.dy_kind == 1) dv = (n0 + c == asel) ? dsel : 0.0f;
-                else dv = (ok && n0 + c < p.Nout) ? p.dY[m * p.ldy + n0 + c] : 0.0f;
-                rdy[2 * u + h] = dv;
-                ra[2 * u + h] = (ok_a && k0 + c < p.K) ? row_elem(p.a_kind, g.bv, rs, k0 + c) : 0.0f;
+                for (int h = 0; h < 2; ++h) {
+                    const int k = k0 + (h ? c1 : c0);
+                    float v = 0.0f;
+                    if (ok && k < p.K) {
+                        if (k < bv.OBS) v = __ldg(po + k);
+                        else if (k < bv.OBS + bv.A) v = t > 0 ? __ldg(ph + (k - bv.OBS)) : 0.0f;
+                        else v = (k - bv.OBS - bv.A) == n ? 1.0f : 0.0f;
+                    }
+                    ra[2 * u + h] = v;
+                }
             }
         }
     };
@@ -268,10 +300,12 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
             const float4 av4 = *reinterpret_cast<const float4 *>(A_s + r * RED_LD + 4 * tx);
             const float dv[4] = {d.x, d.y, d.z, d.w}, avv[4] = {av4.x, av4.y, av4.z, av4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                bsum[i] += dv[i];
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], avv[j], acc[i][j]);
+            if (want_bias) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bsum[i] += dv[i];
             }
         }
     }
@@ -285,7 +319,7 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
             const int k = k0 + 4 * tx + j;
             if (k < p.K) pw[(int64_t)n * p.K + k] = acc[i][j];
         }
-        if (p.partB && kt == 0 && tx == 0) p.partB[(int64_t)chunk * p.Nout + n] = bsum[i];
+        if (want_bias && tx == 0) p.partB[(int64_t)chunk * p.Nout + n] = bsum[i];
     }
 }
 

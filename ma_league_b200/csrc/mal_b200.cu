@@ -262,11 +262,14 @@ static void chunking(int64_t M, int tiles, int sms, int *n_chunks, int64_t *rows
     *rows_per_chunk = rpc;
 }
 
-// offsets (in floats) inside the partials scratch
+// offsets (in floats) inside the partials scratch; every reduction launch (one per loader kind) gets its own
+// chunking so that each launch fills the machine
 struct PartLayout {
-    int nc_a; int64_t rpc_a;        // agent reductions over M1 rows (fc2: over T*R rows with the same chunk size)
-    int nc_a2;
-    int nc_m; int64_t rpc_m;        // mixer reductions over BT rows
+    int nc_a; int64_t rpc_a;        // dense agent reductions (W_ih, W_hh x2) over M1 rows
+    int nc_f1; int64_t rpc_f1;      // fc1 (agent-input loader) over M1 rows
+    int nc_f2; int64_t rpc_f2;      // fc2 (one-hot dY) over T*R rows
+    int nc_m2; int64_t rpc_m2;      // mixer layer-2 problems over BT rows
+    int nc_m1; int64_t rpc_m1;      // mixer layer-1 block over BT rows
     int nblk_mix;
     int nblk_norm;
     int64_t wih_w, wih_b, whha_w, whha_b, whhb_w, whhb_b, fc1_w, fc1_b, fc2_w, fc2_b;
@@ -280,12 +283,17 @@ static int tiles_of(int Nout, int K) { return ((Nout + 63) / 64) * ((K + 63) / 6
 static PartLayout part_layout(const Dims &d, int sms) {
     PartLayout p;
     memset(&p, 0, sizeof(p));
-    const int tiles_a = tiles_of(G3, HID) + tiles_of(128, HID) + tiles_of(64, HID) + tiles_of(HID, d.d_in) + tiles_of(d.A, HID);
-    chunking(d.M1, tiles_a, sms, &p.nc_a, &p.rpc_a);
-    p.nc_a2 = (int)ceil_div64((int64_t)d.T * d.R, p.rpc_a);
+    chunking(d.M1, tiles_of(G3, HID) + tiles_of(128, HID) + tiles_of(64, HID), sms, &p.nc_a, &p.rpc_a);
+    chunking(d.M1, tiles_of(HID, d.d_in), sms, &p.nc_f1, &p.rpc_f1);
+    chunking((int64_t)d.T * d.R, tiles_of(d.A, HID), sms, &p.nc_f2, &p.rpc_f2);
     const int K2 = d.two ? d.HE : d.S;
-    const int tiles_m = d.mixer == MAL_MIXER_VDN ? 1 : tiles_of(d.E * d.N, K2) + tiles_of(d.E, K2) + tiles_of(d.ld1, d.S);
-    chunking(d.BT, tiles_m, sms, &p.nc_m, &p.rpc_m);
+    if (d.mixer == MAL_MIXER_QMIX2) {
+        chunking(d.BT, tiles_of(d.E * d.N, K2) + tiles_of(d.E, K2), sms, &p.nc_m2, &p.rpc_m2);
+        chunking(d.BT, tiles_of(d.ld1, d.S), sms, &p.nc_m1, &p.rpc_m1);
+    } else if (d.mixer == MAL_MIXER_QMIX1) {   // all three problems share the state loader -> one launch
+        chunking(d.BT, tiles_of(d.E * d.N, K2) + tiles_of(d.E, K2) + tiles_of(d.ld1, d.S), sms, &p.nc_m2, &p.rpc_m2);
+        p.nc_m1 = p.nc_m2; p.rpc_m1 = p.rpc_m2;
+    }
     int64_t nm = ceil_div64(d.BT, 8); if (nm > (int64_t)sms * 4) nm = (int64_t)sms * 4; if (nm < 1) nm = 1;
     p.nblk_mix = (int)nm;
     const int64_t P = agent_layout(d.d_in, d.A).total + mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
@@ -295,12 +303,12 @@ static PartLayout part_layout(const Dims &d, int sms) {
     p.wih_w = take((int64_t)p.nc_a * G3 * HID);   p.wih_b = take((int64_t)p.nc_a * G3);
     p.whha_w = take((int64_t)p.nc_a * 128 * HID); p.whha_b = take((int64_t)p.nc_a * 128);
     p.whhb_w = take((int64_t)p.nc_a * 64 * HID);  p.whhb_b = take((int64_t)p.nc_a * 64);
-    p.fc1_w = take((int64_t)p.nc_a * HID * d.d_in); p.fc1_b = take((int64_t)p.nc_a * HID);
-    p.fc2_w = take((int64_t)p.nc_a2 * d.A * HID);   p.fc2_b = take((int64_t)p.nc_a2 * d.A);
+    p.fc1_w = take((int64_t)p.nc_f1 * HID * d.d_in); p.fc1_b = take((int64_t)p.nc_f1 * HID);
+    p.fc2_w = take((int64_t)p.nc_f2 * d.A * HID);    p.fc2_b = take((int64_t)p.nc_f2 * d.A);
     if (d.mixer != MAL_MIXER_VDN) {
-        p.m_l2a_w = take((int64_t)p.nc_m * d.E * d.N * K2); p.m_l2a_b = take((int64_t)p.nc_m * d.E * d.N);
-        p.m_l2b_w = take((int64_t)p.nc_m * d.E * K2);       p.m_l2b_b = take((int64_t)p.nc_m * d.E);
-        p.m_l1_w = take((int64_t)p.nc_m * d.ld1 * d.S);     p.m_l1_b = take((int64_t)p.nc_m * d.ld1);
+        p.m_l2a_w = take((int64_t)p.nc_m2 * d.E * d.N * K2); p.m_l2a_b = take((int64_t)p.nc_m2 * d.E * d.N);
+        p.m_l2b_w = take((int64_t)p.nc_m2 * d.E * K2);       p.m_l2b_b = take((int64_t)p.nc_m2 * d.E);
+        p.m_l1_w = take((int64_t)p.nc_m1 * d.ld1 * d.S);     p.m_l1_b = take((int64_t)p.nc_m1 * d.ld1);
         p.mix_v2 = take((int64_t)p.nblk_mix * (d.E + 1));
         p.mix_v2_sum = take(d.E + 1);
     }
@@ -675,7 +683,8 @@ static RedProb red(int64_t M, int K, int Nout, const float *dY, int64_t ldy, int
     return p;
 }
 
-static int launch_reduce(RedGroup &g, cudaStream_t st, const char *tag) {
+template <int AK, int DK>
+static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag) {
     int tiles = 0, maxc = 0;
     for (int i = 0; i < g.n; ++i) {
         g.p[i].tile0 = tiles;
@@ -683,8 +692,30 @@ static int launch_reduce(RedGroup &g, cudaStream_t st, const char *tag) {
         if (g.p[i].n_chunks > maxc) maxc = g.p[i].n_chunks;
     }
     dim3 grid(maxc, tiles);
-    { ProfScope _ps(tag, st); k_reduce_group<<<grid, 256, 0, st>>>(g); }
+    { ProfScope _ps(tag, st); k_reduce_group<AK, DK><<<grid, 256, 0, st>>>(g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
+    return 0;
+}
+
+// one launch per (A loader, dY kind) so that every kernel instance is straight-line code
+static int launch_reduce(RedGroup &g, cudaStream_t st, const char *tag) {
+    const int kinds[4][2] = {{A_DENSE, 0}, {A_STATE, 0}, {A_AGENT_IN, 0}, {A_DENSE, 1}};
+    for (int q = 0; q < 4; ++q) {
+        RedGroup h;
+        h.bv = g.bv;
+        h.n = 0;
+        for (int i = 0; i < g.n; ++i)
+            if (g.p[i].a_kind == kinds[q][0] && g.p[i].dy_kind == kinds[q][1]) h.p[h.n++] = g.p[i];
+        if (h.n == 0) continue;
+        int rc = 0;
+        if (q == 0) rc = launch_reduce_inst<A_DENSE, 0>(h, st, tag);
+        else if (q == 1) rc = launch_reduce_inst<A_STATE, 0>(h, st, tag);
+        else if (q == 2) rc = launch_reduce_inst<A_AGENT_IN, 0>(h, st, tag);
+        else rc = launch_reduce_inst<A_DENSE, 1>(h, st, tag);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < g.n; ++i)
+        MAL_REQUIRE((g.p[i].dy_kind == 0) || g.p[i].a_kind == A_DENSE, "launch_reduce: unsupported loader combination");
     return 0;
 }
 
@@ -714,15 +745,15 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         g.p[1] = lin(d.BT, d.E, d.HE, A_DENSE, 0, d_a2 + d.E * d.N, d.ld2, mixer + ML.wfb_w, d.HE, 1, nullptr, EPI_MASKPOS, y1 + d.HE, d.ld1, d_y1 + d.HE, d.ld1);
         if (int rc = launch_linear(g, d.BT, d.E * d.N, st, "k_linear_group:mixer_bwd_dh")) return rc;
         RedGroup r; r.n = 3; r.bv = bv;
-        r.p[0] = red(d.BT, d.HE, d.E * d.N, d_a2, d.ld2, A_DENSE, 0, y1, d.ld1, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m, pl.rpc_m);
-        r.p[1] = red(d.BT, d.HE, d.E, d_a2 + d.E * d.N, d.ld2, A_DENSE, 0, y1 + d.HE, d.ld1, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m, pl.rpc_m);
-        r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m, pl.rpc_m);
+        r.p[0] = red(d.BT, d.HE, d.E * d.N, d_a2, d.ld2, A_DENSE, 0, y1, d.ld1, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m2, pl.rpc_m2);
+        r.p[1] = red(d.BT, d.HE, d.E, d_a2 + d.E * d.N, d.ld2, A_DENSE, 0, y1 + d.HE, d.ld1, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m2, pl.rpc_m2);
+        r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m1, pl.rpc_m1);
         if (int rc = launch_reduce(r, st, "k_reduce_group:mixer")) return rc;
     } else if (d.mixer == MAL_MIXER_QMIX1) {
         RedGroup r; r.n = 3; r.bv = bv;
-        r.p[0] = red(d.BT, d.S, d.E * d.N, d_a2, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m, pl.rpc_m);
-        r.p[1] = red(d.BT, d.S, d.E, d_a2 + d.E * d.N, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m, pl.rpc_m);
-        r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m, pl.rpc_m);
+        r.p[0] = red(d.BT, d.S, d.E * d.N, d_a2, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m2, pl.rpc_m2);
+        r.p[1] = red(d.BT, d.S, d.E, d_a2 + d.E * d.N, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m2, pl.rpc_m2);
+        r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m1, pl.rpc_m1);
         if (int rc = launch_reduce(r, st, "k_reduce_group:mixer")) return rc;
     }
 
@@ -753,9 +784,9 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)
         r.p[1] = red(d.M1, HID, 128, d_g, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whha_w, parts + pl.whha_b, pl.nc_a, pl.rpc_a);
         r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
-        r.p[3] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_a, pl.rpc_a);
+        r.p[3] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
         // fc2: dY = one-hot(action) * d_chosen over the T*R transition rows, A = h_t
-        r.p[4] = red((int64_t)d.T * d.R, HID, d.A, F(plan->d_chosen), 0, A_DENSE, 0, F(plan->h_on), HID, parts + pl.fc2_w, parts + pl.fc2_b, pl.nc_a2, pl.rpc_a);
+        r.p[4] = red((int64_t)d.T * d.R, HID, d.A, F(plan->d_chosen), 0, A_DENSE, 0, F(plan->h_on), HID, parts + pl.fc2_w, parts + pl.fc2_b, pl.nc_f2, pl.rpc_f2);
         r.p[4].dy_kind = 1;
         if (int rc = launch_reduce(r, st, "k_reduce_group:agent")) return rc;
     }
@@ -768,37 +799,37 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
             a.s[n].grad_off = off; a.s[n].count = (int)count; a.s[n].part = part; a.s[n].n_chunks = n_chunks;
             a.s[n].chunk_stride = stride; ++n;
         };
-        seg(AL.fc1_w, (int64_t)HID * d.d_in, parts + pl.fc1_w, pl.nc_a, (int64_t)HID * d.d_in);
-        seg(AL.fc1_b, HID, parts + pl.fc1_b, pl.nc_a, HID);
+        seg(AL.fc1_w, (int64_t)HID * d.d_in, parts + pl.fc1_w, pl.nc_f1, (int64_t)HID * d.d_in);
+        seg(AL.fc1_b, HID, parts + pl.fc1_b, pl.nc_f1, HID);
         seg(AL.w_ih, (int64_t)G3 * HID, parts + pl.wih_w, pl.nc_a, (int64_t)G3 * HID);
         seg(AL.w_hh, 128 * HID, parts + pl.whha_w, pl.nc_a, 128 * HID);
         seg(AL.w_hh + 128 * HID, 64 * HID, parts + pl.whhb_w, pl.nc_a, 64 * HID);
         seg(AL.b_ih, G3, parts + pl.wih_b, pl.nc_a, G3);
         seg(AL.b_hh, 128, parts + pl.whha_b, pl.nc_a, 128);
         seg(AL.b_hh + 128, 64, parts + pl.whhb_b, pl.nc_a, 64);
-        seg(AL.fc2_w, (int64_t)d.A * HID, parts + pl.fc2_w, pl.nc_a2, (int64_t)d.A * HID);
-        seg(AL.fc2_b, d.A, parts + pl.fc2_b, pl.nc_a2, d.A);
+        seg(AL.fc2_w, (int64_t)d.A * HID, parts + pl.fc2_w, pl.nc_f2, (int64_t)d.A * HID);
+        seg(AL.fc2_b, d.A, parts + pl.fc2_b, pl.nc_f2, d.A);
         const int64_t o = AL.total;
         if (d.mixer != MAL_MIXER_VDN) {
             const int K2 = d.two ? d.HE : d.S;
             const int64_t l1w = (int64_t)d.ld1 * d.S;
             const int b1row = d.two ? 2 * d.HE : 0;
             if (d.two) {
-                seg(o + ML.w1a_w, (int64_t)d.HE * d.S, parts + pl.m_l1_w, pl.nc_m, l1w);
-                seg(o + ML.w1a_b, d.HE, parts + pl.m_l1_b, pl.nc_m, d.ld1);
+                seg(o + ML.w1a_w, (int64_t)d.HE * d.S, parts + pl.m_l1_w, pl.nc_m1, l1w);
+                seg(o + ML.w1a_b, d.HE, parts + pl.m_l1_b, pl.nc_m1, d.ld1);
             }
-            seg(o + ML.w1b_w, (int64_t)d.E * d.N * K2, parts + pl.m_l2a_w, pl.nc_m, (int64_t)d.E * d.N * K2);
-            seg(o + ML.w1b_b, d.E * d.N, parts + pl.m_l2a_b, pl.nc_m, d.E * d.N);
+            seg(o + ML.w1b_w, (int64_t)d.E * d.N * K2, parts + pl.m_l2a_w, pl.nc_m2, (int64_t)d.E * d.N * K2);
+            seg(o + ML.w1b_b, d.E * d.N, parts + pl.m_l2a_b, pl.nc_m2, d.E * d.N);
             if (d.two) {
-                seg(o + ML.wfa_w, (int64_t)d.HE * d.S, parts + pl.m_l1_w + (int64_t)d.HE * d.S, pl.nc_m, l1w);
-                seg(o + ML.wfa_b, d.HE, parts + pl.m_l1_b + d.HE, pl.nc_m, d.ld1);
+                seg(o + ML.wfa_w, (int64_t)d.HE * d.S, parts + pl.m_l1_w + (int64_t)d.HE * d.S, pl.nc_m1, l1w);
+                seg(o + ML.wfa_b, d.HE, parts + pl.m_l1_b + d.HE, pl.nc_m1, d.ld1);
             }
-            seg(o + ML.wfb_w, (int64_t)d.E * K2, parts + pl.m_l2b_w, pl.nc_m, (int64_t)d.E * K2);
-            seg(o + ML.wfb_b, d.E, parts + pl.m_l2b_b, pl.nc_m, d.E);
-            seg(o + ML.b1_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)b1row * d.S, pl.nc_m, l1w);
-            seg(o + ML.b1_b, d.E, parts + pl.m_l1_b + b1row, pl.nc_m, d.ld1);
-            seg(o + ML.v0_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)(b1row + d.E) * d.S, pl.nc_m, l1w);
-            seg(o + ML.v0_b, d.E, parts + pl.m_l1_b + b1row + d.E, pl.nc_m, d.ld1);
+            seg(o + ML.wfb_w, (int64_t)d.E * K2, parts + pl.m_l2b_w, pl.nc_m2, (int64_t)d.E * K2);
+            seg(o + ML.wfb_b, d.E, parts + pl.m_l2b_b, pl.nc_m2, d.E);
+            seg(o + ML.b1_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)b1row * d.S, pl.nc_m1, l1w);
+            seg(o + ML.b1_b, d.E, parts + pl.m_l1_b + b1row, pl.nc_m1, d.ld1);
+            seg(o + ML.v0_w, (int64_t)d.E * d.S, parts + pl.m_l1_w + (int64_t)(b1row + d.E) * d.S, pl.nc_m1, l1w);
+            seg(o + ML.v0_b, d.E, parts + pl.m_l1_b + b1row + d.E, pl.nc_m1, d.ld1);
             seg(o + ML.v2_w, d.E, parts + pl.mix_v2_sum, 1, d.E + 1);
             seg(o + ML.v2_b, 1, parts + pl.mix_v2_sum + d.E, 1, d.E + 1);
         }
