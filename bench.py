@@ -95,7 +95,9 @@ def kernel_bytes(d, mixer):
         "k_q_head": M1 * (2 * 64 * f + A * 4 + 8) + 3 * BT * N * f,
         "k_gru_bwd": M1 * (256 + 64 + 256) * f + BT * N * 12,
         "k_linear_group:dx": M1 * (192 + 64 + 64) * f,
-        "k_reduce_group:agent": M1 * (256 + 64 + 64 + 64 + (OBS + A)) * f,
+        "k_reduce_group:agent_dense": M1 * (256 + 64 + 64) * f,
+        "k_reduce_group:agent_fc1": M1 * (64 + (OBS + A)) * f,
+        "k_reduce_group:agent_fc2": T * R * (64 * f + 12),
         "k_fc2_grad": T * R * (64 * f + 12),
         "k_mask_prep": BT * (8 + 1 + 4),
     }
@@ -105,7 +107,8 @@ def kernel_bytes(d, mixer):
             "k_linear_group:mixer_l2": 2 * BT * (2 * HE + ld2) * f,
             "k_mix_td": BT * (2 * (ld1 - 2 * HE + ld2) + ld2 + 2 * E + 3 * N + 12) * f,
             "k_linear_group:mixer_bwd_dh": BT * (ld2 + 2 * HE + 2 * HE) * f,
-            "k_reduce_group:mixer": BT * (ld2 + 2 * HE + ld1 + S) * f,
+            "k_reduce_group:mixer_dense": BT * (ld2 + 2 * HE) * f,
+            "k_reduce_group:mixer_state": BT * (ld1 + S) * f,
         })
     else:
         out["k_mix_td"] = BT * (3 * N + 12) * f

@@ -109,6 +109,45 @@ static int device_sm_count(int *sms, int *threads_per_sm) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// side streams: independent kernel chains of one learner step run concurrently (the recurrences are latency-bound
+// and leave most SMs idle).  Fork/join with events only, so the pattern is also capturable into a CUDA graph.
+// ---------------------------------------------------------------------------------------------
+struct SideStreams {
+    int dev = -1;
+    cudaStream_t s[2];
+    cudaEvent_t fork_ev[4], join_ev[2];
+};
+static thread_local SideStreams g_side;
+static int g_overlap = 1;
+
+static int side_streams(SideStreams **out) {
+    int dev = 0;
+    MAL_CUDA(cudaGetDevice(&dev));
+    if (g_side.dev != dev) {
+        for (int i = 0; i < 2; ++i) MAL_CUDA(cudaStreamCreateWithFlags(&g_side.s[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) MAL_CUDA(cudaEventCreateWithFlags(&g_side.fork_ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) MAL_CUDA(cudaEventCreateWithFlags(&g_side.join_ev[i], cudaEventDisableTiming));
+        g_side.dev = dev;
+    }
+    *out = &g_side;
+    return 0;
+}
+// `side` starts after everything enqueued on `main` so far
+static int fork_to(cudaStream_t main, cudaStream_t side, cudaEvent_t ev) {
+    if (side == main) return 0;
+    MAL_CUDA(cudaEventRecord(ev, main));
+    MAL_CUDA(cudaStreamWaitEvent(side, ev, 0));
+    return 0;
+}
+// `main` continues after everything enqueued on `side` so far
+static int join_from(cudaStream_t main, cudaStream_t side, cudaEvent_t ev) {
+    if (side == main) return 0;
+    MAL_CUDA(cudaEventRecord(ev, side));
+    MAL_CUDA(cudaStreamWaitEvent(main, ev, 0));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // replay
 // ---------------------------------------------------------------------------------------------
 extern "C" int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst_ids, const void *src,
@@ -369,6 +408,7 @@ static int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM
 extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
+    if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
 }
@@ -508,6 +548,11 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     float *hh[2] = {F(plan->h_on), F(plan->h_tg)};
     float *y1[2] = {F(plan->y1_on), F(plan->y1_tg)}, *a2[2] = {F(plan->a2_on), F(plan->a2_tg)};
 
+    SideStreams *ss;
+    if (side_streams(&ss)) return 2;
+    cudaStream_t sm = g_overlap ? ss->s[0] : st;    // mixer hypernets only depend on the state: run beside the agent path
+    if (fork_to(st, sm, ss->fork_ev[0])) return 2;
+
     // x = relu(fc1([obs | last action | agent id]))  for every (t,b,n), both nets   basic_controller.py:80-92
     {
         LinGroup g; g.n = 2; g.bv = bv;
@@ -563,14 +608,14 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             g.p[net * 4 + 2] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.b1_w, d.S, 0, P + ML.b1_b, EPI_BIAS, nullptr, 0, y1[net] + 2 * d.HE, d.ld1);
             g.p[net * 4 + 3] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.v0_w, d.S, 0, P + ML.v0_b, EPI_RELU, nullptr, 0, y1[net] + 2 * d.HE + d.E, d.ld1);
         }
-        if (int rc = launch_linear(g, d.BT, d.S, st, "k_linear_group:mixer_l1")) return rc;
+        if (int rc = launch_linear(g, d.BT, d.S, sm, "k_linear_group:mixer_l1")) return rc;
         LinGroup h; h.n = 4; h.bv = bv;
         for (int net = 0; net < 2; ++net) {
             const float *P = mp[net];
             h.p[net * 2 + 0] = lin(d.BT, d.HE, d.E * d.N, A_DENSE, 0, y1[net], d.ld1, P + ML.w1b_w, d.HE, 0, P + ML.w1b_b, EPI_BIAS, nullptr, 0, a2[net], d.ld2);
             h.p[net * 2 + 1] = lin(d.BT, d.HE, d.E, A_DENSE, 0, y1[net] + d.HE, d.ld1, P + ML.wfb_w, d.HE, 0, P + ML.wfb_b, EPI_BIAS, nullptr, 0, a2[net] + d.E * d.N, d.ld2);
         }
-        if (int rc = launch_linear(h, d.BT, d.HE, st, "k_linear_group:mixer_l2")) return rc;
+        if (int rc = launch_linear(h, d.BT, d.HE, sm, "k_linear_group:mixer_l2")) return rc;
     } else if (d.mixer == MAL_MIXER_QMIX1) {
         LinGroup g; g.n = 8; g.bv = bv;
         for (int net = 0; net < 2; ++net) {
@@ -580,8 +625,9 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             g.p[net * 4 + 2] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.b1_w, d.S, 0, P + ML.b1_b, EPI_BIAS, nullptr, 0, y1[net], d.ld1);
             g.p[net * 4 + 3] = lin(d.BT, d.S, d.E, A_STATE, net, nullptr, 0, P + ML.v0_w, d.S, 0, P + ML.v0_b, EPI_RELU, nullptr, 0, y1[net] + d.E, d.ld1);
         }
-        if (int rc = launch_linear(g, d.BT, d.S, st, "k_linear_group:mixer_l1")) return rc;
+        if (int rc = launch_linear(g, d.BT, d.S, sm, "k_linear_group:mixer_l1")) return rc;
     }
+    if (join_from(st, sm, ss->join_ev[0])) return 2;
     // mixing + TD error + masked loss + element-wise mixer backward          q_learner.py:81-98
     {
         MixArgs a;
@@ -708,10 +754,11 @@ static int launch_reduce(RedGroup &g, cudaStream_t st, const char *tag) {
             if (g.p[i].a_kind == kinds[q][0] && g.p[i].dy_kind == kinds[q][1]) h.p[h.n++] = g.p[i];
         if (h.n == 0) continue;
         int rc = 0;
-        if (q == 0) rc = launch_reduce_inst<A_DENSE, 0>(h, st, tag);
-        else if (q == 1) rc = launch_reduce_inst<A_STATE, 0>(h, st, tag);
-        else if (q == 2) rc = launch_reduce_inst<A_AGENT_IN, 0>(h, st, tag);
-        else rc = launch_reduce_inst<A_DENSE, 1>(h, st, tag);
+        const bool agent = strstr(tag, "agent") != nullptr;
+        if (q == 0) rc = launch_reduce_inst<A_DENSE, 0>(h, st, agent ? "k_reduce_group:agent_dense" : "k_reduce_group:mixer_dense");
+        else if (q == 1) rc = launch_reduce_inst<A_STATE, 0>(h, st, "k_reduce_group:mixer_state");
+        else if (q == 2) rc = launch_reduce_inst<A_AGENT_IN, 0>(h, st, "k_reduce_group:agent_fc1");
+        else rc = launch_reduce_inst<A_DENSE, 1>(h, st, "k_reduce_group:agent_fc2");
         if (rc) return rc;
     }
     for (int i = 0; i < g.n; ++i)
@@ -738,26 +785,39 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     float *d_g = F(plan->d_g), *d_x = F(plan->d_x), *d_a2 = F(plan->d_a2), *d_y1 = F(plan->d_y1);
     float *y1 = F(plan->y1_on);
 
-    // ---- mixer: hypernet backward
+    SideStreams *ss;
+    if (side_streams(&ss)) return 2;
+    cudaStream_t s1 = g_overlap ? ss->s[0] : st, s2 = g_overlap ? ss->s[1] : st;
+    if (fork_to(st, s1, ss->fork_ev[0])) return 2;
+    if (fork_to(st, s2, ss->fork_ev[1])) return 2;
+
+    // ---- side stream 1: mixer hypernet backward (independent of the agent BPTT)
     if (d.mixer == MAL_MIXER_QMIX2) {
         LinGroup g; g.n = 2; g.bv = bv;   // d h1 = (d a1 . W12) * (h1 > 0) ; d hf = (d af . Wf2) * (hf > 0)
         g.p[0] = lin(d.BT, d.E * d.N, d.HE, A_DENSE, 0, d_a2, d.ld2, mixer + ML.w1b_w, d.HE, 1, nullptr, EPI_MASKPOS, y1, d.ld1, d_y1, d.ld1);
         g.p[1] = lin(d.BT, d.E, d.HE, A_DENSE, 0, d_a2 + d.E * d.N, d.ld2, mixer + ML.wfb_w, d.HE, 1, nullptr, EPI_MASKPOS, y1 + d.HE, d.ld1, d_y1 + d.HE, d.ld1);
-        if (int rc = launch_linear(g, d.BT, d.E * d.N, st, "k_linear_group:mixer_bwd_dh")) return rc;
+        if (int rc = launch_linear(g, d.BT, d.E * d.N, s1, "k_linear_group:mixer_bwd_dh")) return rc;
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.BT, d.HE, d.E * d.N, d_a2, d.ld2, A_DENSE, 0, y1, d.ld1, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m2, pl.rpc_m2);
         r.p[1] = red(d.BT, d.HE, d.E, d_a2 + d.E * d.N, d.ld2, A_DENSE, 0, y1 + d.HE, d.ld1, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m2, pl.rpc_m2);
         r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m1, pl.rpc_m1);
-        if (int rc = launch_reduce(r, st, "k_reduce_group:mixer")) return rc;
+        if (int rc = launch_reduce(r, s1, "k_reduce_group:mixer")) return rc;
     } else if (d.mixer == MAL_MIXER_QMIX1) {
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.BT, d.S, d.E * d.N, d_a2, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m2, pl.rpc_m2);
         r.p[1] = red(d.BT, d.S, d.E, d_a2 + d.E * d.N, d.ld2, A_STATE, 0, nullptr, 0, parts + pl.m_l2b_w, parts + pl.m_l2b_b, pl.nc_m2, pl.rpc_m2);
         r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m1, pl.rpc_m1);
-        if (int rc = launch_reduce(r, st, "k_reduce_group:mixer")) return rc;
+        if (int rc = launch_reduce(r, s1, "k_reduce_group:mixer")) return rc;
+    }
+    // ---- side stream 2: fc2 gradients only need d_chosen and h (both forward products)
+    {
+        RedGroup r; r.n = 1; r.bv = bv;
+        r.p[0] = red((int64_t)d.T * d.R, HID, d.A, F(plan->d_chosen), 0, A_DENSE, 0, F(plan->h_on), HID, parts + pl.fc2_w, parts + pl.fc2_b, pl.nc_f2, pl.rpc_f2);
+        r.p[0].dy_kind = 1;
+        if (int rc = launch_reduce(r, s2, "k_reduce_group:agent")) return rc;
     }
 
-    // ---- agent: BPTT recurrence
+    // ---- main stream: BPTT recurrence
     {
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
@@ -771,25 +831,26 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         }
         MAL_LAUNCH_CHECK("k_gru_bwd");
     }
-    // d x = (d gi . W_ih) * (x > 0)
+    // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads
+    if (fork_to(st, s2, ss->fork_ev[2])) return 2;
     {
-        LinGroup g; g.n = 1; g.bv = bv;
-        g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, agent + AL.w_ih, HID, 1, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);
-        if (int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx")) return rc;
-    }
-    // weight gradients of the agent
-    {
-        RedGroup r; r.n = 5; r.bv = bv;
+        RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.M1, HID, G3, d_g, 4 * HID, A_DENSE, 0, F(plan->x_on), HID, parts + pl.wih_w, parts + pl.wih_b, pl.nc_a, pl.rpc_a);
         // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)
         r.p[1] = red(d.M1, HID, 128, d_g, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whha_w, parts + pl.whha_b, pl.nc_a, pl.rpc_a);
         r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
-        r.p[3] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
-        // fc2: dY = one-hot(action) * d_chosen over the T*R transition rows, A = h_t
-        r.p[4] = red((int64_t)d.T * d.R, HID, d.A, F(plan->d_chosen), 0, A_DENSE, 0, F(plan->h_on), HID, parts + pl.fc2_w, parts + pl.fc2_b, pl.nc_f2, pl.rpc_f2);
-        r.p[4].dy_kind = 1;
+        if (int rc = launch_reduce(r, s2, "k_reduce_group:agent")) return rc;
+    }
+    {
+        LinGroup g; g.n = 1; g.bv = bv;
+        g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, agent + AL.w_ih, HID, 1, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);
+        if (int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx")) return rc;
+        RedGroup r; r.n = 1; r.bv = bv;
+        r.p[0] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
         if (int rc = launch_reduce(r, st, "k_reduce_group:agent")) return rc;
     }
+    if (join_from(st, s1, ss->join_ev[0])) return 2;
+    if (join_from(st, s2, ss->join_ev[1])) return 2;
     // ---- gather partials into the flat gradient (state_dict order) + sum of squares
     {
         GradReduceArgs a;
