@@ -47,8 +47,9 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)      # let the first samples start before the timed region
         except Exception:
             self.p = None
 
@@ -81,38 +82,47 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ algorithmic bytes
 def kernel_bytes(d, mixer):
-    """Algorithmic bytes per launch of each learner kernel (DESIGN.md 'kernels'); M1 = TT*B*N rows, BT = B*T."""
+    """Algorithmic bytes per launch of each learner kernel; M1 = TT*B*N rows, BT = B*T."""
     B, TT, N, A, OBS, S = d["B"], d["TT"], d["N"], d["A"], d["OBS"], d["S"]
     T, R = TT - 1, B * N
-    M1, BT, D = TT * R, B * T, OBS + A + N
+    M1, BT = TT * R, B * T
     E, HE = 32, 64
     ld1, ld2 = 2 * HE + 2 * E, E * N + E
     f = 4
+    P = 64 * (OBS + A + N) + 64 + 2 * 192 * 64 + 2 * 192 + 64 * A + A
     out = {
         "k_linear_group:fc1": M1 * (OBS + A) * f + 2 * M1 * 64 * f,
         "k_linear_group:w_ih": 2 * M1 * (64 + 192) * f,
         "k_gru_fwd": M1 * (2 * 192 + 2 * 64 + 256) * f,
         "k_q_head": M1 * (2 * 64 * f + A * 4 + 8) + 3 * BT * N * f,
-        "k_gru_bwd": M1 * (256 + 64 + 256) * f + BT * N * 12,
+        "k_gru_bwd": M1 * (256 + 64 + 64 + 256) * f,
         "k_linear_group:dx": M1 * (192 + 64 + 64) * f,
         "k_reduce_group:agent_dense": M1 * (256 + 64 + 64) * f,
         "k_reduce_group:agent_fc1": M1 * (64 + (OBS + A)) * f,
         "k_reduce_group:agent_fc2": T * R * (64 * f + 12),
-        "k_fc2_grad": T * R * (64 * f + 12),
-        "k_mask_prep": BT * (8 + 1 + 4),
     }
     if mixer == "qmix":
+        P += (S * HE + HE + HE * E * N + E * N) + (S * HE + HE + HE * E + E) + (S * E + E) + (S * E + E + E + 1)
         out.update({
             "k_linear_group:mixer_l1": 2 * BT * (S + ld1) * f,
             "k_linear_group:mixer_l2": 2 * BT * (2 * HE + ld2) * f,
-            "k_mix_td": BT * (2 * (ld1 - 2 * HE + ld2) + ld2 + 2 * E + 3 * N + 12) * f,
+            "k_mix_td": BT * (2 * (ld1 - 2 * HE + ld2) + ld2 + 2 * E + 3 * N + 12) * f + BT * N * 64 * f,
             "k_linear_group:mixer_bwd_dh": BT * (ld2 + 2 * HE + 2 * HE) * f,
             "k_reduce_group:mixer_dense": BT * (ld2 + 2 * HE) * f,
             "k_reduce_group:mixer_state": BT * (ld1 + S) * f,
         })
     else:
-        out["k_mix_td"] = BT * (3 * N + 12) * f
+        out["k_mix_td"] = BT * (3 * N + 12) * f + BT * N * 64 * f
+    out["k_clip_rmsprop"] = 20 * P
     return out
+
+
+def load_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full summary."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -150,13 +160,14 @@ def run_ours(a, rank, world, device):
     # NB pre-sampled batches whose total size exceeds L2 (126 MB): inputs come from HBM on every step
     rb = buf._layout.record_bytes
     nb = max(4, -(-160 * 2 ** 20 // (B * rb)))
-    batches = []
+    batches, parents = [], []
     for _ in range(nb):
         smp = buf.sample(B)
         smp._storage.view(B, rb)[0].copy_(buf._storage.view(a.buffer_size, rb)[0])   # one full-length episode
         mt = int(smp.max_t_filled())
         assert mt == TT, mt
-        batches.append(smp[:, :mt])
+        parents.append(smp)
+        batches.append(smp[:, :mt])                    # ma_experiment.py:235-236
     transitions = B * (TT - 1)
 
     def dist_max(x):
@@ -176,7 +187,7 @@ def run_ours(a, rank, world, device):
         learner.train(batches[i % nb], t_env=i, episode_num=0)
     barrier()
     launches0 = lib.mal_launch_count()
-    sampler = ClockSampler(th.cuda.current_device() if world == 1 else int(os.environ.get("LOCAL_RANK", 0)))
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)) if world > 1 else th.cuda.current_device())
     evs = [(th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
     wall0 = time.perf_counter()
@@ -188,18 +199,12 @@ def run_ours(a, rank, world, device):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     launches = lib.mal_launch_count() - launches0
-    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-    dev_ms = dist_max(dev_ms)
+    dev_ms = dist_max(sum(s.elapsed_time(e) for s, e in evs))
     wall = dist_max(wall)
     ms_per_step = dev_ms / a.steps
     value = world * transitions / (ms_per_step * 1e-3)
 
-    # ---------------- per-kernel profile (same steps again, CUDA events around every launch)
-    nat.profile_begin()
-    for i in range(a.steps):
-        learner.train(batches[i % nb], t_env=i, episode_num=0)
-    prof = nat.profile_end()
-    kb = kernel_bytes(d, d["mixer"])
+    # ---------------- per-kernel profile (same steps again, CUDA events around every launch on its own stream)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -207,27 +212,30 @@ def run_ours(a, rank, world, device):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650"
+    nat.profile_begin()
+    for i in range(a.steps):
+        learner.train(batches[i % nb], t_env=i, episode_num=0)
+    prof = nat.profile_end()
+    kb = kernel_bytes(d, d["mixer"])
+    traffic = load_traffic()
     kern = []
     tot_ms = sum(ms for _, ms in prof.values())
     for name, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         per = ms / n
         byts = kb.get(name)
-        kern.append({"kernel": name, "launches_per_step": n / a.steps, "us": round(per * 1e3, 2),
-                     "share": round(ms / tot_ms, 4),
-                     "gbs": round(byts / (per * 1e-3) / 1e9, 1) if byts else None})
+        kern.append({"kernel": name, "launches_per_step": round(n / a.steps, 2), "us_per_launch": round(per * 1e3, 2),
+                     "us_per_step": round(ms / a.steps * 1e3, 2), "share": round(ms / tot_ms, 4),
+                     "algo_gbs": round(byts / (per * 1e-3) / 1e9, 1) if byts else None,
+                     "frac_of_hbm_peak": round(byts / (per * 1e-3) / 1e9 / peak, 4) if byts else None})
     top = kern[0]
-    roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": round(top["gbs"] / peak, 4) if top["gbs"] else None, "traffic": None,
-                "peak_source": peak_src, "us_per_launch": top["us"],
-                "note": "B=32 step is latency-bound (201-step serial chain, 6400 transitions); see DESIGN.md"}
+    roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["algo_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["frac_of_hbm_peak"], "traffic": traffic.get(top["kernel"].split(":")[0]),
+                "peak_source": peak_src, "us_per_launch": top["us_per_launch"],
+                "algorithmic_bytes_per_launch": kb.get(top["kernel"]),
+                "note": "dominant kernel of the B=32 step = the serial 201-step GRU recurrence: latency-bound "
+                        "(cycles per timestep), not bandwidth-bound; memory-bound kernels are listed under hbm_kernels"}
 
     # ---------------- e2e: batch in pinned host memory, H2D + train + D2H every step
-    # fresh packed samples (B whole records each) staged in pinned host memory
-    parents = []
-    for i in range(nb):
-        smp = buf.sample(B)
-        smp._storage.view(B, rb)[0].copy_(buf._storage.view(a.buffer_size, rb)[0])
-        parents.append(smp)
     pinned = [p_._storage.cpu().pin_memory() for p_ in parents]
     stage = [M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=device) for _ in range(2)]
     out_host = th.empty(8, dtype=th.float32).pin_memory()
@@ -244,15 +252,16 @@ def run_ours(a, rank, world, device):
 
     def e2e_steps(k, t0):
         prefetch(t0)
+        cur = th.cuda.current_stream(device)
         for i in range(t0, t0 + k):
             slot = i % 2
             if i + 1 < t0 + k:
                 prefetch(i + 1)
-            th.cuda.current_stream(device).wait_event(ready[slot])
+            cur.wait_event(ready[slot])
             learner.train(stage[slot], t_env=i, episode_num=0)
             consumed[slot].record()
             out_host.copy_(learner.scalars()[:8], non_blocking=True)
-            th.cuda.current_stream(device).synchronize()      # the step's loss is on the host
+            cur.synchronize()      # the step's loss is on the host
         return float(out_host[1])
 
     for c in consumed:
@@ -268,38 +277,67 @@ def run_ours(a, rank, world, device):
            "how": "pinned host batch -> double-buffered H2D on a copy stream -> QLearner.train -> loss D2H + sync"}
     assert np.isfinite(last_loss)
 
-    # ---------------- second headline metric: act-select agent-steps/s, and replay sample GB/s
+    # ---------------- second headline metric: act-select agent-steps/s (public API, default RNG = torch's Philox stream)
     extra = {}
-    for bs in (1, B):
+    mac.action_selector.validate = False    # the reference-style ValueError check costs a device sync per call
+    for bs in (1, B, 1024):
         eb = M.EpisodeBatch(scheme, groups, bs, TT, preprocess=pre, device=device)
-        eb._storage.copy_(buf._storage[:bs * rb])
+        for r_ in range(0, bs, a.buffer_size):
+            n_ = min(a.buffer_size, bs - r_)
+            eb._storage[r_ * rb:(r_ + n_) * rb].copy_(buf._storage[:n_ * rb])
         mac.init_hidden(bs)
-        mac.action_selector.validate = False
         for i in range(10):
             mac.select_actions(eb, t_ep=1 + i % 100, t_env=i)
         th.cuda.synchronize(device)
         reps = 200
         s_, e_ = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
         s_.record()
         for i in range(reps):
             mac.select_actions(eb, t_ep=1 + i % 100, t_env=i)
         e_.record()
         th.cuda.synchronize(device)
-        extra["act_select_agent_steps_per_s_bs%d" % bs] = round(bs * N * reps / (s_.elapsed_time(e_) * 1e-3), 1)
-    s_, e_ = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        api_us = (time.perf_counter() - w0) / reps * 1e6
+        nat.profile_begin()
+        for i in range(50):
+            mac.select_actions(eb, t_ep=1 + i % 100, t_env=i)
+        pk = nat.profile_end()["k_agent_step"]
+        extra["act_select_bs%d" % bs] = {
+            "agent_steps_per_s": round(bs * N * reps / (s_.elapsed_time(e_) * 1e-3), 1),
+            "api_us_per_call": round(api_us, 2), "kernel_us": round(pk[1] / pk[0] * 1e3, 2),
+            "kernel_agent_steps_per_s": round(bs * N / (pk[1] / pk[0] * 1e-3), 1)}
+
+    # ---------------- memory-bound kernels against the HBM roofline (kernel time from CUDA events around the launch)
+    hbm = []
     ids = [th.as_tensor(np.random.choice(a.buffer_size, B, replace=False), device=device) for _ in range(20)]
     for i in ids[:3]:
         buf[i]
     th.cuda.synchronize(device)
-    s_.record()
+    w0 = time.perf_counter()
+    nat.profile_begin()
     for i in ids:
         buf[i]
-    e_.record()
-    th.cuda.synchronize(device)
-    us = s_.elapsed_time(e_) / len(ids) * 1e3
-    extra["replay_sample"] = {"us": round(us, 2), "gbs": round(2 * B * rb / (us * 1e-6) / 1e9, 1),
-                              "frac_of_hbm_peak": round(2 * B * rb / (us * 1e-6) / 1e9 / peak, 4),
-                              "bytes": 2 * B * rb}
+    pk = nat.profile_end()["k_record_copy_tma"]
+    api_us = (time.perf_counter() - w0) / len(ids) * 1e6
+    us = pk[1] / pk[0] * 1e3
+    hbm.append({"kernel": "k_record_copy_tma", "what": "ReplayBuffer.sample(%d) gather" % B, "bytes": 2 * B * rb,
+                "us": round(us, 2), "gbs": round(2 * B * rb / (us * 1e-6) / 1e9, 1),
+                "frac_of_hbm_peak": round(2 * B * rb / (us * 1e-6) / 1e9 / peak, 4), "api_us_per_call": round(api_us, 1)})
+    nbig = min(a.buffer_size, 768)
+    big_ids = th.as_tensor(np.random.choice(a.buffer_size, nbig, replace=False), device=device)
+    buf[big_ids]
+    nat.profile_begin()
+    for _ in range(5):
+        buf[big_ids]
+    pk = nat.profile_end()["k_record_copy_tma"]
+    us = pk[1] / pk[0] * 1e3
+    hbm.append({"kernel": "k_record_copy_tma", "what": "gather of %d episodes (> L2)" % nbig, "bytes": 2 * nbig * rb,
+                "us": round(us, 2), "gbs": round(2 * nbig * rb / (us * 1e-6) / 1e9, 1),
+                "frac_of_hbm_peak": round(2 * nbig * rb / (us * 1e-6) / 1e9 / peak, 4)})
+    for k in kern:
+        if k["kernel"] in ("k_mix_td", "k_q_head", "k_clip_rmsprop"):
+            hbm.append({"kernel": k["kernel"], "what": "learner step", "us": k["us_per_launch"], "gbs": k["algo_gbs"],
+                        "frac_of_hbm_peak": k["frac_of_hbm_peak"]})
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -308,9 +346,11 @@ def run_ours(a, rank, world, device):
                                    "H=64, one independent league matchup per GPU" % (a.workload, B, TT - 1, N, A, OBS, S),
                        "transitions_per_step": transitions, "parallelism": "league-sharded x%d (no collective)" % world,
                        "l2": "inputs rotate over %d sampled batches (%.0f MB) > 126 MB L2" % (nb, nb * B * rb / 2 ** 20),
-                       "replay_buffer_episodes": a.buffer_size},
+                       "replay_buffer_episodes": a.buffer_size,
+                       "math": "fp32; batched projections on tcgen05 3xTF32 (fp32-accurate), recurrences fp32 FFMA"},
             "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / a.steps,
-            "wall_ms_per_step": wall / a.steps * 1e3, "clocks": clocks, "roofline": roofline, "kernels": kern}
+            "wall_ms_per_step": wall / a.steps * 1e3, "clocks": clocks, "roofline": roofline, "kernels": kern,
+            "hbm_kernels": hbm}
     line.update(extra)
     return line
 

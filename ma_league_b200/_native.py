@@ -170,8 +170,41 @@ def ptr(t):
 
 
 def current_stream(device=None):
+    """Raw cudaStream_t of torch's current stream on `device` (torch is only the stream/memory plumbing)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    if device is None:
+        idx = torch.cuda.current_device()
+    else:
+        idx = device if isinstance(device, int) else torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+    except AttributeError:   # older / newer torch without the private fast path
+        return C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
+
+
+class on_device:
+    """`with on_device(dev):` -- like torch.cuda.device(dev) but free when `dev` is already current."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        import torch
+        self.idx = device if isinstance(device, int) else torch.device(device).index
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def field_of(t, inner_numel: int) -> Field:

@@ -19,6 +19,19 @@ class Selector:
         raise NotImplementedError()
 
 
+_ADVANCE_CACHE = {}
+
+
+def philox_advance(rows, n_actions, device_index):
+    key = (rows, n_actions, device_index)
+    adv = _ADVANCE_CACHE.get(key)
+    if adv is None:
+        out = C.c_uint64(0)
+        nat.check(nat.lib().mal_select_philox_advance(rows, n_actions, C.byref(out)), "mal_select_philox_advance")
+        adv = _ADVANCE_CACHE[key] = out.value
+    return adv
+
+
 def make_select_struct(avail, epsilon, actions, greedy, status, u=None, e=None, generator=None):
     """Fill the C `mal_select_t` for avail [bs, N, A] (inner dims contiguous)."""
     bs, N, A = avail.shape
@@ -44,10 +57,9 @@ def make_select_struct(avail, epsilon, actions, greedy, status, u=None, e=None, 
         keep += [u, e]
     else:
         gen = generator if generator is not None else th.cuda.default_generators[avail.device.index]
-        adv = C.c_uint64(0)
-        nat.check(nat.lib().mal_select_philox_advance(bs * N, A, C.byref(adv)), "mal_select_philox_advance")
-        s.rng_mode, s.seed, s.offset = 1, gen.initial_seed(), gen.get_offset()
-        gen.set_offset(gen.get_offset() + adv.value)
+        off = gen.get_offset()
+        s.rng_mode, s.seed, s.offset = 1, gen.initial_seed(), off
+        gen.set_offset(off + philox_advance(bs * N, A, avail.device.index))
     return s, keep
 
 
@@ -77,7 +89,7 @@ class EpsilonGreedyActionSelector(Selector):
         greedy = th.empty(bs, N, dtype=th.long, device=q.device)
         status = th.zeros(1, dtype=th.int32, device=q.device) if self.validate else None
         s, keep = make_select_struct(avail_actions, eps, actions, greedy, status, u, e)
-        with th.cuda.device(q.device):
+        with nat.on_device(q.device):
             nat.check(nat.lib().mal_eps_greedy_select(nat.ptr(q), A, bs * N, N, A, C.byref(s),
                                                       nat.current_stream(q.device)), "mal_eps_greedy_select")
         if status is not None and int(status.item()) != 0:

@@ -26,20 +26,20 @@ class BasicMAC(MultiAgentController):
 
     # ------------------------------------------------------------------ public API
     def select_actions(self, ep_batch, t_ep, t_env, bs=slice(None), test_mode=False, u=None, e=None):
-        avail_actions = ep_batch["avail_actions"][:, t_ep]
         if self._fusable() and isinstance(bs, slice) and bs == slice(None):
             sel = self.action_selector
             eps = sel._epsilon(t_env, test_mode)
+            avail_actions = ep_batch["avail_actions"][:, t_ep]
             B = ep_batch.batch_size
             dev = avail_actions.device
-            actions = th.empty(B, self.n_agents, dtype=th.long, device=dev)
-            greedy = th.empty(B, self.n_agents, dtype=th.long, device=dev)
+            out = th.empty(2, B, self.n_agents, dtype=th.long, device=dev)     # actions | greedy, one allocation
             status = th.zeros(1, dtype=th.int32, device=dev) if sel.validate else None
-            s, keep = make_select_struct(avail_actions, eps, actions, greedy, status, u, e)
+            s, keep = make_select_struct(avail_actions, eps, out[0], out[1], status, u, e)
             self._step(ep_batch, t_ep, s)
             if status is not None and int(status.item()) != 0:
                 raise ValueError("Expected at least one available action per agent (Categorical probs are all zero)")
-            return actions, greedy
+            return out[0], out[1]
+        avail_actions = ep_batch["avail_actions"][:, t_ep]
         agent_outs = self.forward(ep_batch, t_ep, test_mode=test_mode)
         return self.action_selector.select(agent_outs[bs], avail_actions[bs], t_env, test_mode, u=u, e=e)
 
@@ -116,33 +116,36 @@ class BasicMAC(MultiAgentController):
     def _step(self, ep_batch, t, select_struct):
         if self.hidden_states is None:
             raise HiddenStateNotInitialized()
-        obs = nat.require_cuda(ep_batch["obs"], "ep_batch")[:, t]
-        B, N, OBS = obs.shape
+        obs_all = nat.require_cuda(ep_batch["obs"], "ep_batch")        # [B, T+1, N, OBS] (strided view of the records)
+        B, _, N, OBS = obs_all.shape
         A = self.n_actions
-        if obs.stride(2) != 1 or obs.stride(1) != OBS:
-            obs = obs.contiguous()
-        last = None
+        if obs_all.stride(3) != 1 or obs_all.stride(2) != OBS or obs_all.dtype != th.float32:
+            raise nat.MalError("obs must be float32 with contiguous [N, OBS] rows")
+        obs_ptr = obs_all.data_ptr() + 4 * t * obs_all.stride(1)
+        last_ptr, last_sb = None, 0
         if t > 0:
-            last = ep_batch["actions_onehot"][:, t - 1]
-            if last.stride(2) != 1 or last.stride(1) != A:
-                last = last.contiguous()
+            oh = ep_batch["actions_onehot"]
+            if oh.stride(3) != 1 or oh.stride(2) != A or oh.dtype != th.float32:
+                raise nat.MalError("actions_onehot must be float32 with contiguous [N, A] rows")
+            last_ptr, last_sb = oh.data_ptr() + 4 * (t - 1) * oh.stride(1), oh.stride(0)
         rows = B * N
+        dev = obs_all.device
         h_in = self.hidden_states
-        if h_in.dim() == 3 and h_in.stride(0) == 0:   # fresh init_hidden(): zeros
+        if h_in.dim() == 3 and h_in.stride(0) == 0 and h_in.stride(1) == 0:   # fresh init_hidden(): zeros
             h_ptr = None
         else:
             h_in = h_in.reshape(rows, nat.HID)
             if not h_in.is_contiguous():
                 h_in = h_in.contiguous()
-            h_ptr = h_in
-        q = th.empty(B, N, A, dtype=th.float32, device=obs.device)
-        h_out = th.empty(rows, nat.HID, dtype=th.float32, device=obs.device)
+            h_ptr = h_in.data_ptr()
+        buf = th.empty(rows * (A + nat.HID), dtype=th.float32, device=dev)      # q | h_out, one allocation
+        q = buf[:rows * A].view(B, N, A)
+        h_out = buf[rows * A:].view(rows, nat.HID)
         flat = self.agent.flat_params()
-        with th.cuda.device(obs.device):
+        with nat.on_device(dev):
             nat.check(nat.lib().mal_agent_step(
-                nat.ptr(flat), rows, N, OBS, A, 0, nat.ptr(obs), obs.stride(0), nat.ptr(last),
-                last.stride(0) if last is not None else 0, nat.ptr(h_ptr), nat.ptr(h_out), nat.ptr(q),
-                C.byref(select_struct) if select_struct is not None else None, nat.current_stream(obs.device)),
-                "mal_agent_step")
+                flat.data_ptr(), rows, N, OBS, A, 0, obs_ptr, obs_all.stride(0), last_ptr, last_sb, h_ptr,
+                h_out.data_ptr(), q.data_ptr(), C.byref(select_struct) if select_struct is not None else None,
+                nat.current_stream(dev)), "mal_agent_step")
         self.hidden_states = h_out
         return q

@@ -134,7 +134,170 @@ struct AgentStepArgs {
     SelectArgs sel;
 };
 
-__global__ void __launch_bounds__(AS_THREADS) k_agent_step(AgentStepArgs a) {
+// Latency plan: a CTA needs every weight exactly once, and nothing but the inputs depends on anything, so ALL
+// global loads (inputs, 48 GRU weight rows per warp, fc1 / fc2 rows, biases) are issued back to back at kernel entry
+// into registers; the phases below then only touch registers and shared memory.
+#define AS_FC1_MAXK 7    // ceil(224 / 32): obs+action columns handled per lane
+__global__ void __launch_bounds__(AS_THREADS, 1) k_agent_step(AgentStepArgs a) {
+    extern __shared__ float as_smem[];
+    const AgentLayout L = agent_layout(a.dense ? a.OBS : a.OBS + a.A + a.N, a.A);
+    const int Kin = a.dense ? a.OBS : a.OBS + a.A;
+    const int ldin = Kin + 1;
+    float *in_s = as_smem;                       // [8][ldin]
+    float *x_s = in_s + AS_ROWS * ldin;          // [8][64]
+    float *h_s = x_s + AS_ROWS * HID;            // [8][64]
+    float *g_s = h_s + AS_ROWS * HID;            // [8][384]  W_ih x | W_hh h (no biases)
+    float *hn_s = g_s + AS_ROWS * 2 * G3;        // [8][64]
+    float *q_s = hn_s + AS_ROWS * HID;           // [8][32]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * AS_ROWS;
+    const float *P = a.params;
+
+    // ---- issue every global load up front ---------------------------------------------------------------------
+    float2 wg[2 * G3 / AS_WARPS];                // GRU rows warp, warp+8, ... of [W_ih ; W_hh]   (48 x float2)
+#pragma unroll
+    for (int i = 0; i < 2 * G3 / AS_WARPS; ++i) {
+        const int jj = warp + AS_WARPS * i;
+        const bool hh = jj >= G3;
+        const int j = hh ? jj - G3 : jj;
+        wg[i] = __ldg(reinterpret_cast<const float2 *>(P + (hh ? L.w_hh : L.w_ih) + (int64_t)j * HID) + lane);
+    }
+    float w1[HID / AS_WARPS][AS_FC1_MAXK];       // fc1 rows warp, warp+8, ...; columns lane, lane+32, ...
+    float b1x[HID / AS_WARPS];                   // fc1 bias + agent-id column, for the row this lane finalises
+#pragma unroll
+    for (int i = 0; i < HID / AS_WARPS; ++i) {
+        const int j = warp + AS_WARPS * i;
+        const float *w = P + L.fc1_w + (int64_t)j * L.d_in;
+#pragma unroll
+        for (int c = 0; c < AS_FC1_MAXK; ++c) w1[i][c] = (lane + 32 * c < Kin) ? __ldg(w + lane + 32 * c) : 0.0f;
+        const int row = r0 + (lane >> 2);
+        const int n = row < a.rows ? row % a.N : 0;
+        b1x[i] = __ldg(P + L.fc1_b + j) + (a.dense ? 0.0f : __ldg(w + Kin + n));
+    }
+    float2 w2[MAL_MAX_ACTIONS / AS_WARPS];
+    float b2[MAL_MAX_ACTIONS / AS_WARPS];
+#pragma unroll
+    for (int i = 0; i < MAL_MAX_ACTIONS / AS_WARPS; ++i) {
+        const int j = warp + AS_WARPS * i;
+        w2[i] = make_float2(0.f, 0.f);
+        b2[i] = 0.0f;
+        if (j < a.A) {
+            w2[i] = __ldg(reinterpret_cast<const float2 *>(P + L.fc2_w + (int64_t)j * HID) + lane);
+            b2[i] = __ldg(P + L.fc2_b + j);
+        }
+    }
+    // gate biases of the hidden unit this thread combines (items tid and tid+256 share i = tid & 63)
+    const int gi_ = tid & 63;
+    const float bir = __ldg(P + L.b_ih + gi_) + __ldg(P + L.b_hh + gi_);
+    const float biz = __ldg(P + L.b_ih + HID + gi_) + __ldg(P + L.b_hh + HID + gi_);
+    const float bin = __ldg(P + L.b_ih + 2 * HID + gi_), bhn = __ldg(P + L.b_hh + 2 * HID + gi_);
+
+    // ---- stage inputs (obs | last action one-hot) and previous hidden state
+    for (int idx = tid; idx < AS_ROWS * Kin; idx += AS_THREADS) {
+        int r = idx / Kin, k = idx - r * Kin, row = r0 + r;
+        float v = 0.0f;
+        if (row < a.rows) {
+            const int b = row / a.N, n = row - b * a.N;
+            if (a.dense) v = a.obs[(int64_t)row * a.obs_sb + k];
+            else if (k < a.OBS) v = a.obs[(int64_t)b * a.obs_sb + (int64_t)n * a.OBS + k];
+            else if (a.onehot) v = a.onehot[(int64_t)b * a.onehot_sb + (int64_t)n * a.A + (k - a.OBS)];
+        }
+        in_s[r * ldin + k] = v;
+    }
+    for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
+        int r = idx >> 6, row = r0 + r;
+        h_s[idx] = (a.h_in && row < a.rows) ? a.h_in[(int64_t)row * HID + (idx & 63)] : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- fc1 + relu (agent-id one-hot column folded in as a bias gather)
+#pragma unroll
+    for (int i = 0; i < HID / AS_WARPS; ++i) {
+        const int j = warp + AS_WARPS * i;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < AS_FC1_MAXK; ++c) {
+            const int k = lane + 32 * c;
+            if (k < Kin) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = fmaf(w1[i][c], in_s[r * ldin + k], acc[r]);
+            }
+        }
+        float s = warp_fold8(acc, lane);
+        if ((lane & 3) == 0) x_s[(lane >> 2) * HID + j] = fmaxf(s + b1x[i], 0.0f);
+    }
+    __syncthreads();
+
+    // ---- W_ih x  and  W_hh h   (384 weight rows of 64, already in registers)
+    {
+        float xv[8][2], hv[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            xv[r][0] = x_s[r * HID + 2 * lane]; xv[r][1] = x_s[r * HID + 2 * lane + 1];
+            hv[r][0] = h_s[r * HID + 2 * lane]; hv[r][1] = h_s[r * HID + 2 * lane + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * G3 / AS_WARPS; ++i) {
+            const int jj = warp + AS_WARPS * i;
+            const bool hh = jj >= G3;          // compile-time per i after unrolling only if warp-independent; cheap anyway
+            float acc[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                acc[r] = hh ? fmaf(wg[i].y, hv[r][1], wg[i].x * hv[r][0]) : fmaf(wg[i].y, xv[r][1], wg[i].x * xv[r][0]);
+            float s = warp_fold8(acc, lane);
+            if ((lane & 3) == 0) g_s[(lane >> 2) * 2 * G3 + jj] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- gate math: r,z,n ; h' = n + z (h - n)
+    for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
+        int r = idx >> 6, i = idx & 63, row = r0 + r;
+        const float *g = g_s + r * 2 * G3;
+        float rr = sigmoidf_acc(g[i] + g[G3 + i] + bir);
+        float zz = sigmoidf_acc(g[HID + i] + g[G3 + HID + i] + biz);
+        float nn = tanhf(g[2 * HID + i] + bin + rr * (g[G3 + 2 * HID + i] + bhn));
+        float hp = h_s[idx];
+        float hn = nn + zz * (hp - nn);
+        hn_s[idx] = hn;
+        if (row < a.rows) a.h_out[(int64_t)row * HID + i] = hn;
+    }
+    __syncthreads();
+
+    // ---- fc2
+    {
+        float hv[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { hv[r][0] = hn_s[r * HID + 2 * lane]; hv[r][1] = hn_s[r * HID + 2 * lane + 1]; }
+#pragma unroll
+        for (int i = 0; i < MAL_MAX_ACTIONS / AS_WARPS; ++i) {
+            const int j = warp + AS_WARPS * i;
+            if (j < a.A) {      // warp-uniform
+                float acc[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = fmaf(w2[i].y, hv[r][1], w2[i].x * hv[r][0]);
+                float s = warp_fold8(acc, lane);
+                if ((lane & 3) == 0) {
+                    int r = lane >> 2, row = r0 + r;
+                    s += b2[i];
+                    q_s[r * 32 + j] = s;
+                    if (row < a.rows) a.q[(int64_t)row * a.A + j] = s;
+                }
+            }
+        }
+    }
+    if (!a.do_select) return;
+    __syncthreads();
+    // ---- epsilon-greedy selection: one warp per row
+    {
+        int row = r0 + warp;
+        if (row < a.rows) select_row(a.sel, row, a.A, lane, lane < a.A ? q_s[warp * 32 + lane] : 0.0f);
+    }
+}
+
+// Throughput variant for large row counts (many CTAs per SM): weight rows are streamed from L2 as they are used
+// instead of being parked in 255 registers per thread.
+__global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs a) {
     extern __shared__ float as_smem[];
     const AgentLayout L = agent_layout(a.dense ? a.OBS : a.OBS + a.A + a.N, a.A);
     const int Kin = a.dense ? a.OBS : a.OBS + a.A;

@@ -252,9 +252,20 @@ extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents
     if (sel) if (int rc = fill_select(sel, rows, n_agents, n_actions, &a.sel)) return rc;
     const int Kin = dense_input ? obs_dim : obs_dim + n_actions;
     const size_t smem = sizeof(float) * (size_t)(AS_ROWS * (Kin + 1) + AS_ROWS * HID * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
-    MAL_REQUIRE(smem <= 200 * 1024, "mal_agent_step: obs_dim too large for the shared-memory staging");
-    if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { ProfScope _ps("k_agent_step", (cudaStream_t)stream); k_agent_step<<<(rows + AS_ROWS - 1) / AS_ROWS, AS_THREADS, smem, (cudaStream_t)stream>>>(a); }
+    MAL_REQUIRE(smem <= 200 * 1024 && Kin <= 32 * AS_FC1_MAXK, "mal_agent_step: input width %d too large (max %d)", Kin,
+                32 * AS_FC1_MAXK);
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    const int ctas = (rows + AS_ROWS - 1) / AS_ROWS;
+    if (ctas <= 2 * sms) {   // latency-bound regime (rollouts): all weights prefetched into registers
+        if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope _ps("k_agent_step", (cudaStream_t)stream);
+        k_agent_step<<<ctas, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope _ps("k_agent_step", (cudaStream_t)stream);
+        k_agent_step_stream<<<ctas, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
+    }
     MAL_LAUNCH_CHECK("k_agent_step");
     return 0;
 }

@@ -10,13 +10,26 @@ import torch as th
 
 def ensure_flat(module, device=None):
     """Return the flat fp32 buffer that backs all parameters of `module` in registration order."""
-    params = list(module.parameters())
+    params = getattr(module, "_mal_params", None)
+    if params is not None and params and next(module.parameters()) is not params[0]:
+        params = None                          # parameters were re-created (e.g. load_state_dict(assign=True))
+        module._mal_total = None
+    if params is None:
+        params = list(module.parameters())
+        module._mal_params = params           # the module structure of this path is fixed after construction
     if not params:
         return None
     dev = th.device(device) if device is not None else params[0].device
     flat = getattr(module, "_mal_flat", None)
-    total = sum(p.numel() for p in params)
+    total = getattr(module, "_mal_total", None)
+    if total is None:
+        total = module._mal_total = sum(p.numel() for p in params)
     ok = flat is not None and flat.numel() == total and flat.device == dev and flat.dtype == th.float32
+    if ok and getattr(module, "_mal_flat_checked", False):
+        # fast path (every kernel call): first and last parameter still alias the buffer
+        last = params[-1]
+        if params[0].data_ptr() == flat.data_ptr() and last.data_ptr() == flat.data_ptr() + 4 * (total - last.numel()):
+            return flat
     if ok:
         off = 0
         base = flat.data_ptr()
@@ -35,6 +48,7 @@ def ensure_flat(module, device=None):
                 p.data = flat[off:off + n].view(p.shape)
                 off += n
         module._mal_flat = flat
+    module._mal_flat_checked = True
     return flat
 
 

@@ -36,6 +36,7 @@ class QLearner(Learner):
         self._ws_key = None
         self._plan = nat.Plan()
         self._grad = None
+        self._grad_views = None
         self.save_q = False      # tests: also materialise mac_out / target_mac_out
 
     def parameters(self):
@@ -93,6 +94,7 @@ class QLearner(Learner):
             raise nat.MalError("parameter count mismatch between the modules and the kernel layout")
         if self._grad is None or self._grad.numel() != n_total or self._grad.device != dev:
             self._grad = th.zeros(n_total, dtype=th.float32, device=dev)
+            self._grad_views = None
         return bs, cfg, flats
 
     def _ws_f32(self, offset, numel):
@@ -107,15 +109,19 @@ class QLearner(Learner):
         if self.optimiser is None:
             raise nat.MalError("call build_optimizer() before train() (ma_experiment.py:61)")
         dev = batch["obs"].device
-        with th.cuda.device(dev):
+        with nat.on_device(dev):
             nat.check(nat.lib().mal_learner_step(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
                                                  nat.ptr(f["tagent"]), nat.ptr(f["mixer"]), nat.ptr(f["tmixer"]),
                                                  nat.ptr(self._ws), nat.ptr(self._grad),
                                                  nat.ptr(self.optimiser.flat_sq), nat.current_stream(dev)),
                       "mal_learner_step")
         self.optimiser._steps += 1
-        for p, g in zip(self.parameters(), flat_views(self._grad, self.parameters())):
-            p.grad = g                                  # clipped gradients, as clip_grad_norm_ leaves them
+        if getattr(self, "_grad_views", None) is None:   # p.grad = views of the flat (clipped) gradient, bound once
+            params = self.parameters()
+            self._grad_views = list(zip(params, flat_views(self._grad, params)))
+        for p, g in self._grad_views:
+            if p.grad is not g:
+                p.grad = g
 
         if (episode_num - self.last_target_update_episode) / self.args.target_update_interval >= 1.0:
             self.update_targets()
@@ -137,7 +143,7 @@ class QLearner(Learner):
         """Forward half of train() (q_learner.py:36-98); intermediates stay in the workspace (tests, debugging)."""
         bs, cfg, f = self._prepare(batch)
         dev = batch["obs"].device
-        with th.cuda.device(dev):
+        with nat.on_device(dev):
             nat.check(nat.lib().mal_learner_forward(C.byref(bs), C.byref(cfg), C.byref(self._plan),
                                                     nat.ptr(f["agent"]), nat.ptr(f["tagent"]), nat.ptr(f["mixer"]),
                                                     nat.ptr(f["tmixer"]), nat.ptr(self._ws), nat.current_stream(dev)),
@@ -148,7 +154,7 @@ class QLearner(Learner):
         """forward + loss.backward() without the optimiser step; returns the flat unclipped gradient."""
         bs, cfg, f = self.forward_only(batch)
         dev = batch["obs"].device
-        with th.cuda.device(dev):
+        with nat.on_device(dev):
             nat.check(nat.lib().mal_learner_backward(C.byref(bs), C.byref(cfg), C.byref(self._plan),
                                                      nat.ptr(f["agent"]), nat.ptr(f["mixer"]), nat.ptr(self._ws),
                                                      nat.ptr(self._grad), nat.current_stream(dev)),
@@ -182,7 +188,7 @@ class QLearner(Learner):
         for dst, src in pairs:
             if dst is None:
                 continue
-            with th.cuda.device(dst.device):
+            with nat.on_device(dst.device):
                 nat.check(nat.lib().mal_copy_f32(nat.ptr(dst), nat.ptr(src), src.numel(),
                                                  nat.current_stream(dst.device)), "mal_copy_f32")
         self.logger.info("Updated {0}target network.".format(self.name))
