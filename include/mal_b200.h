@@ -60,6 +60,8 @@ typedef struct mal_learner_cfg {
     int32_t hyper_embed;              /* hypernet_embed */
     float gamma, lr, alpha, eps, clip;
     int32_t save_q;                   /* also materialise mac_out / target_mac_out (tests, debugging) */
+    int32_t unnormalized;             /* data-parallel mode: mal_learner_backward leaves the gradient WITHOUT the
+                                         1/mask.sum() factor so that ranks can all-reduce grads and mask sums first */
 } mal_learner_cfg_t;
 
 /* Byte offsets of every intermediate inside the caller-owned workspace (filled by mal_learner_plan).
@@ -91,7 +93,10 @@ typedef struct mal_plan {
 /* indices into the scalars block (all float32 except where noted) */
 enum {
     MAL_SC_MASK_SUM = 0, MAL_SC_LOSS = 1, MAL_SC_TD_ABS = 2, MAL_SC_Q_TAKEN = 3, MAL_SC_TARGET = 4,
-    MAL_SC_GRAD_NORM = 5, MAL_SC_MASK_COUNT = 6 /* int32 bits */, MAL_SC_STATUS = 7 /* int32 bits */
+    MAL_SC_GRAD_NORM = 5, MAL_SC_MASK_COUNT = 6 /* int32 bits */, MAL_SC_STATUS = 7 /* int32 bits */,
+    /* raw (un-normalised) sums of this rank, for the data-parallel reduction:
+       sum (td*mask)^2, sum |td*mask|, sum q_tot*mask, sum targets*mask, sum mask, count(mask != 0) */
+    MAL_SC_RAW0 = 8
 };
 
 int mal_version(void);
@@ -128,7 +133,9 @@ int mal_learner_backward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg,
  * scratch needs ceil((n_agent+n_mixer)/256) floats. */
 int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                      float *square_avg, float lr, float alpha, float eps, float clip, float *scalars,
-                     float *scratch, void *stream);
+                     float *scratch, const float *denominator, void *stream);
+/* denominator: NULL, or a DEVICE pointer to the global mask sum; the gradient is divided by it first (data-parallel
+ * mode: grads and mask sums are all-reduced across ranks, then every rank applies the identical update). */
 
 /* forward + backward + clip + RMSprop in one call (the whole of q_learner.py:34-105). */
 int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,

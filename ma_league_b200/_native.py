@@ -18,6 +18,7 @@ ABI_VERSION = 1
 
 MIXER_VDN, MIXER_QMIX2, MIXER_QMIX1 = 0, 1, 2
 SC_MASK_SUM, SC_LOSS, SC_TD_ABS, SC_Q_TAKEN, SC_TARGET, SC_GRAD_NORM, SC_MASK_COUNT, SC_STATUS = range(8)
+SC_RAW0 = 8     # raw sums: sum mtd^2, sum |mtd|, sum q_tot*m, sum targets*m, sum m, count
 HID = 64
 MAX_ACTIONS = 32
 MAX_EMBED = 32
@@ -40,7 +41,7 @@ class Batch(C.Structure):
 class LearnerCfg(C.Structure):
     _fields_ = [("mixer", C.c_int32), ("double_q", C.c_int32), ("embed", C.c_int32), ("hyper_embed", C.c_int32),
                 ("gamma", C.c_float), ("lr", C.c_float), ("alpha", C.c_float), ("eps", C.c_float),
-                ("clip", C.c_float), ("save_q", C.c_int32)]
+                ("clip", C.c_float), ("save_q", C.c_int32), ("unnormalized", C.c_int32)]
 
 
 _PLAN_FIELDS = ["total_bytes", "n_agent_params", "n_mixer_params", "x_on", "x_tg", "gi_on", "gi_tg", "h_on", "h_tg",
@@ -77,7 +78,7 @@ _PROTOS = {
     "mal_learner_backward": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_clip_rmsprop": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
-                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_learner_step": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_copy_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

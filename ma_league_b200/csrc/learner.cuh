@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(256) k_stats_finalize(const float *part_stats,
         scalars[MAL_SC_Q_TAKEN] = s[2] / (msum * n_agents);
         scalars[MAL_SC_TARGET] = s[3] / (msum * n_agents);
         reinterpret_cast<int *>(scalars)[MAL_SC_MASK_COUNT] = (int)(s[5] + 0.5f);
+        for (int k = 0; k < MIX_NSTAT; ++k) scalars[MAL_SC_RAW0 + k] = s[k];
     }
 }
 
@@ -854,12 +855,13 @@ struct GradReduceArgs {
     float *grad;
     float *norm_part;        // [gridDim.x]
     const float *scalars;    // mask sum
+    int unnormalized;        // leave out the 1/mask.sum() factor (data-parallel mode)
 };
 
 __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ GradReduceArgs a) {
     __shared__ float s_sq[8];
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const float inv = 1.0f / a.scalars[MAL_SC_MASK_SUM];
+    const float inv = a.unnormalized ? 1.0f : 1.0f / a.scalars[MAL_SC_MASK_SUM];
     float v = 0.0f;
     if (p < a.total) {
         int si = 0;
@@ -892,10 +894,11 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ Gra
 }
 
 // sum of squares of an arbitrary flat gradient (used when mal_clip_rmsprop is called stand-alone)
-__global__ void __launch_bounds__(256) k_sumsq(const float *g, int64_t n, float *norm_part) {
+__global__ void __launch_bounds__(256) k_sumsq(const float *g, int64_t n, float *norm_part, const float *denominator) {
     __shared__ float s_sq[8];
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    float v = p < n ? g[p] : 0.0f;
+    const float inv = denominator ? 1.0f / denominator[0] : 1.0f;
+    float v = p < n ? g[p] * inv : 0.0f;
     float sq = warp_sum(v * v);
     if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
     __syncthreads();
@@ -911,7 +914,8 @@ __global__ void __launch_bounds__(256) k_sumsq(const float *g, int64_t n, float 
 // =============================================================================================
 __global__ void __launch_bounds__(256) k_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer,
                                                       float *grad, float *sq, const float *norm_part, int n_part,
-                                                      float lr, float alpha, float eps, float clip, float *scalars) {
+                                                      float lr, float alpha, float eps, float clip, float *scalars,
+                                                      const float *denominator) {
     __shared__ float s_red[8];
     __shared__ float s_coef;
     // every block recomputes the global norm from the per-block partials in the same fixed order
@@ -933,7 +937,7 @@ __global__ void __launch_bounds__(256) k_clip_rmsprop(float *agent, int64_t n_ag
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= n_agent + n_mixer) return;
     float *param = p < n_agent ? agent + p : mixer + (p - n_agent);
-    const float gv = grad[p] * coef;
+    const float gv = grad[p] * (denominator ? 1.0f / denominator[0] : 1.0f) * coef;
     grad[p] = gv;   // clip_grad_norm_ scales .grad in place
     const float v = alpha * sq[p] + (1.0f - alpha) * gv * gv;
     sq[p] = v;

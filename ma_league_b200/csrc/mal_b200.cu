@@ -910,6 +910,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         a.grad = grad;
         a.norm_part = parts + pl.norm;
         a.scalars = F(plan->scalars);
+        a.unnormalized = cfg->unnormalized ? 1 : 0;
         { ProfScope _ps("k_grad_reduce", st); k_grad_reduce<<<pl.nblk_norm, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_grad_reduce");
     }
@@ -918,32 +919,33 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
 
 static int launch_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                                float *sq, const float *norm_part, int n_part, float lr, float alpha, float eps,
-                               float clip, float *scalars, cudaStream_t st) {
+                               float clip, float *scalars, const float *denominator, cudaStream_t st) {
     const int64_t P = n_agent + n_mixer;
     { ProfScope _ps("k_clip_rmsprop", st); k_clip_rmsprop<<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
-                                                                n_part, lr, alpha, eps, clip, scalars); }
+                                                                n_part, lr, alpha, eps, clip, scalars, denominator); }
     MAL_LAUNCH_CHECK("k_clip_rmsprop");
     return 0;
 }
 
 extern "C" int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                                 float *square_avg, float lr, float alpha, float eps, float clip, float *scalars,
-                                float *scratch, void *stream) {
+                                float *scratch, const float *denominator, void *stream) {
     MAL_REQUIRE(agent && grad && square_avg && scalars && scratch && n_agent > 0 && n_mixer >= 0,
                 "mal_clip_rmsprop: bad arguments (scratch needs ceil(P/256) floats)");
     MAL_REQUIRE(n_mixer == 0 || mixer, "mal_clip_rmsprop: mixer buffer missing");
     const int64_t P = n_agent + n_mixer;
     const int nb = (int)ceil_div64(P, 256);
-    { ProfScope _ps("k_sumsq", (cudaStream_t)stream); k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch); }
+    { ProfScope _ps("k_sumsq", (cudaStream_t)stream); k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch, denominator); }
     MAL_LAUNCH_CHECK("k_sumsq");
     return launch_clip_rmsprop(agent, n_agent, mixer, n_mixer, grad, square_avg, scratch, nb, lr, alpha, eps, clip,
-                               scalars, (cudaStream_t)stream);
+                               scalars, denominator, (cudaStream_t)stream);
 }
 
 extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
                                 float *agent, const float *target_agent, float *mixer, const float *target_mixer,
                                 void *workspace, float *grad, float *square_avg, void *stream) {
     MAL_REQUIRE(square_avg, "mal_learner_step: square_avg missing");
+    MAL_REQUIRE(!cfg || !cfg->unnormalized, "mal_learner_step: unnormalized (data-parallel) mode needs the split calls");
     if (int rc = mal_learner_forward(batch, cfg, plan, agent, target_agent, mixer, target_mixer, workspace, stream)) return rc;
     if (int rc = mal_learner_backward(batch, cfg, plan, agent, mixer, workspace, grad, stream)) return rc;
     Dims d;
@@ -956,7 +958,7 @@ extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_
     float *scalars = reinterpret_cast<float *>(ws + plan->scalars);
     return launch_clip_rmsprop(agent, plan->n_agent_params, mixer, plan->n_mixer_params, grad, square_avg,
                                parts + pl.norm, pl.nblk_norm, cfg->lr, cfg->alpha, cfg->eps, cfg->clip, scalars,
-                               (cudaStream_t)stream);
+                               nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int mal_copy_f32(float *dst, const float *src, int64_t n, void *stream) {

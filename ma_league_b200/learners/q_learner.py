@@ -16,6 +16,22 @@ from ..modules.mixers.vdn import VDNMixer
 from .learner import Learner
 
 
+DP_RAW = 6     # raw sums written by k_stats_finalize at scalars[SC_RAW0:]: sum mtd^2, sum|mtd|, sum q_tot*m,
+DP_TAIL = 8    # sum targets*m, sum m, count(m != 0); the tail is padded to 8 floats
+
+
+def global_stats(raw, n_agents, scalars=None):
+    """Logged statistics of q_learner.py:117-124 from the all-reduced raw sums (host tensor of >= DP_RAW floats)."""
+    out = th.zeros(8) if scalars is None else scalars.clone()
+    msum = float(raw[4])
+    out[nat.SC_MASK_SUM] = msum
+    out[nat.SC_LOSS] = float(raw[0]) / msum
+    out[nat.SC_TD_ABS] = float(raw[1]) / msum
+    out[nat.SC_Q_TAKEN] = float(raw[2]) / (msum * n_agents)
+    out[nat.SC_TARGET] = float(raw[3]) / (msum * n_agents)
+    return out
+
+
 class QLearner(Learner):
     def __init__(self, mac, scheme, logger, args, name=None):
         super().__init__(mac, scheme, logger, args, name)
@@ -51,7 +67,15 @@ class QLearner(Learner):
         qm = isinstance(self.mixer, QMixer)
         return nat.LearnerCfg(self._mixer_kind(), int(bool(a.double_q)), self.mixer.embed_dim if qm else 0,
                               self.mixer.hypernet_embed if qm else 0, a.gamma, a.lr, a.optim_alpha, a.optim_eps,
-                              a.grad_norm_clip, int(self.save_q))
+                              a.grad_norm_clip, int(self.save_q), int(self._dp_world() > 1))
+
+    def _dp_world(self):
+        """>1 when `args.data_parallel` is set and a process group exists: the batch given to train() is this rank's
+        shard of the global batch."""
+        if not getattr(self.args, "data_parallel", False):
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
     def _batch_struct(self, batch):
         obs = nat.require_cuda(batch["obs"], "batch")
@@ -93,7 +117,10 @@ class QLearner(Learner):
                 (flats["mixer"].numel() if flats["mixer"] is not None else 0) != self._plan.n_mixer_params:
             raise nat.MalError("parameter count mismatch between the modules and the kernel layout")
         if self._grad is None or self._grad.numel() != n_total or self._grad.device != dev:
-            self._grad = th.zeros(n_total, dtype=th.float32, device=dev)
+            # + DP_TAIL floats: the rank's raw statistic sums ride in the same all-reduce as the gradient
+            self._grad_store = th.zeros(n_total + DP_TAIL, dtype=th.float32, device=dev)
+            self._grad = self._grad_store[:n_total]
+            self._dp_scratch = th.empty((n_total + 255) // 256, dtype=th.float32, device=dev)
             self._grad_views = None
         return bs, cfg, flats
 
@@ -109,12 +136,16 @@ class QLearner(Learner):
         if self.optimiser is None:
             raise nat.MalError("call build_optimizer() before train() (ma_experiment.py:61)")
         dev = batch["obs"].device
-        with nat.on_device(dev):
-            nat.check(nat.lib().mal_learner_step(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
-                                                 nat.ptr(f["tagent"]), nat.ptr(f["mixer"]), nat.ptr(f["tmixer"]),
-                                                 nat.ptr(self._ws), nat.ptr(self._grad),
-                                                 nat.ptr(self.optimiser.flat_sq), nat.current_stream(dev)),
-                      "mal_learner_step")
+        dp = cfg.unnormalized != 0
+        if dp:
+            self._train_data_parallel(bs, cfg, f, dev)
+        else:
+            with nat.on_device(dev):
+                nat.check(nat.lib().mal_learner_step(C.byref(bs), C.byref(cfg), C.byref(self._plan),
+                                                     nat.ptr(f["agent"]), nat.ptr(f["tagent"]), nat.ptr(f["mixer"]),
+                                                     nat.ptr(f["tmixer"]), nat.ptr(self._ws), nat.ptr(self._grad),
+                                                     nat.ptr(self.optimiser.flat_sq), nat.current_stream(dev)),
+                          "mal_learner_step")
         self.optimiser._steps += 1
         if getattr(self, "_grad_views", None) is None:   # p.grad = views of the flat (clipped) gradient, bound once
             params = self.parameters()
@@ -128,16 +159,48 @@ class QLearner(Learner):
             self.last_target_update_episode = episode_num
 
         sc = self.scalars()
-        self.mac.update_trained_steps(sc[nat.SC_MASK_COUNT:nat.SC_MASK_COUNT + 1].view(th.int32))
+        if dp:
+            n_total = self._grad.numel()
+            self.mac.update_trained_steps(self._grad_store[n_total + 5:n_total + 6].round())   # global count
+        else:
+            self.mac.update_trained_steps(sc[nat.SC_MASK_COUNT:nat.SC_MASK_COUNT + 1].view(th.int32))
 
         if t_env - self.log_stats_t >= self.args.learner_log_interval:
             h = sc[:8].cpu()                            # the only device->host sync of the step
+            if dp:
+                h = global_stats(self._grad_store[self._grad.numel():].cpu(), self.args.n_agents, h)
             self.logger.log_stat(self.name + "loss", float(h[nat.SC_LOSS]), t_env)
             self.logger.log_stat(self.name + "grad_norm", h[nat.SC_GRAD_NORM].numpy(), t_env)
             self.logger.log_stat(self.name + "td_error_abs", float(h[nat.SC_TD_ABS]), t_env)
             self.logger.log_stat(self.name + "q_taken_mean", float(h[nat.SC_Q_TAKEN]), t_env)
             self.logger.log_stat(self.name + "target_mean", float(h[nat.SC_TARGET]), t_env)
             self.log_stats_t = t_env
+
+    def _train_data_parallel(self, bs, cfg, f, dev):
+        """Config 5: every rank back-propagates the UN-normalised sum over its batch shard, one
+        all-reduce(sum) carries the flat gradient plus the raw statistic sums (incl. mask.sum()), then every rank
+        divides by the global mask sum and applies the identical clip + RMSprop, which reproduces
+        `loss = sum(masked_td^2) / mask.sum()` of q_learner.py:98 over the global batch."""
+        import torch.distributed as dist
+        lib, st = nat.lib(), nat.current_stream(dev)
+        n_total = self._grad.numel()
+        with nat.on_device(dev):
+            nat.check(lib.mal_learner_forward(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
+                                              nat.ptr(f["tagent"]), nat.ptr(f["mixer"]), nat.ptr(f["tmixer"]),
+                                              nat.ptr(self._ws), st), "mal_learner_forward")
+            nat.check(lib.mal_learner_backward(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
+                                               nat.ptr(f["mixer"]), nat.ptr(self._ws), nat.ptr(self._grad), st),
+                      "mal_learner_backward")
+        self._grad_store[n_total:n_total + DP_RAW].copy_(self.scalars()[nat.SC_RAW0:nat.SC_RAW0 + DP_RAW])
+        dist.all_reduce(self._grad_store, op=dist.ReduceOp.SUM)
+        denom = self._grad_store[n_total + 4:]            # global mask.sum()
+        a = self.args
+        with nat.on_device(dev):
+            nat.check(lib.mal_clip_rmsprop(nat.ptr(f["agent"]), self._plan.n_agent_params, nat.ptr(f["mixer"]),
+                                           self._plan.n_mixer_params, nat.ptr(self._grad),
+                                           nat.ptr(self.optimiser.flat_sq), a.lr, a.optim_alpha, a.optim_eps,
+                                           a.grad_norm_clip, nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
+                                           nat.ptr(denom), st), "mal_clip_rmsprop")
 
     def forward_only(self, batch):
         """Forward half of train() (q_learner.py:36-98); intermediates stay in the workspace (tests, debugging)."""
