@@ -324,122 +324,112 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
 }
 
 // =============================================================================================
-// GRU recurrence, forward.  grid (ceil(R/RT), nets), 192 threads: thread j owns gate row j of W_hh (64 registers).
-// The per-step input-gate rows gi[t] (RT x 192 floats, contiguous) are fed by the bulk-copy engine (cp.async.bulk)
-// into a DEPTH-deep shared-memory ring several timesteps ahead, so no global-memory latency sits on the serial chain.
+// GRU recurrence: argument blocks
 // =============================================================================================
 struct GruFwdArgs {
     const float *params[2];    // online, target (flat agent buffers)
     const float *gi[2];        // [TT*R,192]
     float *hout[2];            // [TT*R,64]
-    float *gates;              // [TT*R,256] online only: r|z|n|ghn
+    float *gates;              // [TT*R,64,4] online only: (r, z, n, gh_n) per unit
     int TT, R, d_in, n_actions;
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+// MUFU-only forms (ex2.approx + rcp.approx): ~2^-22 relative error on sigmoid, ~1.5e-7 absolute on tanh
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_mufu(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_mufu(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 
-template <int RT>
-__global__ void __launch_bounds__(192, 1) k_gru_fwd(GruFwdArgs a) {
-    constexpr int ITEMS = RT * HID;
-    constexpr int IPT = (ITEMS + 191) / 192;
-    constexpr int DEPTH = RT >= 8 ? 4 : 8;
-    __shared__ __align__(128) float gi_s[DEPTH][RT * G3];
-    __shared__ __align__(16) float h_s[RT * HID];
-    __shared__ float rz_s[RT * 2 * HID];     // sigmoid(r), sigmoid(z) per row
-    __shared__ float ghn_s[RT * HID];        // W_hn h + b_hn per row
-    __shared__ __align__(8) uint64_t bars[DEPTH];
-    const int tid = threadIdx.x, net = blockIdx.y;
-    const int g = tid >> 6;                  // 0: reset gate rows, 1: update gate rows, 2: candidate rows
-    const int r0 = blockIdx.x * RT;
+// =============================================================================================
+// GRU recurrence, forward, v4: ONE batch row per CTA, 64 threads (thread = hidden unit), several CTAs per SM.
+// grid (R, nets).  Thread i keeps the three gate rows r/z/n of W_hh for unit i in registers (192 weights), so a
+// timestep is: 16 broadcast LDS.128 of h_{t-1}, 192 FMAs, both sigmoids + the candidate tanh + the blend (h_{t-1} of
+// the unit stays in a register), one h store, one float4 store of the saved gates, and ONE barrier between the two
+// warps (h is double-buffered in shared memory).  No shuffles, no redundant gate math: the kernel is bound by
+// instruction issue on the SMs that host ceil(rows / SMs) rows, so the instruction count per row-step is what counts.
+// The gi[t] terms are per-thread cp.async copies running PF steps ahead (one commit group per timestep).
+// Saved gates layout (private to k_gru_fwd4 / k_gru_bwd4): [m][unit][r, z, n, gh_n].
+// =============================================================================================
+template <int DBG = 0>   // DBG (probe only): 1 no global stores, 4 cheap gate math, 8 no matvec, 128 libm expf/tanhf gate math
+__global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
+    constexpr int PF = 8;
+    __shared__ __align__(16) float h_s[2][HID];
+    __shared__ float st_s[PF][3][HID];
+    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
-    const float *P = a.params[net];
-    const float *gi = a.gi[net];
-    float *hout = a.hout[net];
-    float *gates = net == 0 ? a.gates : nullptr;
-    const int nrows = (a.R - r0) < RT ? (a.R - r0) : RT;
-    const uint32_t bytes = (uint32_t)nrows * G3 * 4;
+    const float *P = net ? a.params[1] : a.params[0];
+    const float *gi = net ? a.gi[1] : a.gi[0];
+    float *hout = net ? a.hout[1] : a.hout[0];
+    float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
 
-    for (int idx = tid; idx < DEPTH * RT * G3; idx += 192) (&gi_s[0][0])[idx] = 0.0f;   // rows past R stay zero
-    for (int idx = tid; idx < ITEMS; idx += 192) h_s[idx] = 0.0f;                       // init_hidden: zeros
-    if (tid == 0) {
-        for (int s = 0; s < DEPTH; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    h_s[0][i] = 0.0f; h_s[1][i] = 0.0f;          // init_hidden: zeros
+    float w[3][HID];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + i) * HID);
+#pragma unroll
+        for (int u = 0; u < HID / 4; ++u) {
+            const float4 v = __ldg(wr + u);
+            w[g][4 * u] = v.x; w[g][4 * u + 1] = v.y; w[g][4 * u + 2] = v.z; w[g][4 * u + 3] = v.w;
+        }
     }
+    const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
+    const int64_t tstride = (int64_t)a.R * G3;
+    const float *p_g = gi + (int64_t)row * G3 + i;
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        if (p < a.TT) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], p_g + p * tstride + g * HID);
+        }
+        cp_async_commit();
+    }
+    float hprev = 0.0f;
     __syncthreads();
-    auto issue = [&](int t) {
-        const int s = t % DEPTH;
-        mbar_expect_tx(&bars[s], bytes);
-        bulk_g2s(gi_s[s], gi + ((int64_t)t * a.R + r0) * G3, bytes, &bars[s]);
-    };
-    if (tid == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");
-        for (int t = 0; t < DEPTH && t < a.TT; ++t) issue(t);
-    }
 
-    float w[HID];
-    {
-        const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)tid * HID);
+    for (int t0 = 0; t0 < a.TT; t0 += 2) {
 #pragma unroll
-        for (int k4 = 0; k4 < HID / 4; ++k4) {
-            float4 v = __ldg(wr + k4);
-            w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w;
-        }
-    }
-    const float bj = __ldg(P + L.b_hh + tid);
-
-    for (int t = 0; t < a.TT; ++t) {
-        const int slot = t % DEPTH;
-        // phase 1: gh[r][j] = b_hh[j] + W_hh[j,:] . h[r,:]; reset/update threads finish their gate right away
-        float acc[RT];
+        for (int p = 0; p < 2; ++p) {
+            const int t = t0 + p;
+            if (t >= a.TT) break;
+            const int buf = p;                   // == t & 1
+            const int slot = t % PF;
+            cp_async_wait<PF - 1>();             // this thread's group of step t has landed
+            const float g_r = st_s[slot][0][i], g_z = st_s[slot][1][i], g_n = st_s[slot][2][i];
+            if (t + PF < a.TT) {
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            float4 hv[HID / 4];
-            const float4 *hp = reinterpret_cast<const float4 *>(h_s + r * HID);
-#pragma unroll
-            for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = hp[k4];
-            float acc0 = bj, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-#pragma unroll
-            for (int k4 = 0; k4 < HID / 4; ++k4) {
-                acc0 = fmaf(w[4 * k4], hv[k4].x, acc0);
-                acc1 = fmaf(w[4 * k4 + 1], hv[k4].y, acc1);
-                acc2 = fmaf(w[4 * k4 + 2], hv[k4].z, acc2);
-                acc3 = fmaf(w[4 * k4 + 3], hv[k4].w, acc3);
+                for (int g = 0; g < 3; ++g) cp_async4(&st_s[slot][g][i], p_g + (int64_t)(t + PF) * tstride + g * HID);
             }
-            acc[r] = (acc0 + acc1) + (acc2 + acc3);
-        }
-        mbar_wait(&bars[slot], (uint32_t)((t / DEPTH) & 1));   // gi[t] staged by the copy engine (long since)
-        if (g < 2) {
+            cp_async_commit();
+            const float4 *hp = reinterpret_cast<const float4 *>(h_s[buf]);
+            float s[3][2] = {{g_r + b_r, 0.0f}, {g_z + b_z, 0.0f}, {b_n, 0.0f}};
 #pragma unroll
-            for (int r = 0; r < RT; ++r) rz_s[r * 2 * HID + tid] = sigmoid_fast(gi_s[slot][r * G3 + tid] + acc[r]);
-        } else {
+            for (int u = 0; u < ((DBG & 8) ? 2 : HID / 4); ++u) {
+                const float4 hv = hp[u];
 #pragma unroll
-            for (int r = 0; r < RT; ++r) ghn_s[r * HID + (tid - 2 * HID)] = acc[r];
-        }
-        __syncthreads();
-        // phase 2: candidate + blend per (row, hidden unit)
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int item = tid + 192 * q;
-            if (item < ITEMS) {
-                const int r = item >> 6, i = item & 63, row = r0 + r;
-                const float rr = rz_s[r * 2 * HID + i], zz = rz_s[r * 2 * HID + HID + i];
-                const float ghn = ghn_s[item];
-                const float nn = tanhf(gi_s[slot][r * G3 + 2 * HID + i] + rr * ghn);
-                const float hp = h_s[item];
-                const float hn = nn + zz * (hp - nn);
-                h_s[item] = hn;
-                if (row < a.R) {
-                    const int64_t m = (int64_t)t * a.R + row;
-                    hout[m * HID + i] = hn;
-                    if (gates) {
-                        float *gp = gates + m * 4 * HID;
-                        gp[i] = rr; gp[HID + i] = zz; gp[2 * HID + i] = nn; gp[3 * HID + i] = ghn;
-                    }
+                for (int g = 0; g < 3; ++g) {
+                    s[g][0] = fmaf(w[g][4 * u], hv.x, s[g][0]);
+                    s[g][1] = fmaf(w[g][4 * u + 1], hv.y, s[g][1]);
+                    s[g][0] = fmaf(w[g][4 * u + 2], hv.z, s[g][0]);
+                    s[g][1] = fmaf(w[g][4 * u + 3], hv.w, s[g][1]);
                 }
             }
+            const float xr = s[0][0] + s[0][1], xz = s[1][0] + s[1][1], ghn = s[2][0] + s[2][1];
+            const float rr = (DBG & 4) ? 0.5f * xr : (DBG & 128) ? sigmoid_fast(xr) : sigmoid_mufu(xr);
+            const float zz = (DBG & 4) ? 0.5f * xz : (DBG & 128) ? sigmoid_fast(xz) : sigmoid_mufu(xz);
+            const float xn = g_n + rr * ghn;
+            const float nn = (DBG & 4) ? 0.1f * xn : (DBG & 128) ? tanhf(xn) : tanh_mufu(xn);
+            const float hn = nn + zz * (hprev - nn);
+            hprev = hn;
+            h_s[buf ^ 1][i] = hn;
+            if (!(DBG & 1)) {
+                const int64_t m = (int64_t)t * a.R + row;
+                hout[m * HID + i] = hn;
+                if (gates) gates[m * HID + i] = make_float4(rr, zz, nn, ghn);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0 && t + DEPTH < a.TT) issue(t + DEPTH);   // slot t%DEPTH is free again
     }
 }
 
@@ -720,119 +710,89 @@ __global__ void __launch_bounds__(256) k_stats_finalize(const float *part_stats,
     }
 }
 
-// =============================================================================================
-// GRU recurrence, backward (BPTT).  grid ceil(R/RT), 192 threads: thread (g,k) owns W_hh[g*64 + :, k].
-// Saved gates, h_{t-1} and the fc2/gather injection of step t arrive through a cp.async.bulk ring.
-// =============================================================================================
 struct GruBwdArgs {
     const float *params;       // online agent
     const float *hout;         // [TT*R,64]
-    const float *gates;        // [TT*R,256]
+    const float *gates;        // [TT*R,64,4]
     const float *dh_head;      // [TT*R,64] (rows of t < TT-1 are valid)
     float *d_g;                // [TT*R,256]: d gi_r | d gi_z | d gi_n | d gh_n
     int TT, R, d_in, n_actions;
 };
 
-template <int RT>
-__global__ void __launch_bounds__(192, 1) k_gru_bwd(GruBwdArgs a) {
-    constexpr int ITEMS = RT * HID;
-    constexpr int IPT = (ITEMS + 191) / 192;
-    constexpr int DEPTH = 16 / RT;
-    constexpr int SLOT = RT * (4 * HID + HID + HID);   // gates | h_prev | dh_head, floats
-    __shared__ __align__(128) float ring[DEPTH][SLOT];
-    __shared__ __align__(16) float dgh_s[RT * G3];
-    __shared__ float part_s[RT * G3];          // [r][g][k]
-    __shared__ __align__(8) uint64_t bars[DEPTH];
-    const int tid = threadIdx.x;
-    const int r0 = blockIdx.x * RT;
+// =============================================================================================
+// GRU recurrence, backward, v4 (same one-row-per-CTA, thread = unit layout as k_gru_fwd4).  grid R, 64 threads.
+// Thread k keeps column k of W_hh (192 weights) in registers:  d h_{t-1}[k] = d h_t[k] z[k] + sum_j d gh[j] W_hh[j][k]
+// is 48 broadcast LDS.128 + 192 FMAs per timestep, then the element-wise gate derivatives of unit k, 3 shared stores
+// (next step's d gh), 4 global stores (the d_g row) and one barrier between the two warps.
+// Saved gates, h_{t-1} and the fc2/gather injection stream through a PF-deep per-thread cp.async ring.
+// =============================================================================================
+__global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
+    constexpr int PF = 8;
+    __shared__ __align__(16) float dg_s[2][G3];   // d gi_r | d gi_z | d gh_n of the previous step
+    __shared__ __align__(16) float4 g4_s[PF][HID];
+    __shared__ float hp_s[PF][HID], dh_s[PF][HID];
+    const int k = threadIdx.x, row = blockIdx.x;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
     const int T = a.TT - 1;
-    const int g = tid >> 6, k = tid & 63;
-    const int nrows = (a.R - r0) < RT ? (a.R - r0) : RT;
 
-    for (int idx = tid; idx < DEPTH * SLOT; idx += 192) (&ring[0][0])[idx] = 0.0f;
-    for (int idx = tid; idx < RT * G3; idx += 192) part_s[idx] = 0.0f;
-    if (tid == 0) {
-        for (int s = 0; s < DEPTH; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // step index i counts down: i = 0 is t = TT-1
-    auto issue = [&](int i) {
+    for (int idx = k; idx < 2 * G3; idx += HID) (&dg_s[0][0])[idx] = 0.0f;
+    float wT[G3];   // wT[j] = W_hh[j][k]
+#pragma unroll
+    for (int j = 0; j < G3; ++j) wT[j] = __ldg(a.params + L.w_hh + (int64_t)j * HID + k);
+
+    const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
+    auto fetch = [&](int i, int slot) {          // step i <-> t = TT-1-i
         const int t = a.TT - 1 - i;
-        const int s = i % DEPTH;
-        const int64_t m = (int64_t)t * a.R + r0;
-        uint32_t bytes = (uint32_t)nrows * 4 * HID * 4;
-        if (t > 0) bytes += (uint32_t)nrows * HID * 4;
-        if (t < T) bytes += (uint32_t)nrows * HID * 4;
-        mbar_expect_tx(&bars[s], bytes);
-        bulk_g2s(ring[s], a.gates + m * 4 * HID, (uint32_t)nrows * 4 * HID * 4, &bars[s]);
-        if (t > 0) bulk_g2s(ring[s] + RT * 4 * HID, a.hout + (m - a.R) * HID, (uint32_t)nrows * HID * 4, &bars[s]);
-        if (t < T) bulk_g2s(ring[s] + RT * 5 * HID, a.dh_head + m * HID, (uint32_t)nrows * HID * 4, &bars[s]);
+        const int64_t m = (int64_t)t * a.R + row;
+        cp_async16(&g4_s[slot][k], gates4 + m * HID + k);
+        cp_async4(&hp_s[slot][k], a.hout + (t > 0 ? (m - a.R) * HID + k : 0), t > 0 ? 4 : 0);    // h_{-1} = 0
+        cp_async4(&dh_s[slot][k], a.dh_head + (t < T ? m * HID + k : 0), t < T ? 4 : 0);          // no q at t = T
     };
-    if (tid == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");
-        for (int i = 0; i < DEPTH && i < a.TT; ++i) issue(i);
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        if (p < a.TT) fetch(p, p);
+        cp_async_commit();
     }
+    float carry = 0.0f;
+    __syncthreads();
 
-    float wT[HID];   // W_hh[g*64 + j][k], j = 0..63
+    for (int i0 = 0; i0 < a.TT; i0 += 2) {
 #pragma unroll
-    for (int j = 0; j < HID; ++j) wT[j] = __ldg(a.params + L.w_hh + (int64_t)(g * HID + j) * HID + k);
-    float carry[IPT];
+        for (int p = 0; p < 2; ++p) {
+            const int i = i0 + p;
+            if (i >= a.TT) break;
+            const int buf = p;
+            const int slot = i % PF;
+            cp_async_wait<PF - 1>();
+            const float4 g4 = g4_s[slot][k];
+            const float hp = hp_s[slot][k], dhh = dh_s[slot][k];
+            if (i + PF < a.TT) fetch(i + PF, slot);
+            cp_async_commit();
+            const float4 *dp = reinterpret_cast<const float4 *>(dg_s[buf]);
+            float s0 = carry + dhh, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-    for (int q = 0; q < IPT; ++q) carry[q] = 0.0f;
-
-    for (int i = 0; i < a.TT; ++i) {
-        const int t = a.TT - 1 - i;
-        const int slot = i % DEPTH;
-        mbar_wait(&bars[slot], (uint32_t)((i / DEPTH) & 1));
-        const float *sg = ring[slot];
-        // phase A: d h_t -> d gates
-#pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            int item = tid + 192 * q;
-            if (item < ITEMS) {
-                int r = item >> 6, ii = item & 63, row = r0 + r;
-                const float *ps = part_s + r * G3;
-                const float *gp = sg + r * 4 * HID;
-                const float hp = t > 0 ? sg[RT * 4 * HID + r * HID + ii] : 0.0f;
-                const float dhh = t < T ? sg[RT * 5 * HID + r * HID + ii] : 0.0f;
-                float dh = carry[q] + ps[ii] + ps[HID + ii] + ps[2 * HID + ii] + dhh;
-                const float rr = gp[ii], zz = gp[HID + ii], nn = gp[2 * HID + ii], ghn = gp[3 * HID + ii];
-                float dn = dh * (1.0f - zz);
-                float dz = dh * (hp - nn);
-                float dnp = dn * (1.0f - nn * nn);
-                float dzp = dz * zz * (1.0f - zz);
-                float drp = dnp * ghn * rr * (1.0f - rr);
-                float dghn = dnp * rr;
-                carry[q] = dh * zz;
-                dgh_s[r * G3 + ii] = drp; dgh_s[r * G3 + HID + ii] = dzp; dgh_s[r * G3 + 2 * HID + ii] = dghn;
-                if (row < a.R) {
-                    float *dp = a.d_g + ((int64_t)t * a.R + row) * 4 * HID;
-                    dp[ii] = drp; dp[HID + ii] = dzp; dp[2 * HID + ii] = dnp; dp[3 * HID + ii] = dghn;
-                }
+            for (int u = 0; u < G3 / 4; ++u) {
+                const float4 d = dp[u];
+                s0 = fmaf(wT[4 * u], d.x, s0);
+                s1 = fmaf(wT[4 * u + 1], d.y, s1);
+                s2 = fmaf(wT[4 * u + 2], d.z, s2);
+                s3 = fmaf(wT[4 * u + 3], d.w, s3);
             }
+            const float dh = (s0 + s1) + (s2 + s3);
+            const float rr = g4.x, zz = g4.y, nn = g4.z, ghn = g4.w;
+            const float dn = dh * (1.0f - zz);
+            const float dz = dh * (hp - nn);
+            const float dnp = dn * (1.0f - nn * nn);
+            const float dzp = dz * zz * (1.0f - zz);
+            const float drp = dnp * ghn * rr * (1.0f - rr);
+            const float dghn = dnp * rr;
+            carry = dh * zz;
+            float *sm = dg_s[buf ^ 1];
+            sm[k] = drp; sm[HID + k] = dzp; sm[2 * HID + k] = dghn;
+            float *dg = a.d_g + ((int64_t)(a.TT - 1 - i) * a.R + row) * 4 * HID + k;
+            dg[0] = drp; dg[HID] = dzp; dg[2 * HID] = dnp; dg[3 * HID] = dghn;
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0 && i + DEPTH < a.TT) issue(i + DEPTH);   // every thread is past its reads of this slot
-        // phase B: part[r][g][k] = sum_j dgh[r][g*64+j] * W_hh[g*64+j][k]
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const float4 *dp = reinterpret_cast<const float4 *>(dgh_s + r * G3 + g * HID);
-            float4 dv[HID / 4];
-#pragma unroll
-            for (int j4 = 0; j4 < HID / 4; ++j4) dv[j4] = dp[j4];
-            float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-#pragma unroll
-            for (int j4 = 0; j4 < HID / 4; ++j4) {
-                acc0 = fmaf(wT[4 * j4], dv[j4].x, acc0);
-                acc1 = fmaf(wT[4 * j4 + 1], dv[j4].y, acc1);
-                acc2 = fmaf(wT[4 * j4 + 2], dv[j4].z, acc2);
-                acc3 = fmaf(wT[4 * j4 + 3], dv[j4].w, acc3);
-            }
-            part_s[r * G3 + tid] = (acc0 + acc1) + (acc2 + acc3);
-        }
-        __syncthreads();
     }
 }
 

@@ -513,24 +513,13 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
     return p;
 }
 
-template <int RT>
 static void launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st) {
-    dim3 grid((a.R + RT - 1) / RT, nets);
     ProfScope _ps("k_gru_fwd", st);
-    k_gru_fwd<RT><<<grid, 192, 0, st>>>(a);
+    k_gru_fwd4<0><<<dim3(a.R, nets), HID, 0, st>>>(a);      // one batch row per CTA, thread = hidden unit
 }
-template <int RT>
 static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st) {
     ProfScope _ps("k_gru_bwd", st);
-    k_gru_bwd<RT><<<(a.R + RT - 1) / RT, 192, 0, st>>>(a);
-}
-static int pick_rt(int rows, int nets, int sms) {
-    // smallest rows-per-CTA with at most one CTA per SM (the recurrences are latency-bound: a second CTA on an SM
-    // stretches every timestep); larger problems queue in waves of 8-row CTAs
-    const int cand[6] = {1, 2, 3, 4, 6, 8};
-    for (int i = 0; i < 6; ++i)
-        if ((int64_t)((rows + cand[i] - 1) / cand[i]) * nets <= sms) return cand[i];
-    return 8;
+    k_gru_bwd4<<<a.R, HID, 0, st>>>(a);
 }
 
 extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
@@ -585,14 +574,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         GruFwdArgs a;
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        switch (pick_rt(d.R, 2, sms)) {
-            case 1: launch_gru_fwd<1>(a, 2, st); break;
-            case 2: launch_gru_fwd<2>(a, 2, st); break;
-            case 3: launch_gru_fwd<3>(a, 2, st); break;
-            case 4: launch_gru_fwd<4>(a, 2, st); break;
-            case 6: launch_gru_fwd<6>(a, 2, st); break;
-            default: launch_gru_fwd<8>(a, 2, st); break;
-        }
+        launch_gru_fwd(a, 2, st);
         MAL_LAUNCH_CHECK("k_gru_fwd");
     }
     // q, chosen-action gather, masked double-Q target max                   q_learner.py:52-78
@@ -833,13 +815,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        switch (pick_rt(d.R, 1, sms)) {
-            case 1: launch_gru_bwd<1>(a, st); break;
-            case 2: launch_gru_bwd<2>(a, st); break;
-            case 4: launch_gru_bwd<4>(a, st); break;
-            case 8: launch_gru_bwd<8>(a, st); break;
-            default: launch_gru_bwd<4>(a, st); break;   // 3 -> 4, 6 -> (two waves of) 4: ring depth is 16/RT
-        }
+        launch_gru_bwd(a, st);
         MAL_LAUNCH_CHECK("k_gru_bwd");
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads

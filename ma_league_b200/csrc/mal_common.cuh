@@ -168,6 +168,15 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint3
                  "r"(bytes)
                  : "memory");
 }
+// per-thread asynchronous copies (LDGSTS): src_bytes < size zero-fills the rest (src_bytes = 0: pure zero fill)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, int src_bytes = 4) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes = 16) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
