@@ -77,6 +77,7 @@ struct LinProb {
 #define LIN_MAX_PROBS 12
 struct LinGroup {
     int n;
+    int dbg;   // probe switches of k_linear_tc2 (0 in production): 1 no epilogue stores, 2 no A loads, 4 no A split/STS, 8 no MMAs
     LinProb p[LIN_MAX_PROBS];
     BatchView bv;
 };

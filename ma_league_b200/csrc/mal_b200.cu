@@ -416,9 +416,13 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
 }
 
 static int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
+static int g_tc_dbg = 0;
+static int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
 extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
+    if (strcmp(name, "tc_dbg") == 0) { g_tc_dbg = value; return 0; }
+    if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value ? 1 : 0; return 0; }
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
@@ -436,6 +440,18 @@ static int launch_tc_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const c
     return 0;
 }
 
+template <int AK, int EK>
+static int launch_tc2_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag) {
+    static thread_local bool attr = false;
+    if (!attr) {
+        MAL_CUDA(cudaFuncSetAttribute(k_linear_tc2<AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
+        attr = true;
+    }
+    { ProfScope _ps(tag, st); k_linear_tc2<AK, EK><<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(g); }
+    MAL_LAUNCH_CHECK("k_linear_tc2");
+    return 0;
+}
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, const char *tag) {
@@ -445,6 +461,7 @@ static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, c
     LinGroup g;
     g.bv = g0.bv;
     g.n = 0;
+    g.dbg = g_tc_dbg;
     int pieces_total = 0;
     for (int i = 0; i < g0.n; ++i) pieces_total += (g0.p[i].Nout + TC_NMAX - 1) / TC_NMAX;
     const bool split = pieces_total <= LIN_MAX_PROBS;
@@ -476,9 +493,30 @@ static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, c
         ek = e;
     }
     const int64_t tiles = ceil_div64(maxM, TC_M);
+    const int ak = dense ? TCA_VEC_DENSE : (state ? TCA_VEC_STATE : TCA_GENERIC);
+    // the warp-specialised pipeline (one 208 KB CTA per SM) pays off once every SM has a long run of tile-steps; small
+    // launches (B = 32 league matchups) keep the lighter kernel, two CTAs per SM, which also co-runs across streams
+    int64_t steps_total = 0;
+    for (int i = 0; i < g.n; ++i) steps_total += ceil_div64(g.p[i].M, TC_M) * ceil_div64(g.p[i].K, TC_KC);
+    const bool long_run = g_tc_pipelined == 2 || steps_total >= (int64_t)16 * sms;
+    if (split && g_tc_pipelined && long_run && maxM < (1 << 24)) {
+        // software-pipelined kernel: one persistent CTA per SM (208 KB of smem, 512 TMEM columns), never a second wave
+        int64_t per1 = sms / g.n; if (per1 < 1) per1 = 1;
+        dim3 grid1((unsigned)(tiles < per1 ? tiles : per1), g.n);
+        if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid1, st, tag);
+        if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc2_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid1, st, tag);
+        if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid1, st, tag);
+        bool agent_vec = ek == TCE_FC1 && maxM < (1 << 24);   // float4 loads over the obs part of the fc1 input rows
+        for (int i = 0; i < g.n; ++i)
+            agent_vec = agent_vec && g.p[i].a_kind == A_AGENT_IN && (g.bv.OBS & 3) == 0 && (g.bv.obs.sb & 3) == 0 &&
+                        (g.bv.obs.st & 3) == 0 && aligned16(g.bv.obs.ptr);
+        if (agent_vec) return launch_tc2_inst<TCA_AGENT, TCE_FC1>(g, grid1, st, tag);
+        if (ek == TCE_FC1) return launch_tc2_inst<TCA_GENERIC, TCE_FC1>(g, grid1, st, tag);
+        if (ek == TCE_MASKPOS) return launch_tc2_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid1, st, tag);
+        return launch_tc2_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid1, st, tag);
+    }
     int64_t per = ceil_div64((int64_t)2 * sms, g.n); if (per < 1) per = 1;     // persistent: ~two CTAs per SM in total
     dim3 grid((unsigned)(tiles < per ? tiles : per), g.n);
-    const int ak = dense ? TCA_VEC_DENSE : (state ? TCA_VEC_STATE : TCA_GENERIC);
     if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid, st, tag);
     if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid, st, tag);
     if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid, st, tag);
@@ -654,10 +692,15 @@ extern "C" int mal_debug_linear(int32_t M, int32_t K, int32_t Nout, const float 
     memset(&g, 0, sizeof(g));
     g.n = 1;
     g.p[0] = lin(M, K, Nout, A_DENSE, 0, A, lda, W, ldw, w_trans, bias, epi, aux, ld_aux, Y, ldy);
-    const int saved = g_use_tc;
-    g_use_tc = use_tc;
+    // use_tc: 0 fp32 FFMA panel GEMM, 1 tcgen05 kernel picked by the launch heuristic, 2 force the pipelined kernel,
+    //         3 force the one-tile-at-a-time kernel
+    const int saved = g_use_tc, saved_p = g_tc_pipelined;
+    g_use_tc = use_tc ? 1 : 0;
+    if (use_tc == 2) g_tc_pipelined = 2;
+    if (use_tc == 3) g_tc_pipelined = 0;
     int rc = launch_linear(g, M, K, (cudaStream_t)stream, use_tc ? "k_linear_tc:debug" : "k_linear_group:debug");
     g_use_tc = saved;
+    g_tc_pipelined = saved_p;
     return rc;
 }
 

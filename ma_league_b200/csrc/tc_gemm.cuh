@@ -319,3 +319,348 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS));
 }
+
+// =============================================================================================
+// k_linear_tc2: warp-specialised, pipelined version of the panel GEMM (same math and epilogues, Nout <= TC_NMAX).
+// One persistent CTA per SM (288 threads) walks a flat sequence of (m-tile, k-chunk) steps with TWO shared-memory
+// stages (A chunk + W chunk each) and TWO TMEM accumulator sets:
+//   warps 0-3  loaders : wait empty[stage]; split/store the A chunk that was register-prefetched one step earlier
+//                        (+ the W chunk unless the stage already holds it); issue the global loads of the next step;
+//                        fence.proxy.async; arrive full[stage]
+//   warp  8    MMA     : wait full[stage] (and acc_empty[set] on a tile's first chunk); 3 tcgen05.mma per k-step;
+//                        tcgen05.commit -> empty[stage] (and -> acc_full[set] after the tile's last chunk)
+//   warps 4-7  epilogue: wait acc_full[set]; tcgen05.ld; bias / ReLU / ReLU-mask / fc1 epilogue; STG.128;
+//                        arrive acc_empty[set]
+// so global-load latency, the operand split, tensor-core time and the TMEM -> registers -> global epilogue of
+// neighbouring tiles all overlap.
+// =============================================================================================
+#define TC2_STAGE_A (4 * TC_SLAB_A)                 // A hi (2 slabs) + A lo (2 slabs) = 64 KB
+#define TC2_STAGE_W (4 * TC_SLAB_W)                 // 40 KB
+#define TC2_STAGE (TC2_STAGE_A + TC2_STAGE_W)
+#define TC2_SMEM_BYTES (2 * TC2_STAGE)              // 208 KB: one CTA per SM
+#define TC2_TMEM_COLS 512
+#define TC2_ACC_COLS (2 * TC_NMAX)                  // D1 | D2 of one accumulator set
+#define TC2_THREADS 288
+#define TC2_LOADERS 128
+
+enum { TCA_AGENT = 3 };   // fc1 input rows [obs | last-action one-hot] with float4 loads over the obs part
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// x = q*d + r for 0 <= x < 2^24 with a float reciprocal (exact after one correction step)
+__device__ __forceinline__ void fast_divmod(int x, int d, float inv_d, int &q, int &r) {
+    q = __float2int_rz(__int2float_rn(x) * inv_d);
+    r = x - q * d;
+    if (r < 0) { --q; r += d; }
+    if (r >= d) { ++q; r -= d; }
+}
+// hi = RNA-rounded TF32, lo = exact fp32 remainder (the tensor core ignores its 13 low mantissa bits)
+__device__ __forceinline__ void split_store2(uint8_t *hi_base, uint8_t *lo_base, uint32_t off, float4 v) {
+    uint4 h;
+    float4 l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = v.x - __uint_as_float(h.x); l.y = v.y - __uint_as_float(h.y);
+    l.z = v.z - __uint_as_float(h.z); l.w = v.w - __uint_as_float(h.w);
+    *reinterpret_cast<uint4 *>(hi_base + off) = h;
+    *reinterpret_cast<float4 *>(lo_base + off) = l;
+}
+// four consecutive columns of one logical input row through the generic fused loaders (kept out of line)
+__device__ __noinline__ float4 tc_load_row4(int a_kind, const BatchView &bv, const float *A, int64_t lda, int shift,
+                                            int64_t m, int kcol, int K) {
+    const RowSrc rs = resolve_row(a_kind, bv, A, lda, shift, m);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = row_elem(a_kind, bv, rs, kcol);
+    if (kcol + 1 < K) v.y = row_elem(a_kind, bv, rs, kcol + 1);
+    if (kcol + 2 < K) v.z = row_elem(a_kind, bv, rs, kcol + 2);
+    if (kcol + 3 < K) v.w = row_elem(a_kind, bv, rs, kcol + 3);
+    return v;
+}
+
+template <int AK, int EK>
+__global__ void __launch_bounds__(TC2_THREADS, 1) k_linear_tc2(const __grid_constant__ LinGroup g) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], accf_bar[2], acce_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[TC_NMAX + 16];
+    __shared__ __align__(16) float4 epi_s[4][32 * 8];   // per epilogue warp: 32 rows x 32 columns, 16-byte chunks XOR-swizzled
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const LinProb &p = g.p[blockIdx.y];
+    const int n_mtiles = (p.M + TC_M - 1) / TC_M;
+    if ((int)blockIdx.x >= n_mtiles) return;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)TC2_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_bar[i], TC2_LOADERS);
+            mbar_init(&empty_bar[i], 1);
+            mbar_init(&accf_bar[i], 1);
+            mbar_init(&acce_bar[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int K = p.K, M = p.M, Nout = p.Nout;
+    const int nw = (Nout + 15) & ~15;                // MMA N (multiple of 16, <= TC_NMAX)
+    if (tid < TC_NMAX + 16) bias_s[tid] = (p.bias && tid < Nout) ? __ldg(p.bias + tid) : 0.0f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int nkc = (K + TC_KC - 1) / TC_KC;
+    const int n_my = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    const int J = n_my * nkc;
+    const float invR = 1.0f / (float)(g.bv.R > 0 ? g.bv.R : 1), invN = 1.0f / (float)(g.bv.N > 0 ? g.bv.N : 1);
+    const float invT = 1.0f / (float)(g.bv.T > 0 ? g.bv.T : 1);
+
+    if (warp < 4) {
+        // ================================================================== loaders
+        const int c4 = tid & 15, rb = tid >> 4;      // float4 column c4 of the 64-wide chunk, rows rb + 8 i
+        const uint32_t a_slab = (uint32_t)(c4 >> 3) * TC_SLAB_A, w_slab = (uint32_t)(c4 >> 3) * TC_SLAB_W;
+        const uint32_t sw = (uint32_t)(((c4 & 7) ^ rb) << 4);    // (r & 7) == rb for every row of this thread
+        int w_st0 = -1, w_st1 = -1;                  // k-chunk of W currently held by stage 0 / 1
+        float4 pre[16];                              // the A chunk of the next step, in flight
+        auto load_chunk = [&](int j) {
+            const int q = j / nkc, kc = j - q * nkc;
+            const int64_t m0 = (int64_t)((int)blockIdx.x + q * (int)gridDim.x) * TC_M;
+            const int kcol = kc * TC_KC + 4 * c4;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int64_t m = m0 + rb + 8 * i;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < M && kcol < K && !(g.dbg & 2)) {
+                    if (AK == TCA_VEC_DENSE) {
+                        v = __ldg(reinterpret_cast<const float4 *>(p.A + m * p.lda + kcol));
+                    } else if (AK == TCA_VEC_STATE) {
+                        int b, t;
+                        fast_divmod((int)m, g.bv.T, invT, b, t);
+                        v = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(g.bv.state, b, t + p.shift) + kcol));
+                    } else if (AK == TCA_AGENT) {
+                        int t, rr, b, n;
+                        fast_divmod((int)m, g.bv.R, invR, t, rr);
+                        fast_divmod(rr, g.bv.N, invN, b, n);
+                        if (kcol < g.bv.OBS) {       // OBS % 4 == 0 (host-checked): the float4 stays inside the obs row
+                            v = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(g.bv.obs, b, t) + (int64_t)n * g.bv.OBS + kcol));
+                        } else if (t > 0) {
+                            const float *oh = field_ptr<float>(g.bv.onehot, b, t - 1) + (int64_t)n * g.bv.A;
+                            const int a0 = kcol - g.bv.OBS;
+                            if (a0 < g.bv.A) v.x = __ldg(oh + a0);
+                            if (a0 + 1 < g.bv.A) v.y = __ldg(oh + a0 + 1);
+                            if (a0 + 2 < g.bv.A) v.z = __ldg(oh + a0 + 2);
+                            if (a0 + 3 < g.bv.A) v.w = __ldg(oh + a0 + 3);
+                        }
+                    } else {
+                        v = tc_load_row4(p.a_kind, g.bv, p.A, p.lda, p.shift, m, kcol, K);
+                    }
+                }
+                pre[i] = v;
+            }
+        };
+        auto stage_w = [&](uint8_t *W_hi, uint8_t *W_lo, int k0) {
+            if (!p.w_trans && (p.ldw & 3) == 0 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0)) {
+                const int kcol = k0 + 4 * c4;
+                float4 wv[TC_NMAX / 8];
+#pragma unroll
+                for (int i = 0; i < TC_NMAX / 8; ++i) {
+                    const int j = rb + 8 * i;
+                    wv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < Nout && kcol < K) wv[i] = __ldg(reinterpret_cast<const float4 *>(p.W + (int64_t)j * p.ldw + kcol));
+                }
+#pragma unroll
+                for (int i = 0; i < TC_NMAX / 8; ++i) {
+                    const int j = rb + 8 * i;
+                    if (j < nw) split_store2(W_hi, W_lo, w_slab + (uint32_t)j * 128u + sw, wv[i]);
+                }
+            } else if (!p.w_trans) {
+                for (int idx = tid; idx < nw * TC_KC; idx += TC2_LOADERS) {
+                    const int j = idx >> 6, kk = idx & 63;
+                    const int k = k0 + kk;
+                    float v = 0.0f;
+                    if (j < Nout && k < K) v = __ldg(p.W + (int64_t)j * p.ldw + k);
+                    const uint32_t off = (uint32_t)(kk >> 5) * TC_SLAB_W + sw128_off(j, kk & 31);
+                    const uint32_t h = tf32_rna(v);
+                    *reinterpret_cast<uint32_t *>(W_hi + off) = h;
+                    *reinterpret_cast<float *>(W_lo + off) = v - __uint_as_float(h);
+                }
+            } else {   // W(n,k) = W[k*ldw + n]: lanes along n (coalesced)
+                for (int idx = tid; idx < nw * TC_KC; idx += TC2_LOADERS) {
+                    const int kk = idx / nw, j = idx - kk * nw;
+                    const int k = k0 + kk;
+                    float v = 0.0f;
+                    if (j < Nout && k < K) v = __ldg(p.W + (int64_t)k * p.ldw + j);
+                    const uint32_t off = (uint32_t)(kk >> 5) * TC_SLAB_W + sw128_off(j, kk & 31);
+                    const uint32_t h = tf32_rna(v);
+                    *reinterpret_cast<uint32_t *>(W_hi + off) = h;
+                    *reinterpret_cast<float *>(W_lo + off) = v - __uint_as_float(h);
+                }
+            }
+        };
+        load_chunk(0);
+        for (int j = 0; j < J; ++j) {
+            const int s = j & 1, u = j >> 1;
+            const int q = j / nkc, kc = j - q * nkc;
+            uint8_t *A_hi = tc_smem + (size_t)s * TC2_STAGE, *A_lo = A_hi + 2 * TC_SLAB_A;
+            uint8_t *W_hi = A_hi + TC2_STAGE_A, *W_lo = W_hi + 2 * TC_SLAB_W;
+            if (u >= 1) mbar_wait(&empty_bar[s], (uint32_t)((u - 1) & 1));   // the MMAs of the stage's previous use are done
+            if (!(g.dbg & 4))
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                split_store2(A_hi, A_lo, a_slab + (uint32_t)(rb + 8 * i) * 128u + sw, pre[i]);
+            if (j + 1 < J) load_chunk(j + 1);
+            if ((s ? w_st1 : w_st0) != kc) {
+                stage_w(W_hi, W_lo, kc * TC_KC);
+                if (s) w_st1 = kc; else w_st0 = kc;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core
+            mbar_arrive(&full_bar[s]);
+        }
+    } else if (warp == 8) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nw >> 3) << 17) |
+                                   ((uint32_t)(TC_M >> 4) << 24);
+            for (int j = 0; j < J; ++j) {
+                const int s = j & 1, u = j >> 1;
+                const int q = j / nkc, kc = j - q * nkc;
+                const int a = q & 1, v = q >> 1;
+                mbar_wait(&full_bar[s], (uint32_t)(u & 1));
+                if (kc == 0 && v >= 1) mbar_wait(&acce_bar[a], (uint32_t)((v - 1) & 1));   // epilogue drained this set
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // descriptors: only the 14-bit start-address field changes between k-steps (+2 per 32 bytes)
+                const uint32_t a_hi = smem_u32(tc_smem + (size_t)s * TC2_STAGE);
+                const uint64_t dA_hi = umma_desc_sw128(a_hi), dA_lo = dA_hi + ((2 * TC_SLAB_A) >> 4);
+                const uint64_t dW_hi = dA_hi + (TC2_STAGE_A >> 4), dW_lo = dW_hi + ((2 * TC_SLAB_W) >> 4);
+                const uint32_t d1 = tmem_base + (uint32_t)(a * TC2_ACC_COLS), d2 = d1 + TC_NMAX;
+                const int k0 = kc * TC_KC;
+                const int ksteps = ((K - k0 < TC_KC ? K - k0 : TC_KC) + 7) / 8;
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                    if (ks < ksteps && !(g.dbg & 8)) {
+                        const uint64_t ao = (uint64_t)(((ks >> 2) * TC_SLAB_A + (ks & 3) * 32) >> 4);
+                        const uint64_t wo = (uint64_t)(((ks >> 2) * TC_SLAB_W + (ks & 3) * 32) >> 4);
+                        const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+                        umma_tf32(d1, dA_hi + ao, dW_hi + wo, idesc, first);
+                        umma_tf32(d2, dA_lo + ao, dW_hi + wo, idesc, first);
+                        umma_tf32(d2, dA_hi + ao, dW_lo + wo, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);                      // stage s may be refilled once these MMAs are done
+                if (kc == nkc - 1) umma_commit(&accf_bar[a]);    // ... and the tile's accumulators are complete
+            }
+        }
+    } else {
+        // ================================================================== epilogue (warps 4-7 <-> TMEM lane quarters)
+        // TMEM hands every lane one ROW of the tile; storing that way scatters 16-byte pieces over 32 cache lines per
+        // instruction.  Each warp therefore transposes 32-column groups through a swizzled 4 KB shared-memory tile and
+        // stores with lanes along the columns (8 lanes x 16 B = one full 128-byte line per row, 4 rows per instruction);
+        // bias / activation / ReLU-mask / fc1 agent-id term are applied after the transposition, on coalesced operands.
+        const int wq = warp - 4;
+        const bool relu = (p.epi == EPI_RELU);
+        float4 *stg = epi_s[wq];
+        float *const Yb = p.Y;
+        const float *const auxb = p.aux, *const Wb = p.W;
+        const int64_t ldy = p.ldy, ld_aux = p.ld_aux, ldw = p.ldw;
+        const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0) &&
+                            (EK != TCE_MASKPOS || (((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
+        for (int q = 0; q < n_my; ++q) {
+            const int a = q & 1, v = q >> 1;
+            mbar_wait(&accf_bar[a], (uint32_t)(v & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t mw = (int64_t)((int)blockIdx.x + q * (int)gridDim.x) * TC_M + wq * 32;   // first row of the warp
+            const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * TC2_ACC_COLS);
+#pragma unroll 1
+            for (int c0 = 0; c0 < nw; c0 += 32) {
+                const int gw = (nw - c0) < 32 ? 16 : 32;      // group width (nw is a multiple of 16)
+                uint32_t d1[32], d2[32];
+                if (gw == 32) {
+                    tmem_ld32_nowait(tlane + (uint32_t)c0, d1);
+                    tmem_ld32_nowait(tlane + (uint32_t)(TC_NMAX + c0), d2);
+                } else {
+                    tmem_ld16_nowait(tlane + (uint32_t)c0, d1);
+                    tmem_ld16_nowait(tlane + (uint32_t)(TC_NMAX + c0), d2);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // lane = row: 16-byte chunk c of the row goes to slot (c ^ (row & 7))
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < (gw >> 2))
+                        stg[lane * 8 + (c ^ (lane & 7))] =
+                            make_float4(__uint_as_float(d1[4 * c]) + __uint_as_float(d2[4 * c]),
+                                        __uint_as_float(d1[4 * c + 1]) + __uint_as_float(d2[4 * c + 1]),
+                                        __uint_as_float(d1[4 * c + 2]) + __uint_as_float(d2[4 * c + 2]),
+                                        __uint_as_float(d1[4 * c + 3]) + __uint_as_float(d2[4 * c + 3]));
+                }
+                __syncwarp();
+                // lanes along the columns: pass k covers rows 4k .. 4k+3 (gw = 32) or 8k .. 8k+7 (gw = 16)
+                const int cpr = gw >> 2;                      // chunks per row: 8 or 4
+                const int ch = lane & (cpr - 1), rsub = lane / cpr;
+                const int rpp = 32 / cpr;                     // rows per pass: 4 or 8
+                const int col = c0 + 4 * ch;
+                float4 xs[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = k * rpp + rsub;
+                    if (r < 32) xs[k] = stg[r * 8 + (ch ^ (r & 7))];
+                }
+                if (col < Nout && !(g.dbg & 1)) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[col]);
+                    const bool vec = vec_ok && col + 4 <= Nout;
+                    float *yp = Yb + (mw + rsub) * ldy + col;
+                    const float *ap = (EK == TCE_MASKPOS) ? auxb + (mw + rsub) * ld_aux + col : nullptr;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = k * rpp + rsub;
+                        const int64_t m = mw + r;
+                        if (r < 32 && m < M) {
+                            float4 x = xs[k];
+                            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                            if (EK == TCE_FC1) {
+                                const int agent = (int)((m % g.bv.R) % g.bv.N);
+                                const float *wa = Wb + (int64_t)col * ldw + K + agent;
+                                x.x = fmaxf(x.x + __ldg(wa), 0.0f);
+                                if (col + 1 < Nout) x.y = fmaxf(x.y + __ldg(wa + ldw), 0.0f);
+                                if (col + 2 < Nout) x.z = fmaxf(x.z + __ldg(wa + 2 * ldw), 0.0f);
+                                if (col + 3 < Nout) x.w = fmaxf(x.w + __ldg(wa + 3 * ldw), 0.0f);
+                            } else if (EK == TCE_BIAS_ACT) {
+                                if (relu) { x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f); }
+                            }
+                            float *y = yp + (int64_t)(k * rpp) * ldy;
+                            if (vec) {
+                                if (EK == TCE_MASKPOS) {
+                                    const float4 av = __ldg(reinterpret_cast<const float4 *>(ap + (int64_t)(k * rpp) * ld_aux));
+                                    x.x = av.x > 0.0f ? x.x : 0.0f; x.y = av.y > 0.0f ? x.y : 0.0f;
+                                    x.z = av.z > 0.0f ? x.z : 0.0f; x.w = av.w > 0.0f ? x.w : 0.0f;
+                                }
+                                *reinterpret_cast<float4 *>(y) = x;
+                            } else {
+                                const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (col + e < Nout) {
+                                        float val = xv[e];
+                                        if (EK == TCE_MASKPOS) val = (ap[(int64_t)(k * rpp) * ld_aux + e] > 0.0f) ? val : 0.0f;
+                                        y[e] = val;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                 // the staging tile is rewritten by the next group
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acce_bar[a]);               // this accumulator set may be overwritten
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC2_TMEM_COLS));
+}

@@ -22,7 +22,7 @@ def run_linear(A, W, bias, epi, aux, w_trans, use_tc, Nout, K):
     return Y[:, :Nout]
 
 
-@pytest.mark.parametrize("use_tc", [1, 0])
+@pytest.mark.parametrize("use_tc", [2, 3, 0])   # 2: warp-specialised pipelined tcgen05 kernel, 3: one-tile-at-a-time tcgen05 kernel, 0: FFMA
 @pytest.mark.parametrize("M,K,Nout,epi,w_trans", [
     (1000, 64, 192, 0, 0), (128, 64, 64, 1, 0), (333, 59, 64, 1, 0), (700, 80, 64, 0, 0), (513, 192, 64, 2, 1),
     (260, 64, 160, 0, 0), (90, 64, 32, 0, 0), (400, 160, 64, 2, 1), (300, 64, 640, 0, 0), (257, 320, 128, 1, 0),
@@ -56,7 +56,9 @@ def test_tc_accuracy_is_fp32_level_not_tf32():
     A = th.randn(4096, 64, generator=g).to(DEV)
     W = th.randn(192, 64, generator=g).to(DEV)
     ref = (A.double() @ W.double().t()).cpu().numpy()
-    y_tc = run_linear(A, W, None, 0, None, 0, 1, 192, 64).cpu().numpy()
+    y_tc = run_linear(A, W, None, 0, None, 0, 3, 192, 64).cpu().numpy()
+    y_tp = run_linear(A, W, None, 0, None, 0, 2, 192, 64).cpu().numpy()
+    assert np.abs(y_tp - ref).max() / np.abs(ref).max() < 4e-6
     y_ff = run_linear(A, W, None, 0, None, 0, 0, 192, 64).cpu().numpy()
     e_tc = np.abs(y_tc - ref).max() / np.abs(ref).max()
     e_ff = np.abs(y_ff - ref).max() / np.abs(ref).max()
