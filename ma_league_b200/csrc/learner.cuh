@@ -436,7 +436,6 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
 
 // =============================================================================================
 // q = fc2 h for both nets, chosen-action gather, avail-masked (double-Q) target max.   q_learner.py:52-78
-// one warp per (t, row); lane = action
 // =============================================================================================
 struct HeadArgs {
     const float *params[2];
@@ -448,65 +447,84 @@ struct HeadArgs {
     int *argmax;                       // [B,T,N]
 };
 
-__global__ void __launch_bounds__(256) k_q_head(HeadArgs a) {
-    __shared__ float w2_s[2][MAL_MAX_ACTIONS * (HID + 1)];
+// Thread pair per (t, row): the even lane owns the online net, the odd lane the target net.  Each thread keeps its
+// h row in registers (16 LDG.128) and walks the actions eight at a time with the fc2 rows broadcast from shared memory
+// (4 FMAs per LDS.128); one shuffle per action swaps q_online / q_target inside the pair, the online lane picks the
+// chosen action's Q, the target lane runs the avail-masked (double-Q) arg-max scan in index order (ties -> lowest index).
+__global__ void __launch_bounds__(128) k_q_head(HeadArgs a) {
+    __shared__ __align__(16) float w2_s[2][MAL_MAX_ACTIONS * HID];
     __shared__ float b2_s[2][MAL_MAX_ACTIONS];
-    __shared__ float hs[8][2][HID];
     const AgentLayout L = agent_layout(a.d_in, a.A);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int idx = tid; idx < 2 * a.A * HID; idx += 256) {
-        int net = idx / (a.A * HID), rem = idx - net * a.A * HID;
-        int j = rem >> 6, k = rem & 63;
-        w2_s[net][j * (HID + 1) + k] = __ldg(a.params[net] + L.fc2_w + rem);
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 2 * a.A * HID; idx += 128) {
+        const int nn = idx / (a.A * HID), rem = idx - nn * a.A * HID;
+        w2_s[nn][rem] = __ldg(a.params[nn] + L.fc2_w + rem);
     }
-    if (tid < 2 * a.A) { int net = tid / a.A, j = tid - net * a.A; b2_s[net][j] = __ldg(a.params[net] + L.fc2_b + j); }
+    if (tid < 2 * a.A) { const int nn = tid / a.A, j = tid - nn * a.A; b2_s[nn][j] = __ldg(a.params[nn] + L.fc2_b + j); }
     __syncthreads();
+    const int net = tid & 1;
     const int T = a.TT - 1;
     const int64_t total = (int64_t)a.TT * a.R;
-    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
-        const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
-        const int b = row / a.N, n = row - b * a.N;
-        __syncwarp();
-        hs[warp][0][lane] = a.hout[0][m * HID + lane];
-        hs[warp][0][lane + 32] = a.hout[0][m * HID + lane + 32];
-        hs[warp][1][lane] = a.hout[1][m * HID + lane];
-        hs[warp][1][lane + 32] = a.hout[1][m * HID + lane + 32];
-        __syncwarp();
-        float qo = 0.0f, qt = 0.0f;
-        if (lane < a.A) {
-            float o0 = b2_s[0][lane], o1 = 0.0f, t0 = b2_s[1][lane], t1 = 0.0f;
-            const float *wo = w2_s[0] + lane * (HID + 1), *wt = w2_s[1] + lane * (HID + 1);
-#pragma unroll 8
-            for (int k = 0; k < HID; k += 2) {
-                o0 = fmaf(wo[k], hs[warp][0][k], o0);
-                o1 = fmaf(wo[k + 1], hs[warp][0][k + 1], o1);
-                t0 = fmaf(wt[k], hs[warp][1][k], t0);
-                t1 = fmaf(wt[k + 1], hs[warp][1][k + 1], t1);
+    const int64_t mreal = (int64_t)blockIdx.x * 64 + (tid >> 1);
+    const bool valid = mreal < total;
+    const int64_t m = valid ? mreal : total - 1;             // out-of-range lanes shadow the last row (shuffles stay full-warp)
+    const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
+    const int b = row / a.N, n = row - b * a.N;
+    float4 hv[HID / 4];
+    {
+        const float4 *hp = reinterpret_cast<const float4 *>((net ? a.hout[1] : a.hout[0]) + m * HID);
+#pragma unroll
+        for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = __ldg(hp + k4);
+    }
+    const int act = t < T ? (int)(field_ptr<long long>(a.actions, b, t)[n]) : -1;
+    const int *av = field_ptr<int>(a.avail, b, t) + (int64_t)n * a.A;
+    const int64_t qoff = (((int64_t)b * a.TT + t) * a.N + n) * a.A;
+    const float *w2 = w2_s[net];
+    float chosen = 0.0f, best_sel = 0.0f, best_mt = 0.0f;
+    int best_i = -1;
+    for (int a0 = 0; a0 < a.A; a0 += 8) {
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = a0 + j < a.A ? b2_s[net][a0 + j] : 0.0f;
+#pragma unroll
+        for (int k4 = 0; k4 < HID / 4; ++k4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (a0 + j < a.A) {                          // warp-uniform
+                    const float4 w4 = *reinterpret_cast<const float4 *>(w2 + (a0 + j) * HID + 4 * k4);
+                    q[j] = fmaf(w4.x, hv[k4].x, q[j]);
+                    q[j] = fmaf(w4.y, hv[k4].y, q[j]);
+                    q[j] = fmaf(w4.z, hv[k4].z, q[j]);
+                    q[j] = fmaf(w4.w, hv[k4].w, q[j]);
+                }
             }
-            qo = o0 + o1;
-            qt = t0 + t1;
-            const int64_t o = (((int64_t)b * a.TT + t) * a.N + n) * a.A + lane;
-            if (a.mac_out) a.mac_out[o] = qo;
-            if (a.target_mac_out) a.target_mac_out[o] = qt;
         }
-        if (t < T) {   // chosen_action_qvals = gather(mac_out[:, :-1], 3, actions)
-            const int act = (int)(field_ptr<long long>(a.actions, b, t)[n]);
-            float c = __shfl_sync(0xffffffffu, qo, act & 31);
-            if (lane == 0) a.chosen[((int64_t)b * T + t) * a.N + n] = c;
-        }
-        if (t >= 1) {  // targets use step t's Q for transition t-1
-            const int av = lane < a.A ? field_ptr<int>(a.avail, b, t)[(int64_t)n * a.A + lane] : 0;
-            const bool valid = lane < a.A;
-            float mt = valid ? (av == 0 ? -9999999.0f : qt) : -INFINITY;
-            float sel = a.double_q ? (valid ? (av == 0 ? -9999999.0f : qo) : -INFINITY) : mt;
-            int si = lane;
-            warp_argmax(sel, si);
-            float tm = __shfl_sync(0xffffffffu, mt, si);
-            if (lane == 0) {
-                const int64_t o = ((int64_t)b * T + (t - 1)) * a.N + n;
-                a.target_max[o] = tm;
-                a.argmax[o] = si;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (a0 + j < a.A) {
+                const float other = __shfl_xor_sync(0xffffffffu, q[j], 1);
+                const float qo = net ? other : q[j], qt = net ? q[j] : other;
+                if (net == 0) {
+                    if (a.mac_out && valid) a.mac_out[qoff + a0 + j] = qo;
+                    if (a0 + j == act) chosen = qo;
+                } else {
+                    if (a.target_mac_out && valid) a.target_mac_out[qoff + a0 + j] = qt;
+                    if (t >= 1) {                            // targets use step t's Q for transition t-1
+                        const int avv = av[a0 + j];
+                        const float mt = avv == 0 ? -9999999.0f : qt;
+                        const float sel = a.double_q ? (avv == 0 ? -9999999.0f : qo) : mt;
+                        if (best_i < 0 || arg_better(sel, a0 + j, best_sel, best_i)) { best_sel = sel; best_i = a0 + j; best_mt = mt; }
+                    }
+                }
             }
+        }
+    }
+    if (valid) {
+        if (net == 0 && t < T) a.chosen[((int64_t)b * T + t) * a.N + n] = chosen;   // gather(mac_out[:, :-1], 3, actions)
+        if (net == 1 && t >= 1) {
+            const int64_t o = ((int64_t)b * T + (t - 1)) * a.N + n;
+            a.target_max[o] = best_mt;
+            a.argmax[o] = best_i;
         }
     }
 }
@@ -798,6 +816,73 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
 }
 
 // =============================================================================================
+// fc2 gradients:  dW2[a, :] = sum_m [a_m == a] d_chosen[m] h_m ,  db2[a] = sum_m [a_m == a] d_chosen[m]
+// (the backward of `gather(mac_out, actions)` through fc2: only the chosen action's row receives a gradient).
+// A segmented scatter-add, HBM-bound on the h rows: warp per row (lanes along the 64 hidden units, one coalesced
+// 256-byte load), warp-private [A][64] accumulators in shared memory, a fixed row -> warp assignment and a fixed
+// cross-warp summation order (bit-reproducible); per-CTA partials go through k_grad_reduce like every other gradient.
+// =============================================================================================
+struct Fc2GradArgs {
+    const float *d_chosen;     // [B,T,N]
+    mal_field_t actions;       // int64 [B,TT,N]
+    const float *hout;         // [TT*R,64]
+    float *partW, *partB;      // [gridDim.x][A*64], [gridDim.x][A]
+    int T, N, A, R;
+    int64_t rows;              // T*R
+};
+
+__global__ void __launch_bounds__(256) k_fc2_grad(Fc2GradArgs a) {
+    extern __shared__ __align__(16) float f2_s[];            // [8 warps][A*64 + 32]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ld = a.A * HID + 32;
+    float *acc = f2_s + warp * ld;
+    for (int e = lane; e < ld; e += 32) acc[e] = 0.0f;
+    __syncwarp();
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    constexpr int U = 4;                                      // rows in flight per warp
+    for (int64_t m0 = (int64_t)blockIdx.x * 8 + warp; m0 < a.rows; m0 += U * stride) {
+        float d[U];
+        int act[U];
+        float2 h[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t m = m0 + u * stride;
+            d[u] = 0.0f; act[u] = 0; h[u] = make_float2(0.f, 0.f);
+            if (m < a.rows) {
+                const int t = (int)(m / a.R), rr = (int)(m - (int64_t)t * a.R);
+                const int b = rr / a.N, n = rr - b * a.N;
+                d[u] = __ldg(a.d_chosen + ((int64_t)b * a.T + t) * a.N + n);
+                act[u] = (int)(field_ptr<long long>(a.actions, b, t)[n]);
+                h[u] = __ldg(reinterpret_cast<const float2 *>(a.hout + m * HID) + lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float2 *p = reinterpret_cast<float2 *>(acc + act[u] * HID) + lane;
+            float2 v = *p;
+            v.x = fmaf(d[u], h[u].x, v.x);
+            v.y = fmaf(d[u], h[u].y, v.y);
+            *p = v;
+            if (lane == 0) acc[a.A * HID + act[u]] += d[u];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < a.A * HID; e += 256) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += f2_s[w * ld + e];
+        a.partW[(int64_t)blockIdx.x * a.A * HID + e] = s;
+    }
+    if (tid < a.A) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += f2_s[w * ld + a.A * HID + tid];
+        a.partB[(int64_t)blockIdx.x * a.A + tid] = s;
+    }
+}
+
+// =============================================================================================
 // gather per-chunk partials into the flat gradient (fixed summation order), apply 1/mask.sum(),
 // per-block sum of squares for the global norm
 // =============================================================================================
@@ -819,10 +904,12 @@ struct GradReduceArgs {
     int unnormalized;        // leave out the 1/mask.sum() factor (data-parallel mode)
 };
 
+#define GRED_EPB 64   // gradient elements per block: 256 threads = 64 elements x 4 chunk slices
 __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ GradReduceArgs a) {
-    __shared__ float s_sq[8];
-    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const float inv = a.unnormalized ? 1.0f : 1.0f / a.scalars[MAL_SC_MASK_SUM];
+    __shared__ float part_s[4][GRED_EPB];
+    __shared__ float s_sq[2];
+    const int e = threadIdx.x & (GRED_EPB - 1), slice = threadIdx.x >> 6;   // slice is warp-uniform
+    const int64_t p = (int64_t)blockIdx.x * GRED_EPB + e;
     float v = 0.0f;
     if (p < a.total) {
         int si = 0;
@@ -830,28 +917,31 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ Gra
         const GradSeg &s = a.s[si];
         const int64_t off = p - s.grad_off;
         if (off < s.count) {
+            // this thread's slice of the chunk partials: c = slice, slice + 4, ...; four loads in flight
             const float *src = s.part + off;
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-            int c = 0;
-            for (; c + 4 <= s.n_chunks; c += 4) {
+            int c = slice;
+            for (; c + 12 < s.n_chunks; c += 16) {
                 v0 += src[(int64_t)c * s.chunk_stride];
-                v1 += src[(int64_t)(c + 1) * s.chunk_stride];
-                v2 += src[(int64_t)(c + 2) * s.chunk_stride];
-                v3 += src[(int64_t)(c + 3) * s.chunk_stride];
+                v1 += src[(int64_t)(c + 4) * s.chunk_stride];
+                v2 += src[(int64_t)(c + 8) * s.chunk_stride];
+                v3 += src[(int64_t)(c + 12) * s.chunk_stride];
             }
-            for (; c < s.n_chunks; ++c) v0 += src[(int64_t)c * s.chunk_stride];
-            v = ((v0 + v1) + (v2 + v3)) * inv;
+            for (; c < s.n_chunks; c += 4) v0 += src[(int64_t)c * s.chunk_stride];
+            v = (v0 + v1) + (v2 + v3);
         }
-        a.grad[p] = v;
     }
-    float sq = warp_sum(v * v);
-    if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
+    part_s[slice][e] = v;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0;
-        for (int w = 0; w < 8; ++w) s += s_sq[w];
-        a.norm_part[blockIdx.x] = s;
+    if (threadIdx.x < GRED_EPB) {
+        const float inv = a.unnormalized ? 1.0f : 1.0f / a.scalars[MAL_SC_MASK_SUM];
+        v = ((part_s[0][e] + part_s[1][e]) + (part_s[2][e] + part_s[3][e])) * inv;   // fixed order: bit-reproducible
+        if (p < a.total) a.grad[p] = v; else v = 0.0f;
+        const float sq = warp_sum(v * v);
+        if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) a.norm_part[blockIdx.x] = s_sq[0] + s_sq[1];
 }
 
 // sum of squares of an arbitrary flat gradient (used when mal_clip_rmsprop is called stand-alone)

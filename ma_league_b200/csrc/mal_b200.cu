@@ -335,7 +335,12 @@ static PartLayout part_layout(const Dims &d, int sms) {
     memset(&p, 0, sizeof(p));
     chunking(d.M1, tiles_of(G3, HID) + tiles_of(128, HID) + tiles_of(64, HID), sms, &p.nc_a, &p.rpc_a);
     chunking(d.M1, tiles_of(HID, d.d_in), sms, &p.nc_f1, &p.rpc_f1);
-    chunking((int64_t)d.T * d.R, tiles_of(d.A, HID), sms, &p.nc_f2, &p.rpc_f2);
+    {   // k_fc2_grad: one partial per CTA, 8 warps x >= 4 rows each, at most one CTA per SM
+        int64_t nb = ceil_div64((int64_t)d.T * d.R, 32);
+        if (nb > sms) nb = sms;
+        if (nb < 1) nb = 1;
+        p.nc_f2 = (int)nb; p.rpc_f2 = 0;
+    }
     const int K2 = d.two ? d.HE : d.S;
     if (d.mixer == MAL_MIXER_QMIX2) {
         chunking(d.BT, tiles_of(d.E * d.N, K2) + tiles_of(d.E, K2), sms, &p.nc_m2, &p.rpc_m2);
@@ -347,7 +352,7 @@ static PartLayout part_layout(const Dims &d, int sms) {
     int64_t nm = ceil_div64(d.BT, 8); if (nm > (int64_t)sms * 4) nm = (int64_t)sms * 4; if (nm < 1) nm = 1;
     p.nblk_mix = (int)nm;
     const int64_t P = agent_layout(d.d_in, d.A).total + mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
-    p.nblk_norm = (int)ceil_div64(P, 256);
+    p.nblk_norm = (int)ceil_div64(P, GRED_EPB);
     int64_t o = 0;
     auto take = [&](int64_t n) { int64_t r = o; o += align_up64(n, 64); return r; };
     p.wih_w = take((int64_t)p.nc_a * G3 * HID);   p.wih_b = take((int64_t)p.nc_a * G3);
@@ -625,8 +630,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.target_mac_out = cfg->save_q ? F(plan->target_mac_out) : nullptr;
         a.chosen = F(plan->chosen); a.target_max = F(plan->target_max);
         a.argmax = reinterpret_cast<int *>(ws + plan->argmax);
-        int64_t grid = ceil_div64(d.M1, 8); if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)grid, 256, 0, st>>>(a); }
+        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)ceil_div64(d.M1, 64), 128, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_q_head");
     }
     // mixer hypernetworks                                                   qmix.py:41-59
@@ -847,10 +851,18 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
     // ---- side stream 2: fc2 gradients only need d_chosen and h (both forward products)
     {
-        RedGroup r; r.n = 1; r.bv = bv;
-        r.p[0] = red((int64_t)d.T * d.R, HID, d.A, F(plan->d_chosen), 0, A_DENSE, 0, F(plan->h_on), HID, parts + pl.fc2_w, parts + pl.fc2_b, pl.nc_f2, pl.rpc_f2);
-        r.p[0].dy_kind = 1;
-        if (int rc = launch_reduce(r, s2, "k_reduce_group:agent")) return rc;
+        Fc2GradArgs a;
+        a.d_chosen = F(plan->d_chosen); a.actions = batch->actions; a.hout = F(plan->h_on);
+        a.partW = parts + pl.fc2_w; a.partB = parts + pl.fc2_b;
+        a.T = d.T; a.N = d.N; a.A = d.A; a.R = d.R; a.rows = (int64_t)d.T * d.R;
+        const size_t smem = sizeof(float) * 8 * ((size_t)d.A * HID + 32);
+        static thread_local size_t attr = 48 * 1024;
+        if (smem > attr) {
+            MAL_CUDA(cudaFuncSetAttribute(k_fc2_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = smem;
+        }
+        { ProfScope _ps("k_fc2_grad", s2); k_fc2_grad<<<pl.nc_f2, 256, smem, s2>>>(a); }
+        MAL_LAUNCH_CHECK("k_fc2_grad");
     }
 
     // ---- main stream: BPTT recurrence
