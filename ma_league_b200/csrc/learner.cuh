@@ -365,14 +365,14 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
 
     h_s[0][i] = 0.0f; h_s[1][i] = 0.0f;          // init_hidden: zeros
-    float w[3][HID];
+    unsigned long long w[3][HID / 2];   // packed pairs (W_hh[g*64+i][2j], W_hh[g*64+i][2j+1]) for FFMA2
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
         const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + i) * HID);
 #pragma unroll
         for (int u = 0; u < HID / 4; ++u) {
             const float4 v = __ldg(wr + u);
-            w[g][4 * u] = v.x; w[g][4 * u + 1] = v.y; w[g][4 * u + 2] = v.z; w[g][4 * u + 3] = v.w;
+            w[g][2 * u] = pack2(v.x, v.y); w[g][2 * u + 1] = pack2(v.z, v.w);
         }
     }
     const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
@@ -404,19 +404,21 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
             }
             cp_async_commit();
             const float4 *hp = reinterpret_cast<const float4 *>(h_s[buf]);
-            float s[3][2] = {{g_r + b_r, 0.0f}, {g_z + b_z, 0.0f}, {b_n, 0.0f}};
+            unsigned long long s[3] = {pack2(g_r + b_r, 0.0f), pack2(g_z + b_z, 0.0f), pack2(b_n, 0.0f)};
 #pragma unroll
             for (int u = 0; u < ((DBG & 8) ? 2 : HID / 4); ++u) {
                 const float4 hv = hp[u];
+                const unsigned long long hxy = pack2(hv.x, hv.y), hzw = pack2(hv.z, hv.w);
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    s[g][0] = fmaf(w[g][4 * u], hv.x, s[g][0]);
-                    s[g][1] = fmaf(w[g][4 * u + 1], hv.y, s[g][1]);
-                    s[g][0] = fmaf(w[g][4 * u + 2], hv.z, s[g][0]);
-                    s[g][1] = fmaf(w[g][4 * u + 3], hv.w, s[g][1]);
+                    s[g] = fma2(w[g][2 * u], hxy, s[g]);
+                    s[g] = fma2(w[g][2 * u + 1], hzw, s[g]);
                 }
             }
-            const float xr = s[0][0] + s[0][1], xz = s[1][0] + s[1][1], ghn = s[2][0] + s[2][1];
+            float sa, sb;
+            unpack2(s[0], sa, sb); const float xr = sa + sb;
+            unpack2(s[1], sa, sb); const float xz = sa + sb;
+            unpack2(s[2], sa, sb); const float ghn = sa + sb;
             const float rr = (DBG & 4) ? 0.5f * xr : (DBG & 128) ? sigmoid_fast(xr) : sigmoid_mufu(xr);
             const float zz = (DBG & 4) ? 0.5f * xz : (DBG & 128) ? sigmoid_fast(xz) : sigmoid_mufu(xz);
             const float xn = g_n + rr * ghn;
@@ -755,9 +757,10 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
     const int T = a.TT - 1;
 
     for (int idx = k; idx < 2 * G3; idx += HID) (&dg_s[0][0])[idx] = 0.0f;
-    float wT[G3];   // wT[j] = W_hh[j][k]
+    unsigned long long wT[G3 / 2];   // packed pairs (W_hh[2j][k], W_hh[2j+1][k]) for FFMA2
 #pragma unroll
-    for (int j = 0; j < G3; ++j) wT[j] = __ldg(a.params + L.w_hh + (int64_t)j * HID + k);
+    for (int j = 0; j < G3 / 2; ++j)
+        wT[j] = pack2(__ldg(a.params + L.w_hh + (int64_t)(2 * j) * HID + k), __ldg(a.params + L.w_hh + (int64_t)(2 * j + 1) * HID + k));
 
     const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
     auto fetch = [&](int i, int slot) {          // step i <-> t = TT-1-i
@@ -788,15 +791,15 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
             if (i + PF < a.TT) fetch(i + PF, slot);
             cp_async_commit();
             const float4 *dp = reinterpret_cast<const float4 *>(dg_s[buf]);
-            float s0 = carry + dhh, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            unsigned long long s01 = pack2(carry + dhh, 0.0f), s23 = pack2(0.0f, 0.0f);
 #pragma unroll
             for (int u = 0; u < G3 / 4; ++u) {
                 const float4 d = dp[u];
-                s0 = fmaf(wT[4 * u], d.x, s0);
-                s1 = fmaf(wT[4 * u + 1], d.y, s1);
-                s2 = fmaf(wT[4 * u + 2], d.z, s2);
-                s3 = fmaf(wT[4 * u + 3], d.w, s3);
+                s01 = fma2(wT[2 * u], pack2(d.x, d.y), s01);
+                s23 = fma2(wT[2 * u + 1], pack2(d.z, d.w), s23);
             }
+            float s0, s1, s2, s3;
+            unpack2(s01, s0, s1); unpack2(s23, s2, s3);
             const float dh = (s0 + s1) + (s2 + s3);
             const float rr = g4.x, zz = g4.y, nn = g4.z, ghn = g4.w;
             const float dn = dh * (1.0f - zz);

@@ -168,6 +168,21 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint3
                  "r"(bytes)
                  : "memory");
 }
+// packed fp32x2 FMA (sm_100 FFMA2): two independent IEEE fp32 fused multiply-adds per instruction
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // per-thread asynchronous copies (LDGSTS): src_bytes < size zero-fills the rest (src_bytes = 0: pure zero fill)
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, int src_bytes = 4) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");

@@ -1,5 +1,6 @@
 // Stand-alone timing + cross-check harness for the GRU recurrence kernels of learner.cuh (not product code).
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/gru_bench tools/gru_bench.cu
+// Checks k_gru_fwd4 / k_gru_bwd4 against an fp64 CPU recurrence on the first rows, then times them.
 #include "../ma_league_b200/csrc/learner.cuh"
 #include <vector>
 #include <random>
@@ -8,22 +9,6 @@ void mal_set_error(const char *, ...) {}
 
 static float *dev(const std::vector<float> &v) {
     float *p; cudaMalloc(&p, v.size() * 4); cudaMemcpy(p, v.data(), v.size() * 4, cudaMemcpyHostToDevice); return p;
-}
-static double maxdiff(const float *a, const float *b, size_t n, double *ref_max) {
-    std::vector<float> ha(n), hb(n);
-    cudaMemcpy(ha.data(), a, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hb.data(), b, n * 4, cudaMemcpyDeviceToHost);
-    double m = 0, rm = 0;
-    for (size_t i = 0; i < n; ++i) { m = fmax(m, fabs((double)ha[i] - hb[i])); rm = fmax(rm, fabs((double)hb[i])); }
-    *ref_max = rm;
-    return m;
-}
-static double maxdiff_gates(const float *v2, const float *v1, size_t M) {   // v2: [m][unit][4]   v1: [m][4][64]
-    std::vector<float> a(M * 256), b(M * 256);
-    cudaMemcpy(a.data(), v2, M * 1024, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), v1, M * 1024, cudaMemcpyDeviceToHost);
-    double m = 0;
-    for (size_t r = 0; r < M; ++r) for (int i = 0; i < 64; ++i) for (int g = 0; g < 4; ++g)
-        m = fmax(m, fabs((double)a[r * 256 + i * 4 + g] - b[r * 256 + g * 64 + i]));
-    return m;
 }
 template <typename F> static float time_us(F f, int reps = 20) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -34,7 +19,7 @@ template <typename F> static float time_us(F f, int reps = 20) {
 
 int main(int argc, char **argv) {
     const int R = argc > 1 ? atoi(argv[1]) : 160, TT = argc > 2 ? atoi(argv[2]) : 201;
-    const int d_in = 64, A = 11;
+    const int d_in = 64, A = 11, NCHK = 3;
     const AgentLayout L = agent_layout(d_in, A);
     std::mt19937 rng(1);
     std::uniform_real_distribution<float> U(-0.125f, 0.125f);
@@ -48,41 +33,61 @@ int main(int argc, char **argv) {
     for (auto &x : gi1) x = Nrm(rng);
     for (auto &x : dhh) x = 0.01f * Nrm(rng);
     float *dP0 = dev(P0), *dP1 = dev(P1), *dgi0 = dev(gi0), *dgi1 = dev(gi1), *ddhh = dev(dhh);
-    float *h[2][2], *gates[2], *dg[2];
-    for (int v = 0; v < 2; ++v) {
-        for (int n = 0; n < 2; ++n) { cudaMalloc(&h[v][n], M * HID * 4); cudaMemset(h[v][n], 0, M * HID * 4); }
-        cudaMalloc(&gates[v], M * 256 * 4); cudaMemset(gates[v], 0, M * 256 * 4);
-        cudaMalloc(&dg[v], M * 256 * 4); cudaMemset(dg[v], 0, M * 256 * 4);
+    float *h[2], *gates, *dg;
+    for (int n = 0; n < 2; ++n) { cudaMalloc(&h[n], M * HID * 4); cudaMemset(h[n], 0, M * HID * 4); }
+    cudaMalloc(&gates, M * 256 * 4); cudaMalloc(&dg, M * 256 * 4);
+    GruFwdArgs fa; fa.params[0] = dP0; fa.params[1] = dP1; fa.gi[0] = dgi0; fa.gi[1] = dgi1; fa.hout[0] = h[0]; fa.hout[1] = h[1];
+    fa.gates = gates; fa.TT = TT; fa.R = R; fa.d_in = d_in; fa.n_actions = A;
+    GruBwdArgs ba; ba.params = dP0; ba.hout = h[0]; ba.gates = gates; ba.dh_head = ddhh; ba.d_g = dg; ba.TT = TT; ba.R = R;
+    ba.d_in = d_in; ba.n_actions = A;
+
+    const float fus = time_us([&] { k_gru_fwd4<0><<<dim3(R, 2), HID>>>(fa); });
+    const float bus = time_us([&] { k_gru_bwd4<<<R, HID>>>(ba); });
+    printf("k_gru_fwd4 grid %dx2: %7.1f us  %5.0f cycles/step    k_gru_bwd4 grid %d: %7.1f us  %5.0f cycles/step   (%s)\n", R, fus,
+           fus * 1965 / TT, R, bus, bus * 1965 / TT, cudaGetErrorString(cudaGetLastError()));
+
+    // ---- fp64 reference on rows 0..NCHK-1 of the online net
+    std::vector<float> hh(M * HID), gg(M * 256), dd(M * 256);
+    cudaMemcpy(hh.data(), h[0], M * HID * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(gg.data(), gates, M * 1024, cudaMemcpyDeviceToHost);
+    cudaMemcpy(dd.data(), dg, M * 1024, cudaMemcpyDeviceToHost);
+    const float *W = P0.data() + L.w_hh, *bh = P0.data() + L.b_hh;
+    double eh = 0, ed = 0, mh = 0, md = 0;
+    for (int row = 0; row < NCHK && row < R; ++row) {
+        std::vector<double> hp(HID, 0.0);
+        std::vector<std::vector<double>> Hs(TT, std::vector<double>(HID)), Rr(TT, Hs[0]), Zz(TT, Hs[0]), Nn(TT, Hs[0]), Gn(TT, Hs[0]);
+        for (int t = 0; t < TT; ++t) {
+            const float *g = gi0.data() + ((size_t)t * R + row) * G3;
+            std::vector<double> hn(HID);
+            for (int i = 0; i < HID; ++i) {
+                double ar = bh[i], az = bh[HID + i], an = bh[2 * HID + i];
+                for (int k = 0; k < HID; ++k) { ar += (double)W[i * HID + k] * hp[k]; az += (double)W[(HID + i) * HID + k] * hp[k]; an += (double)W[(2 * HID + i) * HID + k] * hp[k]; }
+                const double r = 1 / (1 + exp(-(g[i] + ar))), z = 1 / (1 + exp(-(g[HID + i] + az))), n = tanh(g[2 * HID + i] + r * an);
+                hn[i] = n + z * (hp[i] - n);
+                Rr[t][i] = r; Zz[t][i] = z; Nn[t][i] = n; Gn[t][i] = an;
+                const double got = hh[((size_t)t * R + row) * HID + i];
+                eh = fmax(eh, fabs(got - hn[i])); mh = fmax(mh, fabs(hn[i]));
+            }
+            Hs[t] = hn; hp = hn;
+        }
+        std::vector<double> carry(HID, 0.0), dgh(G3, 0.0);
+        for (int t = TT - 1; t >= 0; --t) {
+            std::vector<double> ndgh(G3);
+            for (int k = 0; k < HID; ++k) {
+                double dh = carry[k] + (t < TT - 1 ? (double)dhh[((size_t)t * R + row) * HID + k] : 0.0);
+                for (int j = 0; j < G3; ++j) dh += dgh[j] * (double)W[j * HID + k];
+                const double r = Rr[t][k], z = Zz[t][k], n = Nn[t][k], gn = Gn[t][k], hprev = t > 0 ? Hs[t - 1][k] : 0.0;
+                const double dn = dh * (1 - z), dz = dh * (hprev - n), dnp = dn * (1 - n * n), dzp = dz * z * (1 - z);
+                const double drp = dnp * gn * r * (1 - r), dghn = dnp * r;
+                carry[k] = dh * z;
+                ndgh[k] = drp; ndgh[HID + k] = dzp; ndgh[2 * HID + k] = dghn;
+                const float *got = dd.data() + ((size_t)t * R + row) * 256;
+                const double ref[4] = {drp, dzp, dnp, dghn};
+                for (int q = 0; q < 4; ++q) { ed = fmax(ed, fabs(got[q * HID + k] - ref[q])); md = fmax(md, fabs(ref[q])); }
+            }
+            dgh = ndgh;
+        }
     }
-    auto fargs = [&](int v) {
-        GruFwdArgs a; a.params[0] = dP0; a.params[1] = dP1; a.gi[0] = dgi0; a.gi[1] = dgi1; a.hout[0] = h[v][0]; a.hout[1] = h[v][1];
-        a.gates = gates[v]; a.TT = TT; a.R = R; a.d_in = d_in; a.n_actions = A; return a;
-    };
-    auto bargs = [&](int v) {
-        GruBwdArgs a; a.params = dP0; a.hout = h[0][0]; a.gates = gates[v]; a.dh_head = ddhh; a.d_g = dg[v]; a.TT = TT; a.R = R;
-        a.d_in = d_in; a.n_actions = A; return a;
-    };
-    double rm;
-#define FWD1(RT) { auto a = fargs(0); float us = time_us([&] { k_gru_fwd<RT><<<dim3((R + RT - 1) / RT, 2), 192>>>(a); }); \
-    printf("fwd v1 RT=%d grid=%4d: %8.1f us  %6.0f cycles/step  (%s)\n", RT, 2 * ((R + RT - 1) / RT), us, us * 1965 / TT, cudaGetErrorString(cudaGetLastError())); }
-#define FWD2(RT) { auto a = fargs(1); float us = time_us([&] { k_gru_fwd4<0><<<dim3(R, 2), 64>>>(a); }); \
-    double d0 = maxdiff(h[1][0], h[0][0], M * HID, &rm), d1 = maxdiff(h[1][1], h[0][1], M * HID, &rm), d2 = maxdiff_gates(gates[1], gates[0], M); \
-    printf("fwd v2 RT=%d grid=%4d: %8.1f us  %6.0f cycles/step  maxdiff h %.2e %.2e gates %.2e (%s)\n", RT, 2 * ((R + RT - 1) / RT), us, us * 1965 / TT, d0, d1, d2, cudaGetErrorString(cudaGetLastError())); }
-#define FWD2D(RT, DBG) { auto a = fargs(1); float us = time_us([&] { k_gru_fwd4<DBG><<<dim3(R, 2), 64>>>(a); }); \
-    double d0 = maxdiff(h[1][0], h[0][0], M * HID, &rm); printf("fwd v2 RT=%d DBG=%3d: %8.1f us  %6.0f cycles/step  maxdiff h %.2e (%s)\n", RT, DBG, us, us * 1965 / TT, d0, cudaGetErrorString(cudaGetLastError())); }
-#define BWD1(RT) { auto a = bargs(0); float us = time_us([&] { k_gru_bwd<RT><<<(R + RT - 1) / RT, 192>>>(a); }); \
-    printf("bwd v1 RT=%d grid=%4d: %8.1f us  %6.0f cycles/step  (%s)\n", RT, (R + RT - 1) / RT, us, us * 1965 / TT, cudaGetErrorString(cudaGetLastError())); }
-#define BWD2(RT) { auto a = bargs(1); float us = time_us([&] { k_gru_bwd4<<<R, 64>>>(a); }); \
-    double d0 = maxdiff(dg[1], dg[0], M * 256, &rm); \
-    printf("bwd v2 RT=%d grid=%4d: %8.1f us  %6.0f cycles/step  maxdiff d_g %.2e (ref max %.2e) (%s)\n", RT, (R + RT - 1) / RT, us, us * 1965 / TT, d0, rm, cudaGetErrorString(cudaGetLastError())); }
-    if (getenv("GRU_ONLY")) { FWD1(2); FWD2(1); BWD2(1); cudaDeviceSynchronize(); return 0; }
-    FWD1(2); FWD1(4);
-    FWD2(1);
-    FWD2D(1, 1); FWD2D(1, 4); FWD2D(1, 8); FWD2D(1, 13); FWD2D(1, 128);
-    FWD2(1);
-    BWD1(1); BWD1(2);
-    BWD2(1);
-    cudaDeviceSynchronize();
-    printf("final: %s\n", cudaGetErrorString(cudaGetLastError()));
+    printf("vs fp64 (rows 0..%d): max |h err| %.2e (max |h| %.2e)   max |d_g err| %.2e (max |d_g| %.2e)\n", NCHK - 1, eh, mh, ed, md);
     return 0;
 }
