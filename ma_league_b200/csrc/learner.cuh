@@ -454,13 +454,15 @@ struct HeadArgs {
 // (4 FMAs per LDS.128); one shuffle per action swaps q_online / q_target inside the pair, the online lane picks the
 // chosen action's Q, the target lane runs the avail-masked (double-Q) arg-max scan in index order (ties -> lowest index).
 __global__ void __launch_bounds__(128) k_q_head(HeadArgs a) {
-    __shared__ __align__(16) float w2_s[2][MAL_MAX_ACTIONS * HID];
+    extern __shared__ __align__(16) float4 qh_smem[];        // hs_s [2*64*17 float4] | w2_s [2][A*64 floats]
     __shared__ float b2_s[2][MAL_MAX_ACTIONS];
+    float4 *hs_s = qh_smem;
+    float *w2_all = reinterpret_cast<float *>(qh_smem + 2 * 64 * 17);
     const AgentLayout L = agent_layout(a.d_in, a.A);
     const int tid = threadIdx.x;
     for (int idx = tid; idx < 2 * a.A * HID; idx += 128) {
         const int nn = idx / (a.A * HID), rem = idx - nn * a.A * HID;
-        w2_s[nn][rem] = __ldg(a.params[nn] + L.fc2_w + rem);
+        w2_all[idx] = __ldg(a.params[nn] + L.fc2_w + rem);
     }
     if (tid < 2 * a.A) { const int nn = tid / a.A, j = tid - nn * a.A; b2_s[nn][j] = __ldg(a.params[nn] + L.fc2_b + j); }
     __syncthreads();
@@ -472,22 +474,37 @@ __global__ void __launch_bounds__(128) k_q_head(HeadArgs a) {
     const int64_t m = valid ? mreal : total - 1;             // out-of-range lanes shadow the last row (shuffles stay full-warp)
     const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
     const int b = row / a.N, n = row - b * a.N;
+    // the CTA's 64 rows of both nets are staged through shared memory with coalesced float4 loads (a thread reading
+    // its own 256-byte row straight from global touches 32 cache lines per warp instruction)
     float4 hv[HID / 4];
     {
-        const float4 *hp = reinterpret_cast<const float4 *>((net ? a.hout[1] : a.hout[0]) + m * HID);
+        const int64_t m_base = (int64_t)blockIdx.x * 64;
 #pragma unroll
-        for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = __ldg(hp + k4);
+        for (int it = 0; it < 16; ++it) {
+            const int idx = tid + 128 * it;                  // 2 nets x 64 rows x 16 float4
+            const int nn = idx >> 10, r = (idx >> 4) & 63, c = idx & 15;
+            const int64_t mm = m_base + r < total ? m_base + r : total - 1;
+            hs_s[(nn * 64 + r) * 17 + c] = __ldg(reinterpret_cast<const float4 *>((nn ? a.hout[1] : a.hout[0]) + mm * HID) + c);
+        }
+        __syncthreads();
+        const float4 *hp = hs_s + (net * 64 + (tid >> 1)) * 17;   // 17-float4 row pitch: conflict-free per 8-lane phase
+#pragma unroll
+        for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = hp[k4];
     }
     const int act = t < T ? (int)(field_ptr<long long>(a.actions, b, t)[n]) : -1;
     const int *av = field_ptr<int>(a.avail, b, t) + (int64_t)n * a.A;
     const int64_t qoff = (((int64_t)b * a.TT + t) * a.N + n) * a.A;
-    const float *w2 = w2_s[net];
+    const float *w2 = w2_all + net * a.A * HID;
     float chosen = 0.0f, best_sel = 0.0f, best_mt = 0.0f;
     int best_i = -1;
     for (int a0 = 0; a0 < a.A; a0 += 8) {
         float q[8];
+        int avr[8];                                          // issued before the FMAs: the loads fly under the dot products
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = a0 + j < a.A ? b2_s[net][a0 + j] : 0.0f;
+        for (int j = 0; j < 8; ++j) {
+            q[j] = a0 + j < a.A ? b2_s[net][a0 + j] : 0.0f;
+            avr[j] = (net == 1 && t >= 1 && a0 + j < a.A) ? __ldg(av + a0 + j) : 1;
+        }
 #pragma unroll
         for (int k4 = 0; k4 < HID / 4; ++k4) {
 #pragma unroll
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(128) k_q_head(HeadArgs a) {
                 } else {
                     if (a.target_mac_out && valid) a.target_mac_out[qoff + a0 + j] = qt;
                     if (t >= 1) {                            // targets use step t's Q for transition t-1
-                        const int avv = av[a0 + j];
+                        const int avv = avr[j];
                         const float mt = avv == 0 ? -9999999.0f : qt;
                         const float sel = a.double_q ? (avv == 0 ? -9999999.0f : qo) : mt;
                         if (best_i < 0 || arg_better(sel, a0 + j, best_sel, best_i)) { best_sel = sel; best_i = a0 + j; best_mt = mt; }
@@ -549,7 +566,7 @@ struct MixArgs {
     float *mask;                       // [B*T] out
     float *q_tot, *target_q_tot, *targets, *td;
     float *d_a2, *d_y1, *d_chosen;     // backward seeds (un-normalised)
-    float *dh_head;                    // [TT*R,64]: rows of t < T
+    float *dh_head;                    // [TT*R,64]: rows of t < T: d_chosen * fc2.weight[a_t, :] (gather + fc2 backward)
     float *part_stats;                 // [gridDim.x][MIX_NSTAT]
     float *part_v2;                    // [gridDim.x][E+1] d V.2.weight | d V.2.bias
 };
@@ -583,33 +600,58 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = (int64_t)a.B * a.T;
     const MixerLayout ML = mixer_layout(a.mixer, a.S, a.N, a.E, a.HE);
-    const AgentLayout AL = agent_layout(a.d_in, a.A);
     const int two = (ML.layers == 2);
     const int ld1 = two ? 2 * a.HE + 2 * a.E : 2 * a.E;
     const int ld2 = a.E * a.N + a.E;
+    const int yo = two ? 2 * a.HE : 0;                    // column of [b1 | v1] inside a y1 row
+    const float *w2p = a.agent + agent_layout(a.d_in, a.A).fc2_w;
+    const bool act = lane < a.E;
     float st[MIX_NSTAT] = {0, 0, 0, 0, 0, 0};
     float dv2w = 0, dv2b = 0;
-    float q[MAL_MAX_ACTIONS];   // N <= 32 agents per team
+    float v2w_o = 0.0f, v2w_t = 0.0f, v2b_o = 0.0f, v2b_t = 0.0f;
+    if (a.mixer != MAL_MIXER_VDN) {
+        v2w_o = act ? __ldg(a.mparams[0] + ML.v2_w + lane) : 0.0f;
+        v2w_t = act ? __ldg(a.mparams[1] + ML.v2_w + lane) : 0.0f;
+        v2b_o = __ldg(a.mparams[0] + ML.v2_b);
+        v2b_t = __ldg(a.mparams[1] + ML.v2_b);
+    }
 
     for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
         const int b = (int)(m / a.T), t = (int)(m - (int64_t)b * a.T);
-        float y, ty, pre = 0, hidden = 0, wf = 0, v1 = 0;
-        if (a.mixer == MAL_MIXER_VDN) {
-            float s0 = 0, s1 = 0;
-            for (int n = 0; n < a.N; ++n) { s0 += a.chosen[m * a.N + n]; s1 += a.target_max[m * a.N + n]; }
-            y = s0; ty = s1;
-        } else {
-            float d0, d1, d2, d3;
-            for (int n = 0; n < a.N; ++n) q[n] = a.target_max[m * a.N + n];
-            ty = qmix_row(a, 1, m, q, lane, &d0, &d1, &d2, &d3);
-            for (int n = 0; n < a.N; ++n) q[n] = a.chosen[m * a.N + n];
-            y = qmix_row(a, 0, m, q, lane, &pre, &hidden, &wf, &v1);
-        }
-        // mask = filled[:, :-1]; mask[:, 1:] *= 1 - terminated[:, :-1]
+        // lane n holds agent n's chosen / target Q (N <= 32): one coalesced load each, broadcast by shuffle
+        const float qc = lane < a.N ? a.chosen[m * a.N + lane] : 0.0f;
+        const float qt = lane < a.N ? a.target_max[m * a.N + lane] : 0.0f;
+        // per-transition scalars (issued early: independent of the mixing arithmetic)
         float mk = (float)(*field_ptr<long long>(a.filled, b, t));
-        if (t > 0) mk = mk * (1.0f - (float)(*field_ptr<unsigned char>(a.terminated, b, t - 1)));
+        if (t > 0) mk = mk * (1.0f - (float)(*field_ptr<unsigned char>(a.terminated, b, t - 1)));   // mask[:, 1:] *= 1 - terminated[:, :-1]
         const float rew = *field_ptr<float>(a.reward, b, t);
         const float term = (float)(*field_ptr<unsigned char>(a.terminated, b, t));
+        float y, ty, pre = 0, hidden = 0, wf = 0, v1 = 0;
+        const float *a2o = a.a2[0] + m * ld2;
+        if (a.mixer == MAL_MIXER_VDN) {
+            y = warp_sum(qc); ty = warp_sum(qt);
+        } else {
+            // online and target mixer rows side by side (lane = embed unit): hidden = elu(q . |w1| + b1), y = hidden . |w_f| + V(s)
+            const float *a2t = a.a2[1] + m * ld2;
+            const float *y1o = a.y1[0] + m * ld1 + yo, *y1t = a.y1[1] + m * ld1 + yo;
+            float pre_t = act ? y1t[lane] : 0.0f;
+            pre = act ? y1o[lane] : 0.0f;
+            const float wf_t = act ? fabsf(a2t[a.N * a.E + lane]) : 0.0f;
+            wf = act ? fabsf(a2o[a.N * a.E + lane]) : 0.0f;
+            const float v1_t = act ? y1t[a.E + lane] : 0.0f;
+            v1 = act ? y1o[a.E + lane] : 0.0f;
+#pragma unroll 4
+            for (int n = 0; n < a.N; ++n) {
+                const float w1o = act ? fabsf(a2o[n * a.E + lane]) : 0.0f;
+                const float w1t = act ? fabsf(a2t[n * a.E + lane]) : 0.0f;
+                pre = fmaf(__shfl_sync(0xffffffffu, qc, n), w1o, pre);
+                pre_t = fmaf(__shfl_sync(0xffffffffu, qt, n), w1t, pre_t);
+            }
+            hidden = pre > 0.0f ? pre : expm1f(pre);
+            const float hidden_t = pre_t > 0.0f ? pre_t : expm1f(pre_t);
+            y = warp_sum(act ? fmaf(hidden, wf, v1 * v2w_o) : 0.0f) + v2b_o;
+            ty = warp_sum(act ? fmaf(hidden_t, wf_t, v1_t * v2w_t) : 0.0f) + v2b_t;
+        }
         const float target = rew + a.gamma * (1.0f - term) * ty;
         const float tdv = y - target;
         const float mtd = tdv * mk;
@@ -620,42 +662,47 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
             st[0] += mtd * mtd; st[1] += fabsf(mtd); st[2] += y * mk; st[3] += target * mk;
             st[4] += mk; st[5] += (mk != 0.0f) ? 1.0f : 0.0f;
         }
-        float *da2 = nullptr, *dy1 = nullptr;
-        const float *a2 = nullptr;
-        float dpre = 0.0f;
-        const bool act = lane < a.E;
-        if (a.mixer != MAL_MIXER_VDN) {   // element-wise mixer backward
-            a2 = a.a2[0] + m * ld2;
-            da2 = a.d_a2 + m * ld2;
-            dy1 = a.d_y1 + m * ld1 + (two ? 2 * a.HE : 0);
-            const float dhidden = gseed * wf;
-            const float dwf = gseed * hidden;
-            dpre = dhidden * (pre > 0.0f ? 1.0f : expf(pre));
-            if (act) {
-                const float af = a2[a.N * a.E + lane];
-                da2[a.N * a.E + lane] = dwf * (af > 0.0f ? 1.0f : (af < 0.0f ? -1.0f : 0.0f));
-                dy1[lane] = dpre;                                                          // d hyper_b_1 out
-                const float v2w = __ldg(a.mparams[0] + ML.v2_w + lane);
-                dy1[a.E + lane] = v1 > 0.0f ? gseed * v2w : 0.0f;                           // d V.0 pre-activation
-                dv2w += gseed * v1;
+        const int act_mine = lane < a.N ? (int)(field_ptr<long long>(a.actions, b, t)[lane]) : 0;
+        // gather + fc2 backward: d h_t[row n] = d_chosen[n] * fc2.weight[a_t[n], :]   (consumed by the BPTT kernel)
+        auto head_inject = [&](float dq_lane) {
+            float *dh = a.dh_head + ((int64_t)t * a.R + (int64_t)b * a.N) * HID;
+#pragma unroll 4
+            for (int n = 0; n < a.N; ++n) {
+                const float dq = __shfl_sync(0xffffffffu, dq_lane, n);
+                const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w2p + (int64_t)__shfl_sync(0xffffffffu, act_mine, n) * HID) + lane);
+                reinterpret_cast<float2 *>(dh + (int64_t)n * HID)[lane] = make_float2(dq * w2.x, dq * w2.y);
             }
-            if (lane == 0) dv2b += gseed;
+        };
+        if (a.mixer == MAL_MIXER_VDN) {
+            if (lane < a.N) a.d_chosen[m * a.N + lane] = gseed;   // d q_tot / d q_n = 1
+            head_inject(gseed);
+            continue;
         }
+        // element-wise mixer backward
+        float *da2 = a.d_a2 + m * ld2;
+        float *dy1 = a.d_y1 + m * ld1 + yo;
+        const float dhidden = gseed * wf;
+        const float dwf = gseed * hidden;
+        const float dpre = dhidden * (pre > 0.0f ? 1.0f : expf(pre));
+        if (act) {
+            const float af = a2o[a.N * a.E + lane];
+            da2[a.N * a.E + lane] = dwf * (af > 0.0f ? 1.0f : (af < 0.0f ? -1.0f : 0.0f));
+            dy1[lane] = dpre;                                                          // d hyper_b_1 out
+            dy1[a.E + lane] = v1 > 0.0f ? gseed * v2w_o : 0.0f;                         // d V.0 pre-activation
+            dv2w += gseed * v1;
+        }
+        if (lane == 0) dv2b += gseed;
+        float dq_mine = 0.0f;                 // lane n ends up with d q_tot / d q_n * seed
+#pragma unroll 4
         for (int n = 0; n < a.N; ++n) {
-            float dq = gseed;   // VDN: d q_tot / d q_n = 1
-            if (a.mixer != MAL_MIXER_VDN) {
-                const float a1 = act ? a2[n * a.E + lane] : 0.0f;
-                dq = warp_sum(act ? dpre * fabsf(a1) : 0.0f);
-                if (act) da2[n * a.E + lane] = q[n] * dpre * (a1 > 0.0f ? 1.0f : (a1 < 0.0f ? -1.0f : 0.0f));
-            }
-            if (lane == 0) a.d_chosen[m * a.N + n] = dq;
-            // gather + fc2 backward: d h_t[row] += dq * fc2.weight[a_t, :]
-            const int actn = (int)(field_ptr<long long>(a.actions, b, t)[n]);
-            const float *w2 = a.agent + AL.fc2_w + (int64_t)actn * HID;
-            float *dh = a.dh_head + ((int64_t)t * a.R + (int64_t)b * a.N + n) * HID;
-            dh[lane] = dq * __ldg(w2 + lane);
-            dh[lane + 32] = dq * __ldg(w2 + lane + 32);
+            const float a1 = act ? a2o[n * a.E + lane] : 0.0f;
+            const float dq = warp_sum(act ? dpre * fabsf(a1) : 0.0f);
+            const float qn = __shfl_sync(0xffffffffu, qc, n);
+            if (act) da2[n * a.E + lane] = qn * dpre * (a1 > 0.0f ? 1.0f : (a1 < 0.0f ? -1.0f : 0.0f));
+            if (lane == n) dq_mine = dq;
         }
+        if (lane < a.N) a.d_chosen[m * a.N + lane] = dq_mine;
+        head_inject(dq_mine);
     }
     // ---- deterministic block partials
     if (lane == 0)
@@ -791,7 +838,7 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
             if (i + PF < a.TT) fetch(i + PF, slot);
             cp_async_commit();
             const float4 *dp = reinterpret_cast<const float4 *>(dg_s[buf]);
-            unsigned long long s01 = pack2(carry + dhh, 0.0f), s23 = pack2(0.0f, 0.0f);
+            unsigned long long s01 = pack2(carry, 0.0f), s23 = pack2(dhh, 0.0f);
 #pragma unroll
             for (int u = 0; u < G3 / 4; ++u) {
                 const float4 d = dp[u];

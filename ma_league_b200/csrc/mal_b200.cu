@@ -630,7 +630,13 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.target_mac_out = cfg->save_q ? F(plan->target_mac_out) : nullptr;
         a.chosen = F(plan->chosen); a.target_max = F(plan->target_max);
         a.argmax = reinterpret_cast<int *>(ws + plan->argmax);
-        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)ceil_div64(d.M1, 64), 128, 0, st>>>(a); }
+        const size_t smem = sizeof(float4) * 2 * 64 * 17 + sizeof(float) * 2 * (size_t)d.A * HID;
+        static thread_local size_t attr = 48 * 1024;
+        if (smem > attr) {
+            MAL_CUDA(cudaFuncSetAttribute(k_q_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = smem;
+        }
+        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)ceil_div64(d.M1, 64), 128, smem, st>>>(a); }
         MAL_LAUNCH_CHECK("k_q_head");
     }
     // mixer hypernetworks                                                   qmix.py:41-59
