@@ -102,13 +102,17 @@ def test_dp_reduction_contract_gloo_world2():
 
 
 # ---------------------------------------------------------------------------------------------- GPU
-def _gpu_worker(rank, world, port, out, fused):
+def _gpu_worker(rank, world, port, out, nccl):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    th.cuda.set_device(0)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = "cuda:%d" % (rank if nccl else 0)      # gloo: both ranks share cuda:0; nccl: one GPU per rank
+    th.cuda.set_device(dev)
+    if nccl:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=th.device(dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from tests.gpu_helpers import seeded_system, np_params
-        s = seeded_system(3, 8, 12, "qmix", True, seed=5, device="cuda:0", data_parallel=True, learner_log_interval=0)
+        s = seeded_system(3, 8, 12, "qmix", True, seed=5, device=dev, data_parallel=True, learner_log_interval=0)
         B = s.batch.batch_size
         lo, hi = rank * B // world, (rank + 1) * B // world
         for i in range(3):
@@ -122,12 +126,15 @@ def _gpu_worker(rank, world, port, out, fused):
 
 
 @pytest.mark.gpu
-def test_dp_train_two_ranks_equals_full_batch():
+@pytest.mark.parametrize("nccl", [False, True])
+def test_dp_train_two_ranks_equals_full_batch(nccl):
     from tests.gpu_helpers import seeded_system, np_params
+    if nccl and th.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gradient all-reduce over NCCL / NVLink)")
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, out, False)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, out, nccl)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([out.get(), out.get()], key=lambda r: r[0])
