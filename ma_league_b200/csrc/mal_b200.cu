@@ -427,7 +427,7 @@ extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_dbg") == 0) { g_tc_dbg = value; return 0; }
-    if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value ? 1 : 0; return 0; }
+    if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;

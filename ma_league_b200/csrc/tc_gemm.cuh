@@ -96,12 +96,104 @@ __device__ __forceinline__ void split_store(uint8_t *hi_base, uint8_t *lo_base, 
     *reinterpret_cast<uint4 *>(lo_base + off) = l;
 }
 
+// Transposed, coalesced epilogue of one 32-row x gw-column group (gw = 16 or 32) of a tile.
+// TMEM hands every lane one ROW (d1 + d2 = the 3xTF32 sum); storing that way scatters 16-byte pieces over 32 cache
+// lines per instruction.  The warp therefore transposes the group through a swizzled 4 KB shared-memory tile (16-byte
+// chunk c of row r lives in slot c ^ (r & 7)) and stores with lanes along the columns: 8 lanes x 16 B = one full
+// 128-byte line per row.  Bias / activation / ReLU-mask / fc1 agent-id term are applied after the transposition.
+struct TcEpi {
+    float *Y; const float *aux, *W;
+    int64_t ldy, ld_aux, ldw;
+    int M, Nout, K, R, N;
+    bool relu, vec_ok;
+};
+template <int EK>
+__device__ __forceinline__ void tc_epilogue_group(const TcEpi &e, float4 *stg, const uint32_t (&d1)[32], const uint32_t (&d2)[32],
+                                                  int gw, int c0, int64_t mw, int lane, const float *bias_s, bool skip) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (c < (gw >> 2))
+            stg[lane * 8 + (c ^ (lane & 7))] =
+                make_float4(__uint_as_float(d1[4 * c]) + __uint_as_float(d2[4 * c]),
+                            __uint_as_float(d1[4 * c + 1]) + __uint_as_float(d2[4 * c + 1]),
+                            __uint_as_float(d1[4 * c + 2]) + __uint_as_float(d2[4 * c + 2]),
+                            __uint_as_float(d1[4 * c + 3]) + __uint_as_float(d2[4 * c + 3]));
+    }
+    __syncwarp();
+    const int cpr = gw >> 2;                      // chunks per row: 8 or 4
+    const int ch = lane & (cpr - 1), rsub = lane / cpr;
+    const int rpp = 32 / cpr;                     // rows per pass: 4 or 8
+    const int col = c0 + 4 * ch;
+    float4 xs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = k * rpp + rsub;
+        if (r < 32) xs[k] = stg[r * 8 + (ch ^ (r & 7))];
+    }
+    if (col < e.Nout && !skip) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[col]);
+        const bool vec = e.vec_ok && col + 4 <= e.Nout;
+        float *yp = e.Y + (mw + rsub) * e.ldy + col;
+        const float *ap = (EK == TCE_MASKPOS) ? e.aux + (mw + rsub) * e.ld_aux + col : nullptr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = k * rpp + rsub;
+            const int64_t m = mw + r;
+            if (r < 32 && m < e.M) {
+                float4 x = xs[k];
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                if (EK == TCE_FC1) {
+                    const int agent = (int)((m % e.R) % e.N);
+                    const float *wa = e.W + (int64_t)col * e.ldw + e.K + agent;
+                    x.x = fmaxf(x.x + __ldg(wa), 0.0f);
+                    if (col + 1 < e.Nout) x.y = fmaxf(x.y + __ldg(wa + e.ldw), 0.0f);
+                    if (col + 2 < e.Nout) x.z = fmaxf(x.z + __ldg(wa + 2 * e.ldw), 0.0f);
+                    if (col + 3 < e.Nout) x.w = fmaxf(x.w + __ldg(wa + 3 * e.ldw), 0.0f);
+                } else if (EK == TCE_BIAS_ACT) {
+                    if (e.relu) { x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f); }
+                }
+                float *y = yp + (int64_t)(k * rpp) * e.ldy;
+                if (vec) {
+                    if (EK == TCE_MASKPOS) {
+                        const float4 av = __ldg(reinterpret_cast<const float4 *>(ap + (int64_t)(k * rpp) * e.ld_aux));
+                        x.x = av.x > 0.0f ? x.x : 0.0f; x.y = av.y > 0.0f ? x.y : 0.0f;
+                        x.z = av.z > 0.0f ? x.z : 0.0f; x.w = av.w > 0.0f ? x.w : 0.0f;
+                    }
+                    *reinterpret_cast<float4 *>(y) = x;
+                } else {
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (col + q < e.Nout) {
+                            float val = xv[q];
+                            if (EK == TCE_MASKPOS) val = (ap[(int64_t)(k * rpp) * e.ld_aux + q] > 0.0f) ? val : 0.0f;
+                            y[q] = val;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();                                 // the staging tile is rewritten by the next group
+}
+
+// hi = RNA-rounded TF32, lo = exact fp32 remainder (the tensor core ignores its 13 low mantissa bits)
+__device__ __forceinline__ void split_store_fast(uint8_t *hi_base, uint8_t *lo_base, uint32_t off, float4 v) {
+    uint4 h;
+    float4 l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = v.x - __uint_as_float(h.x); l.y = v.y - __uint_as_float(h.y);
+    l.z = v.z - __uint_as_float(h.z); l.w = v.w - __uint_as_float(h.w);
+    *reinterpret_cast<uint4 *>(hi_base + off) = h;
+    *reinterpret_cast<float4 *>(lo_base + off) = l;
+}
+
 template <int AK, int EK>
 __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_constant__ LinGroup g) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[TC_NMAX];
+    __shared__ __align__(16) float bias_s[TC_NMAX + 16];
     uint8_t *A_hi = tc_smem, *A_lo = tc_smem + 2 * TC_SLAB_A;
     uint8_t *W_hi = tc_smem + 4 * TC_SLAB_A, *W_lo = W_hi + 2 * TC_SLAB_W;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,19 +227,42 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
     const int c4 = tid & 15, rbase = tid >> 4;
     const uint32_t a_slab = (uint32_t)(c4 >> 3) * TC_SLAB_A, w_slab = (uint32_t)(c4 >> 3) * TC_SLAB_W;
 
+    // vector loaders: the A rows of the CTA's NEXT m-tile are prefetched into registers while the tensor core and the
+    // epilogue work on the current one (single n-tile, single k-chunk problems: fc1-sized K, w_ih, mixer layer 2)
+    float4 pre[8];
+    bool have_pre = false;
+    const bool can_prefetch = (AK != TCA_GENERIC) && nkc == 1 && n_ntiles == 1;
+    auto load_a = [&](int64_t m0_, int k0_, float4 (&v)[8]) {
+        const int kcol = k0_ + 4 * c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0_ + rbase + 16 * i;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && kcol < K && !(g.dbg & 2)) {
+                const float *rp;
+                if (AK == TCA_VEC_DENSE) rp = p.A + m * p.lda;
+                else {
+                    const int b = (int)(m / g.bv.T), t = (int)(m - (int64_t)b * g.bv.T);
+                    rp = field_ptr<float>(g.bv.state, b, t + p.shift);
+                }
+                v[i] = __ldg(reinterpret_cast<const float4 *>(rp + kcol));
+            }
+        }
+    };
+
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
         const int64_t m0 = (int64_t)mt * TC_M;
         for (int nt = 0; nt < n_ntiles; ++nt) {
             const int n0 = nt * nt_w;
             const int nw = (Nout - n0) < nt_w ? (((Nout - n0) + 15) & ~15) : nt_w;   // MMA N (multiple of 16)
             if (bias_cached != nt) {
-                if (tid < TC_NMAX) bias_s[tid] = (p.bias && n0 + tid < Nout) ? __ldg(p.bias + n0 + tid) : 0.0f;
+                if (tid < TC_NMAX + 16) bias_s[tid] = (p.bias && n0 + tid < Nout) ? __ldg(p.bias + n0 + tid) : 0.0f;
                 bias_cached = nt;    // made visible by the barrier below
             }
             for (int kc = 0; kc < nkc; ++kc) {
                 const int k0 = kc * TC_KC;
                 // ---------------- stage the A chunk [128 x 64]
-                if (nkc > 1 || nt == 0) {
+                {   // (the epilogue's transposition reuses A_hi as scratch, so the chunk is staged for every n-tile)
                     if (AK == TCA_GENERIC) {
                         // lanes along k (coalesced scalar loads), 4 rows in flight per warp iteration
 #pragma unroll 1
@@ -175,25 +290,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                         }
                     } else {
                         float4 v[8];
-                        const int kcol = k0 + 4 * c4;
+                        if (have_pre) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int64_t m = m0 + rbase + 16 * i;
-                            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (m < M && kcol < K) {
-                                const float *rp;
-                                if (AK == TCA_VEC_DENSE) rp = p.A + m * p.lda;
-                                else {
-                                    const int b = (int)(m / g.bv.T), t = (int)(m - (int64_t)b * g.bv.T);
-                                    rp = field_ptr<float>(g.bv.state, b, t + p.shift);
-                                }
-                                v[i] = __ldg(reinterpret_cast<const float4 *>(rp + kcol));
-                            }
+                            for (int i = 0; i < 8; ++i) v[i] = pre[i];
+                        } else {
+                            load_a(m0, k0, v);
                         }
+                        if (!(g.dbg & 4))
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int r = rbase + 16 * i;
-                            split_store(A_hi, A_lo, a_slab + (uint32_t)r * 128u + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4), v[i]);
+                            split_store_fast(A_hi, A_lo, a_slab + (uint32_t)r * 128u + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4), v[i]);
                         }
                     }
                 }
@@ -207,7 +314,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                             const int n = n0 + j;
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (n < Nout && kcol < K) v = __ldg(reinterpret_cast<const float4 *>(p.W + (int64_t)n * p.ldw + kcol));
-                            split_store(W_hi, W_lo, w_slab + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+                            split_store_fast(W_hi, W_lo, w_slab + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
                         }
                     } else if (!p.w_trans) {
                         for (int idx = tid; idx < nw * TC_KC; idx += TC_THREADS) {
@@ -242,72 +349,61 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                 if (tid == 0) {
                     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nw >> 3) << 17) |
                                            ((uint32_t)(TC_M >> 4) << 24);
-                    const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), w_hi = smem_u32(W_hi), w_lo = smem_u32(W_lo);
+                    const uint64_t dA_hi = umma_desc_sw128(smem_u32(A_hi)), dA_lo = umma_desc_sw128(smem_u32(A_lo));
+                    const uint64_t dW_hi = umma_desc_sw128(smem_u32(W_hi)), dW_lo = umma_desc_sw128(smem_u32(W_lo));
                     const int ksteps = ((K - k0 < TC_KC ? K - k0 : TC_KC) + 7) / 8;
-#pragma unroll 1
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t ao = (uint32_t)(ks >> 2) * TC_SLAB_A + (uint32_t)(ks & 3) * 32u;
-                        const uint32_t wo = (uint32_t)(ks >> 2) * TC_SLAB_W + (uint32_t)(ks & 3) * 32u;
-                        const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
-                        umma_tf32(tmem_base, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_hi + wo), idesc, first);
-                        umma_tf32(tmem_base + TC_D2_COL, umma_desc_sw128(a_lo + ao), umma_desc_sw128(w_hi + wo), idesc, first);
-                        umma_tf32(tmem_base + TC_D2_COL, umma_desc_sw128(a_hi + ao), umma_desc_sw128(w_lo + wo), idesc, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        if (ks < ksteps && !(g.dbg & 8)) {       // only the 14-bit start-address field changes between k-steps
+                            const uint64_t ao = (uint64_t)(((ks >> 2) * TC_SLAB_A + (ks & 3) * 32) >> 4);
+                            const uint64_t wo = (uint64_t)(((ks >> 2) * TC_SLAB_W + (ks & 3) * 32) >> 4);
+                            const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+                            umma_tf32(tmem_base, dA_hi + ao, dW_hi + wo, idesc, first);
+                            umma_tf32(tmem_base + TC_D2_COL, dA_lo + ao, dW_hi + wo, idesc, first);
+                            umma_tf32(tmem_base + TC_D2_COL, dA_hi + ao, dW_lo + wo, idesc, 1u);
+                        }
                     }
                     // arrives once every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      smem_u32(&mma_bar))
                                  : "memory");
                 }
+                have_pre = false;
+                if (can_prefetch && mt + (int)gridDim.x < n_mtiles) {      // next tile's rows fly under the MMA + epilogue
+                    load_a((int64_t)(mt + (int)gridDim.x) * TC_M, 0, pre);
+                    have_pre = true;
+                }
                 mbar_wait(&mma_bar, bar_phase);   // smem chunks are free again, this chunk's products are in TMEM
                 bar_phase ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            // ---------------- epilogue: thread <-> row (TMEM lane 32*(warp&3)+lane); warps 0-3 take the even 16-column
-            //                  groups, warps 4-7 the odd ones
+            // ---------------- epilogue: warp <-> TMEM lane quarter (warp & 3); warps 0-3 take the even 32-column groups,
+            //                  warps 4-7 the odd ones; each group is transposed through the (now idle) A_hi staging
+            //                  buffer so that the stores are full 128-byte lines (tc_epilogue_group)
             {
                 const int q = warp & 3;
-                const int64_t m = m0 + q * 32 + lane;
-                int agent = 0;
-                if (EK == TCE_FC1 && m < M) agent = (int)((m % g.bv.R) % g.bv.N);
+                const int64_t mw = m0 + q * 32;
                 const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+                float4 *stg = reinterpret_cast<float4 *>(A_hi) + warp * 256;
+                TcEpi e;
+                e.Y = p.Y + n0; e.aux = p.aux ? p.aux + n0 : nullptr; e.W = p.W + (int64_t)n0 * p.ldw;
+                e.ldy = p.ldy; e.ld_aux = p.ld_aux; e.ldw = p.ldw;
+                e.M = M; e.Nout = Nout - n0; e.K = K; e.R = g.bv.R; e.N = g.bv.N; e.relu = relu;
+                e.vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Y) & 15) == 0) &&
+                           (EK != TCE_MASKPOS || (((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.aux) & 15) == 0)));
 #pragma unroll 1
-                for (int c0 = (warp >> 2) * 16; c0 < nw; c0 += 32) {
+                for (int c0 = (warp >> 2) * 32; c0 < nw; c0 += 64) {
+                    const int gw = (nw - c0) < 32 ? 16 : 32;
                     uint32_t d1[32], d2[32];
-                    tmem_ld16_nowait(tlane + (uint32_t)c0, d1);
-                    tmem_ld16_nowait(tlane + (uint32_t)(TC_D2_COL + c0), d2);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (m < M) {
-                        float x[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float s = (__uint_as_float(d1[i]) + __uint_as_float(d2[i])) + bias_s[c0 + i];
-                            if (EK == TCE_FC1) {
-                                const int n = n0 + c0 + i;
-                                if (n < Nout) s += __ldg(p.W + (int64_t)n * p.ldw + K + agent);
-                                s = fmaxf(s, 0.0f);
-                            } else if (EK == TCE_BIAS_ACT) {
-                                s = relu ? fmaxf(s, 0.0f) : s;
-                            }
-                            x[i] = s;
-                        }
-                        float *yrow = p.Y + m * p.ldy + n0 + c0;
-                        const bool full = (n0 + c0 + 16 <= Nout);
-                        if (EK == TCE_MASKPOS) {
-                            const float *arow = p.aux + m * p.ld_aux + n0 + c0;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (full || n0 + c0 + i < Nout) x[i] = (arow[i] > 0.0f) ? x[i] : 0.0f;
-                        }
-                        if (full && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0)) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4 *>(yrow + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n0 + c0 + i < Nout) yrow[i] = x[i];
-                        }
+                    if (gw == 32) {
+                        tmem_ld32_nowait(tlane + (uint32_t)c0, d1);
+                        tmem_ld32_nowait(tlane + (uint32_t)(TC_D2_COL + c0), d2);
+                    } else {
+                        tmem_ld16_nowait(tlane + (uint32_t)c0, d1);
+                        tmem_ld16_nowait(tlane + (uint32_t)(TC_D2_COL + c0), d2);
                     }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tc_epilogue_group<EK>(e, stg, d1, d2, gw, c0, mw, lane, bias_s, (g.dbg & 1) != 0);
                 }
             }
             // TMEM is overwritten by the next tile's first MMA: order the loads before it
@@ -564,11 +660,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_linear_tc2(const __grid_cons
         const int wq = warp - 4;
         const bool relu = (p.epi == EPI_RELU);
         float4 *stg = epi_s[wq];
-        float *const Yb = p.Y;
-        const float *const auxb = p.aux, *const Wb = p.W;
-        const int64_t ldy = p.ldy, ld_aux = p.ld_aux, ldw = p.ldw;
-        const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0) &&
-                            (EK != TCE_MASKPOS || (((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
+        TcEpi epi;
+        epi.Y = p.Y; epi.aux = p.aux; epi.W = p.W; epi.ldy = p.ldy; epi.ld_aux = p.ld_aux; epi.ldw = p.ldw;
+        epi.M = M; epi.Nout = Nout; epi.K = K; epi.R = g.bv.R; epi.N = g.bv.N; epi.relu = relu;
+        epi.vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0) &&
+                     (EK != TCE_MASKPOS || (((p.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
         for (int q = 0; q < n_my; ++q) {
             const int a = q & 1, v = q >> 1;
             mbar_wait(&accf_bar[a], (uint32_t)(v & 1));
@@ -587,73 +683,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_linear_tc2(const __grid_cons
                     tmem_ld16_nowait(tlane + (uint32_t)(TC_NMAX + c0), d2);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // lane = row: 16-byte chunk c of the row goes to slot (c ^ (row & 7))
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < (gw >> 2))
-                        stg[lane * 8 + (c ^ (lane & 7))] =
-                            make_float4(__uint_as_float(d1[4 * c]) + __uint_as_float(d2[4 * c]),
-                                        __uint_as_float(d1[4 * c + 1]) + __uint_as_float(d2[4 * c + 1]),
-                                        __uint_as_float(d1[4 * c + 2]) + __uint_as_float(d2[4 * c + 2]),
-                                        __uint_as_float(d1[4 * c + 3]) + __uint_as_float(d2[4 * c + 3]));
-                }
-                __syncwarp();
-                // lanes along the columns: pass k covers rows 4k .. 4k+3 (gw = 32) or 8k .. 8k+7 (gw = 16)
-                const int cpr = gw >> 2;                      // chunks per row: 8 or 4
-                const int ch = lane & (cpr - 1), rsub = lane / cpr;
-                const int rpp = 32 / cpr;                     // rows per pass: 4 or 8
-                const int col = c0 + 4 * ch;
-                float4 xs[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int r = k * rpp + rsub;
-                    if (r < 32) xs[k] = stg[r * 8 + (ch ^ (r & 7))];
-                }
-                if (col < Nout && !(g.dbg & 1)) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[col]);
-                    const bool vec = vec_ok && col + 4 <= Nout;
-                    float *yp = Yb + (mw + rsub) * ldy + col;
-                    const float *ap = (EK == TCE_MASKPOS) ? auxb + (mw + rsub) * ld_aux + col : nullptr;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int r = k * rpp + rsub;
-                        const int64_t m = mw + r;
-                        if (r < 32 && m < M) {
-                            float4 x = xs[k];
-                            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                            if (EK == TCE_FC1) {
-                                const int agent = (int)((m % g.bv.R) % g.bv.N);
-                                const float *wa = Wb + (int64_t)col * ldw + K + agent;
-                                x.x = fmaxf(x.x + __ldg(wa), 0.0f);
-                                if (col + 1 < Nout) x.y = fmaxf(x.y + __ldg(wa + ldw), 0.0f);
-                                if (col + 2 < Nout) x.z = fmaxf(x.z + __ldg(wa + 2 * ldw), 0.0f);
-                                if (col + 3 < Nout) x.w = fmaxf(x.w + __ldg(wa + 3 * ldw), 0.0f);
-                            } else if (EK == TCE_BIAS_ACT) {
-                                if (relu) { x.x = fmaxf(x.x, 0.0f); x.y = fmaxf(x.y, 0.0f); x.z = fmaxf(x.z, 0.0f); x.w = fmaxf(x.w, 0.0f); }
-                            }
-                            float *y = yp + (int64_t)(k * rpp) * ldy;
-                            if (vec) {
-                                if (EK == TCE_MASKPOS) {
-                                    const float4 av = __ldg(reinterpret_cast<const float4 *>(ap + (int64_t)(k * rpp) * ld_aux));
-                                    x.x = av.x > 0.0f ? x.x : 0.0f; x.y = av.y > 0.0f ? x.y : 0.0f;
-                                    x.z = av.z > 0.0f ? x.z : 0.0f; x.w = av.w > 0.0f ? x.w : 0.0f;
-                                }
-                                *reinterpret_cast<float4 *>(y) = x;
-                            } else {
-                                const float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    if (col + e < Nout) {
-                                        float val = xv[e];
-                                        if (EK == TCE_MASKPOS) val = (ap[(int64_t)(k * rpp) * ld_aux + e] > 0.0f) ? val : 0.0f;
-                                        y[e] = val;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();                                 // the staging tile is rewritten by the next group
+                tc_epilogue_group<EK>(epi, stg, d1, d2, gw, c0, mw, lane, bias_s, (g.dbg & 1) != 0);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acce_bar[a]);               // this accumulator set may be overwritten

@@ -35,6 +35,14 @@ def bench(M, K, Nout, epi=0, w_trans=0, use_tc=1, reps=20, pipelined=1):
         M, K, Nout, epi, w_trans, use_tc, pipelined, us, byts / us / 1e3, 2.0 * M * K * Nout / us / 1e6))
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "light":
+    for dbg in (0, 1, 2, 4, 8, 3, 6, 7, 15):
+        lib.mal_set_option(b"tc_dbg", dbg)
+        print("light dbg", dbg, end="  ")
+        bench(32160, 64, 192, pipelined=0)
+    lib.mal_set_option(b"tc_dbg", 0)
+    sys.exit(0)
+
 if __name__ == "__main__" and len(sys.argv) > 1:
     for dbg in (0, 1, 2, 4, 8, 3, 6, 7, 15):
         lib.mal_set_option(b"tc_dbg", dbg)
