@@ -499,6 +499,10 @@ static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, c
     }
     const int64_t tiles = ceil_div64(maxM, TC_M);
     const int ak = dense ? TCA_VEC_DENSE : (state ? TCA_VEC_STATE : TCA_GENERIC);
+    bool agent_vec = ek == TCE_FC1 && maxM < (1 << 24);   // float4 loads over the obs part of the fc1 input rows
+    for (int i = 0; i < g.n; ++i)
+        agent_vec = agent_vec && g.p[i].a_kind == A_AGENT_IN && (g.bv.OBS & 3) == 0 && (g.bv.obs.sb & 3) == 0 &&
+            (g.bv.obs.st & 3) == 0 && aligned16(g.bv.obs.ptr);
     // the warp-specialised pipeline (one 208 KB CTA per SM) pays off once every SM has a long run of tile-steps; small
     // launches (B = 32 league matchups) keep the lighter kernel, two CTAs per SM, which also co-runs across streams
     int64_t steps_total = 0;
@@ -511,10 +515,6 @@ static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, c
         if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid1, st, tag);
         if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc2_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid1, st, tag);
         if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid1, st, tag);
-        bool agent_vec = ek == TCE_FC1 && maxM < (1 << 24);   // float4 loads over the obs part of the fc1 input rows
-        for (int i = 0; i < g.n; ++i)
-            agent_vec = agent_vec && g.p[i].a_kind == A_AGENT_IN && (g.bv.OBS & 3) == 0 && (g.bv.obs.sb & 3) == 0 &&
-                        (g.bv.obs.st & 3) == 0 && aligned16(g.bv.obs.ptr);
         if (agent_vec) return launch_tc2_inst<TCA_AGENT, TCE_FC1>(g, grid1, st, tag);
         if (ek == TCE_FC1) return launch_tc2_inst<TCA_GENERIC, TCE_FC1>(g, grid1, st, tag);
         if (ek == TCE_MASKPOS) return launch_tc2_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid1, st, tag);
@@ -525,6 +525,7 @@ static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, c
     if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid, st, tag);
     if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid, st, tag);
     if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid, st, tag);
+    if (agent_vec) return launch_tc_inst<TCA_AGENT, TCE_FC1>(g, grid, st, tag);
     if (ek == TCE_FC1) return launch_tc_inst<TCA_GENERIC, TCE_FC1>(g, grid, st, tag);
     if (ek == TCE_MASKPOS) return launch_tc_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid, st, tag);
     return launch_tc_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid, st, tag);

@@ -31,7 +31,7 @@
 #define TC_D2_COL 128             // TMEM column of the correction-term accumulator
 #define TC_SMEM_BYTES (4 * TC_SLAB_A + 4 * TC_SLAB_W)
 
-enum { TCA_VEC_DENSE = 0, TCA_VEC_STATE = 1, TCA_GENERIC = 2 };
+enum { TCA_VEC_DENSE = 0, TCA_VEC_STATE = 1, TCA_GENERIC = 2, TCA_AGENT = 3 };   // TCA_AGENT: fc1 input rows [obs | last-action one-hot], float4 loads over the obs part
 enum { TCE_BIAS_ACT = 0, TCE_MASKPOS = 1, TCE_FC1 = 2 };
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
@@ -96,6 +96,13 @@ __device__ __forceinline__ void split_store(uint8_t *hi_base, uint8_t *lo_base, 
     *reinterpret_cast<uint4 *>(lo_base + off) = l;
 }
 
+// x = q*d + r for 0 <= x < 2^24 with a float reciprocal (exact after one correction step)
+__device__ __forceinline__ void fast_divmod(int x, int d, float inv_d, int &q, int &r) {
+    q = __float2int_rz(__int2float_rn(x) * inv_d);
+    r = x - q * d;
+    if (r < 0) { --q; r += d; }
+    if (r >= d) { ++q; r -= d; }
+}
 // Transposed, coalesced epilogue of one 32-row x gw-column group (gw = 16 or 32) of a tile.
 // TMEM hands every lane one ROW (d1 + d2 = the 3xTF32 sum); storing that way scatters 16-byte pieces over 32 cache
 // lines per instruction.  The warp therefore transposes the group through a swizzled 4 KB shared-memory tile (16-byte
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
     float4 pre[8];
     bool have_pre = false;
     const bool can_prefetch = (AK != TCA_GENERIC) && nkc == 1 && n_ntiles == 1;
+    const float invR = 1.0f / (float)(g.bv.R > 0 ? g.bv.R : 1), invN = 1.0f / (float)(g.bv.N > 0 ? g.bv.N : 1);
     auto load_a = [&](int64_t m0_, int k0_, float4 (&v)[8]) {
         const int kcol = k0_ + 4 * c4;
 #pragma unroll
@@ -239,13 +247,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
             const int64_t m = m0_ + rbase + 16 * i;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < M && kcol < K && !(g.dbg & 2)) {
-                const float *rp;
-                if (AK == TCA_VEC_DENSE) rp = p.A + m * p.lda;
-                else {
-                    const int b = (int)(m / g.bv.T), t = (int)(m - (int64_t)b * g.bv.T);
-                    rp = field_ptr<float>(g.bv.state, b, t + p.shift);
+                if (AK == TCA_AGENT) {
+                    int t, rr, b, n;
+                    fast_divmod((int)m, g.bv.R, invR, t, rr);
+                    fast_divmod(rr, g.bv.N, invN, b, n);
+                    if (kcol < g.bv.OBS) {       // OBS % 4 == 0 (host-checked): the float4 stays inside the obs row
+                        v[i] = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(g.bv.obs, b, t) + (int64_t)n * g.bv.OBS + kcol));
+                    } else if (t > 0) {
+                        const float *oh = field_ptr<float>(g.bv.onehot, b, t - 1) + (int64_t)n * g.bv.A;
+                        const int a0 = kcol - g.bv.OBS;
+                        if (a0 < g.bv.A) v[i].x = __ldg(oh + a0);
+                        if (a0 + 1 < g.bv.A) v[i].y = __ldg(oh + a0 + 1);
+                        if (a0 + 2 < g.bv.A) v[i].z = __ldg(oh + a0 + 2);
+                        if (a0 + 3 < g.bv.A) v[i].w = __ldg(oh + a0 + 3);
+                    }
+                } else {
+                    const float *rp;
+                    if (AK == TCA_VEC_DENSE) rp = p.A + m * p.lda;
+                    else {
+                        const int b = (int)(m / g.bv.T), t = (int)(m - (int64_t)b * g.bv.T);
+                        rp = field_ptr<float>(g.bv.state, b, t + p.shift);
+                    }
+                    v[i] = __ldg(reinterpret_cast<const float4 *>(rp + kcol));
                 }
-                v[i] = __ldg(reinterpret_cast<const float4 *>(rp + kcol));
             }
         }
     };
@@ -439,20 +463,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
 #define TC2_THREADS 288
 #define TC2_LOADERS 128
 
-enum { TCA_AGENT = 3 };   // fc1 input rows [obs | last-action one-hot] with float4 loads over the obs part
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// x = q*d + r for 0 <= x < 2^24 with a float reciprocal (exact after one correction step)
-__device__ __forceinline__ void fast_divmod(int x, int d, float inv_d, int &q, int &r) {
-    q = __float2int_rz(__int2float_rn(x) * inv_d);
-    r = x - q * d;
-    if (r < 0) { --q; r += d; }
-    if (r >= d) { ++q; r -= d; }
 }
 // hi = RNA-rounded TF32, lo = exact fp32 remainder (the tensor core ignores its 13 low mantissa bits)
 __device__ __forceinline__ void split_store2(uint8_t *hi_base, uint8_t *lo_base, uint32_t off, float4 v) {
