@@ -300,10 +300,10 @@ static int get_dims(const mal_batch_t *b, const mal_learner_cfg_t *c, Dims *d) {
     return 0;
 }
 
-// split an M-row reduction into chunks so that chunks * tiles gives ~2 CTAs per SM (>= 128 rows per chunk, <= 64 chunks)
+// split an M-row reduction into chunks so that chunks * tiles gives ~2 CTAs per SM (>= 128 rows per chunk, <= 256 chunks)
 static void chunking(int64_t M, int tiles, int sms, int *n_chunks, int64_t *rows_per_chunk) {
     int64_t nc = ceil_div64((int64_t)2 * sms, tiles > 0 ? tiles : 1);
-    if (nc > 64) nc = 64;
+    if (nc > 256) nc = 256;
     if (nc > ceil_div64(M, 128)) nc = ceil_div64(M, 128);
     if (nc < 1) nc = 1;
     int64_t rpc = align_up64(ceil_div64(M, nc), RED_MR);
