@@ -183,6 +183,9 @@ def run_ours(a, rank, world, device):
         th.cuda.synchronize(device)
 
     # ---------------- value: batch resident in HBM
+    # untimed: every rotating batch is seen twice (eager, then CUDA-graph capture) before the W warm-up steps
+    for i in range(2 * nb):
+        learner.train(batches[i % nb], t_env=i, episode_num=0)
     for i in range(a.warmup):
         learner.train(batches[i % nb], t_env=i, episode_num=0)
     barrier()
@@ -215,12 +218,14 @@ def run_ours(a, rank, world, device):
     # kernels timed ALONE: the step normally runs 2-3 kernel chains concurrently (fork/join side streams), where a
     # launch's event time includes queueing for SM resources behind its neighbours; the profile pass serialises them
     lib.mal_set_option(b"overlap", 0)
+    learner.use_graphs = False              # replayed graphs bypass the per-launch events
     th.cuda.synchronize(device)
     nat.profile_begin()
     for i in range(a.steps):
         learner.train(batches[i % nb], t_env=i, episode_num=0)
     prof = nat.profile_end()
     lib.mal_set_option(b"overlap", 1)
+    learner.use_graphs = True
     kb = kernel_bytes(d, d["mixer"])
     traffic = load_traffic()
     kern = []
@@ -354,7 +359,8 @@ def run_ours(a, rank, world, device):
                        "transitions_per_step": transitions, "parallelism": "league-sharded x%d (no collective)" % world,
                        "l2": "inputs rotate over %d sampled batches (%.0f MB) > 126 MB L2" % (nb, nb * B * rb / 2 ** 20),
                        "replay_buffer_episodes": a.buffer_size,
-                       "math": "fp32; batched projections on tcgen05 3xTF32 (fp32-accurate), recurrences fp32 FFMA"},
+                       "math": "fp32; batched projections on tcgen05 3xTF32 (fp32-accurate), recurrences fp32 FFMA2",
+                       "launch": "one CUDA graph per batch address set (captured on the 2nd sighting, replayed after)"},
             "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / a.steps,
             "wall_ms_per_step": wall / a.steps * 1e3, "sum_of_kernels_ms_per_step": serial_ms_per_step, "clocks": clocks, "roofline": roofline, "kernels": kern,
             "hbm_kernels": hbm}

@@ -106,6 +106,8 @@ const char *mal_last_error(void);
  * brackets every launch with CUDA events on the launching stream.  mal_profile_end synchronises and writes one
  * text line per kernel name: "<name> <launches> <total_ms>\n". */
 uint64_t mal_launch_count(void);
+/* kernels launched through a replayed CUDA graph that captured calls of this library (added to mal_launch_count) */
+void mal_count_launches(uint64_t n);
 int mal_profile_begin(void);
 int mal_profile_end(char *out, int64_t out_len);
 

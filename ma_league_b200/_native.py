@@ -64,6 +64,7 @@ _PROTOS = {
     "mal_version": (C.c_int, []),
     "mal_last_error": (C.c_char_p, []),
     "mal_launch_count": (C.c_uint64, []),
+    "mal_count_launches": (None, [C.c_uint64]),
     "mal_profile_begin": (C.c_int, []),
     "mal_profile_end": (C.c_int, [C.c_char_p, C.c_int64]),
     "mal_set_option": (C.c_int, [C.c_char_p, C.c_int]),

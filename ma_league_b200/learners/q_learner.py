@@ -54,6 +54,12 @@ class QLearner(Learner):
         self._grad = None
         self._grad_views = None
         self.save_q = False      # tests: also materialise mac_out / target_mac_out
+        # CUDA graphs: the ~18 launches + fork/join events of one step are captured once per (batch storage, shape,
+        # hyper-parameter) key and replayed; a step on a batch whose tensors live at addresses seen before costs one
+        # graph launch on the host.  `args.cuda_graphs = False` (or `learner.use_graphs = False`) keeps eager launches.
+        self.use_graphs = bool(getattr(args, "cuda_graphs", True))
+        self._graphs = {}        # key -> (CUDAGraph, kernels per replay) ; key -> None after the first (eager) sighting
+        self._graph_cap = 32
 
     def parameters(self):
         return list(self.mac.parameters()) + list(self.mixer.parameters())
@@ -139,13 +145,10 @@ class QLearner(Learner):
         dp = cfg.unnormalized != 0
         if dp:
             self._train_data_parallel(bs, cfg, f, dev)
+        elif self.use_graphs and not self.save_q:
+            self._step_graphed(bs, cfg, f, dev)
         else:
-            with nat.on_device(dev):
-                nat.check(nat.lib().mal_learner_step(C.byref(bs), C.byref(cfg), C.byref(self._plan),
-                                                     nat.ptr(f["agent"]), nat.ptr(f["tagent"]), nat.ptr(f["mixer"]),
-                                                     nat.ptr(f["tmixer"]), nat.ptr(self._ws), nat.ptr(self._grad),
-                                                     nat.ptr(self.optimiser.flat_sq), nat.current_stream(dev)),
-                          "mal_learner_step")
+            self._step_eager(bs, cfg, f, dev)
         self.optimiser._steps += 1
         if getattr(self, "_grad_views", None) is None:   # p.grad = views of the flat (clipped) gradient, bound once
             params = self.parameters()
@@ -175,6 +178,47 @@ class QLearner(Learner):
             self.logger.log_stat(self.name + "q_taken_mean", float(h[nat.SC_Q_TAKEN]), t_env)
             self.logger.log_stat(self.name + "target_mean", float(h[nat.SC_TARGET]), t_env)
             self.log_stats_t = t_env
+
+    def _step_eager(self, bs, cfg, f, dev):
+        with nat.on_device(dev):
+            nat.check(nat.lib().mal_learner_step(C.byref(bs), C.byref(cfg), C.byref(self._plan),
+                                                 nat.ptr(f["agent"]), nat.ptr(f["tagent"]), nat.ptr(f["mixer"]),
+                                                 nat.ptr(f["tmixer"]), nat.ptr(self._ws), nat.ptr(self._grad),
+                                                 nat.ptr(self.optimiser.flat_sq), nat.current_stream(dev)),
+                      "mal_learner_step")
+
+    def _step_graphed(self, bs, cfg, f, dev):
+        """Replay the captured step when this exact set of device addresses / shapes / hyper-parameters was seen
+        before; first sighting runs eagerly (it also warms the library's streams and kernel attributes), the second
+        one captures."""
+        fields = (bs.obs, bs.onehot, bs.actions, bs.avail, bs.state, bs.reward, bs.terminated, bs.filled)
+        key = (tuple((x.ptr, x.sb, x.st) for x in fields), bs.B, bs.TT, bs.N, bs.A, bs.OBS, bs.S,
+               tuple(getattr(cfg, n) for n, _ in cfg._fields_),
+               tuple(0 if v is None else v.data_ptr() for v in f.values()), self._ws.data_ptr(), self._grad.data_ptr(),
+               self.optimiser.flat_sq.data_ptr(), str(dev))
+        entry = self._graphs.get(key, False)
+        if entry:
+            graph, n_kernels = entry
+            graph.replay()
+            nat.lib().mal_count_launches(n_kernels)
+            return
+        if entry is False:                      # first sighting: eager
+            if len(self._graphs) >= self._graph_cap:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = None
+            self._step_eager(bs, cfg, f, dev)
+            return
+        # second sighting: capture (the capture stream becomes torch's current stream, which the C ABI call reads)
+        lib = nat.lib()
+        graph = th.cuda.CUDAGraph()
+        th.cuda.synchronize(dev)
+        n0 = lib.mal_launch_count()
+        with th.cuda.graph(graph):
+            self._step_eager(bs, cfg, f, dev)
+        n_kernels = lib.mal_launch_count() - n0
+        self._graphs[key] = (graph, n_kernels)
+        graph.replay()                          # capture only records: this performs the step
+        return
 
     def _train_data_parallel(self, bs, cfg, f, dev):
         """Config 5: every rank back-propagates the UN-normalised sum over its batch shard, one

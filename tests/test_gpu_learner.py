@@ -138,6 +138,28 @@ def test_both_tensor_core_gemm_kernels_inside_the_learner(mode):
         assert_close(grads["mixer." + k], v, TOL, "grad mixer " + k)
 
 
+def test_cuda_graph_replay_equals_eager_launches():
+    """train() replays a captured CUDA graph from the third sighting of a batch on; parameters, optimiser state and
+    logged statistics must be bit-identical to eager launches, including when two batches alternate."""
+    def run(graphs):
+        s = seeded_system(3, 4, 9, "qmix", True, seed=21, learner_log_interval=0)
+        s.learner.use_graphs = graphs
+        s2 = seeded_system(3, 4, 9, "qmix", True, seed=22)          # a second batch at other addresses
+        for i in range(8):
+            s.learner.train(s.batch if i % 2 == 0 else s2.batch, t_env=i, episode_num=i)
+        th.cuda.synchronize()
+        if graphs:
+            assert sum(1 for v in s.learner._graphs.values() if v) == 2
+        return np_params(s.mac.agent), np_params(s.learner.mixer), s.learner.optimiser.flat_sq.cpu().numpy(), \
+            {k: v[0] for k, v in s.logger.stats.items()}, s.mac.agent.trained_steps
+    a, b = run(True), run(False)
+    for x, y in zip(a[:2], b[:2]):
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3] and a[4] == b[4]
+
+
 def test_properties_and_determinism_at_full_size():
     s = seeded_system(5, 32, 201, "qmix", True, seed=5)
     g1 = s.learner.forward_backward(s.batch).clone()
