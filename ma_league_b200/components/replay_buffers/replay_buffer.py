@@ -59,6 +59,28 @@ class ReplayBuffer(EpisodeBatch):
         ep_ids = np.random.choice(self.episodes_in_buffer, batch_size, replace=False)
         return self[ep_ids]
 
+    def sample_into(self, out: EpisodeBatch) -> EpisodeBatch:
+        """`sample(out.batch_size)` written into the caller's packed batch `out` (same scheme, on this device) instead of
+        a fresh one: same episode ids as `sample` for the same numpy RNG state, one bulk record-copy launch, and
+        stable device addresses from step to step (so the learner's captured CUDA graph can be replayed)."""
+        n = out.batch_size
+        assert self.can_sample(n)
+        if self._layout is None or out._layout is None or not self._layout.same_as(out._layout):
+            raise nat.MalError("sample_into needs packed batches with the buffer's record layout")
+        if self._storage.device.type != "cuda" or out._storage.device != self._storage.device:
+            raise nat.MalError("sample_into: the buffer and the output batch must live on the same CUDA device")
+        if self.episodes_in_buffer == n:
+            ids = np.arange(n, dtype=np.int64)       # replay_buffer.py:48-49 returns the first n episodes
+        else:
+            ids = np.random.choice(self.episodes_in_buffer, n, replace=False).astype(np.int64)
+        dev = self._storage.device
+        ids_d = th.from_numpy(ids).to(dev, non_blocking=True)
+        rb = self._layout.record_bytes
+        with th.cuda.device(dev):
+            nat.check(nat.lib().mal_record_copy(nat.ptr(out._storage), rb, None, nat.ptr(self._storage), rb,
+                                                nat.ptr(ids_d), n, rb, nat.current_stream(dev)), "mal_record_copy")
+        return out
+
     def __repr__(self):
         return "ReplayBuffer. {}/{} episodes. Keys:{} Groups:{}".format(
             self.episodes_in_buffer, self.buffer_size, self.scheme.keys(), self.groups.keys())

@@ -1,4 +1,5 @@
 from .basic_controller import BasicMAC
+from .ensemble_agent_controller import EnsembleMAC
 
-# reference registry: marl/controllers/__init__.py:6-11 (the other entries are outside the hot path)
-REGISTRY = {"basic": BasicMAC}
+# reference registry: marl/controllers/__init__.py:6-11 ("distinct" and "gpe" are outside the hot path)
+REGISTRY = {"basic": BasicMAC, "ensemble": EnsembleMAC}

@@ -246,6 +246,30 @@ class QLearner(Learner):
                                            a.grad_norm_clip, nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
                                            nat.ptr(denom), st), "mal_clip_rmsprop")
 
+    def train_from_buffer(self, buffer, batch_size: int, t_env: int, episode_num: int, truncate: bool = False):
+        """The learner-side input pipeline of runs/train/ma_experiment.py:231-239 in one call:
+        `sample(batch_size)` -> [`max_t_filled` -> truncate] -> `train`.
+
+        The sampled records land in a persistent staging batch (one bulk record-copy launch, stable addresses, so the
+        step replays its CUDA graph) and, by default, the padding is MASKED instead of truncated: the step runs over
+        the buffer's full sequence length and transitions past an episode's end carry mask 0, which gives the same
+        loss, gradients and update as the reference's truncation (steps after the longest episode's last one are
+        unfilled) without the host sync that `max_t_filled` as a Python slice bound costs.  `truncate=True` keeps the
+        reference's exact sequence (one device->host sync per step, less arithmetic when episodes are short).
+        Precondition of the masked form, as in the reference's steppers: an episode shorter than the sequence length
+        ends with `terminated = 1` on its last transition."""
+        st = getattr(self, "_stage", None)
+        if st is None or st.batch_size != batch_size or st.max_seq_length != buffer.max_seq_length or \
+                st._storage.device != buffer._storage.device or not st._layout.same_as(buffer._layout):
+            st = buffer._gather_records(th.zeros(batch_size, dtype=th.long))   # a packed batch with the buffer's layout
+            self._stage = st
+        buffer.sample_into(st)
+        batch = st
+        if truncate:
+            batch = st[:, :int(st.max_t_filled())]
+        self.train(batch, t_env, episode_num)
+        return batch
+
     def forward_only(self, batch):
         """Forward half of train() (q_learner.py:36-98); intermediates stay in the workspace (tests, debugging)."""
         bs, cfg, f = self._prepare(batch)

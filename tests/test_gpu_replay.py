@@ -68,3 +68,44 @@ def test_full_size_gather_scatter_properties():
     assert th.equal(dup["reward"][0], dup["reward"][1])
     dev_ids = buf[th.tensor([5, 9], device=DEV)]
     assert th.equal(dev_ids["avail_actions"][1], buf["avail_actions"][9])
+
+
+def test_train_from_buffer_equals_sample_truncate_train():
+    """the fused input pipeline (sample into a persistent batch, mask instead of truncate, no host
+    sync) lands on the same update as the reference's sample -> max_t_filled -> truncate -> train sequence."""
+    import numpy as np
+    from tests.gpu_helpers import seeded_system, np_params
+    from tests.helpers import assert_close
+
+    def run(fused, truncate=False):
+        s = seeded_system(3, 6, 14, "qmix", True, seed=31, buffer_size=24, learner_log_interval=0)
+        gen = th.Generator().manual_seed(77)
+        from ma_league_b200.synthetic import synth_episode_data, fill_episode_batch
+        import ma_league_b200 as M
+        for _ in range(4):      # 24 episodes of varying length (none of full length: truncation is exercised)
+            data, lens = synth_episode_data(6, 14, 3, 9, 32, 48, gen, var_len=True, device="cuda")
+            lens = th.clamp(lens, max=10)
+            data["terminated"].zero_()
+            data["terminated"][th.arange(6), lens - 1] = 1
+            eb = fill_episode_batch(M.EpisodeBatch(s.scheme, s.groups, 6, 14, preprocess=s.pre, device="cuda"), data, lens)
+            s.buf.insert_episode_batch(eb)
+        np.random.seed(5)
+        for i in range(3):
+            if fused:
+                b = s.learner.train_from_buffer(s.buf, 6, t_env=i, episode_num=i, truncate=truncate)
+                assert b.max_seq_length == (14 if not truncate else int(b.max_t_filled()))
+            else:
+                smp = s.buf.sample(6)
+                mt = int(smp.max_t_filled())
+                assert mt < 14
+                s.learner.train(smp[:, :mt], t_env=i, episode_num=i)
+        th.cuda.synchronize()
+        return np_params(s.mac.agent), np_params(s.learner.mixer), {k: v[0] for k, v in s.logger.stats.items()}
+
+    ref = run(False)
+    for variant in (run(True, False), run(True, True)):
+        for x, y in zip(variant[:2], ref[:2]):
+            for k in y:
+                assert_close(x[k], y[k], 1e-5, k)
+        for k, v in ref[2].items():
+            assert abs(variant[2][k] - v) <= 1e-5 * max(1.0, abs(v)), (k, variant[2][k], v)

@@ -141,3 +141,55 @@ def test_agent_and_mixer_modules_standalone():
     assert_close(out.cpu().numpy(), ref, 1e-5, "qmix")
     v = M.VDNMixer()(qs.to(DEV), None)
     assert_close(v.cpu().numpy(), qs.numpy().sum(2, keepdims=True), 1e-6, "vdn")
+
+
+def test_ensemble_mac_matches_oracle_per_agent():
+    """EnsembleMAC (ensemble_agent_controller.py:46-57): agents 1 and 3 infer with their own networks, the others with
+    the native one; Q-values, per-network hidden states and greedy actions are checked over three steps against the
+    numpy oracle's single-network step applied agent by agent."""
+    from oracle import np_oracle as O
+    from tests.gpu_helpers import np_params, np_batch
+    from ma_league_b200.synthetic import make_args, make_scheme, synth_episode_data, fill_episode_batch
+    N, A, OBS, S, B, TT = 4, 10, 40, 64, 3, 6
+    th.manual_seed(3)
+    args = make_args(N, A, S, mixer="vdn", device=DEV)
+    scheme, groups, pre = make_scheme(N, A, OBS, S)
+    buf = M.ReplayBuffer(scheme, groups, B, TT, preprocess=pre, device=DEV)
+    mac = M.mac_REGISTRY["ensemble"](buf.scheme, groups, args)
+    donors = {aid: M.mac_REGISTRY["basic"](buf.scheme, groups, args) for aid in (1, 3)}      # differently initialised nets
+    mac.load_state_dict(ensemble={aid: d.agent.state_dict() for aid, d in donors.items()})
+    assert sorted(mac.ensemble_ids) == [1, 3] and mac.n_native_agents == 2 and mac.native_agents_ids == [0, 2]
+    gen = th.Generator().manual_seed(4)
+    data, lens = synth_episode_data(B, TT, N, A, OBS, S, gen, var_len=False, device=DEV)
+    eb = fill_episode_batch(M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=DEV), data, lens)
+    nb = np_batch(eb)
+    p_nat = np_params(mac.agent)
+    p_ens = {aid: np_params(mac.ensemble[aid]) for aid in (1, 3)}
+    with pytest.raises(Exception):
+        mac.forward(eb, 0)                               # HiddenStateNotInitialized
+    mac.init_hidden(B)
+    h_nat = np.zeros((B * N, 64), np.float32)
+    h_ens = {aid: np.zeros((B, 64), np.float32) for aid in (1, 3)}
+    for t in range(3):
+        acts, greedy = mac.select_actions(eb, t_ep=t, t_env=0, test_mode=True)
+        inp = O.build_inputs(nb["obs"], nb["actions_onehot"], t)                     # [B*N, D_in]
+        q_ref, h_nat, _ = O.drqn_step(p_nat, inp, h_nat)
+        q_ref = q_ref.reshape(B, N, A).copy()
+        for aid in (1, 3):
+            qa, h_ens[aid], _ = O.drqn_step(p_ens[aid], inp.reshape(B, N, -1)[:, aid], h_ens[aid])
+            q_ref[:, aid] = qa
+        masked = np.where(nb["avail_actions"][:, t] == 0, -np.inf, q_ref)
+        assert np.array_equal(acts.cpu().numpy(), masked.argmax(-1)), t
+        assert bool((greedy == 1).all())
+        assert_close(mac.native_hidden_states.reshape(B * N, 64).cpu().numpy(), h_nat, 1e-5, "native hidden t=%d" % t)
+        for aid in (1, 3):
+            assert_close(mac.ensemble_hidden_states[aid].reshape(B, 64).cpu().numpy(), h_ens[aid], 1e-5, "ensemble hidden")
+    # without ensemble members it is BasicMAC
+    plain = M.mac_REGISTRY["ensemble"](buf.scheme, groups, args)
+    plain.load_state_dict(agent=mac.agent.state_dict())
+    base = M.mac_REGISTRY["basic"](buf.scheme, groups, args)
+    base.load_state(mac)
+    plain.init_hidden(B); base.init_hidden(B)
+    a1, _ = plain.select_actions(eb, 0, 0, test_mode=True)
+    a2, _ = base.select_actions(eb, 0, 0, test_mode=True)
+    assert th.equal(a1, a2)
