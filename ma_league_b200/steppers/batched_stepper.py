@@ -1,0 +1,150 @@
+"""Batched, device-resident rollout loop: the caller either side of `select_actions`.
+
+Restates `EpisodeStepper.run` (steppers/episode_stepper.py:86-186) and `SelfPlayStepper.run`
+(steppers/self_play_stepper.py:44-147) for `batch_size_run = B >= 1` matches that advance in lock-step, which is what the
+reference's `ParallelStepper` was meant to do (it does not run).  Per timestep and team the
+episode batch receives one pre-transition update (state / avail_actions / obs), the controller's fused act-select
+launch picks the actions of all B x N agents, and one post-transition update stores actions / reward / terminated --
+all on device tensors: no Python lists, no host round trip inside the step (the reference converts lists to tensors
+twice per step, episode_stepper.py:177-199).
+
+A match that has ended stops writing: with `running[t]` = "match still alive at step t",
+    state / avail_actions / obs / filled at index t   are written iff running[t-1]   (index 0 always)
+    actions                                 at index t   iff running[t-1]   (the last stored state gets actions too, :156-165)
+    reward / terminated                     at index t   iff running[t]
+and everything else stays zero, so every row of the returned batch is exactly the batch a single-match run of the
+reference loop would have produced for that match.  The loop leaves as soon as every match has ended; that check is
+the only host synchronisation (every `sync_every` steps).
+"""
+from functools import partial
+
+import torch as th
+
+from ..components.episode_batch import EpisodeBatch
+
+
+class BatchedEpisodeStepper:
+    def __init__(self, args, logger, env, log_start_t=0, sync_every=1):
+        self.args = args
+        self.logger = logger
+        self.env = env
+        self.batch_size = env.n_envs
+        self.episode_limit = env.episode_limit
+        self.n_teams = env.n_teams
+        self.t = 0
+        self.t_env = 0
+        self.log_start_t = log_start_t
+        self.sync_every = max(1, int(sync_every))
+        self.home_mac = self.away_mac = None
+        self.home_batch = self.away_batch = None
+        self.new_batch_fn = None
+        self.is_initalized = False          # (sic) attribute name of the reference's EnvStepper
+
+    def initialize(self, scheme, groups, preprocess, home_mac, away_mac=None):
+        self.new_batch_fn = partial(EpisodeBatch, scheme, groups, self.batch_size, self.episode_limit + 1,
+                                    preprocess=preprocess, device=self.args.device)
+        self.home_mac, self.away_mac = home_mac, away_mac
+        if self.n_teams == 2 and away_mac is None:
+            raise ValueError("a two-team environment needs an away controller (self-play)")
+        self.is_initalized = True
+
+    def get_env_info(self):
+        return self.env.get_env_info()
+
+    def close_env(self):
+        self.env.close()
+
+    @property
+    def epsilon(self):
+        return getattr(self.home_mac.action_selector, "epsilon", None)
+
+    @property
+    def epsilons(self):
+        return [getattr(m.action_selector, "epsilon", None) for m in self._macs()]
+
+    @property
+    def log_t(self):
+        return self.log_start_t + self.t_env
+
+    def _macs(self):
+        return [self.home_mac] if self.n_teams == 1 else [self.home_mac, self.away_mac]
+
+    def reset(self):
+        self.home_batch = self.new_batch_fn()
+        self.away_batch = self.new_batch_fn() if self.n_teams == 2 else None
+        self.env.reset()
+        self.t = 0
+
+    def run(self, test_mode=False):
+        """Run B matches to their ends.  Returns (home_batch, env_info) or (home_batch, away_batch, env_info)."""
+        if self.home_mac is None:
+            raise RuntimeError("MultiAgentControllerNotInitialized")     # exceptions/runner_exceptions.py
+        self.reset()
+        macs = self._macs()
+        batches = [self.home_batch] if self.n_teams == 1 else [self.home_batch, self.away_batch]
+        B, dev = self.batch_size, self.home_batch["filled"].device
+        for m in macs:
+            m.init_hidden(batch_size=B)
+        running_prev = th.ones(B, dtype=th.bool, device=dev)       # running[t-1]; every match stores index 0
+        running = th.ones(B, dtype=th.bool, device=dev)            # running[t]
+        returns = [th.zeros(B, device=dev) for _ in macs]
+        steps = th.zeros(B, dtype=th.long, device=dev)
+        env_info = {}
+        t = 0
+        while True:
+            wmask = running_prev
+            for k, (mac, batch) in enumerate(zip(macs, batches)):
+                pre = self.env.observe(k)
+                batch.update({"state": pre["state"], "avail_actions": pre["avail_actions"], "obs": pre["obs"]}, ts=t)
+            acts = []
+            for mac, batch in zip(macs, batches):
+                a, _ = mac.select_actions(batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+                acts.append(a)
+                batch.update({"actions": a}, ts=t)
+            # matches that ended before step t-1 selected on valid inputs (the selector rejects all-zero avail rows) but
+            # store nothing: index t of their rows goes back to the zeros of an untouched batch
+            for batch in batches:
+                self._keep(batch, t, wmask)
+            if t == self.episode_limit:
+                break
+            rewards, done, env_info = self.env.step(acts)
+            for k, batch in enumerate(batches):
+                self._write(batch, {"reward": rewards[k].view(B, 1), "terminated": done.view(B, 1)}, t, running)
+                returns[k] += rewards[k] * running
+            steps += running
+            running_prev = running
+            running = running & ~done
+            t += 1
+            # the iteration after the last match ended still writes that match's last stored state and its actions;
+            # once no match was alive at the previous step there is nothing left to write
+            if t % self.sync_every == 0 and not bool(running_prev.any()):
+                break
+        n_steps = int(steps.sum())
+        self.t = int(steps.max())                 # transitions of the longest match (the reference's self.t for one match)
+        if not test_mode:
+            self.t_env += n_steps
+        if self.logger is not None and hasattr(self.logger, "log_stat"):
+            self.logger.log_stat("home_epsilon", self.epsilon, self.log_t)
+            self.logger.log_stat("home_return_mean", float(returns[0].mean()), self.log_t)
+            self.logger.log_stat("ep_length_mean", n_steps / B, self.log_t)
+        env_info = dict(env_info)
+        env_info.update(episode_returns=returns, episode_steps=steps)
+        if self.n_teams == 1:
+            return self.home_batch, env_info
+        return self.home_batch, self.away_batch, env_info
+
+    @staticmethod
+    def _write(batch, data, t, mask):
+        """batch.update(data, ts=t) for the matches selected by `mask` [B]; zeros for the others."""
+        masked = {}
+        for k, v in data.items():
+            m = mask.view((-1,) + (1,) * (v.dim() - 1))
+            masked[k] = th.where(m, v, th.zeros((), dtype=v.dtype, device=v.device))
+        batch.update(masked, ts=t, mark_filled=False)
+
+    @staticmethod
+    def _keep(batch, t, mask):
+        """Zero index t of every transition key (incl. `filled` and derived keys) for the matches NOT in `mask`."""
+        for v in batch.data.transition_data.values():
+            m = mask.view((-1,) + (1,) * (v.dim() - 2))
+            v[:, t] = th.where(m, v[:, t], th.zeros((), dtype=v.dtype, device=v.device))
