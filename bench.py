@@ -319,6 +319,24 @@ def run_ours(a, rank, world, device):
             "api_us_per_call": round(api_us, 2), "kernel_us": round(pk[1] / pk[0] * 1e3, 2),
             "kernel_agent_steps_per_s": round(bs * N / (pk[1] / pk[0] * 1e-3), 1)}
 
+    # ---------------- the rollout loop around act-select: B lock-step matches, device-resident batches
+    try:
+        from ma_league_b200.steppers import BatchedEpisodeStepper, SyntheticVecEnv
+        env = SyntheticVecEnv(B, N, A, OBS, S, TT - 1, n_teams=1, seed=3, device=device, min_len=TT - 1)
+        stp = BatchedEpisodeStepper(args, None, env, sync_every=50)
+        stp.initialize(scheme, groups, pre, mac)
+        stp.run(test_mode=False)
+        th.cuda.synchronize(device)
+        w0 = time.perf_counter()
+        stp.run(test_mode=False)
+        th.cuda.synchronize(device)
+        dt = time.perf_counter() - w0
+        extra["rollout_loop_bs%d" % B] = {"agent_steps_per_s": round(B * N * (TT - 1) / dt, 1),
+                                          "env_steps_per_s": round(B * (TT - 1) / dt, 1), "ms_per_timestep": round(dt / (TT - 1) * 1e3, 4),
+                                          "what": "BatchedEpisodeStepper.run: pre-transition update + fused act-select + post-transition update per step"}
+    except Exception as ex:                                  # the extra leg must never take the headline down
+        extra["rollout_loop_error"] = repr(ex)
+
     # ---------------- memory-bound kernels against the HBM roofline (kernel time from CUDA events around the launch)
     hbm = []
     ids = [th.as_tensor(np.random.choice(a.buffer_size, B, replace=False), device=device) for _ in range(20)]

@@ -8,7 +8,7 @@ launch picks the actions of all B x N agents, and one post-transition update sto
 all on device tensors: no Python lists, no host round trip inside the step (the reference converts lists to tensors
 twice per step, episode_stepper.py:177-199).
 
-A match that has ended stops writing: with `running[t]` = "match still alive at step t",
+A match that has ended leaves nothing behind: with `running[t]` = "match still alive at step t",
     state / avail_actions / obs / filled at index t   are written iff running[t-1]   (index 0 always)
     actions                                 at index t   iff running[t-1]   (the last stored state gets actions too, :156-165)
     reward / terminated                     at index t   iff running[t]
@@ -90,26 +90,32 @@ class BatchedEpisodeStepper:
         returns = [th.zeros(B, device=dev) for _ in macs]
         steps = th.zeros(B, dtype=th.long, device=dev)
         env_info = {}
+        views = [bt.data.transition_data for bt in batches]        # strided views into the packed episode records
         t = 0
         while True:
-            wmask = running_prev
-            for k, (mac, batch) in enumerate(zip(macs, batches)):
+            # every match writes index t unconditionally (a match that has ended still selects on valid inputs: the
+            # selector rejects all-zero avail rows); what lies past a match's end is cleared once, after the loop
+            for k, tv in enumerate(views):
                 pre = self.env.observe(k)
-                batch.update({"state": pre["state"], "avail_actions": pre["avail_actions"], "obs": pre["obs"]}, ts=t)
+                tv["state"][:, t].copy_(pre["state"])
+                tv["avail_actions"][:, t].copy_(pre["avail_actions"])
+                tv["obs"][:, t].copy_(pre["obs"])
             acts = []
-            for mac, batch in zip(macs, batches):
+            for mac, batch, tv in zip(macs, batches, views):
                 a, _ = mac.select_actions(batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
                 acts.append(a)
-                batch.update({"actions": a}, ts=t)
-            # matches that ended before step t-1 selected on valid inputs (the selector rejects all-zero avail rows) but
-            # store nothing: index t of their rows goes back to the zeros of an untouched batch
-            for batch in batches:
-                self._keep(batch, t, wmask)
+                tv["actions"][:, t].copy_(a.view_as(tv["actions"][:, t]))
+                for key, (new_key, transforms) in batch.preprocess.items():       # actions -> actions_onehot
+                    v = tv[key][:, t]
+                    for tr in transforms:
+                        v = tr.transform(v)
+                    tv[new_key][:, t].copy_(v)
             if t == self.episode_limit:
                 break
             rewards, done, env_info = self.env.step(acts)
-            for k, batch in enumerate(batches):
-                self._write(batch, {"reward": rewards[k].view(B, 1), "terminated": done.view(B, 1)}, t, running)
+            for k, tv in enumerate(views):
+                tv["reward"][:, t, 0].copy_(rewards[k])
+                tv["terminated"][:, t, 0].copy_(done)
                 returns[k] += rewards[k] * running
             steps += running
             running_prev = running
@@ -119,6 +125,17 @@ class BatchedEpisodeStepper:
             # once no match was alive at the previous step there is nothing left to write
             if t % self.sync_every == 0 and not bool(running_prev.any()):
                 break
+        # a match of L transitions keeps indices 0..L of the pre-transition keys / actions / filled and 0..L-1 of
+        # reward / terminated; the rest goes back to the zeros of an untouched batch
+        TT = self.episode_limit + 1
+        idx = th.arange(TT, device=dev).view(1, TT)
+        keep_state = idx <= steps.view(B, 1)
+        keep_trans = idx < steps.view(B, 1)
+        for tv in views:
+            for key, v in tv.items():
+                m = keep_trans if key in ("reward", "terminated") else keep_state
+                v.mul_(m.view((B, TT) + (1,) * (v.dim() - 2)).to(v.dtype))
+            tv["filled"][:, :, 0].copy_(keep_state)
         n_steps = int(steps.sum())
         self.t = int(steps.max())                 # transitions of the longest match (the reference's self.t for one match)
         if not test_mode:
@@ -132,19 +149,3 @@ class BatchedEpisodeStepper:
         if self.n_teams == 1:
             return self.home_batch, env_info
         return self.home_batch, self.away_batch, env_info
-
-    @staticmethod
-    def _write(batch, data, t, mask):
-        """batch.update(data, ts=t) for the matches selected by `mask` [B]; zeros for the others."""
-        masked = {}
-        for k, v in data.items():
-            m = mask.view((-1,) + (1,) * (v.dim() - 1))
-            masked[k] = th.where(m, v, th.zeros((), dtype=v.dtype, device=v.device))
-        batch.update(masked, ts=t, mark_filled=False)
-
-    @staticmethod
-    def _keep(batch, t, mask):
-        """Zero index t of every transition key (incl. `filled` and derived keys) for the matches NOT in `mask`."""
-        for v in batch.data.transition_data.values():
-            m = mask.view((-1,) + (1,) * (v.dim() - 2))
-            v[:, t] = th.where(m, v[:, t], th.zeros((), dtype=v.dtype, device=v.device))
