@@ -92,6 +92,7 @@ def kernel_bytes(d, mixer):
     P = 64 * (OBS + A + N) + 64 + 2 * 192 * 64 + 2 * 192 + 64 * A + A
     out = {
         "k_linear_group:fc1": M1 * (OBS + A) * f + 2 * M1 * 64 * f,
+        "k_agent_in_tc": 2 * M1 * (OBS + A + 64 + 192) * f,
         "k_linear_group:w_ih": 2 * M1 * (64 + 192) * f,
         "k_gru_fwd": M1 * (2 * 192 + 2 * 64 + 256) * f,
         "k_q_head": M1 * (2 * 64 * f + A * 4 + 8) + 3 * BT * N * f,

@@ -1,0 +1,248 @@
+// Fused agent-input projection:  gi = W_ih relu(fc1([obs | onehot(a_{t-1}) | agent id])) + b_ih  for all (t, b, n) rows of
+// both nets, in ONE launch (basic_controller.py:80-92 + drqn_agent.py:30-31 + the W_ih half of GRUCell).
+//
+// Same 3xTF32 tcgen05 building blocks as tc_gemm.cuh; what the fusion buys on top of two k_linear_tc launches:
+//   * x = relu(fc1(.)) goes from the first accumulator (TMEM) through registers straight into the A-operand staging of
+//     the second MMA -- it is written to global once (the backward needs it) and never read back;
+//   * one kernel skeleton (launch, TMEM allocation, weight staging, pipeline fill) instead of two, and one M-tile walk;
+//   * W_ih (192 x 64, hi + lo = 96 KB) stays resident in shared memory, N = 192 is a single MMA.
+// One persistent CTA per SM and net: 256 threads, M tiles of 128 rows.
+//   TMEM (512 columns): fc1 D1 | D2 at 0 | 64, W_ih D1 | D2 at 128 | 320.
+//   smem: A staging (input chunk, later x; hi + lo = 64 KB, reused as the epilogue's transposition scratch) |
+//         W_fc1 chunk (hi + lo = 32 KB) | W_ih (96 KB).
+#pragma once
+#include "tc_gemm.cuh"
+
+#define AI_SLAB_A (TC_M * 128)            // 16 KB: [128 rows x 32 floats]
+#define AI_SLAB_W1 (HID * 128)            //  8 KB: [64 rows x 32 floats]
+#define AI_SLAB_W2 (G3 * 128)             // 24 KB: [192 rows x 32 floats]
+#define AI_OFF_W1 (4 * AI_SLAB_A)
+#define AI_OFF_W2 (AI_OFF_W1 + 4 * AI_SLAB_W1)
+#define AI_SMEM_BYTES (AI_OFF_W2 + 4 * AI_SLAB_W2)     // 64 + 32 + 96 = 192 KB
+#define AI_COL_X1 0
+#define AI_COL_X2 64
+#define AI_COL_G1 128
+#define AI_COL_G2 320
+
+struct AgentInArgs {
+    const float *params[2];    // online, target flat agent buffers
+    float *x[2];               // [M1, 64]
+    float *gi[2];              // [M1, 192]
+    int64_t M1;
+    int d_in, n_actions;
+    BatchView bv;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_constant__ AgentInArgs a) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float b1_s[HID], bih_s[G3];
+    uint8_t *A_hi = tc_smem, *A_lo = tc_smem + 2 * AI_SLAB_A;
+    uint8_t *W1_hi = tc_smem + AI_OFF_W1, *W1_lo = W1_hi + 2 * AI_SLAB_W1;
+    uint8_t *W2_hi = tc_smem + AI_OFF_W2, *W2_lo = W2_hi + 2 * AI_SLAB_W2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, net = blockIdx.y;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const float *P = a.params[net];
+    const int64_t M = a.M1;
+    const int n_mtiles = (int)((M + TC_M - 1) / TC_M);
+    if ((int)blockIdx.x >= n_mtiles) return;
+    const BatchView &bv = a.bv;
+    const int K1 = bv.OBS + bv.A;                       // the agent-id columns are a bias gather in the epilogue
+    const int nkc1 = (K1 + TC_KC - 1) / TC_KC;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < HID) b1_s[tid] = __ldg(P + L.fc1_b + tid);
+    if (tid < G3) bih_s[tid] = __ldg(P + L.b_ih + tid);
+    const int c4 = tid & 15, rbase = tid >> 4;          // staging map: float4 column c4 of a 64-wide chunk, rows rbase + 16 i
+    const uint32_t a_slab = (uint32_t)(c4 >> 3) * AI_SLAB_A;
+    // W_ih [192 x 64], resident for the whole kernel
+    for (int j = rbase; j < G3; j += 16) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(P + L.w_ih + (int64_t)j * HID + 4 * c4));
+        split_store_fast(W2_hi, W2_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W2 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+    }
+    auto stage_w1 = [&](int kc) {                       // fc1.weight[:, kc*64 .. +64) (columns >= K1 are zero)
+        const int kcol = kc * TC_KC + 4 * c4;
+        for (int j = rbase; j < HID; j += 16) {
+            const float *wr = P + L.fc1_w + (int64_t)j * a.d_in + kcol;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kcol < K1) v.x = __ldg(wr);             // d_in is not a multiple of 4 in general: scalar loads
+            if (kcol + 1 < K1) v.y = __ldg(wr + 1);
+            if (kcol + 2 < K1) v.z = __ldg(wr + 2);
+            if (kcol + 3 < K1) v.w = __ldg(wr + 3);
+            split_store_fast(W1_hi, W1_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W1 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+        }
+    };
+    int w1_staged = -1;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    uint32_t bar_phase = 0;
+    const float invR = 1.0f / (float)bv.R, invN = 1.0f / (float)bv.N;
+
+    auto load_in = [&](int64_t m0, int kc, float4 (&v)[8]) {   // [obs | last-action one-hot] rows, float4 over the obs part
+        const int kcol = kc * TC_KC + 4 * c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + rbase + 16 * i;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && kcol < K1) {
+                int t, rr, b, n;
+                fast_divmod((int)m, bv.R, invR, t, rr);
+                fast_divmod(rr, bv.N, invN, b, n);
+                if (kcol < bv.OBS) {                    // OBS % 4 == 0 (host-checked)
+                    v[i] = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS + kcol));
+                } else if (t > 0) {
+                    const float *oh = field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A;
+                    const int a0 = kcol - bv.OBS;
+                    if (a0 < bv.A) v[i].x = __ldg(oh + a0);
+                    if (a0 + 1 < bv.A) v[i].y = __ldg(oh + a0 + 1);
+                    if (a0 + 2 < bv.A) v[i].z = __ldg(oh + a0 + 2);
+                    if (a0 + 3 < bv.A) v[i].w = __ldg(oh + a0 + 3);
+                }
+            }
+        }
+    };
+    auto wait_mma = [&]() {
+        mbar_wait(&mma_bar, bar_phase);
+        bar_phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(G3 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    float4 pre[8];
+    bool have_pre = false;
+    for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+        const int64_t m0 = (int64_t)mt * TC_M;
+        // ---------------------------------------------------------------- x = fc1(input): nkc1 k-chunks into acc 1
+        for (int kc = 0; kc < nkc1; ++kc) {
+            float4 v[8];
+            if (kc == 0 && have_pre) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = pre[i];
+            } else {
+                load_in(m0, kc, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                split_store_fast(A_hi, A_lo, a_slab + (uint32_t)r * 128u + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4), v[i]);
+            }
+            if (w1_staged != kc) { stage_w1(kc); w1_staged = kc; }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                const uint64_t dA_hi = umma_desc_sw128(smem_u32(A_hi)), dA_lo = umma_desc_sw128(smem_u32(A_lo));
+                const uint64_t dW_hi = umma_desc_sw128(smem_u32(W1_hi)), dW_lo = umma_desc_sw128(smem_u32(W1_lo));
+                const int k0 = kc * TC_KC;
+                const int ksteps = ((K1 - k0 < TC_KC ? K1 - k0 : TC_KC) + 7) / 8;
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                    if (ks < ksteps) {
+                        const uint64_t ao = (uint64_t)(((ks >> 2) * AI_SLAB_A + (ks & 3) * 32) >> 4);
+                        const uint64_t wo = (uint64_t)(((ks >> 2) * AI_SLAB_W1 + (ks & 3) * 32) >> 4);
+                        const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+                        umma_tf32(tmem_base + AI_COL_X1, dA_hi + ao, dW_hi + wo, idesc1, first);
+                        umma_tf32(tmem_base + AI_COL_X2, dA_lo + ao, dW_hi + wo, idesc1, first);
+                        umma_tf32(tmem_base + AI_COL_X2, dA_hi + ao, dW_lo + wo, idesc1, 1u);
+                    }
+                }
+                umma_commit(&mma_bar);
+            }
+            if (kc == nkc1 - 1) {                       // next tile's first input chunk flies under the rest of this tile
+                have_pre = false;
+                if (mt + (int)gridDim.x < n_mtiles) {
+                    load_in((int64_t)(mt + (int)gridDim.x) * TC_M, 0, pre);
+                    have_pre = true;
+                }
+            }
+            wait_mma();
+        }
+        // ---------------------------------------------------------------- epilogue 1: x = relu(. + b1 + W1[:, K1 + agent])
+        // lane = row (TMEM lane quarter warp & 3); warps 0-3 take columns 0-31, warps 4-7 columns 32-63.  x goes to global
+        // (backward) and, split hi/lo, into the A staging of the second MMA (the input chunk there is consumed).
+        {
+            const int q = warp & 3, half = warp >> 2;
+            const int r = q * 32 + lane;
+            const int64_t m = m0 + r;
+            uint32_t d1[32], d2[32];
+            const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+            tmem_ld32_nowait(tl + AI_COL_X1, d1);
+            tmem_ld32_nowait(tl + AI_COL_X2, d2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            int agent = 0;
+            if (m < M) { int t, rr, b; fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, agent); }
+            const float *wid = P + L.fc1_w + K1 + agent;          // fc1.weight[n, K1 + agent]
+            float *xrow = a.x[net] + m * HID + half * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 xv;
+                float *xp = &xv.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int n = half * 32 + 4 * c + e;
+                    float s = (__uint_as_float(d1[4 * c + e]) + __uint_as_float(d2[4 * c + e])) + b1_s[n];
+                    if (m < M) s += __ldg(wid + (int64_t)n * a.d_in);
+                    xp[e] = m < M ? fmaxf(s, 0.0f) : 0.0f;
+                }
+                if (m < M) *reinterpret_cast<float4 *>(xrow + 4 * c) = xv;
+                const int cc = half * 8 + c;                      // 16-byte chunk of the 64-float row: slab cc >> 3
+                split_store_fast(A_hi, A_lo, (uint32_t)(cc >> 3) * AI_SLAB_A + (uint32_t)r * 128u + (uint32_t)(((cc & 7) ^ (r & 7)) << 4), xv);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---------------------------------------------------------------- gi = W_ih x: one N = 192 MMA chain into acc 2
+        if (tid == 0) {
+            const uint64_t dA_hi = umma_desc_sw128(smem_u32(A_hi)), dA_lo = umma_desc_sw128(smem_u32(A_lo));
+            const uint64_t dW_hi = umma_desc_sw128(smem_u32(W2_hi)), dW_lo = umma_desc_sw128(smem_u32(W2_lo));
+#pragma unroll
+            for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                const uint64_t ao = (uint64_t)(((ks >> 2) * AI_SLAB_A + (ks & 3) * 32) >> 4);
+                const uint64_t wo = (uint64_t)(((ks >> 2) * AI_SLAB_W2 + (ks & 3) * 32) >> 4);
+                const uint32_t first = ks == 0 ? 0u : 1u;
+                umma_tf32(tmem_base + AI_COL_G1, dA_hi + ao, dW_hi + wo, idesc2, first);
+                umma_tf32(tmem_base + AI_COL_G2, dA_lo + ao, dW_hi + wo, idesc2, first);
+                umma_tf32(tmem_base + AI_COL_G2, dA_hi + ao, dW_lo + wo, idesc2, 1u);
+            }
+            umma_commit(&mma_bar);
+        }
+        wait_mma();
+        // ---------------------------------------------------------------- epilogue 2: gi = . + b_ih, transposed coalesced stores
+        {
+            const int q = warp & 3;
+            const int64_t mw = m0 + q * 32;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+            float4 *stg = reinterpret_cast<float4 *>(A_hi) + warp * 256;      // the x operand is consumed: 4 KB per warp
+            TcEpi e;
+            e.Y = a.gi[net]; e.aux = nullptr; e.W = nullptr; e.ldy = G3; e.ld_aux = 0; e.ldw = 0;
+            e.M = (int)M; e.Nout = G3; e.K = 0; e.R = bv.R; e.N = bv.N; e.relu = false; e.vec_ok = true;
+#pragma unroll 1
+            for (int c0 = (warp >> 2) * 32; c0 < G3; c0 += 64) {
+                uint32_t d1[32], d2[32];
+                tmem_ld32_nowait(tlane + (uint32_t)(AI_COL_G1 + c0), d1);
+                tmem_ld32_nowait(tlane + (uint32_t)(AI_COL_G2 + c0), d2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_epilogue_group<TCE_BIAS_ACT>(e, stg, d1, d2, 32, c0, mw, lane, bih_s, false);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}

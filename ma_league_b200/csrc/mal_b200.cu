@@ -7,6 +7,7 @@
 #include "actsel.cuh"
 #include "learner.cuh"
 #include "tc_gemm.cuh"
+#include "agent_in_gemm.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -424,11 +425,13 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
 
 static int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
 static int g_tc_dbg = 0;
+static int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc); 0: two grouped GEMM launches
 static int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
 extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_dbg") == 0) { g_tc_dbg = value; return 0; }
+    if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
@@ -599,7 +602,25 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     cudaStream_t sm = g_overlap ? ss->s[0] : st;    // mixer hypernets only depend on the state: run beside the agent path
     if (fork_to(st, sm, ss->fork_ev[0])) return 2;
 
-    // x = relu(fc1([obs | last action | agent id]))  for every (t,b,n), both nets   basic_controller.py:80-92
+    // x = relu(fc1([obs | last action | agent id])) and gi = W_ih x + b_ih for every (t,b,n), both nets
+    //                                                  basic_controller.py:80-92, drqn_agent.py:30-31, GRUCell input half
+    const bool fused_in = g_use_tc && g_fuse_agent_in && d.M1 < (1 << 24) && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 &&
+                          (bv.obs.st & 3) == 0 && aligned16(bv.obs.ptr);
+    if (fused_in) {
+        AgentInArgs a;
+        for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.x[net] = x[net]; a.gi[net] = gi[net]; }
+        a.M1 = d.M1; a.d_in = d.d_in; a.n_actions = d.A; a.bv = bv;
+        static thread_local bool attr = false;
+        if (!attr) {
+            MAL_CUDA(cudaFuncSetAttribute(k_agent_in_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AI_SMEM_BYTES));
+            attr = true;
+        }
+        const int64_t tiles = ceil_div64(d.M1, TC_M);
+        int64_t per = sms / 2; if (per < 1) per = 1;
+        dim3 grid((unsigned)(tiles < per ? tiles : per), 2);
+        { ProfScope _ps("k_agent_in_tc", st); k_agent_in_tc<<<grid, TC_THREADS, AI_SMEM_BYTES, st>>>(a); }
+        MAL_LAUNCH_CHECK("k_agent_in_tc");
+    } else {
     {
         LinGroup g; g.n = 2; g.bv = bv;
         for (int net = 0; net < 2; ++net)
@@ -614,6 +635,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             g.p[net] = lin(d.M1, HID, G3, A_DENSE, 0, x[net], HID, ap[net] + AL.w_ih, HID, 0, ap[net] + AL.b_ih,
                            EPI_BIAS, nullptr, 0, gi[net], G3);
         if (int rc = launch_linear(g, d.M1, HID, st, "k_linear_group:w_ih")) return rc;
+    }
     }
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
     {
