@@ -453,7 +453,7 @@ struct HeadArgs {
 // h row in registers (16 LDG.128) and walks the actions eight at a time with the fc2 rows broadcast from shared memory
 // (4 FMAs per LDS.128); one shuffle per action swaps q_online / q_target inside the pair, the online lane picks the
 // chosen action's Q, the target lane runs the avail-masked (double-Q) arg-max scan in index order (ties -> lowest index).
-__global__ void __launch_bounds__(128) k_q_head(HeadArgs a) {
+__global__ void __launch_bounds__(128, 4) k_q_head(HeadArgs a) {   // <= 128 registers: four CTAs per SM, the whole grid in one wave at B = 32
     extern __shared__ __align__(16) float4 qh_smem[];        // hs_s [2*64*17 float4] | w2_s [2][A*64 floats]
     __shared__ float b2_s[2][MAL_MAX_ACTIONS];
     float4 *hs_s = qh_smem;
