@@ -122,6 +122,7 @@ struct SideStreams {
 };
 static thread_local SideStreams g_side;
 static int g_overlap = 1;
+static thread_local bool g_defer_stats = false;   // set by mal_learner_step around its forward half
 
 static int side_streams(SideStreams **out) {
     int dev = 0;
@@ -709,7 +710,11 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
         { ProfScope _ps("k_mix_td", st); k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a); }
         MAL_LAUNCH_CHECK("k_mix_td");
-        { ProfScope _ps("k_stats_finalize", st); k_stats_finalize<<<1 + (d.mixer != MAL_MIXER_VDN ? (d.E + 1 + 7) / 8 : 0), 256, 0, st>>>(
+        // nothing before the gradient gather reads the scalars: inside mal_learner_step the finalize runs on the side
+        // stream (the backward joins that stream before k_grad_reduce) and leaves the critical path
+        cudaStream_t sf = (g_defer_stats && g_overlap) ? ss->s[0] : st;
+        if (fork_to(st, sf, ss->fork_ev[3])) return 2;
+        { ProfScope _ps("k_stats_finalize", sf); k_stats_finalize<<<1 + (d.mixer != MAL_MIXER_VDN ? (d.E + 1 + 7) / 8 : 0), 256, 0, sf>>>(
                                                        parts + pl.mix_stats, pl.nblk_mix, d.N, scalars, parts + pl.mix_v2,
                                                        d.E + 1, parts + pl.mix_v2_sum); }
         MAL_LAUNCH_CHECK("k_stats_finalize");
@@ -1008,7 +1013,10 @@ extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_
                                 void *workspace, float *grad, float *square_avg, void *stream) {
     MAL_REQUIRE(square_avg, "mal_learner_step: square_avg missing");
     MAL_REQUIRE(!cfg || !cfg->unnormalized, "mal_learner_step: unnormalized (data-parallel) mode needs the split calls");
-    if (int rc = mal_learner_forward(batch, cfg, plan, agent, target_agent, mixer, target_mixer, workspace, stream)) return rc;
+    g_defer_stats = true;
+    const int rc_f = mal_learner_forward(batch, cfg, plan, agent, target_agent, mixer, target_mixer, workspace, stream);
+    g_defer_stats = false;
+    if (rc_f) return rc_f;
     if (int rc = mal_learner_backward(batch, cfg, plan, agent, mixer, workspace, grad, stream)) return rc;
     Dims d;
     if (int rc = get_dims(batch, cfg, &d)) return rc;
