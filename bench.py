@@ -115,6 +115,9 @@ def kernel_bytes(d, mixer):
     else:
         out["k_mix_td"] = BT * (3 * N + 12) * f + BT * N * 64 * f
     out["k_clip_rmsprop"] = 20 * P
+    for k in list(out):                       # the tensor-core variants of the reductions move the same bytes
+        if k.startswith("k_reduce_group:"):
+            out["k_reduce_tc:" + k.split(":")[1]] = out[k]
     return out
 
 
@@ -133,6 +136,9 @@ def run_ours(a, rank, world, device):
     from ma_league_b200.synthetic import make_args, make_scheme, synth_episode_data, fill_episode_batch
     nat.build()
     lib = nat.lib()
+    for kv in a.opt:
+        k, v = kv.split("=")
+        nat.check(lib.mal_set_option(k.encode(), int(v)), "mal_set_option")
     d = workload_dims(a.workload)
     N, A, OBS, S, B, TT = d["N"], d["A"], d["OBS"], d["S"], d["B"], d["TT"]
     th.manual_seed(1000 + rank)
@@ -431,6 +437,7 @@ def main():
     ap.add_argument("--workload", default="qmix_5v5_b32")
     ap.add_argument("--buffer-size", dest="buffer_size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library switch name=int (mal_set_option), e.g. reduce_tc=0")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

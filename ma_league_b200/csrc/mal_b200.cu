@@ -8,6 +8,7 @@
 #include "learner.cuh"
 #include "tc_gemm.cuh"
 #include "agent_in_gemm.cuh"
+#include "tc_reduce.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -304,9 +305,10 @@ static int get_dims(const mal_batch_t *b, const mal_learner_cfg_t *c, Dims *d) {
     return 0;
 }
 
-// split an M-row reduction into chunks so that chunks * tiles gives ~2 CTAs per SM (>= 128 rows per chunk, <= 256 chunks)
+// split an M-row reduction into chunks: chunks * (128 x 64 output tiles) = at most one CTA per SM for the tensor-core
+// reduction (which the 64 x 64-tile FFMA kernel then over-subscribes by < 2x); >= 128 rows per chunk, <= 256 chunks
 static void chunking(int64_t M, int tiles, int sms, int *n_chunks, int64_t *rows_per_chunk) {
-    int64_t nc = ceil_div64((int64_t)2 * sms, tiles > 0 ? tiles : 1);
+    int64_t nc = sms / (tiles > 0 ? tiles : 1);
     if (nc > 256) nc = 256;
     if (nc > ceil_div64(M, 128)) nc = ceil_div64(M, 128);
     if (nc < 1) nc = 1;
@@ -332,7 +334,7 @@ struct PartLayout {
     int64_t total;
 };
 
-static int tiles_of(int Nout, int K) { return ((Nout + 63) / 64) * ((K + 63) / 64); }
+static int tiles_of(int Nout, int K) { return ((Nout + RT_NT - 1) / RT_NT) * ((K + RT_KT - 1) / RT_KT); }   // 128 x 64 tiles
 
 static PartLayout part_layout(const Dims &d, int sms) {
     PartLayout p;
@@ -426,12 +428,14 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
 
 static int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
 static int g_tc_dbg = 0;
+static int g_reduce_tc = 1;       // weight-gradient reductions on tcgen05 (k_reduce_tc); 0: fp32 FFMA k_reduce_group
 static int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc); 0: two grouped GEMM launches
 static int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
 extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_dbg") == 0) { g_tc_dbg = value; return 0; }
+    if (strcmp(name, "reduce_tc") == 0) { g_reduce_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
@@ -806,14 +810,29 @@ static RedProb red(int64_t M, int K, int Nout, const float *dY, int64_t ldy, int
 }
 
 template <int AK, int DK>
-static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag) {
+static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, const char *tag_tc) {
+    // the tensor-core kernel pays a per-CTA setup and two barriers per 32-row block: it wins once a CTA has a long run
+    // of blocks (>= 512 rows per chunk); short reductions (B = 32 mixer / fc1 problems) stay on the FFMA kernel
+    int64_t min_rpc = 1 << 30;
+    for (int i = 0; i < g.n; ++i) if (g.p[i].rows_per_chunk < min_rpc) min_rpc = g.p[i].rows_per_chunk;
+    const bool tc = g_use_tc && DK == 0 && (g_reduce_tc == 2 || (g_reduce_tc == 1 && min_rpc >= 512));
     int tiles = 0, maxc = 0;
     for (int i = 0; i < g.n; ++i) {
         g.p[i].tile0 = tiles;
-        tiles += ((g.p[i].Nout + 63) / 64) * g.p[i].n_ktiles;
+        tiles += ((g.p[i].Nout + (tc ? RT_NT : 64) - 1) / (tc ? RT_NT : 64)) * g.p[i].n_ktiles;
         if (g.p[i].n_chunks > maxc) maxc = g.p[i].n_chunks;
     }
     dim3 grid(maxc, tiles);
+    if (tc) {
+        static thread_local bool attr = false;
+        if (!attr) {
+            MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
+            attr = true;
+        }
+        { ProfScope _ps(tag_tc, st); k_reduce_tc<AK><<<grid, 256, RT_SMEM_BYTES, st>>>(g); }
+        MAL_LAUNCH_CHECK("k_reduce_tc");
+        return 0;
+    }
     { ProfScope _ps(tag, st); k_reduce_group<AK, DK><<<grid, 256, 0, st>>>(g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
     return 0;
@@ -831,10 +850,11 @@ static int launch_reduce(RedGroup &g, cudaStream_t st, const char *tag) {
         if (h.n == 0) continue;
         int rc = 0;
         const bool agent = strstr(tag, "agent") != nullptr;
-        if (q == 0) rc = launch_reduce_inst<A_DENSE, 0>(h, st, agent ? "k_reduce_group:agent_dense" : "k_reduce_group:mixer_dense");
-        else if (q == 1) rc = launch_reduce_inst<A_STATE, 0>(h, st, "k_reduce_group:mixer_state");
-        else if (q == 2) rc = launch_reduce_inst<A_AGENT_IN, 0>(h, st, "k_reduce_group:agent_fc1");
-        else rc = launch_reduce_inst<A_DENSE, 1>(h, st, "k_reduce_group:agent_fc2");
+        if (q == 0) rc = launch_reduce_inst<A_DENSE, 0>(h, st, agent ? "k_reduce_group:agent_dense" : "k_reduce_group:mixer_dense",
+                                                        agent ? "k_reduce_tc:agent_dense" : "k_reduce_tc:mixer_dense");
+        else if (q == 1) rc = launch_reduce_inst<A_STATE, 0>(h, st, "k_reduce_group:mixer_state", "k_reduce_tc:mixer_state");
+        else if (q == 2) rc = launch_reduce_inst<A_AGENT_IN, 0>(h, st, "k_reduce_group:agent_fc1", "k_reduce_tc:agent_fc1");
+        else rc = launch_reduce_inst<A_DENSE, 1>(h, st, "k_reduce_group:agent_fc2", "k_reduce_group:agent_fc2");
         if (rc) return rc;
     }
     for (int i = 0; i < g.n; ++i)

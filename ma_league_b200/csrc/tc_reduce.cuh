@@ -1,0 +1,243 @@
+// Weight-gradient reductions on the tensor cores:  dW[n, k] = sum_m dY[m, n] * A[m, k]   (split over row chunks of m)
+// -- the `addmm` weight-gradient nodes of the reference's autograd graph (q_learner.py:103) as a split-M tcgen05 GEMM.
+//
+// The contraction runs over the ROW index m, so both MMA operands are the TRANSPOSES of what lies in memory.  Per
+// 32-row block the CTA stages the raw [32 x 128] dY and [32 x 64] A tiles in shared memory with coalesced float4 loads,
+// then every thread reads them column-wise (lanes along n / k: conflict-free), splits each value into TF32 hi + lo
+// (3xTF32, as in tc_gemm.cuh) and writes 16-byte pieces into the K-major SWIZZLE_128B operand tiles
+// (row = n or k, the 128-byte row = the block's 32 m values).  Two operand stages: the 12 MMAs of block j
+// (M = 128, N = 64, K = 8 x 4 k-steps x {hi*hi, lo*hi, hi*lo}) run while block j+1 is loaded, transposed and split.
+// TMEM accumulators (hi*hi and the correction terms apart) are folded into fp32 REGISTER accumulators every RT_FLUSH
+// blocks, so the tensor core's truncating accumulation never spans more than a few hundred rows.
+// Output: per-chunk partials [chunk][Nout][K] (+ per-chunk column sums of dY for the bias gradient), gathered in a
+// fixed order by k_grad_reduce exactly like the FFMA kernel's.
+#pragma once
+#include "tc_gemm.cuh"
+
+#define RT_BM 32                          // rows (m) per block: one 128-byte swizzle row of the contraction dimension
+#define RT_NT 128                         // n-tile (MMA M)
+#define RT_KT 64                          // k-tile (MMA N)
+#define RT_OP_A (RT_NT * 128)             // 16 KB: one of hi / lo of the dY^T operand
+#define RT_OP_B (RT_KT * 128)             //  8 KB
+#define RT_STAGE (2 * RT_OP_A + 2 * RT_OP_B)          // 48 KB
+#define RT_RAW_Y (RT_BM * RT_NT * 4)      // 16 KB
+#define RT_RAW_A (RT_BM * RT_KT * 4)      //  8 KB
+#define RT_SMEM_BYTES (2 * RT_STAGE + RT_RAW_Y + RT_RAW_A)   // 120 KB
+#define RT_FLUSH 8                        // blocks between TMEM -> register folds (256 rows)
+
+template <int AK>
+__global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ RedGroup g) {
+    extern __shared__ __align__(1024) uint8_t rt_smem[];
+    __shared__ __align__(8) uint64_t st_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bsum_s[2][RT_NT];
+    int pi = 0;
+    while (pi + 1 < g.n && (int)blockIdx.y >= g.p[pi + 1].tile0) ++pi;
+    const RedProb p = g.p[pi];
+    const BatchView &bv = g.bv;
+    const int chunk = blockIdx.x;
+    if (chunk >= p.n_chunks) return;
+    const int tile = blockIdx.y - p.tile0;
+    const int nt = tile / p.n_ktiles, kt = tile - nt * p.n_ktiles;
+    const int n0 = nt * RT_NT, k0 = kt * RT_KT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t mb = p.M0 + (int64_t)chunk * p.rows_per_chunk;
+    int64_t me = mb + p.rows_per_chunk;
+    if (me > p.M) me = p.M;
+    const int nblk = me > mb ? (int)((me - mb + RT_BM - 1) / RT_BM) : 0;
+    const bool want_bias = p.partB && kt == 0;
+
+    float *rawY = reinterpret_cast<float *>(rt_smem + 2 * RT_STAGE);
+    float *rawA = reinterpret_cast<float *>(rt_smem + 2 * RT_STAGE + RT_RAW_Y);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&st_bar[0], 1);
+        mbar_init(&st_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    const bool y_vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dY + n0) & 15) == 0);
+    const bool a_vec = AK == A_DENSE && ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A + k0) & 15) == 0);
+    const bool fast_ok = p.M < (1 << 24);
+    const float invR = 1.0f / (float)(bv.R > 0 ? bv.R : 1), invN = 1.0f / (float)(bv.N > 0 ? bv.N : 1);
+    const float invT = 1.0f / (float)(bv.T > 0 ? bv.T : 1);
+    const bool s_vec = AK == A_STATE && (bv.state.sb & 3) == 0 && (bv.state.st & 3) == 0 && (k0 & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(bv.state.ptr) & 15) == 0);
+    const bool o_vec = AK == A_AGENT_IN && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 && (bv.obs.st & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(bv.obs.ptr) & 15) == 0);
+    float4 py[4], pa[2];
+    auto load_block = [&](int j) {
+        const int64_t mm = mb + (int64_t)j * RT_BM;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                 // dY: 32 rows x 32 float4
+            const int idx = tid + 256 * i, r = idx >> 5, c = idx & 31;
+            const int64_t m = mm + r;
+            const int n = n0 + 4 * c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < me && n < p.Nout) {
+                const float *src = p.dY + m * p.ldy + n;
+                if (y_vec && n + 4 <= p.Nout) v = __ldg(reinterpret_cast<const float4 *>(src));
+                else {
+                    v.x = __ldg(src);
+                    if (n + 1 < p.Nout) v.y = __ldg(src + 1);
+                    if (n + 2 < p.Nout) v.z = __ldg(src + 2);
+                    if (n + 3 < p.Nout) v.w = __ldg(src + 3);
+                }
+            }
+            py[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                 // A: 32 rows x 16 float4
+            const int idx = tid + 256 * i, r = idx >> 4, c = idx & 15;
+            const int64_t m = mm + r;
+            const int k = k0 + 4 * c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < me && k < p.K) {
+                if (AK == A_DENSE) {
+                    if (m >= p.shift) {
+                        const float *src = p.A + (m - p.shift) * p.lda + k;
+                        if (a_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
+                        else {
+                            v.x = __ldg(src);
+                            if (k + 1 < p.K) v.y = __ldg(src + 1);
+                            if (k + 2 < p.K) v.z = __ldg(src + 2);
+                            if (k + 3 < p.K) v.w = __ldg(src + 3);
+                        }
+                    }
+                } else if (AK == A_STATE) {
+                    int b, t;
+                    if (fast_ok) fast_divmod((int)m, bv.T, invT, b, t);
+                    else { b = (int)(m / bv.T); t = (int)(m - (int64_t)b * bv.T); }
+                    const float *src = field_ptr<float>(bv.state, b, t + p.shift) + k;
+                    if (s_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
+                    else {
+                        v.x = __ldg(src);
+                        if (k + 1 < p.K) v.y = __ldg(src + 1);
+                        if (k + 2 < p.K) v.z = __ldg(src + 2);
+                        if (k + 3 < p.K) v.w = __ldg(src + 3);
+                    }
+                } else {   // [obs | last-action one-hot | agent-id one-hot]: float4 over the obs part
+                    int t, rr, b, n;
+                    if (fast_ok) { fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, n); }
+                    else { t = (int)(m / bv.R); rr = (int)(m - (int64_t)t * bv.R); b = rr / bv.N; n = rr - b * bv.N; }
+                    if (o_vec && k + 4 <= bv.OBS) {
+                        v = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS + k));
+                    } else {
+                        RowSrc rs;
+                        rs.agent = n;
+                        rs.p0 = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
+                        rs.p1 = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
+                        v.x = row_elem(A_AGENT_IN, bv, rs, k);
+                        if (k + 1 < p.K) v.y = row_elem(A_AGENT_IN, bv, rs, k + 1);
+                        if (k + 2 < p.K) v.z = row_elem(A_AGENT_IN, bv, rs, k + 2);
+                        if (k + 3 < p.K) v.w = row_elem(A_AGENT_IN, bv, rs, k + 3);
+                    }
+                }
+            }
+            pa[i] = v;
+        }
+    };
+
+    const int q = warp & 3, half = warp >> 2;         // accumulator ownership: TMEM lane quarter q, columns half*32 .. +32
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+    float bsum = 0.0f;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24);
+    bool fresh = true;                                // the next MMA overwrites the TMEM accumulators
+    auto fold = [&](int j) {                          // all MMAs up to block j -> register accumulators
+        mbar_wait(&st_bar[j & 1], (uint32_t)((j >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t d1[32], d2[32];
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+        tmem_ld32_nowait(tl, d1);
+        tmem_ld32_nowait(tl + RT_KT, d2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(d1[c]) + __uint_as_float(d2[c]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    if (nblk > 0) load_block(0);
+    for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        uint8_t *Ah = rt_smem + (size_t)s * RT_STAGE, *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
+        // ---- raw tiles (coalesced) -> shared
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i;
+            reinterpret_cast<float4 *>(rawY)[idx] = py[i];            // [r][c] with r = idx >> 5, c = idx & 31
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) reinterpret_cast<float4 *>(rawA)[tid + 256 * i] = pa[i];
+        __syncthreads();
+        if (j + 1 < nblk) load_block(j + 1);                             // flies under the transposition + MMAs
+        if (j >= 2) mbar_wait(&st_bar[s], (uint32_t)(((j - 2) >> 1) & 1));   // the MMAs of block j-2 released this stage
+        // ---- transpose + split: one 16-byte piece = 4 consecutive m of one operand row
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i, n = idx & (RT_NT - 1), mq = idx >> 7;      // n fixed per thread, mq = 0..7
+            float4 v;
+            v.x = rawY[(4 * mq) * RT_NT + n]; v.y = rawY[(4 * mq + 1) * RT_NT + n];
+            v.z = rawY[(4 * mq + 2) * RT_NT + n]; v.w = rawY[(4 * mq + 3) * RT_NT + n];
+            bsum += (v.x + v.y) + (v.z + v.w);
+            split_store_fast(Ah, Al, (uint32_t)n * 128u + (uint32_t)((mq ^ (n & 7)) << 4), v);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + 256 * i, k = idx & (RT_KT - 1), mq = idx >> 6;
+            float4 v;
+            v.x = rawA[(4 * mq) * RT_KT + k]; v.y = rawA[(4 * mq + 1) * RT_KT + k];
+            v.z = rawA[(4 * mq + 2) * RT_KT + k]; v.w = rawA[(4 * mq + 3) * RT_KT + k];
+            split_store_fast(Bh, Bl, (uint32_t)k * 128u + (uint32_t)((mq ^ (k & 7)) << 4), v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const uint64_t dAh = umma_desc_sw128(smem_u32(Ah)), dAl = umma_desc_sw128(smem_u32(Al));
+            const uint64_t dBh = umma_desc_sw128(smem_u32(Bh)), dBl = umma_desc_sw128(smem_u32(Bl));
+#pragma unroll
+            for (int ks = 0; ks < RT_BM / 8; ++ks) {
+                const uint64_t o = (uint64_t)((ks * 32) >> 4);
+                const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
+                umma_tf32(tmem_base + RT_KT, dAl + o, dBh + o, idesc, first);
+                umma_tf32(tmem_base + RT_KT, dAh + o, dBl + o, idesc, 1u);
+            }
+            umma_commit(&st_bar[s]);
+        }
+        fresh = false;
+        if ((j % RT_FLUSH) == RT_FLUSH - 1 || j == nblk - 1) {
+            fold(j);
+            fresh = true;
+        }
+    }
+    // ---- partials
+    {
+        const int n = n0 + q * 32 + lane;
+        if (n < p.Nout) {
+            float *pw = p.partW + ((int64_t)chunk * p.Nout + n) * p.K + k0 + half * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (k0 + half * 32 + c < p.K) pw[c] = acc[c];
+        }
+    }
+    if (want_bias) {
+        bsum_s[tid >> 7][tid & (RT_NT - 1)] = bsum;      // two threads per n (m-quads of parity tid >> 7)
+        __syncthreads();
+        if (tid < RT_NT && n0 + tid < p.Nout) p.partB[(int64_t)chunk * p.Nout + n0 + tid] = bsum_s[0][tid] + bsum_s[1][tid];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+}

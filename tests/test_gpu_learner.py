@@ -118,18 +118,21 @@ def test_full_size_metric_config_against_oracle():
 
 @pytest.mark.parametrize("mode", [2, 0])
 def test_both_tensor_core_gemm_kernels_inside_the_learner(mode):
-    """The launch heuristic picks the warp-specialised pipelined GEMM only for long runs (10v10 / 20v20 batches);
-    force each tcgen05 kernel (2: pipelined, 0: one tile at a time) through a whole forward/backward at the metric's
-    shape and hold both to the oracle."""
+    """The launch heuristics pick the warp-specialised pipelined GEMM and the tensor-core weight-gradient reductions
+    only for long runs (10v10 / 20v20 batches); force each variant (2: pipelined GEMM + tcgen05 reductions, 0: one
+    tile at a time + FFMA reductions) through a whole forward/backward at the metric's shape and hold both to the
+    oracle."""
     from ma_league_b200 import _native as nat
     s = seeded_system(5, 32, 201, "qmix", True, seed=13)
     ref = _oracle_run(s, "qmix", True, dtype=np.float64)
     nat.check(nat.lib().mal_set_option(b"tc_pipelined", mode), "mal_set_option")
+    nat.check(nat.lib().mal_set_option(b"reduce_tc", mode), "mal_set_option")     # 2: tcgen05 split-M reductions, 0: FFMA
     try:
         grads = split_grad(s.learner.forward_backward(s.batch), s.learner)
         it = {k: v.cpu().numpy() for k, v in s.learner.intermediates(s.batch).items()}
     finally:
         nat.check(nat.lib().mal_set_option(b"tc_pipelined", 1), "mal_set_option")
+        nat.check(nat.lib().mal_set_option(b"reduce_tc", 1), "mal_set_option")
     assert_close(it["q_tot"], ref["q_tot"], TOL, "q_tot")
     assert int((it["argmax"].astype(np.int64) != ref["argmax"]).sum()) == 0
     for k, v in ref["agent_grads"].items():
