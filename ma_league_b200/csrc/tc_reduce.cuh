@@ -2,8 +2,8 @@
 // -- the `addmm` weight-gradient nodes of the reference's autograd graph (q_learner.py:103) as a split-M tcgen05 GEMM.
 //
 // The contraction runs over the ROW index m, so both MMA operands are the TRANSPOSES of what lies in memory.  Per
-// 32-row block the CTA stages the raw [32 x 128] dY and [32 x 64] A tiles in shared memory with coalesced float4 loads,
-// then every thread reads them column-wise (lanes along n / k: conflict-free), splits each value into TF32 hi + lo
+// 32-row block every warp loads four rows of the [32 x 128] dY and [32 x 64] A tiles (coalesced float4), parks them in
+// its private shared-memory scratch, reads them back column-wise (lanes along n / k: conflict-free), splits each value into TF32 hi + lo
 // (3xTF32, as in tc_gemm.cuh) and writes 16-byte pieces into the K-major SWIZZLE_128B operand tiles
 // (row = n or k, the 128-byte row = the block's 32 m values).  Two operand stages: the 12 MMAs of block j
 // (M = 128, N = 64, K = 8 x 4 k-steps x {hi*hi, lo*hi, hi*lo}) run while block j+1 is loaded, transposed and split.
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     extern __shared__ __align__(1024) uint8_t rt_smem[];
     __shared__ __align__(8) uint64_t st_bar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bsum_s[2][RT_NT];
+    __shared__ float bsum_s[8][RT_NT];
     int pi = 0;
     while (pi + 1 < g.n && (int)blockIdx.y >= g.p[pi + 1].tile0) ++pi;
     const RedProb p = g.p[pi];
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     auto load_block = [&](int j) {
         const int64_t mm = mb + (int64_t)j * RT_BM;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                 // dY: 32 rows x 32 float4
-            const int idx = tid + 256 * i, r = idx >> 5, c = idx & 31;
+        for (int i = 0; i < 4; ++i) {                 // dY: warp w owns rows 4w .. 4w+3 (one 16-byte piece of every operand row)
+            const int r = 4 * warp + i, c = lane;
             const int64_t m = mm + r;
             const int n = n0 + 4 * c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             py[i] = v;
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {                 // A: 32 rows x 16 float4
-            const int idx = tid + 256 * i, r = idx >> 4, c = idx & 15;
+        for (int i = 0; i < 2; ++i) {                 // A: the same four rows, 16 float4 each
+            const int r = 4 * warp + 2 * i + (lane >> 4), c = lane & 15;
             const int64_t m = mm + r;
             const int k = k0 + 4 * c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
-    float bsum = 0.0f;
+    float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // column sums of dY (bias gradient): n = lane + 32 i, this warp's rows
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24);
     bool fresh = true;                                // the next MMA overwrites the TMEM accumulators
     auto fold = [&](int j) {                          // all MMAs up to block j -> register accumulators
@@ -169,35 +169,30 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
         uint8_t *Ah = rt_smem + (size_t)s * RT_STAGE, *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
-        // ---- raw tiles (coalesced) -> shared
+        // ---- raw rows (coalesced) -> the warp's private scratch; only this warp reads them back: __syncwarp suffices
+        float *ry = rawY + warp * (4 * RT_NT), *ra = rawA + warp * (4 * RT_KT);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + 256 * i;
-            reinterpret_cast<float4 *>(rawY)[idx] = py[i];            // [r][c] with r = idx >> 5, c = idx & 31
-        }
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4 *>(ry)[i * 32 + lane] = py[i];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) reinterpret_cast<float4 *>(rawA)[tid + 256 * i] = pa[i];
-        __syncthreads();
+        for (int i = 0; i < 2; ++i) reinterpret_cast<float4 *>(ra)[(2 * i + (lane >> 4)) * 16 + (lane & 15)] = pa[i];
+        __syncwarp();
         if (j + 1 < nblk) load_block(j + 1);                             // flies under the transposition + MMAs
         if (j >= 2) mbar_wait(&st_bar[s], (uint32_t)(((j - 2) >> 1) & 1));   // the MMAs of block j-2 released this stage
-        // ---- transpose + split: one 16-byte piece = 4 consecutive m of one operand row
+        // ---- transpose + split: the warp's four rows are 16-byte piece `warp` of every operand row
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int idx = tid + 256 * i, n = idx & (RT_NT - 1), mq = idx >> 7;      // n fixed per thread, mq = 0..7
-            float4 v;
-            v.x = rawY[(4 * mq) * RT_NT + n]; v.y = rawY[(4 * mq + 1) * RT_NT + n];
-            v.z = rawY[(4 * mq + 2) * RT_NT + n]; v.w = rawY[(4 * mq + 3) * RT_NT + n];
-            bsum += (v.x + v.y) + (v.z + v.w);
-            split_store_fast(Ah, Al, (uint32_t)n * 128u + (uint32_t)((mq ^ (n & 7)) << 4), v);
+            const int n = lane + 32 * i;
+            const float4 v = make_float4(ry[n], ry[RT_NT + n], ry[2 * RT_NT + n], ry[3 * RT_NT + n]);
+            bsum[i] += (v.x + v.y) + (v.z + v.w);
+            split_store_fast(Ah, Al, (uint32_t)n * 128u + (uint32_t)((warp ^ (n & 7)) << 4), v);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int idx = tid + 256 * i, k = idx & (RT_KT - 1), mq = idx >> 6;
-            float4 v;
-            v.x = rawA[(4 * mq) * RT_KT + k]; v.y = rawA[(4 * mq + 1) * RT_KT + k];
-            v.z = rawA[(4 * mq + 2) * RT_KT + k]; v.w = rawA[(4 * mq + 3) * RT_KT + k];
-            split_store_fast(Bh, Bl, (uint32_t)k * 128u + (uint32_t)((mq ^ (k & 7)) << 4), v);
+            const int k = lane + 32 * i;
+            const float4 v = make_float4(ra[k], ra[RT_KT + k], ra[2 * RT_KT + k], ra[3 * RT_KT + k]);
+            split_store_fast(Bh, Bl, (uint32_t)k * 128u + (uint32_t)((warp ^ (k & 7)) << 4), v);
         }
+        __syncwarp();                                                    // scratch is rewritten by the next block
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -232,9 +227,15 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         }
     }
     if (want_bias) {
-        bsum_s[tid >> 7][tid & (RT_NT - 1)] = bsum;      // two threads per n (m-quads of parity tid >> 7)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bsum_s[warp][lane + 32 * i] = bsum[i];
         __syncthreads();
-        if (tid < RT_NT && n0 + tid < p.Nout) p.partB[(int64_t)chunk * p.Nout + n0 + tid] = bsum_s[0][tid] + bsum_s[1][tid];
+        if (tid < RT_NT && n0 + tid < p.Nout) {
+            float sacc = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sacc += bsum_s[w][tid];
+            p.partB[(int64_t)chunk * p.Nout + n0 + tid] = sacc;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
