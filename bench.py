@@ -285,6 +285,16 @@ def run_ours(a, rank, world, device):
 
     for c in consumed:
         c.record()
+    # the H2D copy alone (pinned -> device on the copy stream): the e2e step cannot be shorter than this
+    hs, he = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    with th.cuda.stream(copy_stream):
+        stage[0]._storage.copy_(pinned[0], non_blocking=True)
+        hs.record(copy_stream)
+        for _ in range(8):
+            stage[0]._storage.copy_(pinned[0], non_blocking=True)
+        he.record(copy_stream)
+    copy_stream.synchronize()
+    h2d_ms = hs.elapsed_time(he) / 8
     e2e_steps(max(a.warmup, 3), 0)
     barrier()
     t0 = time.perf_counter()
@@ -292,7 +302,8 @@ def run_ours(a, rank, world, device):
     barrier()
     e2e_s = dist_max(time.perf_counter() - t0)
     e2e = {"value": world * transitions * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * rb,
-           "d2h_bytes_per_step": 32, "ms_per_step": e2e_s / a.steps * 1e3,
+           "d2h_bytes_per_step": 32, "ms_per_step": e2e_s / a.steps * 1e3, "h2d_copy_alone_ms": round(h2d_ms, 4),
+           "h2d_gbs": round(B * rb / (h2d_ms * 1e-3) / 1e9, 1),
            "how": "pinned host batch -> double-buffered H2D on a copy stream -> QLearner.train -> loss D2H + sync"}
     assert np.isfinite(last_loss)
 

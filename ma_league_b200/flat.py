@@ -11,12 +11,20 @@ import torch as th
 def ensure_flat(module, device=None):
     """Return the flat fp32 buffer that backs all parameters of `module` in registration order."""
     params = getattr(module, "_mal_params", None)
-    if params is not None and params and next(module.parameters()) is not params[0]:
-        params = None                          # parameters were re-created (e.g. load_state_dict(assign=True))
-        module._mal_total = None
+    if params is not None and params:
+        owner, attr = module._mal_first       # O(1) probe of the first registered parameter (no generator walk)
+        if owner._parameters.get(attr) is not params[0]:
+            params = None                      # parameters were re-created (e.g. load_state_dict(assign=True))
+            module._mal_total = None
     if params is None:
         params = list(module.parameters())
         module._mal_params = params           # the module structure of this path is fixed after construction
+        module._mal_first = None
+        for sub in module.modules():
+            if sub._parameters:
+                name = next(k for k, v in sub._parameters.items() if v is not None)
+                module._mal_first = (sub, name)
+                break
     if not params:
         return None
     dev = th.device(device) if device is not None else params[0].device

@@ -60,6 +60,7 @@ class QLearner(Learner):
         self.use_graphs = bool(getattr(args, "cuda_graphs", True))
         self._graphs = {}        # key -> (CUDAGraph, kernels per replay) ; key -> None after the first (eager) sighting
         self._graph_cap = 32
+        self._bs_cache = {}
 
     def parameters(self):
         return list(self.mac.parameters()) + list(self.mixer.parameters())
@@ -85,6 +86,18 @@ class QLearner(Learner):
 
     def _batch_struct(self, batch):
         obs = nat.require_cuda(batch["obs"], "batch")
+        # the marshalled struct only depends on where the batch's tensors live: reuse it for a batch seen before
+        ck = (obs.data_ptr(), obs.shape, obs.stride(), batch["filled"].data_ptr(), batch["state"].data_ptr())
+        hit = self._bs_cache.get(ck)
+        if hit is not None:
+            return hit
+        if len(self._bs_cache) >= 64:
+            self._bs_cache.clear()
+        bs = self._batch_struct_build(batch, obs)
+        self._bs_cache[ck] = bs
+        return bs
+
+    def _batch_struct_build(self, batch, obs):
         B, TT, N, OBS = obs.shape
         A = self.args.n_actions
         state = batch["state"]
@@ -143,10 +156,11 @@ class QLearner(Learner):
             raise nat.MalError("call build_optimizer() before train() (ma_experiment.py:61)")
         dev = batch["obs"].device
         dp = cfg.unnormalized != 0
+        counted = False                          # True: the trained-steps counter was advanced inside the replayed graph
         if dp:
             self._train_data_parallel(bs, cfg, f, dev)
         elif self.use_graphs and not self.save_q:
-            self._step_graphed(bs, cfg, f, dev)
+            counted = self._step_graphed(bs, cfg, f, dev)
         else:
             self._step_eager(bs, cfg, f, dev)
         self.optimiser._steps += 1
@@ -165,7 +179,7 @@ class QLearner(Learner):
         if dp:
             n_total = self._grad.numel()
             self.mac.update_trained_steps(self._grad_store[n_total + 5:n_total + 6].round())   # global count
-        else:
+        elif not counted:
             self.mac.update_trained_steps(sc[nat.SC_MASK_COUNT:nat.SC_MASK_COUNT + 1].view(th.int32))
 
         if t_env - self.log_stats_t >= self.args.learner_log_interval:
@@ -201,24 +215,27 @@ class QLearner(Learner):
             graph, n_kernels = entry
             graph.replay()
             nat.lib().mal_count_launches(n_kernels)
-            return
+            return True
         if entry is False:                      # first sighting: eager
             if len(self._graphs) >= self._graph_cap:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = None
             self._step_eager(bs, cfg, f, dev)
-            return
+            return False
         # second sighting: capture (the capture stream becomes torch's current stream, which the C ABI call reads)
         lib = nat.lib()
         graph = th.cuda.CUDAGraph()
         th.cuda.synchronize(dev)
         n0 = lib.mal_launch_count()
+        sc = self.scalars()
+        self.mac.update_trained_steps(th.zeros(1, dtype=th.int32, device=dev))      # the device counter exists before capture
         with th.cuda.graph(graph):
             self._step_eager(bs, cfg, f, dev)
+            self.mac.update_trained_steps(sc[nat.SC_MASK_COUNT:nat.SC_MASK_COUNT + 1].view(th.int32))
         n_kernels = lib.mal_launch_count() - n0
         self._graphs[key] = (graph, n_kernels)
         graph.replay()                          # capture only records: this performs the step
-        return
+        return True
 
     def _train_data_parallel(self, bs, cfg, f, dev):
         """Config 5: every rank back-propagates the UN-normalised sum over its batch shard, one

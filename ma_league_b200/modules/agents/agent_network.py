@@ -19,7 +19,8 @@ class AgentNetwork(nn.Module):
     @trained_steps.setter
     def trained_steps(self, value):
         self._trained_steps_host = int(value)
-        self._trained_steps_dev = None
+        if self._trained_steps_dev is not None:
+            self._trained_steps_dev.zero_()   # in place: a captured CUDA graph of the learner step keeps adding into it
 
     def init_hidden(self):
         raise NotImplementedError()
