@@ -139,6 +139,16 @@ int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixe
 /* denominator: NULL, or a DEVICE pointer to the global mask sum; the gradient is divided by it first (data-parallel
  * mode: grads and mask sums are all-reduced across ranks, then every rank applies the identical update). */
 
+/* Data-parallel mode, fused exchange: peer_bufs[r] = device pointer of rank r's symmetric buffer holding its UN-normalised
+ * gradient [n_agent + n_mixer] followed by `tail` raw statistic sums (element 4 = its mask sum), all peer-mapped into
+ * this process (torch symmetric memory / cudaIpc).  One kernel sums them in rank order over NVLink, normalises by the
+ * global mask sum into the LOCAL grad_out, writes the reduced tail to tail_out, then clip + RMSprop run as usual.
+ * The caller separates steps with a cross-rank barrier (nobody rewrites a buffer that a peer may still be reading). */
+int mal_peer_allreduce_clip_rmsprop(const void *const *peer_bufs, int32_t world, float *agent, int64_t n_agent, float *mixer,
+                                    int64_t n_mixer, float *grad_out, float *tail_out, int32_t tail, float *square_avg,
+                                    float lr, float alpha, float eps, float clip, float *scalars, float *scratch,
+                                    void *stream);
+
 /* forward + backward + clip + RMSprop in one call (the whole of q_learner.py:34-105). */
 int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
                      float *agent, const float *target_agent, float *mixer, const float *target_mixer,

@@ -1028,6 +1028,29 @@ extern "C" int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int
                                scalars, denominator, (cudaStream_t)stream);
 }
 
+extern "C" int mal_peer_allreduce_clip_rmsprop(const void *const *peer_bufs, int32_t world, float *agent, int64_t n_agent,
+                                               float *mixer, int64_t n_mixer, float *grad_out, float *tail_out, int32_t tail,
+                                               float *square_avg, float lr, float alpha, float eps, float clip,
+                                               float *scalars, float *scratch, void *stream) {
+    MAL_REQUIRE(peer_bufs && world >= 1 && world <= PEER_MAX, "mal_peer_allreduce_clip_rmsprop: world size must be in [1, %d]", PEER_MAX);
+    MAL_REQUIRE(agent && grad_out && tail_out && square_avg && scalars && scratch && n_agent > 0 && n_mixer >= 0 && tail >= 5 && tail <= 32,
+                "mal_peer_allreduce_clip_rmsprop: bad arguments (scratch needs ceil(P/256) floats, tail >= 5)");
+    PeerBufs pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.world = world;
+    for (int r = 0; r < world; ++r) {
+        MAL_REQUIRE(peer_bufs[r], "mal_peer_allreduce_clip_rmsprop: null peer buffer");
+        pb.p[r] = reinterpret_cast<const float *>(peer_bufs[r]);
+    }
+    const int64_t P = n_agent + n_mixer;
+    const int nb = (int)ceil_div64(P, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    { ProfScope _ps("k_peer_allreduce_grad", st); k_peer_allreduce_grad<<<nb, 256, 0, st>>>(pb, P, tail, grad_out, tail_out, scratch); }
+    MAL_LAUNCH_CHECK("k_peer_allreduce_grad");
+    return launch_clip_rmsprop(agent, n_agent, mixer, n_mixer, grad_out, square_avg, scratch, nb, lr, alpha, eps, clip,
+                               scalars, nullptr, st);
+}
+
 extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
                                 float *agent, const float *target_agent, float *mixer, const float *target_mixer,
                                 void *workspace, float *grad, float *square_avg, void *stream) {

@@ -243,6 +243,9 @@ class QLearner(Learner):
         divides by the global mask sum and applies the identical clip + RMSprop, which reproduces
         `loss = sum(masked_td^2) / mask.sum()` of q_learner.py:98 over the global batch."""
         import torch.distributed as dist
+        sym = self._dp_symmetric(self._grad.numel(), dev)
+        if sym is not None:
+            return self._train_data_parallel_fused(bs, cfg, f, dev, sym)
         lib, st = nat.lib(), nat.current_stream(dev)
         n_total = self._grad.numel()
         with nat.on_device(dev):
@@ -262,6 +265,60 @@ class QLearner(Learner):
                                            nat.ptr(self.optimiser.flat_sq), a.lr, a.optim_alpha, a.optim_eps,
                                            a.grad_norm_clip, nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
                                            nat.ptr(denom), st), "mal_clip_rmsprop")
+
+    # ---- fused exchange: peer-memory all-reduce inside the optimiser prologue (no NCCL call on the path)
+    def _dp_symmetric(self, n_total, dev):
+        """Two symmetric (peer-mapped) halves of [n_total + DP_TAIL] floats, rendezvoused over the default group.
+        Returns None when the platform cannot provide them (then the NCCL all-reduce path is used)."""
+        st = getattr(self, "_dp_sym", None)
+        if st is not None and (st is False or st[0].shape[1] == n_total + DP_TAIL):
+            return st or None
+        self._dp_sym = False
+        if not getattr(self.args, "dp_fused", True):
+            return None
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            if dist.get_backend() != "nccl":
+                return None
+            buf = symm_mem.empty(2, n_total + DP_TAIL, dtype=th.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if hdl.world_size > 16:
+                return None
+            buf.zero_()
+            ptrs = [(C.c_void_p * hdl.world_size)(*[int(p) + 4 * h * (n_total + DP_TAIL) for p in hdl.buffer_ptrs])
+                    for h in range(2)]
+            hdl.barrier(channel=0)
+            self._dp_sym = (buf, hdl, ptrs)
+            self._dp_step = 0
+        except Exception as ex:                         # no peer access / symmetric memory on this platform
+            self._dp_sym_error = repr(ex)
+            return None
+        return self._dp_sym
+
+    def _train_data_parallel_fused(self, bs, cfg, f, dev, sym):
+        buf, hdl, ptrs = sym
+        lib, st = nat.lib(), nat.current_stream(dev)
+        n_total = self._grad.numel()
+        h = self._dp_step & 1                            # double-buffered: ONE cross-rank barrier per step is enough
+        half = buf[h]
+        with nat.on_device(dev):
+            nat.check(lib.mal_learner_forward(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
+                                              nat.ptr(f["tagent"]), nat.ptr(f["mixer"]), nat.ptr(f["tmixer"]),
+                                              nat.ptr(self._ws), st), "mal_learner_forward")
+            nat.check(lib.mal_learner_backward(C.byref(bs), C.byref(cfg), C.byref(self._plan), nat.ptr(f["agent"]),
+                                               nat.ptr(f["mixer"]), nat.ptr(self._ws), nat.ptr(half), st),
+                      "mal_learner_backward")
+        half[n_total:n_total + DP_RAW].copy_(self.scalars()[nat.SC_RAW0:nat.SC_RAW0 + DP_RAW])
+        hdl.barrier(channel=0)                           # every rank's half h is complete (and half h^1 is free again)
+        a = self.args
+        with nat.on_device(dev):
+            nat.check(lib.mal_peer_allreduce_clip_rmsprop(
+                ptrs[h], hdl.world_size, nat.ptr(f["agent"]), self._plan.n_agent_params, nat.ptr(f["mixer"]),
+                self._plan.n_mixer_params, nat.ptr(self._grad), nat.ptr(self._grad_store[n_total:]), DP_TAIL,
+                nat.ptr(self.optimiser.flat_sq), a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip,
+                nat.ptr(self.scalars()), nat.ptr(self._dp_scratch), st), "mal_peer_allreduce_clip_rmsprop")
+        self._dp_step += 1
 
     def train_from_buffer(self, buffer, batch_size: int, t_env: int, episode_num: int, truncate: bool = False):
         """The learner-side input pipeline of runs/train/ma_experiment.py:231-239 in one call:

@@ -102,7 +102,7 @@ def test_dp_reduction_contract_gloo_world2():
 
 
 # ---------------------------------------------------------------------------------------------- GPU
-def _gpu_worker(rank, world, port, out, nccl):
+def _gpu_worker(rank, world, port, out, nccl, fused=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = "cuda:%d" % (rank if nccl else 0)      # gloo: both ranks share cuda:0; nccl: one GPU per rank
     th.cuda.set_device(dev)
@@ -112,29 +112,33 @@ def _gpu_worker(rank, world, port, out, nccl):
         dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from tests.gpu_helpers import seeded_system, np_params
-        s = seeded_system(3, 8, 12, "qmix", True, seed=5, device=dev, data_parallel=True, learner_log_interval=0)
+        s = seeded_system(3, 8, 12, "qmix", True, seed=5, device=dev, data_parallel=True, learner_log_interval=0,
+                          dp_fused=fused)
         B = s.batch.batch_size
         lo, hi = rank * B // world, (rank + 1) * B // world
         for i in range(3):
             s.learner.train(s.batch[lo:hi], t_env=i, episode_num=i)
         th.cuda.synchronize()
         out.put((rank, np_params(s.mac.agent), np_params(s.learner.mixer),
-                 {k: v[0] for k, v in s.logger.stats.items()}, s.mac.agent.trained_steps))
+                 {k: v[0] for k, v in s.logger.stats.items()}, s.mac.agent.trained_steps,
+                 bool(getattr(s.learner, "_dp_sym", None)), getattr(s.learner, "_dp_sym_error", "")))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nccl", [False, True])
-def test_dp_train_two_ranks_equals_full_batch(nccl):
+@pytest.mark.parametrize("nccl,fused", [(False, False), (True, False), (True, True)])
+def test_dp_train_two_ranks_equals_full_batch(nccl, fused):
+    """gloo on one GPU and NCCL on two GPUs use the all-reduce path; (True, True) is the fused exchange: the peer-memory
+    all-reduce kernel reads both ranks' symmetric gradient buffers over NVLink inside the optimiser prologue."""
     from tests.gpu_helpers import seeded_system, np_params
     if nccl and th.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gradient all-reduce over NCCL / NVLink)")
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, out, nccl)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, out, nccl, fused)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([out.get(), out.get()], key=lambda r: r[0])
@@ -145,7 +149,8 @@ def test_dp_train_two_ranks_equals_full_batch(nccl):
     for i in range(3):
         s.learner.train(s.batch, t_env=i, episode_num=i)
     ref_a, ref_m = np_params(s.mac.agent), np_params(s.learner.mixer)
-    for _, pa, pm, stats, steps in res:
+    for _, pa, pm, stats, steps, was_fused, err in res:
+        assert was_fused == fused, err
         for k in ref_a:
             assert_close(pa[k], ref_a[k], 1e-5, "dp agent " + k)
         for k in ref_m:
