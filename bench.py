@@ -143,7 +143,12 @@ def run_ours(a, rank, world, device):
     N, A, OBS, S, B, TT = d["N"], d["A"], d["OBS"], d["S"], d["B"], d["TT"]
     th.manual_seed(1000 + rank)
     np.random.seed(1000 + rank)
-    args = make_args(N, A, S, mixer=d["mixer"], double_q=True, device=device, batch_size=B, buffer_size=a.buffer_size)
+    B_global = B
+    if a.dp:
+        assert B % world == 0, "--dp needs the batch to divide by the number of ranks"
+        B = B // world                                   # this rank's shard of the global batch
+    args = make_args(N, A, S, mixer=d["mixer"], double_q=True, device=device, batch_size=B, buffer_size=a.buffer_size,
+                     data_parallel=bool(a.dp), dp_fused=not a.dp_nccl)
     scheme, groups, pre = make_scheme(N, A, OBS, S)
     buf = M.ReplayBuffer(scheme, groups, a.buffer_size, TT, preprocess=pre, device=device)
     mac = M.mac_REGISTRY[args.mac](buf.scheme, groups, args)
@@ -388,11 +393,15 @@ def run_ours(a, rank, world, device):
                         "frac_of_hbm_peak": k["frac_of_hbm_peak"]})
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if a.dp else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: QMIX (2-layer hypernet, double-Q), B=%d, T=%d, N=%d, A=%d, OBS=%d, S=%d, "
                                    "H=64, one independent league matchup per GPU" % (a.workload, B, TT - 1, N, A, OBS, S),
-                       "transitions_per_step": transitions, "parallelism": "league-sharded x%d (no collective)" % world,
+                       "transitions_per_step": transitions,
+                       "parallelism": ("data-parallel x%d: global batch %d split over the ranks, %s" % (
+                           world, B_global, "NCCL all_reduce of gradient + statistic sums" if a.dp_nccl or not getattr(learner, "_dp_sym", None)
+                           else "peer-memory all-reduce fused into the clip+RMSprop prologue")) if a.dp
+                       else "league-sharded x%d (no collective)" % world,
                        "l2": "inputs rotate over %d sampled batches (%.0f MB) > 126 MB L2" % (nb, nb * B * rb / 2 ** 20),
                        "replay_buffer_episodes": a.buffer_size,
                        "math": "fp32; batched projections on tcgen05 3xTF32 (fp32-accurate), recurrences fp32 FFMA2",
@@ -448,6 +457,9 @@ def main():
     ap.add_argument("--workload", default="qmix_5v5_b32")
     ap.add_argument("--buffer-size", dest="buffer_size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", action="store_true", help="data-parallel mode (config 5): the batch is split over the ranks, "
+                    "gradients meet in the fused peer-memory all-reduce (strong scaling)")
+    ap.add_argument("--dp-nccl", dest="dp_nccl", action="store_true", help="with --dp: exchange through NCCL all_reduce instead")
     ap.add_argument("--opt", action="append", default=[], help="library switch name=int (mal_set_option), e.g. reduce_tc=0")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
