@@ -74,6 +74,8 @@ def _oracle_run(s, mixer, double_q, dtype=np.float64):
 @pytest.mark.parametrize("N,B,TT,mixer,double_q,layers", [
     (5, 8, 21, "qmix", True, 2), (5, 8, 21, "vdn", True, 2), (3, 5, 12, "qmix", False, 1), (10, 3, 7, "qmix", True, 2),
     (2, 1, 2, "qmix", True, 2), (20, 2, 5, "qmix", True, 2),
+    (26, 1, 3, "qmix", True, 2),      # n_actions = 32 = MAL_MAX_ACTIONS, widest agent input (246 columns)
+    (1, 2, 3, "vdn", False, 2),       # a single agent
 ])
 def test_against_oracle_seeded(N, B, TT, mixer, double_q, layers):
     s = seeded_system(N, B, TT, mixer, double_q, seed=N + B, hypernet_layers=layers)
