@@ -63,21 +63,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     if (tid < G3) bih_s[tid] = __ldg(P + L.b_ih + tid);
     const int c4 = tid & 15, rbase = tid >> 4;          // staging map: float4 column c4 of a 64-wide chunk, rows rbase + 16 i
     const uint32_t a_slab = (uint32_t)(c4 >> 3) * AI_SLAB_A;
-    // W_ih [192 x 64], resident for the whole kernel
-    for (int j = rbase; j < G3; j += 16) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(P + L.w_ih + (int64_t)j * HID + 4 * c4));
-        split_store_fast(W2_hi, W2_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W2 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+    // W_ih [192 x 64], resident for the whole kernel (all twelve loads of a thread in flight before the first split)
+    {
+        float4 wv[G3 / 16];
+#pragma unroll
+        for (int i = 0; i < G3 / 16; ++i)
+            wv[i] = __ldg(reinterpret_cast<const float4 *>(P + L.w_ih + (int64_t)(rbase + 16 * i) * HID + 4 * c4));
+#pragma unroll
+        for (int i = 0; i < G3 / 16; ++i) {
+            const int j = rbase + 16 * i;
+            split_store_fast(W2_hi, W2_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W2 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
+        }
     }
     auto stage_w1 = [&](int kc) {                       // fc1.weight[:, kc*64 .. +64) (columns >= K1 are zero)
         const int kcol = kc * TC_KC + 4 * c4;
-        for (int j = rbase; j < HID; j += 16) {
-            const float *wr = P + L.fc1_w + (int64_t)j * a.d_in + kcol;
+        float4 wv[HID / 16];
+#pragma unroll
+        for (int i = 0; i < HID / 16; ++i) {
+            const float *wr = P + L.fc1_w + (int64_t)(rbase + 16 * i) * a.d_in + kcol;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kcol < K1) v.x = __ldg(wr);             // d_in is not a multiple of 4 in general: scalar loads
             if (kcol + 1 < K1) v.y = __ldg(wr + 1);
             if (kcol + 2 < K1) v.z = __ldg(wr + 2);
             if (kcol + 3 < K1) v.w = __ldg(wr + 3);
-            split_store_fast(W1_hi, W1_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W1 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+            wv[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < HID / 16; ++i) {
+            const int j = rbase + 16 * i;
+            split_store_fast(W1_hi, W1_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W1 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
         }
     };
     int w1_staged = -1;

@@ -333,12 +333,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                 if (w_id != w_cached) {
                     if (!p.w_trans && (p.ldw & 3) == 0 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0)) {
                         const int kcol = k0 + 4 * c4;
-#pragma unroll 1
-                        for (int j = rbase; j < nw; j += 16) {
-                            const int n = n0 + j;
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (n < Nout && kcol < K) v = __ldg(reinterpret_cast<const float4 *>(p.W + (int64_t)n * p.ldw + kcol));
-                            split_store_fast(W_hi, W_lo, w_slab + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), v);
+                        float4 wv[TC_NMAX / 16];          // all loads in flight before the first conversion
+#pragma unroll
+                        for (int i = 0; i < TC_NMAX / 16; ++i) {
+                            const int j = rbase + 16 * i, n = n0 + j;
+                            wv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (j < nw && n < Nout && kcol < K) wv[i] = __ldg(reinterpret_cast<const float4 *>(p.W + (int64_t)n * p.ldw + kcol));
+                        }
+#pragma unroll
+                        for (int i = 0; i < TC_NMAX / 16; ++i) {
+                            const int j = rbase + 16 * i;
+                            if (j < nw) split_store_fast(W_hi, W_lo, w_slab + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
                         }
                     } else if (!p.w_trans) {
                         for (int idx = tid; idx < nw * TC_KC; idx += TC_THREADS) {
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                             const uint32_t off = (uint32_t)(kk >> 5) * TC_SLAB_W + sw128_off(j, kk & 31);
                             const uint32_t h = tf32_rna(v);
                             *reinterpret_cast<uint32_t *>(W_hi + off) = h;
-                            *reinterpret_cast<uint32_t *>(W_lo + off) = tf32_rna(v - __uint_as_float(h));
+                            *reinterpret_cast<float *>(W_lo + off) = v - __uint_as_float(h);
                         }
                     } else {   // W(n,k) = W[k*ldw + n]: lanes along n (coalesced)
                         for (int idx = tid; idx < nw * TC_KC; idx += TC_THREADS) {
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                             const uint32_t off = (uint32_t)(kk >> 5) * TC_SLAB_W + sw128_off(j, kk & 31);
                             const uint32_t h = tf32_rna(v);
                             *reinterpret_cast<uint32_t *>(W_hi + off) = h;
-                            *reinterpret_cast<uint32_t *>(W_lo + off) = tf32_rna(v - __uint_as_float(h));
+                            *reinterpret_cast<float *>(W_lo + off) = v - __uint_as_float(h);
                         }
                     }
                     w_cached = w_id;
