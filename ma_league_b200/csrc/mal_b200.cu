@@ -605,7 +605,6 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     SideStreams *ss;
     if (side_streams(&ss)) return 2;
     cudaStream_t sm = g_overlap ? ss->s[0] : st;    // mixer hypernets only depend on the state: run beside the agent path
-    if (fork_to(st, sm, ss->fork_ev[0])) return 2;
 
     // x = relu(fc1([obs | last action | agent id])) and gi = W_ih x + b_ih for every (t,b,n), both nets
     //                                                  basic_controller.py:80-92, drqn_agent.py:30-31, GRUCell input half
@@ -642,6 +641,9 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         if (int rc = launch_linear(g, d.M1, HID, st, "k_linear_group:w_ih")) return rc;
     }
     }
+    // the mixer hypernet GEMMs start here, beside the (latency-bound) recurrence, not beside the agent-input GEMMs
+    // they would compete with for shared memory and tensor cores
+    if (fork_to(st, sm, ss->fork_ev[0])) return 2;
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
     {
         GruFwdArgs a;
