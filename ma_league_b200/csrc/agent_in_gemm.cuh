@@ -29,6 +29,7 @@ struct AgentInArgs {
     float *x[2];               // [M1, 64]
     float *gi[2];              // [M1, 192]
     int64_t M1;
+    int64_t m_begin, m_end;    // row range of this launch (time-chunked forward: rows of t in [t0, t1))
     int d_in, n_actions;
     BatchView bv;
 };
@@ -44,8 +45,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, net = blockIdx.y;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
     const float *P = a.params[net];
-    const int64_t M = a.M1;
-    const int n_mtiles = (int)((M + TC_M - 1) / TC_M);
+    const int64_t M = a.m_end;                          // rows >= m_end belong to another launch
+    const int n_mtiles = (int)((a.m_end - a.m_begin + TC_M - 1) / TC_M);
     if ((int)blockIdx.x >= n_mtiles) return;
     const BatchView &bv = a.bv;
     const int K1 = bv.OBS + bv.A;                       // the agent-id columns are a bias gather in the epilogue
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     float4 pre[8];
     bool have_pre = false;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-        const int64_t m0 = (int64_t)mt * TC_M;
+        const int64_t m0 = a.m_begin + (int64_t)mt * TC_M;
         // ---------------------------------------------------------------- x = fc1(input): nkc1 k-chunks into acc 1
         for (int kc = 0; kc < nkc1; ++kc) {
             float4 v[8];
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
             if (kc == nkc1 - 1) {                       // next tile's first input chunk flies under the rest of this tile
                 have_pre = false;
                 if (mt + (int)gridDim.x < n_mtiles) {
-                    load_in((int64_t)(mt + (int)gridDim.x) * TC_M, 0, pre);
+                    load_in(a.m_begin + (int64_t)(mt + (int)gridDim.x) * TC_M, 0, pre);
                     have_pre = true;
                 }
             }

@@ -373,6 +373,7 @@ struct GruFwdArgs {
     float *hout[2];            // [TT*R,64]
     float *gates;              // [TT*R,64,4] online only: (r, z, n, gh_n) per unit
     int TT, R, d_in, n_actions;
+    int t0, t1;                // timesteps of this launch: [t0, t1); h_{t0-1} comes from hout (zeros for t0 = 0)
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
@@ -404,7 +405,9 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     float *hout = net ? a.hout[1] : a.hout[0];
     float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
 
-    h_s[0][i] = 0.0f; h_s[1][i] = 0.0f;          // init_hidden: zeros
+    const int t0 = a.t0, t1 = a.t1;
+    float hprev = t0 > 0 ? hout[((int64_t)(t0 - 1) * a.R + row) * HID + i] : 0.0f;   // init_hidden: zeros
+    h_s[0][i] = hprev; h_s[1][i] = 0.0f;
     unsigned long long w[3][HID / 2];   // packed pairs (W_hh[g*64+i][2j], W_hh[g*64+i][2j+1]) for FFMA2
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
@@ -420,25 +423,24 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     const float *p_g = gi + (int64_t)row * G3 + i;
 #pragma unroll
     for (int p = 0; p < PF; ++p) {
-        if (p < a.TT) {
+        if (t0 + p < t1) {
 #pragma unroll
-            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], p_g + p * tstride + g * HID);
+            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], p_g + (int64_t)(t0 + p) * tstride + g * HID);
         }
         cp_async_commit();
     }
-    float hprev = 0.0f;
     __syncthreads();
 
-    for (int t0 = 0; t0 < a.TT; t0 += 2) {
+    for (int tt = t0; tt < t1; tt += 2) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const int t = t0 + p;
-            if (t >= a.TT) break;
-            const int buf = p;                   // == t & 1
-            const int slot = t % PF;
+            const int t = tt + p;
+            if (t >= t1) break;
+            const int buf = p;                   // == (t - t0) & 1
+            const int slot = (t - t0) % PF;
             cp_async_wait<PF - 1>();             // this thread's group of step t has landed
             const float g_r = st_s[slot][0][i], g_z = st_s[slot][1][i], g_n = st_s[slot][2][i];
-            if (t + PF < a.TT) {
+            if (t + PF < t1) {
 #pragma unroll
                 for (int g = 0; g < 3; ++g) cp_async4(&st_s[slot][g][i], p_g + (int64_t)(t + PF) * tstride + g * HID);
             }

@@ -37,7 +37,7 @@ int main(int argc, char **argv) {
     for (int n = 0; n < 2; ++n) { cudaMalloc(&h[n], M * HID * 4); cudaMemset(h[n], 0, M * HID * 4); }
     cudaMalloc(&gates, M * 256 * 4); cudaMalloc(&dg, M * 256 * 4);
     GruFwdArgs fa; fa.params[0] = dP0; fa.params[1] = dP1; fa.gi[0] = dgi0; fa.gi[1] = dgi1; fa.hout[0] = h[0]; fa.hout[1] = h[1];
-    fa.gates = gates; fa.TT = TT; fa.R = R; fa.d_in = d_in; fa.n_actions = A;
+    fa.gates = gates; fa.TT = TT; fa.R = R; fa.d_in = d_in; fa.n_actions = A; fa.t0 = 0; fa.t1 = TT;
     GruBwdArgs ba; ba.params = dP0; ba.hout = h[0]; ba.gates = gates; ba.dh_head = ddhh; ba.d_g = dg; ba.TT = TT; ba.R = R;
     ba.d_in = d_in; ba.n_actions = A;
 
