@@ -704,7 +704,8 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
             st[0] += mtd * mtd; st[1] += fabsf(mtd); st[2] += y * mk; st[3] += target * mk;
             st[4] += mk; st[5] += (mk != 0.0f) ? 1.0f : 0.0f;
         }
-        const int act_mine = lane < a.N ? (int)(field_ptr<long long>(a.actions, b, t)[lane]) : 0;
+        int act_mine = lane < a.N ? (int)(field_ptr<long long>(a.actions, b, t)[lane]) : 0;
+        act_mine = act_mine < 0 ? 0 : (act_mine >= a.A ? a.A - 1 : act_mine);            // never read outside fc2.weight
         // gather + fc2 backward: d h_t[row n] = d_chosen[n] * fc2.weight[a_t[n], :]   (consumed by the BPTT kernel)
         auto head_inject = [&](float dq_lane) {
             float *dh = a.dh_head + ((int64_t)t * a.R + (int64_t)b * a.N) * HID;
@@ -945,6 +946,7 @@ __global__ void __launch_bounds__(256) k_fc2_grad(Fc2GradArgs a) {
                 const int b = rr / a.N, n = rr - b * a.N;
                 d[u] = __ldg(a.d_chosen + ((int64_t)b * a.T + t) * a.N + n);
                 act[u] = (int)(field_ptr<long long>(a.actions, b, t)[n]);
+                act[u] = act[u] < 0 ? 0 : (act[u] >= a.A ? a.A - 1 : act[u]);   // never index outside the accumulators
                 h[u] = __ldg(reinterpret_cast<const float2 *>(a.hout + m * HID) + lane);
             }
         }
