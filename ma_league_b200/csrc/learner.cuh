@@ -548,16 +548,19 @@ __global__ void __launch_bounds__(128, 4) k_q_head(HeadArgs a) {   // <= 128 reg
             avr[j] = (net == 1 && t >= 1 && a0 + j < a.A) ? __ldg(av + a0 + j) : 1;
         }
 #pragma unroll
-        for (int k4 = 0; k4 < HID / 4; ++k4) {
+        for (int j = 0; j < 8; ++j) {
+            if (a0 + j < a.A) {                              // warp-uniform, once per action (not per k)
+                const float4 *wj = reinterpret_cast<const float4 *>(w2 + (a0 + j) * HID);
+                float e0 = q[j];                             // one chain in ascending k: the summation order of the fixtures
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (a0 + j < a.A) {                          // warp-uniform
-                    const float4 w4 = *reinterpret_cast<const float4 *>(w2 + (a0 + j) * HID + 4 * k4);
-                    q[j] = fmaf(w4.x, hv[k4].x, q[j]);
-                    q[j] = fmaf(w4.y, hv[k4].y, q[j]);
-                    q[j] = fmaf(w4.z, hv[k4].z, q[j]);
-                    q[j] = fmaf(w4.w, hv[k4].w, q[j]);
+                for (int k4 = 0; k4 < HID / 4; ++k4) {
+                    const float4 wa = wj[k4];
+                    e0 = fmaf(wa.x, hv[k4].x, e0);
+                    e0 = fmaf(wa.y, hv[k4].y, e0);
+                    e0 = fmaf(wa.z, hv[k4].z, e0);
+                    e0 = fmaf(wa.w, hv[k4].w, e0);
                 }
+                q[j] = e0;
             }
         }
 #pragma unroll
