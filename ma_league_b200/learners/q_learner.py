@@ -60,6 +60,7 @@ class QLearner(Learner):
         self.use_graphs = bool(getattr(args, "cuda_graphs", True))
         self._graphs = {}        # key -> (CUDAGraph, kernels per replay) ; key -> None after the first (eager) sighting
         self._graph_cap = 32
+        self._graph_captures_left = 64   # a capture costs ~10 ms: batches whose addresses never repeat stay eager
         self._bs_cache = {}
 
     def parameters(self):
@@ -222,6 +223,10 @@ class QLearner(Learner):
             self._graphs[key] = None
             self._step_eager(bs, cfg, f, dev)
             return False
+        if self._graph_captures_left <= 0:
+            self._step_eager(bs, cfg, f, dev)
+            return False
+        self._graph_captures_left -= 1
         # second sighting: capture (the capture stream becomes torch's current stream, which the C ABI call reads)
         lib = nat.lib()
         graph = th.cuda.CUDAGraph()
