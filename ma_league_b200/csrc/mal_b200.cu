@@ -334,7 +334,12 @@ struct PartLayout {
     int64_t total;
 };
 
-static int tiles_of(int Nout, int K) { return ((Nout + RT_NT - 1) / RT_NT) * ((K + RT_KT - 1) / RT_KT); }   // 128 x 64 tiles
+// narrow outputs with a wide inner dimension (fc1 at d_in > 64) are reduced in the transposed orientation (k_reduce_tc SWAP)
+static bool red_swapped(int Nout, int K) { return Nout <= RT_KT && K > RT_KT; }
+static int tiles_of(int Nout, int K) {   // 128 x 64 output tiles of the tensor-core reduction
+    if (red_swapped(Nout, K)) return ((K + RT_NT - 1) / RT_NT) * ((Nout + RT_KT - 1) / RT_KT);
+    return ((Nout + RT_NT - 1) / RT_NT) * ((K + RT_KT - 1) / RT_KT);
+}
 
 static PartLayout part_layout(const Dims &d, int sms) {
     PartLayout p;
@@ -840,20 +845,25 @@ static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, con
     int64_t min_rpc = 1 << 30;
     for (int i = 0; i < g.n; ++i) if (g.p[i].rows_per_chunk < min_rpc) min_rpc = g.p[i].rows_per_chunk;
     const bool tc = g_use_tc && DK == 0 && (g_reduce_tc == 2 || (g_reduce_tc == 1 && min_rpc >= 512));
+    bool swap = tc;
+    for (int i = 0; i < g.n; ++i) swap = swap && red_swapped(g.p[i].Nout, g.p[i].K);
     int tiles = 0, maxc = 0;
     for (int i = 0; i < g.n; ++i) {
         g.p[i].tile0 = tiles;
-        tiles += ((g.p[i].Nout + (tc ? RT_NT : 64) - 1) / (tc ? RT_NT : 64)) * g.p[i].n_ktiles;
+        if (swap) tiles += ((g.p[i].K + RT_NT - 1) / RT_NT) * ((g.p[i].Nout + RT_KT - 1) / RT_KT);
+        else tiles += ((g.p[i].Nout + (tc ? RT_NT : 64) - 1) / (tc ? RT_NT : 64)) * g.p[i].n_ktiles;
         if (g.p[i].n_chunks > maxc) maxc = g.p[i].n_chunks;
     }
     dim3 grid(maxc, tiles);
     if (tc) {
         static thread_local bool attr = false;
         if (!attr) {
-            MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
+            MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
+            MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
             attr = true;
         }
-        { ProfScope _ps(tag_tc, st); k_reduce_tc<AK><<<grid, 256, RT_SMEM_BYTES, st>>>(g); }
+        if (swap) { ProfScope _ps(tag_tc, st); k_reduce_tc<AK, 1><<<grid, 256, RT_SMEM_BYTES, st>>>(g); }
+        else { ProfScope _ps(tag_tc, st); k_reduce_tc<AK, 0><<<grid, 256, RT_SMEM_BYTES, st>>>(g); }
         MAL_LAUNCH_CHECK("k_reduce_tc");
         return 0;
     }

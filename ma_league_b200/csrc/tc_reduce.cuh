@@ -25,7 +25,10 @@
 #define RT_SMEM_BYTES (2 * RT_STAGE + RT_RAW_Y + RT_RAW_A)   // 120 KB
 #define RT_FLUSH 8                        // blocks between TMEM -> register folds (256 rows)
 
-template <int AK>
+// SWAP = 1 computes the transposed tile dW^T[k, n] (MMA rows <- 128 columns of A, MMA columns <- 64 columns of dY): for
+// narrow outputs with a wide inner dimension (fc1: Nout = 64, K = d_in up to 246) this fills the 128-row operand
+// instead of padding half of it, and halves the number of tiles.
+template <int AK, int SWAP>
 __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ RedGroup g) {
     extern __shared__ __align__(1024) uint8_t rt_smem[];
     __shared__ __align__(8) uint64_t st_bar[2];
@@ -38,14 +41,17 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     const int chunk = blockIdx.x;
     if (chunk >= p.n_chunks) return;
     const int tile = blockIdx.y - p.tile0;
-    const int nt = tile / p.n_ktiles, kt = tile - nt * p.n_ktiles;
-    const int n0 = nt * RT_NT, k0 = kt * RT_KT;
+    // wide operand (128 MMA rows) / narrow operand (64 MMA columns): dY / A, or A / dY when SWAP
+    const int n_narrow = SWAP ? (p.Nout + RT_KT - 1) / RT_KT : p.n_ktiles;
+    const int wt = tile / n_narrow, st_ = tile - wt * n_narrow;
+    const int n0 = SWAP ? st_ * RT_KT : wt * RT_NT;      // first dY column of this tile
+    const int k0 = SWAP ? wt * RT_NT : st_ * RT_KT;      // first A column of this tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t mb = p.M0 + (int64_t)chunk * p.rows_per_chunk;
     int64_t me = mb + p.rows_per_chunk;
     if (me > p.M) me = p.M;
     const int nblk = me > mb ? (int)((me - mb + RT_BM - 1) / RT_BM) : 0;
-    const bool want_bias = p.partB && kt == 0;
+    const bool want_bias = p.partB && (SWAP ? wt == 0 : st_ == 0);
 
     float *rawY = reinterpret_cast<float *>(rt_smem + 2 * RT_STAGE);
     float *rawA = reinterpret_cast<float *>(rt_smem + 2 * RT_STAGE + RT_RAW_Y);
@@ -72,76 +78,79 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
                        ((reinterpret_cast<uintptr_t>(bv.state.ptr) & 15) == 0);
     const bool o_vec = AK == A_AGENT_IN && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 && (bv.obs.st & 3) == 0 &&
                        ((reinterpret_cast<uintptr_t>(bv.obs.ptr) & 15) == 0);
-    float4 py[4], pa[2];
-    auto load_block = [&](int j) {
-        const int64_t mm = mb + (int64_t)j * RT_BM;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                 // dY: warp w owns rows 4w .. 4w+3 (one 16-byte piece of every operand row)
-            const int r = 4 * warp + i, c = lane;
-            const int64_t m = mm + r;
-            const int n = n0 + 4 * c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < me && n < p.Nout) {
-                const float *src = p.dY + m * p.ldy + n;
-                if (y_vec && n + 4 <= p.Nout) v = __ldg(reinterpret_cast<const float4 *>(src));
-                else {
-                    v.x = __ldg(src);
-                    if (n + 1 < p.Nout) v.y = __ldg(src + 1);
-                    if (n + 2 < p.Nout) v.z = __ldg(src + 2);
-                    if (n + 3 < p.Nout) v.w = __ldg(src + 3);
-                }
+    auto load_dy4 = [&](int64_t m, int n) -> float4 {      // dY[m, n .. n+3]
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < me && n < p.Nout) {
+            const float *src = p.dY + m * p.ldy + n;
+            if (y_vec && n + 4 <= p.Nout) v = __ldg(reinterpret_cast<const float4 *>(src));
+            else {
+                v.x = __ldg(src);
+                if (n + 1 < p.Nout) v.y = __ldg(src + 1);
+                if (n + 2 < p.Nout) v.z = __ldg(src + 2);
+                if (n + 3 < p.Nout) v.w = __ldg(src + 3);
             }
-            py[i] = v;
         }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {                 // A: the same four rows, 16 float4 each
-            const int r = 4 * warp + 2 * i + (lane >> 4), c = lane & 15;
-            const int64_t m = mm + r;
-            const int k = k0 + 4 * c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < me && k < p.K) {
-                if (AK == A_DENSE) {
-                    if (m >= p.shift) {
-                        const float *src = p.A + (m - p.shift) * p.lda + k;
-                        if (a_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
-                        else {
-                            v.x = __ldg(src);
-                            if (k + 1 < p.K) v.y = __ldg(src + 1);
-                            if (k + 2 < p.K) v.z = __ldg(src + 2);
-                            if (k + 3 < p.K) v.w = __ldg(src + 3);
-                        }
-                    }
-                } else if (AK == A_STATE) {
-                    int b, t;
-                    if (fast_ok) fast_divmod((int)m, bv.T, invT, b, t);
-                    else { b = (int)(m / bv.T); t = (int)(m - (int64_t)b * bv.T); }
-                    const float *src = field_ptr<float>(bv.state, b, t + p.shift) + k;
-                    if (s_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
+        return v;
+    };
+    auto load_a4 = [&](int64_t m, int k) -> float4 {       // A[m, k .. k+3] through the fused loaders
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < me && k < p.K) {
+            if (AK == A_DENSE) {
+                if (m >= p.shift) {
+                    const float *src = p.A + (m - p.shift) * p.lda + k;
+                    if (a_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
                     else {
                         v.x = __ldg(src);
                         if (k + 1 < p.K) v.y = __ldg(src + 1);
                         if (k + 2 < p.K) v.z = __ldg(src + 2);
                         if (k + 3 < p.K) v.w = __ldg(src + 3);
                     }
-                } else {   // [obs | last-action one-hot | agent-id one-hot]: float4 over the obs part
-                    int t, rr, b, n;
-                    if (fast_ok) { fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, n); }
-                    else { t = (int)(m / bv.R); rr = (int)(m - (int64_t)t * bv.R); b = rr / bv.N; n = rr - b * bv.N; }
-                    if (o_vec && k + 4 <= bv.OBS) {
-                        v = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS + k));
-                    } else {
-                        RowSrc rs;
-                        rs.agent = n;
-                        rs.p0 = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
-                        rs.p1 = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
-                        v.x = row_elem(A_AGENT_IN, bv, rs, k);
-                        if (k + 1 < p.K) v.y = row_elem(A_AGENT_IN, bv, rs, k + 1);
-                        if (k + 2 < p.K) v.z = row_elem(A_AGENT_IN, bv, rs, k + 2);
-                        if (k + 3 < p.K) v.w = row_elem(A_AGENT_IN, bv, rs, k + 3);
-                    }
+                }
+            } else if (AK == A_STATE) {
+                int b, t;
+                if (fast_ok) fast_divmod((int)m, bv.T, invT, b, t);
+                else { b = (int)(m / bv.T); t = (int)(m - (int64_t)b * bv.T); }
+                const float *src = field_ptr<float>(bv.state, b, t + p.shift) + k;
+                if (s_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
+                else {
+                    v.x = __ldg(src);
+                    if (k + 1 < p.K) v.y = __ldg(src + 1);
+                    if (k + 2 < p.K) v.z = __ldg(src + 2);
+                    if (k + 3 < p.K) v.w = __ldg(src + 3);
+                }
+            } else {   // [obs | last-action one-hot | agent-id one-hot]: float4 over the obs part
+                int t, rr, b, n;
+                if (fast_ok) { fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, n); }
+                else { t = (int)(m / bv.R); rr = (int)(m - (int64_t)t * bv.R); b = rr / bv.N; n = rr - b * bv.N; }
+                if (o_vec && k + 4 <= bv.OBS) {
+                    v = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS + k));
+                } else {
+                    RowSrc rs;
+                    rs.agent = n;
+                    rs.p0 = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
+                    rs.p1 = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
+                    v.x = row_elem(A_AGENT_IN, bv, rs, k);
+                    if (k + 1 < p.K) v.y = row_elem(A_AGENT_IN, bv, rs, k + 1);
+                    if (k + 2 < p.K) v.z = row_elem(A_AGENT_IN, bv, rs, k + 2);
+                    if (k + 3 < p.K) v.w = row_elem(A_AGENT_IN, bv, rs, k + 3);
                 }
             }
-            pa[i] = v;
+        }
+        return v;
+    };
+    float4 py[4], pa[2];                              // wide rows (32 float4 each) / narrow rows (16 float4 each)
+    auto load_block = [&](int j) {
+        const int64_t mm = mb + (int64_t)j * RT_BM;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                 // warp w owns rows 4w .. 4w+3 (one 16-byte piece of every operand row)
+            const int64_t m = mm + 4 * warp + i;
+            py[i] = SWAP ? load_a4(m, k0 + 4 * lane) : load_dy4(m, n0 + 4 * lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int64_t m = mm + 4 * warp + 2 * i + (lane >> 4);
+            const int c = lane & 15;
+            pa[i] = SWAP ? load_dy4(m, n0 + 4 * c) : load_a4(m, k0 + 4 * c);
         }
     };
 
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
-    float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // column sums of dY (bias gradient): n = lane + 32 i, this warp's rows
+    float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // column sums of dY (bias gradient) over this warp's rows: columns lane + 32 i
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24);
     bool fresh = true;                                // the next MMA overwrites the TMEM accumulators
     auto fold = [&](int j) {                          // all MMAs up to block j -> register accumulators
@@ -183,13 +192,14 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         for (int i = 0; i < 4; ++i) {
             const int n = lane + 32 * i;
             const float4 v = make_float4(ry[n], ry[RT_NT + n], ry[2 * RT_NT + n], ry[3 * RT_NT + n]);
-            bsum[i] += (v.x + v.y) + (v.z + v.w);
+            if (!SWAP) bsum[i] += (v.x + v.y) + (v.z + v.w);
             split_store_fast(Ah, Al, (uint32_t)n * 128u + (uint32_t)((warp ^ (n & 7)) << 4), v);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int k = lane + 32 * i;
             const float4 v = make_float4(ra[k], ra[RT_KT + k], ra[2 * RT_KT + k], ra[3 * RT_KT + k]);
+            if (SWAP) bsum[i] += (v.x + v.y) + (v.z + v.w);
             split_store_fast(Bh, Bl, (uint32_t)k * 128u + (uint32_t)((warp ^ (k & 7)) << 4), v);
         }
         __syncwarp();                                                    // scratch is rewritten by the next block
@@ -216,8 +226,8 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             fresh = true;
         }
     }
-    // ---- partials
-    {
+    // ---- partials: partW[chunk][n][k]; TMEM lane = wide-operand row, columns = narrow-operand rows
+    if (!SWAP) {
         const int n = n0 + q * 32 + lane;
         if (n < p.Nout) {
             float *pw = p.partW + ((int64_t)chunk * p.Nout + n) * p.K + k0 + half * 32;
@@ -225,12 +235,21 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             for (int c = 0; c < 32; ++c)
                 if (k0 + half * 32 + c < p.K) pw[c] = acc[c];
         }
+    } else {
+        const int k = k0 + q * 32 + lane;
+        if (k < p.K) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int n = n0 + half * 32 + c;
+                if (n < p.Nout) p.partW[((int64_t)chunk * p.Nout + n) * p.K + k] = acc[c];
+            }
+        }
     }
     if (want_bias) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) bsum_s[warp][lane + 32 * i] = bsum[i];
         __syncthreads();
-        if (tid < RT_NT && n0 + tid < p.Nout) {
+        if (tid < (SWAP ? RT_KT : RT_NT) && n0 + tid < p.Nout) {
             float sacc = 0.0f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) sacc += bsum_s[w][tid];

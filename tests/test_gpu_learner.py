@@ -143,6 +143,27 @@ def test_both_tensor_core_gemm_kernels_inside_the_learner(mode):
         assert_close(grads["mixer." + k], v, TOL, "grad mixer " + k)
 
 
+@pytest.mark.parametrize("N,B,TT", [(10, 4, 9), (20, 3, 6), (26, 2, 4)])
+def test_tensor_core_reductions_forced_on_small_wide_problems(N, B, TT):
+    """fc1 weight gradients with d_in > 64 take the transposed (SWAP) orientation of k_reduce_tc, which the launch
+    heuristic only selects for long row chunks: force the tensor-core reductions and the pipelined GEMM on small
+    batches of the wide configs and hold every gradient to the oracle."""
+    from ma_league_b200 import _native as nat
+    s = seeded_system(N, B, TT, "qmix", True, seed=N + TT)
+    ref = _oracle_run(s, "qmix", True, dtype=np.float64)
+    nat.check(nat.lib().mal_set_option(b"reduce_tc", 2), "mal_set_option")
+    nat.check(nat.lib().mal_set_option(b"tc_pipelined", 2), "mal_set_option")
+    try:
+        grads = split_grad(s.learner.forward_backward(s.batch), s.learner)
+    finally:
+        nat.check(nat.lib().mal_set_option(b"reduce_tc", 1), "mal_set_option")
+        nat.check(nat.lib().mal_set_option(b"tc_pipelined", 1), "mal_set_option")
+    for k, v in ref["agent_grads"].items():
+        assert_close(grads["agent." + k], v, TOL, "grad " + k)
+    for k, v in ref["mixer_grads"].items():
+        assert_close(grads["mixer." + k], v, TOL, "grad mixer " + k)
+
+
 def test_cuda_graph_replay_equals_eager_launches():
     """train() replays a captured CUDA graph from the third sighting of a batch on; parameters, optimiser state and
     logged statistics must be bit-identical to eager launches, including when two batches alternate."""
