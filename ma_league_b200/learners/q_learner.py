@@ -234,7 +234,7 @@ class QLearner(Learner):
         n0 = lib.mal_launch_count()
         sc = self.scalars()
         self.mac.update_trained_steps(th.zeros(1, dtype=th.int32, device=dev))      # the device counter exists before capture
-        with th.cuda.graph(graph):
+        with th.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads may keep using CUDA meanwhile
             self._step_eager(bs, cfg, f, dev)
             self.mac.update_trained_steps(sc[nat.SC_MASK_COUNT:nat.SC_MASK_COUNT + 1].view(th.int32))
         n_kernels = lib.mal_launch_count() - n0
