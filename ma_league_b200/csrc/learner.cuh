@@ -491,106 +491,154 @@ struct HeadArgs {
     int *argmax;                       // [B,T,N]
 };
 
-// Thread pair per (t, row): the even lane owns the online net, the odd lane the target net.  Each thread keeps its
-// h row in registers (16 LDG.128) and walks the actions eight at a time with the fc2 rows broadcast from shared memory
-// (4 FMAs per LDS.128); one shuffle per action swaps q_online / q_target inside the pair, the online lane picks the
-// chosen action's Q, the target lane runs the avail-masked (double-Q) arg-max scan in index order (ties -> lowest index).
-__global__ void __launch_bounds__(128, 4) k_q_head(HeadArgs a) {   // <= 128 registers: four CTAs per SM, the whole grid in one wave at B = 32
-    extern __shared__ __align__(16) float4 qh_smem[];        // hs_s [2*64*17 float4] | w2_s [2][A*64 floats]
+// A CTA stages both nets' fc2 once and then walks 64-row tiles.  Warps 0-1 serve the online net, warps 2-3 the target
+// net, thread = row: the tile's h rows (both nets) arrive through a cp.async stage (coalesced 16-byte copies), each
+// thread takes its row into registers, and the stage is refilled with the next tile right away, so that copy flies under
+// the dot products.  The actions are walked four at a time with the fc2 rows broadcast from shared memory (the net is
+// warp-uniform, so an LDS.128 is a single-address broadcast: one wavefront per 16 FMAs) -- four independent FMA chains,
+// each in ascending k and seeded with the bias: the summation order of the fixtures.  Q goes through shared memory to
+// the epilogue: thread r < 64 runs row r's avail-masked (double-Q) arg-max scan in index order (ties -> lowest index)
+// on avail rows that were requested (4-byte cp.async) before the dot products; thread 64 + r picks row r's
+// chosen-action Q.
+#define QH_NET_F4 (64 * 17)         // float4 pitch between the two nets' h tiles (17-float4 rows: conflict-free per 8-lane phase)
+#define QH_HS_F4 (2 * QH_NET_F4)
+__host__ __device__ inline int qh_w2_pitch(int A) { return ((A + 3) & ~3) * HID; }       // floats between the nets' fc2 copies
+__host__ __device__ inline int qh_q_pitch(int A) { return ((A + 3) & ~3) | 1; }          // odd: row-per-lane accesses are conflict-free
+__host__ __device__ inline size_t qh_smem_bytes(int A) {
+    return sizeof(float4) * QH_HS_F4 + sizeof(float) * (2 * (size_t)qh_w2_pitch(A) + 3 * 64 * (size_t)qh_q_pitch(A));
+}
+
+__global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
+    extern __shared__ __align__(16) float4 qh_smem[];        // hs_s [QH_HS_F4] | w2_s [2][w2_pitch] | q_s [2][64*qpitch] | av_s [64*qpitch]
     __shared__ float b2_s[2][MAL_MAX_ACTIONS];
     float4 *hs_s = qh_smem;
-    float *w2_all = reinterpret_cast<float *>(qh_smem + 2 * 64 * 17);
     const AgentLayout L = agent_layout(a.d_in, a.A);
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < 2 * a.A * HID; idx += 128) {
-        const int nn = idx / (a.A * HID), rem = idx - nn * a.A * HID;
-        w2_all[idx] = __ldg(a.params[nn] + L.fc2_w + rem);
-    }
-    if (tid < 2 * a.A) { const int nn = tid / a.A, j = tid - nn * a.A; b2_s[nn][j] = __ldg(a.params[nn] + L.fc2_b + j); }
-    __syncthreads();
-    const int net = tid & 1;
+    const int Apad = (a.A + 3) & ~3, w2_pitch = qh_w2_pitch(a.A), qpitch = qh_q_pitch(a.A);
+    float *w2_all = reinterpret_cast<float *>(qh_smem + QH_HS_F4);
+    float *q_s = w2_all + 2 * w2_pitch;
+    const int q_net = 64 * qpitch;                           // floats between the nets' Q tiles
+    int *av_s = reinterpret_cast<int *>(q_s + 2 * q_net);    // [64][qpitch] avail rows of the tile
     const int T = a.TT - 1;
     const int64_t total = (int64_t)a.TT * a.R;
-    const int64_t mreal = (int64_t)blockIdx.x * 64 + (tid >> 1);
-    const bool valid = mreal < total;
-    const int64_t m = valid ? mreal : total - 1;             // out-of-range lanes shadow the last row (shuffles stay full-warp)
-    const int t = (int)(m / a.R), row = (int)(m - (int64_t)t * a.R);
-    const int b = row / a.N, n = row - b * a.N;
-    // the CTA's 64 rows of both nets are staged through shared memory with coalesced float4 loads (a thread reading
-    // its own 256-byte row straight from global touches 32 cache lines per warp instruction)
-    float4 hv[HID / 4];
-    {
-        const int64_t m_base = (int64_t)blockIdx.x * 64;
+    const int64_t n_tiles = (total + 63) >> 6;
+    auto issue_h = [&](int64_t tile) {                       // 2 nets x 64 rows x 16 float4, rows past the end shadow the last row
+        const int64_t m_base = tile * 64;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
-            const int idx = tid + 128 * it;                  // 2 nets x 64 rows x 16 float4
+            const int idx = tid + 128 * it;
             const int nn = idx >> 10, r = (idx >> 4) & 63, c = idx & 15;
             const int64_t mm = m_base + r < total ? m_base + r : total - 1;
-            hs_s[(nn * 64 + r) * 17 + c] = __ldg(reinterpret_cast<const float4 *>((nn ? a.hout[1] : a.hout[0]) + mm * HID) + c);
+            cp_async16(hs_s + nn * QH_NET_F4 + r * 17 + c, (nn ? a.hout[1] : a.hout[0]) + mm * HID + 4 * c);
         }
-        __syncthreads();
-        const float4 *hp = hs_s + (net * 64 + (tid >> 1)) * 17;   // 17-float4 row pitch: conflict-free per 8-lane phase
-#pragma unroll
-        for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = hp[k4];
-    }
-    const int act = t < T ? (int)(field_ptr<long long>(a.actions, b, t)[n]) : -1;
-    const int *av = field_ptr<int>(a.avail, b, t) + (int64_t)n * a.A;
-    const int64_t qoff = (((int64_t)b * a.TT + t) * a.N + n) * a.A;
-    const float *w2 = w2_all + net * a.A * HID;
-    float chosen = 0.0f, best_sel = 0.0f, best_mt = 0.0f;
-    int best_i = -1;
-    for (int a0 = 0; a0 < a.A; a0 += 8) {
-        float q[8];
-        int avr[8];                                          // issued before the FMAs: the loads fly under the dot products
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            q[j] = a0 + j < a.A ? b2_s[net][a0 + j] : 0.0f;
-            avr[j] = (net == 1 && t >= 1 && a0 + j < a.A) ? __ldg(av + a0 + j) : 1;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (a0 + j < a.A) {                              // warp-uniform, once per action (not per k)
-                const float4 *wj = reinterpret_cast<const float4 *>(w2 + (a0 + j) * HID);
-                float e0 = q[j];                             // one chain in ascending k: the summation order of the fixtures
-#pragma unroll
-                for (int k4 = 0; k4 < HID / 4; ++k4) {
-                    const float4 wa = wj[k4];
-                    e0 = fmaf(wa.x, hv[k4].x, e0);
-                    e0 = fmaf(wa.y, hv[k4].y, e0);
-                    e0 = fmaf(wa.z, hv[k4].z, e0);
-                    e0 = fmaf(wa.w, hv[k4].w, e0);
-                }
-                q[j] = e0;
+        cp_async_commit();
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) issue_h(tile);
+    {   // fc2.weight of both nets (rows >= A zero), fc2.bias
+        const bool vec = ((reinterpret_cast<uintptr_t>(a.params[0] + L.fc2_w) | reinterpret_cast<uintptr_t>(a.params[1] + L.fc2_w)) & 15) == 0;
+        for (int idx = tid; idx < 2 * Apad * 16; idx += 128) {
+            const int nn = idx >= Apad * 16, rem = idx - nn * Apad * 16;     // rem = action * 16 + float4 column
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((rem >> 4) < a.A) {
+                const float *src = a.params[nn] + L.fc2_w + rem * 4;
+                if (vec) v = __ldg(reinterpret_cast<const float4 *>(src));
+                else { v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3); }
             }
+            *reinterpret_cast<float4 *>(w2_all + nn * w2_pitch + rem * 4) = v;
         }
+        if (tid < 2 * MAL_MAX_ACTIONS) {
+            const int nn = tid / MAL_MAX_ACTIONS, j = tid - nn * MAL_MAX_ACTIONS;
+            b2_s[nn][j] = j < a.A ? __ldg(a.params[nn] + L.fc2_b + j) : 0.0f;
+        }
+    }
+    const int net = tid >> 6, r = tid & 63;                  // warp-uniform net
+    const float4 *w2 = reinterpret_cast<const float4 *>(w2_all + net * w2_pitch);
+    for (; tile < n_tiles; tile += gridDim.x) {
+        // this thread's row: the same row for the dot products (net = tid >> 6) and for the epilogue
+        const int64_t m = tile * 64 + r;
+        int t = -1, b = 0, n = 0;
+        if (m < total) {
+            t = (int)(m / a.R);
+            const int row = (int)(m - (int64_t)t * a.R);
+            b = row / a.N; n = row - b * a.N;
+        }
+        cp_async_wait<0>();
+        __syncthreads();                                     // the tile (and, first time round, fc2) is in shared memory
+        float4 hv[HID / 4];
+        {
+            const float4 *hp = hs_s + net * QH_NET_F4 + r * 17;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (a0 + j < a.A) {
-                const float other = __shfl_xor_sync(0xffffffffu, q[j], 1);
-                const float qo = net ? other : q[j], qt = net ? q[j] : other;
-                if (net == 0) {
-                    if (a.mac_out && valid) a.mac_out[qoff + a0 + j] = qo;
-                    if (a0 + j == act) chosen = qo;
-                } else {
-                    if (a.target_mac_out && valid) a.target_mac_out[qoff + a0 + j] = qt;
-                    if (t >= 1) {                            // targets use step t's Q for transition t-1
-                        const int avv = avr[j];
-                        const float mt = avv == 0 ? -9999999.0f : qt;
-                        const float sel = a.double_q ? (avv == 0 ? -9999999.0f : qo) : mt;
-                        if (best_i < 0 || arg_better(sel, a0 + j, best_sel, best_i)) { best_sel = sel; best_i = a0 + j; best_mt = mt; }
+            for (int k4 = 0; k4 < HID / 4; ++k4) hv[k4] = hp[k4];
+        }
+        __syncthreads();                                     // every thread holds its row: the stage is free
+        // the epilogue's operands are requested now and fly under the dot products: the row's avail flags
+        // (thread r < 64, 4-byte cp.async) and its action (thread 64 + r, a register), then the next tile's h rows
+        long long act_ll = 0;
+        if (tid < 64) {
+            if (t >= 1) {
+                const int *av = field_ptr<int>(a.avail, b, t) + (int64_t)n * a.A;
+                for (int j = 0; j < a.A; ++j) cp_async4(av_s + r * qpitch + j, av + j);
+            }
+        } else if (t >= 0 && t < T) {
+            act_ll = field_ptr<long long>(a.actions, b, t)[n];
+        }
+        cp_async_commit();
+        const bool more = tile + gridDim.x < n_tiles;
+        if (more) issue_h(tile + gridDim.x);
+        float *qp = q_s + net * q_net + r * qpitch;
+#pragma unroll 1
+        for (int a0 = 0; a0 < Apad; a0 += 4) {
+            float q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = b2_s[net][a0 + j];
+            const float4 *wj = w2 + a0 * (HID / 4);
+#pragma unroll
+            for (int k4 = 0; k4 < HID / 4; ++k4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                // one chain per action in ascending k
+                    const float4 wa = wj[j * (HID / 4) + k4];
+                    q[j] = fmaf(wa.x, hv[k4].x, q[j]);
+                    q[j] = fmaf(wa.y, hv[k4].y, q[j]);
+                    q[j] = fmaf(wa.z, hv[k4].z, q[j]);
+                    q[j] = fmaf(wa.w, hv[k4].w, q[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qp[a0 + j] = q[j];
+        }
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();   // the avail rows (the next tile's h may still be in flight)
+        __syncthreads();                                     // Q of the tile is complete
+        if (t >= 0) {
+            const float *qo_s = q_s + r * qpitch, *qt_s = q_s + q_net + r * qpitch;
+            if (tid < 64) {
+                if (t >= 1) {                                // targets use step t's Q for transition t-1
+                    const int *av = av_s + r * qpitch;
+                    float best_sel = 0.0f, best_mt = 0.0f;
+                    int best_i = -1;
+                    for (int j = 0; j < a.A; ++j) {
+                        const int avv = av[j];
+                        const float mt = avv == 0 ? -9999999.0f : qt_s[j];
+                        const float sel = a.double_q ? (avv == 0 ? -9999999.0f : qo_s[j]) : mt;
+                        if (best_i < 0 || arg_better(sel, j, best_sel, best_i)) { best_sel = sel; best_i = j; best_mt = mt; }
                     }
+                    const int64_t o = ((int64_t)b * T + (t - 1)) * a.N + n;
+                    a.target_max[o] = best_mt;
+                    a.argmax[o] = best_i;
                 }
+            } else if (t < T) {                              // gather(mac_out[:, :-1], 3, actions)
+                const int act = (int)act_ll;
+                a.chosen[((int64_t)b * T + t) * a.N + n] = (act >= 0 && act < a.A) ? qo_s[act] : 0.0f;
+            }
+            if (a.mac_out) {                                 // save_q only (not on the training path)
+                const int64_t qoff = (((int64_t)b * a.TT + t) * a.N + n) * a.A;
+                float *dst = tid < 64 ? a.mac_out : a.target_mac_out;
+                const float *src = tid < 64 ? qo_s : qt_s;
+                if (dst) for (int j = 0; j < a.A; ++j) dst[qoff + j] = src[j];
             }
         }
     }
-    if (valid) {
-        if (net == 0 && t < T) a.chosen[((int64_t)b * T + t) * a.N + n] = chosen;   // gather(mac_out[:, :-1], 3, actions)
-        if (net == 1 && t >= 1) {
-            const int64_t o = ((int64_t)b * T + (t - 1)) * a.N + n;
-            a.target_max[o] = best_mt;
-            a.argmax[o] = best_i;
-        }
-    }
+    cp_async_wait<0>();
 }
 
 // =============================================================================================

@@ -689,13 +689,15 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.target_mac_out = cfg->save_q ? F(plan->target_mac_out) : nullptr;
         a.chosen = F(plan->chosen); a.target_max = F(plan->target_max);
         a.argmax = reinterpret_cast<int *>(ws + plan->argmax);
-        const size_t smem = sizeof(float4) * 2 * 64 * 17 + sizeof(float) * 2 * (size_t)d.A * HID;
+        const size_t smem = qh_smem_bytes(d.A);
+        const int64_t qh_tiles = ceil_div64(d.M1, 64), qh_slots = 3 * (int64_t)sms;      // balanced: every CTA walks the same
+        const int64_t qh_grid = ceil_div64(qh_tiles, ceil_div64(qh_tiles, qh_slots));    // number of tiles (+-1), in one wave
         static thread_local size_t attr = 48 * 1024;
         if (smem > attr) {
             MAL_CUDA(cudaFuncSetAttribute(k_q_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = smem;
         }
-        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)ceil_div64(d.M1, 64), 128, smem, st>>>(a); }
+        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)qh_grid, 128, smem, st>>>(a); }
         MAL_LAUNCH_CHECK("k_q_head");
     }
     // mixer hypernetworks                                                   qmix.py:41-59
