@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     bool have_pre = false;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
         const int64_t m0 = a.m_begin + (int64_t)mt * TC_M;
+        if (mt + (int)gridDim.x >= n_mtiles) pdl_trigger();   // last tile of this CTA: the recurrence may be scheduled and load W_hh
         // ---------------------------------------------------------------- x = fc1(input): nkc1 k-chunks into acc 1
         for (int kc = 0; kc < nkc1; ++kc) {
             float4 v[8];

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
     int64_t me = mb + p.rows_per_chunk;
     if (me > p.M) me = p.M;
     const bool want_bias = p.partB && kt == 0;
+    pdl_wait();
 
     float acc[4][4];
     float bsum[4] = {0, 0, 0, 0};
@@ -393,6 +394,7 @@ __device__ __forceinline__ float tanh_mufu(float x) { return fmaf(2.0f, rcp_appr
 // The gi[t] terms are per-thread cp.async copies running PF steps ahead (one commit group per timestep).
 // Saved gates layout (private to k_gru_fwd4 / k_gru_bwd4): [m][unit][r, z, n, gh_n].
 // =============================================================================================
+#define PDL_LEAD_STEPS 6   // timesteps before the end of a recurrence at which its dependent kernel may start its prologue
 template <int DBG = 0>   // DBG (probe only): 1 no global stores, 4 cheap gate math, 8 no matvec, 128 libm expf/tanhf gate math
 __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     constexpr int PF = 8;
@@ -406,8 +408,8 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
 
     const int t0 = a.t0, t1 = a.t1;
-    float hprev = t0 > 0 ? hout[((int64_t)(t0 - 1) * a.R + row) * HID + i] : 0.0f;   // init_hidden: zeros
-    h_s[0][i] = hprev; h_s[1][i] = 0.0f;
+    __shared__ float pdl_anchor_s[HID];
+    float anchor = 0.0f;
     unsigned long long w[3][HID / 2];   // packed pairs (W_hh[g*64+i][2j], W_hh[g*64+i][2j+1]) for FFMA2
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
@@ -416,9 +418,17 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
         for (int u = 0; u < HID / 4; ++u) {
             const float4 v = __ldg(wr + u);
             w[g][2 * u] = pack2(v.x, v.y); w[g][2 * u + 1] = pack2(v.z, v.w);
+            anchor += v.x;
         }
     }
     const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
+    // The weights above are step constants and are loaded BEFORE the dependency wait (they fly under the predecessor's
+    // tail); gi / hout come from the predecessor.  The shared store of a value that depends on every load pins the
+    // loads above the wait (ptxas sinks free-standing loads below it).
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;
+    pdl_wait();
+    float hprev = t0 > 0 ? hout[((int64_t)(t0 - 1) * a.R + row) * HID + i] : 0.0f;   // init_hidden: zeros
+    h_s[0][i] = hprev; h_s[1][i] = 0.0f;
     const int64_t tstride = (int64_t)a.R * G3;
     const float *p_g = gi + (int64_t)row * G3 + i;
 #pragma unroll
@@ -438,6 +448,7 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
             if (t >= t1) break;
             const int buf = p;                   // == (t - t0) & 1
             const int slot = (t - t0) % PF;
+            if (t + PDL_LEAD_STEPS == t1) pdl_trigger();   // late: dependents parked at their wait would take issue slots from this latency-bound loop
             cp_async_wait<PF - 1>();             // this thread's group of step t has landed
             const float g_r = st_s[slot][0][i], g_z = st_s[slot][1][i], g_n = st_s[slot][2][i];
             if (t + PF < t1) {
@@ -534,7 +545,6 @@ __global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
         cp_async_commit();
     };
     int64_t tile = blockIdx.x;
-    if (tile < n_tiles) issue_h(tile);
     {   // fc2.weight of both nets (rows >= A zero), fc2.bias
         const bool vec = ((reinterpret_cast<uintptr_t>(a.params[0] + L.fc2_w) | reinterpret_cast<uintptr_t>(a.params[1] + L.fc2_w)) & 15) == 0;
         for (int idx = tid; idx < 2 * Apad * 16; idx += 128) {
@@ -552,6 +562,8 @@ __global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
             b2_s[nn][j] = j < a.A ? __ldg(a.params[nn] + L.fc2_b + j) : 0.0f;
         }
     }
+    pdl_wait();                                              // fc2 is a step constant; the h rows come from the recurrence
+    if (tile < n_tiles) issue_h(tile);
     const int net = tid >> 6, r = tid & 63;                  // warp-uniform net
     const float4 *w2 = reinterpret_cast<const float4 *>(w2_all + net * w2_pitch);
     for (; tile < n_tiles; tile += gridDim.x) {
@@ -586,6 +598,7 @@ __global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
         cp_async_commit();
         const bool more = tile + gridDim.x < n_tiles;
         if (more) issue_h(tile + gridDim.x);
+        else pdl_trigger();                                  // last tile of this CTA
         float *qp = q_s + net * q_net + r * qpitch;
 #pragma unroll 1
         for (int a0 = 0; a0 < Apad; a0 += 4) {
@@ -708,6 +721,7 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
         v2b_o = __ldg(a.mparams[0] + ML.v2_b);
         v2b_t = __ldg(a.mparams[1] + ML.v2_b);
     }
+    pdl_wait();
 
     for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
         const int b = (int)(m / a.T), t = (int)(m - (int64_t)b * a.T);
@@ -805,6 +819,7 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
         if (lane < a.E) s_v2[warp][lane] = dv2w;
         if (lane == 0) s_v2[warp][a.E] = dv2b;
     }
+    pdl_trigger();                               // the BPTT recurrence may be scheduled and load W_hh under this tail
     __syncthreads();
     if (tid < MIX_NSTAT) {
         float s = 0;
@@ -897,12 +912,20 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
     const int T = a.TT - 1;
 
+    __shared__ float pdl_anchor_s[HID];
+    float anchor = 0.0f;
     for (int idx = k; idx < 2 * G3; idx += HID) (&dg_s[0][0])[idx] = 0.0f;
     unsigned long long wT[G3 / 2];   // packed pairs (W_hh[2j][k], W_hh[2j+1][k]) for FFMA2
 #pragma unroll
     for (int j = 0; j < G3 / 2; ++j)
-        wT[j] = pack2(__ldg(a.params + L.w_hh + (int64_t)(2 * j) * HID + k), __ldg(a.params + L.w_hh + (int64_t)(2 * j + 1) * HID + k));
+    {
+        const float w0 = __ldg(a.params + L.w_hh + (int64_t)(2 * j) * HID + k), w1 = __ldg(a.params + L.w_hh + (int64_t)(2 * j + 1) * HID + k);
+        wT[j] = pack2(w0, w1);
+        anchor += w0 + w1;
+    }
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[k]) = anchor;   // pins the loads above the wait (see k_gru_fwd4)
 
+    pdl_wait();                                  // W_hh is a step constant; gates / h / dh_head come from the predecessors
     const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
     auto fetch = [&](int i, int slot) {          // step i <-> t = TT-1-i
         const int t = a.TT - 1 - i;
@@ -926,6 +949,7 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
             if (i >= a.TT) break;
             const int buf = p;
             const int slot = i % PF;
+            if (i + PDL_LEAD_STEPS == a.TT) pdl_trigger();
             cp_async_wait<PF - 1>();
             const float4 g4 = g4_s[slot][k];
             const float hp = hp_s[slot][k], dhh = dh_s[slot][k];
@@ -1051,6 +1075,8 @@ struct GradReduceArgs {
 
 #define GRED_EPB 64   // gradient elements per block: 256 threads = 64 elements x 4 chunk slices
 __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ GradReduceArgs a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float part_s[4][GRED_EPB];
     __shared__ float s_sq[2];
     const int e = threadIdx.x & (GRED_EPB - 1), slice = threadIdx.x >> 6;   // slice is warp-uniform
@@ -1114,6 +1140,7 @@ __global__ void __launch_bounds__(256) k_clip_rmsprop(float *agent, int64_t n_ag
                                                       const float *denominator) {
     __shared__ float s_red[8];
     __shared__ float s_coef;
+    pdl_wait();
     // every block recomputes the global norm from the per-block partials in the same fixed order
     float s = 0.0f;
     for (int i = threadIdx.x; i < n_part; i += 256) s += norm_part[i];

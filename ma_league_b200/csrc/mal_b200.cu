@@ -2,6 +2,7 @@
 // workspace planning and launches only.  No allocation, no synchronisation, no CPU fallback.
 #include <stdarg.h>
 #include <string.h>
+#include <utility>
 #include "mal_common.cuh"
 #include "replay.cuh"
 #include "actsel.cuh"
@@ -123,7 +124,25 @@ struct SideStreams {
 };
 static thread_local SideStreams g_side;
 static int g_overlap = 1;
+static int g_pdl = 1;              // programmatic dependent launch on the main kernel chain (prologues overlap the predecessor's tail)
 static thread_local bool g_defer_stats = false;   // set by mal_learner_step around its forward half
+static thread_local bool g_next_pdl = false;      // the next launch_linear / launch_reduce call may start under its stream predecessor
+static thread_local bool g_in_step = false;       // inside mal_learner_step: the stream predecessors of backward / update are ours
+
+// Launch with (pdl = true) the programmatic-serialization attribute: the kernel may be scheduled before its stream
+// predecessor has finished and must call pdl_wait() before it touches anything but step constants.
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && g_pdl && g_overlap) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through MAL_LAUNCH_CHECK
+}
 
 static int side_streams(SideStreams **out) {
     int dev = 0;
@@ -446,30 +465,31 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
+    if (strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
 }
 
 template <int AK, int EK>
-static int launch_tc_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag) {
+static int launch_tc_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag, bool pdl) {
     static thread_local bool attr = false;
     if (!attr) {
         MAL_CUDA(cudaFuncSetAttribute(k_linear_tc<AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         attr = true;
     }
-    { ProfScope _ps(tag, st); k_linear_tc<AK, EK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g); }
+    { ProfScope _ps(tag, st); launch_k(k_linear_tc<AK, EK>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, pdl, g); }
     MAL_LAUNCH_CHECK("k_linear_tc");
     return 0;
 }
 
 template <int AK, int EK>
-static int launch_tc2_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag) {
+static int launch_tc2_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag, bool pdl) {
     static thread_local bool attr = false;
     if (!attr) {
         MAL_CUDA(cudaFuncSetAttribute(k_linear_tc2<AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
         attr = true;
     }
-    { ProfScope _ps(tag, st); k_linear_tc2<AK, EK><<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(g); }
+    { ProfScope _ps(tag, st); launch_k(k_linear_tc2<AK, EK>, grid, dim3(TC2_THREADS), TC2_SMEM_BYTES, st, pdl, g); }
     MAL_LAUNCH_CHECK("k_linear_tc2");
     return 0;
 }
@@ -529,23 +549,23 @@ static int launch_linear_tc(const LinGroup &g0, int64_t maxM, cudaStream_t st, c
         // software-pipelined kernel: one persistent CTA per SM (208 KB of smem, 512 TMEM columns), never a second wave
         int64_t per1 = sms / g.n; if (per1 < 1) per1 = 1;
         dim3 grid1((unsigned)(tiles < per1 ? tiles : per1), g.n);
-        if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid1, st, tag);
-        if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc2_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid1, st, tag);
-        if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid1, st, tag);
-        if (agent_vec) return launch_tc2_inst<TCA_AGENT, TCE_FC1>(g, grid1, st, tag);
-        if (ek == TCE_FC1) return launch_tc2_inst<TCA_GENERIC, TCE_FC1>(g, grid1, st, tag);
-        if (ek == TCE_MASKPOS) return launch_tc2_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid1, st, tag);
-        return launch_tc2_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid1, st, tag);
+        if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid1, st, tag, g_next_pdl);
+        if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc2_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid1, st, tag, g_next_pdl);
+        if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc2_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid1, st, tag, g_next_pdl);
+        if (agent_vec) return launch_tc2_inst<TCA_AGENT, TCE_FC1>(g, grid1, st, tag, g_next_pdl);
+        if (ek == TCE_FC1) return launch_tc2_inst<TCA_GENERIC, TCE_FC1>(g, grid1, st, tag, g_next_pdl);
+        if (ek == TCE_MASKPOS) return launch_tc2_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid1, st, tag, g_next_pdl);
+        return launch_tc2_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid1, st, tag, g_next_pdl);
     }
     int64_t per = ceil_div64((int64_t)2 * sms, g.n); if (per < 1) per = 1;     // persistent: ~two CTAs per SM in total
     dim3 grid((unsigned)(tiles < per ? tiles : per), g.n);
-    if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid, st, tag);
-    if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid, st, tag);
-    if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid, st, tag);
-    if (agent_vec) return launch_tc_inst<TCA_AGENT, TCE_FC1>(g, grid, st, tag);
-    if (ek == TCE_FC1) return launch_tc_inst<TCA_GENERIC, TCE_FC1>(g, grid, st, tag);
-    if (ek == TCE_MASKPOS) return launch_tc_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid, st, tag);
-    return launch_tc_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid, st, tag);
+    if (ak == TCA_VEC_DENSE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_DENSE, TCE_BIAS_ACT>(g, grid, st, tag, g_next_pdl);
+    if (ak == TCA_VEC_DENSE && ek == TCE_MASKPOS) return launch_tc_inst<TCA_VEC_DENSE, TCE_MASKPOS>(g, grid, st, tag, g_next_pdl);
+    if (ak == TCA_VEC_STATE && ek == TCE_BIAS_ACT) return launch_tc_inst<TCA_VEC_STATE, TCE_BIAS_ACT>(g, grid, st, tag, g_next_pdl);
+    if (agent_vec) return launch_tc_inst<TCA_AGENT, TCE_FC1>(g, grid, st, tag, g_next_pdl);
+    if (ek == TCE_FC1) return launch_tc_inst<TCA_GENERIC, TCE_FC1>(g, grid, st, tag, g_next_pdl);
+    if (ek == TCE_MASKPOS) return launch_tc_inst<TCA_GENERIC, TCE_MASKPOS>(g, grid, st, tag, g_next_pdl);
+    return launch_tc_inst<TCA_GENERIC, TCE_BIAS_ACT>(g, grid, st, tag, g_next_pdl);
 }
 
 static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st, const char *tag) {
@@ -574,13 +594,13 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
     return p;
 }
 
-static void launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st) {
+static void launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_fwd", st);
-    k_gru_fwd4<0><<<dim3(a.R, nets), HID, 0, st>>>(a);      // one batch row per CTA, thread = hidden unit
+    launch_k(k_gru_fwd4<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);      // one batch row per CTA, thread = hidden unit
 }
-static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st) {
+static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_bwd", st);
-    k_gru_bwd4<<<a.R, HID, 0, st>>>(a);
+    launch_k(k_gru_bwd4, dim3(a.R), dim3(HID), 0, st, pdl, a);
 }
 
 extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
@@ -670,12 +690,12 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         a.t0 = 0; a.t1 = t_split;
-        launch_gru_fwd(a, 2, st);
+        launch_gru_fwd(a, 2, st, fused_in && t_split == d.TT);   // stream predecessor: k_agent_in_tc
         MAL_LAUNCH_CHECK("k_gru_fwd");
         if (t_split < d.TT) {
             if (join_from(st, ss->s[1], ss->join_ev[1])) return 2;    // second half of gi is ready
             a.t0 = t_split; a.t1 = d.TT;
-            launch_gru_fwd(a, 2, st);
+            launch_gru_fwd(a, 2, st, false);
             MAL_LAUNCH_CHECK("k_gru_fwd");
         }
     }
@@ -697,7 +717,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             MAL_CUDA(cudaFuncSetAttribute(k_q_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = smem;
         }
-        { ProfScope _ps("k_q_head", st); k_q_head<<<(unsigned)qh_grid, 128, smem, st>>>(a); }
+        { ProfScope _ps("k_q_head", st); launch_k(k_q_head, dim3((unsigned)qh_grid), dim3(128), smem, st, true, a); }   // predecessor: k_gru_fwd4
         MAL_LAUNCH_CHECK("k_q_head");
     }
     // mixer hypernetworks                                                   qmix.py:41-59
@@ -743,7 +763,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.q_tot = F(plan->q_tot); a.target_q_tot = F(plan->target_q_tot); a.targets = F(plan->targets); a.td = F(plan->td);
         a.d_a2 = F(plan->d_a2); a.d_y1 = F(plan->d_y1); a.d_chosen = F(plan->d_chosen);
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
-        { ProfScope _ps("k_mix_td", st); k_mix_td<<<pl.nblk_mix, 256, 0, st>>>(a); }
+        { ProfScope _ps("k_mix_td", st); launch_k(k_mix_td, dim3(pl.nblk_mix), dim3(256), 0, st, true, a); }   // stream predecessor: k_q_head
         MAL_LAUNCH_CHECK("k_mix_td");
         // nothing before the gradient gather reads the scalars: inside mal_learner_step the finalize runs on the side
         // stream (the backward joins that stream before k_grad_reduce) and leaves the critical path
@@ -864,12 +884,12 @@ static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, con
             MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
             attr = true;
         }
-        if (swap) { ProfScope _ps(tag_tc, st); k_reduce_tc<AK, 1><<<grid, 256, RT_SMEM_BYTES, st>>>(g); }
-        else { ProfScope _ps(tag_tc, st); k_reduce_tc<AK, 0><<<grid, 256, RT_SMEM_BYTES, st>>>(g); }
+        if (swap) { ProfScope _ps(tag_tc, st); launch_k(k_reduce_tc<AK, 1>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g); }
+        else { ProfScope _ps(tag_tc, st); launch_k(k_reduce_tc<AK, 0>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g); }
         MAL_LAUNCH_CHECK("k_reduce_tc");
         return 0;
     }
-    { ProfScope _ps(tag, st); k_reduce_group<AK, DK><<<grid, 256, 0, st>>>(g); }
+    { ProfScope _ps(tag, st); launch_k(k_reduce_group<AK, DK>, grid, dim3(256), 0, st, g_next_pdl, g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
     return 0;
 }
@@ -962,7 +982,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        launch_gru_bwd(a, st);
+        launch_gru_bwd(a, st, g_in_step);        // inside a step the stream predecessor is k_mix_td
         MAL_LAUNCH_CHECK("k_gru_bwd");
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads
@@ -978,10 +998,16 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     {
         LinGroup g; g.n = 1; g.bv = bv;
         g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, agent + AL.w_ih, HID, 1, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);
-        if (int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx")) return rc;
+        g_next_pdl = true;                       // stream predecessor: k_gru_bwd4 (W_ih staging flies under its last timesteps)
+        int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx");
+        g_next_pdl = false;
+        if (rc) return rc;
         RedGroup r; r.n = 1; r.bv = bv;
         r.p[0] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
-        if (int rc = launch_reduce(r, st, "k_reduce_group:agent")) return rc;
+        g_next_pdl = g_use_tc != 0;              // stream predecessor: the dx GEMM (the tcgen05 kernels trigger at their last tile)
+        rc = launch_reduce(r, st, "k_reduce_group:agent");
+        g_next_pdl = false;
+        if (rc) return rc;
     }
     if (join_from(st, s1, ss->join_ev[0])) return 2;
     if (join_from(st, s2, ss->join_ev[1])) return 2;
@@ -1034,7 +1060,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         a.norm_part = parts + pl.norm;
         a.scalars = F(plan->scalars);
         a.unnormalized = cfg->unnormalized ? 1 : 0;
-        { ProfScope _ps("k_grad_reduce", st); k_grad_reduce<<<pl.nblk_norm, 256, 0, st>>>(a); }
+        { ProfScope _ps("k_grad_reduce", st); launch_k(k_grad_reduce, dim3(pl.nblk_norm), dim3(256), 0, st, true, a); }   // stream predecessor: the fc1 reduction
         MAL_LAUNCH_CHECK("k_grad_reduce");
     }
     return 0;
@@ -1042,9 +1068,9 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
 
 static int launch_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                                float *sq, const float *norm_part, int n_part, float lr, float alpha, float eps,
-                               float clip, float *scalars, const float *denominator, cudaStream_t st) {
+                               float clip, float *scalars, const float *denominator, cudaStream_t st, bool pdl = false) {
     const int64_t P = n_agent + n_mixer;
-    { ProfScope _ps("k_clip_rmsprop", st); k_clip_rmsprop<<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
+    { ProfScope _ps("k_clip_rmsprop", st); launch_k(k_clip_rmsprop, dim3((unsigned)ceil_div64(P, 256)), dim3(256), 0, st, pdl, agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
                                                                 n_part, lr, alpha, eps, clip, scalars, denominator); }
     MAL_LAUNCH_CHECK("k_clip_rmsprop");
     return 0;
@@ -1096,7 +1122,10 @@ extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_
     const int rc_f = mal_learner_forward(batch, cfg, plan, agent, target_agent, mixer, target_mixer, workspace, stream);
     g_defer_stats = false;
     if (rc_f) return rc_f;
-    if (int rc = mal_learner_backward(batch, cfg, plan, agent, mixer, workspace, grad, stream)) return rc;
+    g_in_step = true;
+    const int rc_b = mal_learner_backward(batch, cfg, plan, agent, mixer, workspace, grad, stream);
+    g_in_step = false;
+    if (rc_b) return rc_b;
     Dims d;
     if (int rc = get_dims(batch, cfg, &d)) return rc;
     int sms, tps;
@@ -1107,7 +1136,7 @@ extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_
     float *scalars = reinterpret_cast<float *>(ws + plan->scalars);
     return launch_clip_rmsprop(agent, plan->n_agent_params, mixer, plan->n_mixer_params, grad, square_avg,
                                parts + pl.norm, pl.nblk_norm, cfg->lr, cfg->alpha, cfg->eps, cfg->clip, scalars,
-                               nullptr, (cudaStream_t)stream);
+                               nullptr, (cudaStream_t)stream, true);   // stream predecessor: k_grad_reduce
 }
 
 extern "C" int mal_copy_f32(float *dst, const float *src, int64_t n, void *stream) {

@@ -192,6 +192,24 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while its
+// stream predecessor is still running; it may only touch what the predecessor produces after pdl_wait() (a no-op when
+// the kernel was launched without the attribute).  pdl_trigger() in the predecessor lets the dependent grid be scheduled
+// as soon as every CTA of the predecessor has issued it (or exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// read-only loads that keep their program position relative to pdl_wait() (the compiler is free to sink a plain __ldg
+// below the wait, which would serialise the weight loads behind the predecessor kernel again)
+__device__ __forceinline__ float ldg_ordered(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_ordered(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

@@ -274,8 +274,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
         }
     };
 
+    pdl_wait();                                                  // the A rows may come from the stream predecessor
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
         const int64_t m0 = (int64_t)mt * TC_M;
+        if (mt + (int)gridDim.x >= n_mtiles) pdl_trigger();      // last tile of this CTA
         for (int nt = 0; nt < n_ntiles; ++nt) {
             const int n0 = nt * nt_w;
             const int nw = (Nout - n0) < nt_w ? (((Nout - n0) + 15) & ~15) : nt_w;   // MMA N (multiple of 16)
@@ -530,6 +532,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_linear_tc2(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();
 
     const int nkc = (K + TC_KC - 1) / TC_KC;
     const int n_my = (n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();
 
     const bool y_vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dY + n0) & 15) == 0);
     const bool a_vec = AK == A_DENSE && ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A + k0) & 15) == 0);
