@@ -88,6 +88,8 @@ typedef struct mal_plan {
     int64_t partials;                 /* f32 scratch for split reductions */
     int64_t partials_bytes;
     int64_t scalars;                  /* f32 [64]: see MAL_SC_* */
+    int64_t w_t;                      /* f32: transposed copies of the weights the backward GEMMs read row-wise, written by the
+                                         forward call: gru.weight_ih^T [64,192] | hyper_w_1.2.weight^T [HE,E*N] | hyper_w_final.2.weight^T [HE,E] */
 } mal_plan_t;
 
 /* indices into the scalars block (all float32 except where noted) */

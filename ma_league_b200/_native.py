@@ -47,7 +47,7 @@ class LearnerCfg(C.Structure):
 _PLAN_FIELDS = ["total_bytes", "n_agent_params", "n_mixer_params", "x_on", "x_tg", "gi_on", "gi_tg", "h_on", "h_tg",
                 "gates", "mac_out", "target_mac_out", "chosen", "target_max", "argmax", "mask", "y1_on", "y1_tg",
                 "a2_on", "a2_tg", "q_tot", "target_q_tot", "targets", "td", "d_a2", "d_y1", "d_chosen", "d_g", "d_x",
-                "dh_head", "partials", "partials_bytes", "scalars"]
+                "dh_head", "partials", "partials_bytes", "scalars", "w_t"]
 
 
 class Plan(C.Structure):

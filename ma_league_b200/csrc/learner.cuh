@@ -489,6 +489,31 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     }
 }
 
+// out[c][r] = in[r][c] for up to three small weight matrices (grid: 32x32 tiles, problem); see mal_plan_t.w_t
+struct TransArgs {
+    const float *in[3];
+    float *out[3];
+    int rows[3], cols[3];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_transpose_w(TransArgs a) {
+    __shared__ float tile[32][33];
+    const int pi = blockIdx.y;
+    const int rows = a.rows[pi], cols = a.cols[pi];
+    const int tc = (cols + 31) / 32;
+    if ((int)blockIdx.x >= ((rows + 31) / 32) * tc) return;
+    const int r0 = ((int)blockIdx.x / tc) * 32, c0 = ((int)blockIdx.x % tc) * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? __ldg(a.in[pi] + (int64_t)r * cols + c) : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) a.out[pi][(int64_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
 // =============================================================================================
 // q = fc2 h for both nets, chosen-action gather, avail-masked (double-Q) target max.   q_learner.py:52-78
 // =============================================================================================

@@ -436,6 +436,7 @@ extern "C" int mal_learner_plan(const mal_batch_t *batch, const mal_learner_cfg_
     PartLayout pl = part_layout(d, sms);
     plan->partials_bytes = pl.total * 4;
     plan->partials = take(pl.total, 4);
+    plan->w_t = take((int64_t)HID * G3 + (d.mixer == MAL_MIXER_QMIX2 ? (int64_t)d.HE * (d.E * d.N + d.E) : 0), 4);
     plan->total_bytes = o;
     return 0;
 }
@@ -684,6 +685,26 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     // the mixer hypernet GEMMs start here, beside the (latency-bound) recurrence, not beside the agent-input GEMMs
     // they would compete with for shared memory and tensor cores
     if (fork_to(st, sm, ss->fork_ev[0])) return 2;
+    // transposed weight copies for the backward GEMMs (d x = d gi . W_ih, mixer d h = d a . W_2): the tensor-core
+    // kernels stage W row-wise with float4 loads; a transposed read would be element-wise.  Off the critical path.
+    {
+        TransArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        float *wt = F(plan->w_t);
+        ta.in[0] = agent + AL.w_ih; ta.out[0] = wt; ta.rows[0] = G3; ta.cols[0] = HID; ta.n = 1;
+        if (d.mixer == MAL_MIXER_QMIX2) {
+            ta.in[1] = mixer + ML.w1b_w; ta.out[1] = wt + (int64_t)HID * G3; ta.rows[1] = d.E * d.N; ta.cols[1] = d.HE;
+            ta.in[2] = mixer + ML.wfb_w; ta.out[2] = ta.out[1] + (int64_t)d.HE * d.E * d.N; ta.rows[2] = d.E; ta.cols[2] = d.HE;
+            ta.n = 3;
+        }
+        int max_tiles = 0;
+        for (int i = 0; i < ta.n; ++i) {
+            const int tl = ((ta.rows[i] + 31) / 32) * ((ta.cols[i] + 31) / 32);
+            if (tl > max_tiles) max_tiles = tl;
+        }
+        { ProfScope _ps("k_transpose_w", sm); k_transpose_w<<<dim3(max_tiles, ta.n), dim3(32, 8), 0, sm>>>(ta); }
+        MAL_LAUNCH_CHECK("k_transpose_w");
+    }
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
     {
         GruFwdArgs a;
@@ -946,8 +967,9 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     // ---- side stream 1: mixer hypernet backward (independent of the agent BPTT)
     if (d.mixer == MAL_MIXER_QMIX2) {
         LinGroup g; g.n = 2; g.bv = bv;   // d h1 = (d a1 . W12) * (h1 > 0) ; d hf = (d af . Wf2) * (hf > 0)
-        g.p[0] = lin(d.BT, d.E * d.N, d.HE, A_DENSE, 0, d_a2, d.ld2, mixer + ML.w1b_w, d.HE, 1, nullptr, EPI_MASKPOS, y1, d.ld1, d_y1, d.ld1);
-        g.p[1] = lin(d.BT, d.E, d.HE, A_DENSE, 0, d_a2 + d.E * d.N, d.ld2, mixer + ML.wfb_w, d.HE, 1, nullptr, EPI_MASKPOS, y1 + d.HE, d.ld1, d_y1 + d.HE, d.ld1);
+        const float *wt1 = F(plan->w_t) + (int64_t)HID * G3, *wtf = wt1 + (int64_t)d.HE * d.E * d.N;   // transposed by the forward call
+        g.p[0] = lin(d.BT, d.E * d.N, d.HE, A_DENSE, 0, d_a2, d.ld2, wt1, d.E * d.N, 0, nullptr, EPI_MASKPOS, y1, d.ld1, d_y1, d.ld1);
+        g.p[1] = lin(d.BT, d.E, d.HE, A_DENSE, 0, d_a2 + d.E * d.N, d.ld2, wtf, d.E, 0, nullptr, EPI_MASKPOS, y1 + d.HE, d.ld1, d_y1 + d.HE, d.ld1);
         if (int rc = launch_linear(g, d.BT, d.E * d.N, s1, "k_linear_group:mixer_bwd_dh")) return rc;
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.BT, d.HE, d.E * d.N, d_a2, d.ld2, A_DENSE, 0, y1, d.ld1, parts + pl.m_l2a_w, parts + pl.m_l2a_b, pl.nc_m2, pl.rpc_m2);
@@ -997,7 +1019,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
     {
         LinGroup g; g.n = 1; g.bv = bv;
-        g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, agent + AL.w_ih, HID, 1, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);
+        g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, F(plan->w_t), G3, 0, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);   // W_ih^T from the forward call
         g_next_pdl = true;                       // stream predecessor: k_gru_bwd4 (W_ih staging flies under its last timesteps)
         int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx");
         g_next_pdl = false;
