@@ -78,13 +78,13 @@ __device__ __forceinline__ RowSrc resolve_row(int kind, const BatchView &bv, con
     if (kind == A_DENSE) {
         r.p0 = A + (m - shift) * lda;   // shift = row shift (h_{t-1} pairing); callers guard m >= shift
     } else if (kind == A_AGENT_IN) {
-        int t = (int)(m / bv.R), rr = (int)(m - (int64_t)t * bv.R);
+        int t = (int)((unsigned)m / (unsigned)bv.R), rr = (int)m - t * bv.R;   // rows < 2^31
         int b = rr / bv.N, n = rr - b * bv.N;
         r.agent = n;
         r.p0 = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
         r.p1 = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
     } else {
-        int b = (int)(m / bv.T), t = (int)(m - (int64_t)b * bv.T);
+        int b = (int)((unsigned)m / (unsigned)bv.T), t = (int)m - b * bv.T;
         r.p0 = field_ptr<float>(bv.state, b, t + shift);
     }
     return r;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
                 rdy[2 * u] = (ok && n_ok0) ? __ldg(dyp + c0) : 0.0f;
                 rdy[2 * u + 1] = (ok && n_ok1) ? __ldg(dyp + c1) : 0.0f;
             } else {   // row m = t*R + b*N + n of the [T*R] transition rows
-                const int t = (int)(m / bv.R), rr = (int)(m - (int64_t)t * bv.R);
+                const int t = (int)((unsigned)m / (unsigned)bv.R), rr = (int)m - t * bv.R;   // rows < 2^31 (host-checked): 32-bit division
                 const int b = rr / bv.N, n = rr - b * bv.N;
                 float dsel = 0.0f;
                 int asel = -1;
@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(256) k_reduce_group(const __grid_constant__ Re
                 ra[2 * u] = (oka && k_ok0) ? __ldg(ap + c0) : 0.0f;
                 ra[2 * u + 1] = (oka && k_ok1) ? __ldg(ap + c1) : 0.0f;
             } else if (AK == A_STATE) {
-                const int b = (int)(m / bv.T), t = (int)(m - (int64_t)b * bv.T);
+                const int b = (int)((unsigned)m / (unsigned)bv.T), t = (int)m - b * bv.T;
                 const float *ap = field_ptr<float>(bv.state, b, t + p.shift) + k0;
                 ra[2 * u] = (ok && k_ok0) ? __ldg(ap + c0) : 0.0f;
                 ra[2 * u + 1] = (ok && k_ok1) ? __ldg(ap + c1) : 0.0f;
             } else {   // [obs | last-action one-hot | agent-id one-hot]
-                const int t = (int)(m / bv.R), rr = (int)(m - (int64_t)t * bv.R);
+                const int t = (int)((unsigned)m / (unsigned)bv.R), rr = (int)m - t * bv.R;   // rows < 2^31 (host-checked): 32-bit division
                 const int b = rr / bv.N, n = rr - b * bv.N;
                 const float *po = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
                 const float *ph = field_ptr<float>(bv.onehot, b, t > 0 ? t - 1 : 0) + (int64_t)n * bv.A;
@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
         const int64_t m = tile * 64 + r;
         int t = -1, b = 0, n = 0;
         if (m < total) {
-            t = (int)(m / a.R);
-            const int row = (int)(m - (int64_t)t * a.R);
+            t = (int)((unsigned)m / (unsigned)a.R);
+            const int row = (int)m - t * a.R;
             b = row / a.N; n = row - b * a.N;
         }
         cp_async_wait<0>();
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
     pdl_wait();
 
     for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < total; m += (int64_t)gridDim.x * 8) {
-        const int b = (int)(m / a.T), t = (int)(m - (int64_t)b * a.T);
+        const int b = (int)((unsigned)m / (unsigned)a.T), t = (int)m - b * a.T;
         // lane n holds agent n's chosen / target Q (N <= 32): one coalesced load each, broadcast by shuffle
         const float qc = lane < a.N ? a.chosen[m * a.N + lane] : 0.0f;
         const float qt = lane < a.N ? a.target_max[m * a.N + lane] : 0.0f;
@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(256) k_fc2_grad(Fc2GradArgs a) {
             const int64_t m = m0 + u * stride;
             d[u] = 0.0f; act[u] = 0; h[u] = make_float2(0.f, 0.f);
             if (m < a.rows) {
-                const int t = (int)(m / a.R), rr = (int)(m - (int64_t)t * a.R);
+                const int t = (int)((unsigned)m / (unsigned)a.R), rr = (int)m - t * a.R;   // rows < 2^31 (host-checked)
                 const int b = rr / a.N, n = rr - b * a.N;
                 d[u] = __ldg(a.d_chosen + ((int64_t)b * a.T + t) * a.N + n);
                 act[u] = (int)(field_ptr<long long>(a.actions, b, t)[n]);

@@ -319,6 +319,7 @@ static int get_dims(const mal_batch_t *b, const mal_learner_cfg_t *c, Dims *d) {
     } else { d->E = 0; d->HE = 0; }
     d->M1 = (int64_t)d->TT * d->R;
     d->BT = (int64_t)d->B * d->T;
+    MAL_REQUIRE(d->M1 < ((int64_t)1 << 31), "batch too large: (T+1)*B*N must be < 2^31 (row indices are 32-bit in the kernels)");
     d->ld1 = d->mixer == MAL_MIXER_VDN ? 0 : (d->two ? 2 * d->HE + 2 * d->E : 2 * d->E);
     d->ld2 = d->mixer == MAL_MIXER_VDN ? 0 : d->E * d->N + d->E;
     return 0;

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_linear_tc(const __grid_consta
                     const float *rp;
                     if (AK == TCA_VEC_DENSE) rp = p.A + m * p.lda;
                     else {
-                        const int b = (int)(m / g.bv.T), t = (int)(m - (int64_t)b * g.bv.T);
+                        const int b = (int)((unsigned)m / (unsigned)g.bv.T), t = (int)m - b * g.bv.T;
                         rp = field_ptr<float>(g.bv.state, b, t + p.shift);
                     }
                     v[i] = __ldg(reinterpret_cast<const float4 *>(rp + kcol));

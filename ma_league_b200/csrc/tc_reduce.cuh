@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             } else if (AK == A_STATE) {
                 int b, t;
                 if (fast_ok) fast_divmod((int)m, bv.T, invT, b, t);
-                else { b = (int)(m / bv.T); t = (int)(m - (int64_t)b * bv.T); }
+                else { b = (int)((unsigned)m / (unsigned)bv.T); t = (int)m - b * bv.T; }
                 const float *src = field_ptr<float>(bv.state, b, t + p.shift) + k;
                 if (s_vec && k + 4 <= p.K) v = __ldg(reinterpret_cast<const float4 *>(src));
                 else {
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             } else {   // [obs | last-action one-hot | agent-id one-hot]: float4 over the obs part
                 int t, rr, b, n;
                 if (fast_ok) { fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, n); }
-                else { t = (int)(m / bv.R); rr = (int)(m - (int64_t)t * bv.R); b = rr / bv.N; n = rr - b * bv.N; }
+                else { t = (int)((unsigned)m / (unsigned)bv.R); rr = (int)m - t * bv.R; b = rr / bv.N; n = rr - b * bv.N; }
                 if (o_vec && k + 4 <= bv.OBS) {
                     v = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS + k));
                 } else {
