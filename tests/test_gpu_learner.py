@@ -186,6 +186,33 @@ def test_cuda_graph_replay_equals_eager_launches():
     assert a[3] == b[3] and a[4] == b[4]
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_programmatic_dependent_launch_does_not_change_results(graphs):
+    """The main kernel chain is launched with programmatic-serialization edges (kernels start under their predecessor's
+    tail and wait before touching its products): parameters, optimiser state and statistics must be bit-identical to
+    fully serialised launches, eagerly and through the captured graph, at the metric's size (every kernel many CTAs)."""
+    from ma_league_b200 import _native as nat
+
+    def run(pdl):
+        nat.check(nat.lib().mal_set_option(b"pdl", pdl), "mal_set_option")
+        try:
+            s = seeded_system(5, 32, 201, "qmix", True, seed=31, learner_log_interval=0)
+            s.learner.use_graphs = graphs
+            for i in range(4):
+                s.learner.train(s.batch, t_env=i, episode_num=i)
+            th.cuda.synchronize()
+            return np_params(s.mac.agent), np_params(s.learner.mixer), s.learner.optimiser.flat_sq.cpu().numpy(), \
+                {k: v[0] for k, v in s.logger.stats.items()}
+        finally:
+            nat.check(nat.lib().mal_set_option(b"pdl", 1), "mal_set_option")
+    a, b = run(1), run(0)
+    for x, y in zip(a[:2], b[:2]):
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3]
+
+
 def test_properties_and_determinism_at_full_size():
     s = seeded_system(5, 32, 201, "qmix", True, seed=5)
     g1 = s.learner.forward_backward(s.batch).clone()
