@@ -9,7 +9,10 @@
 // One persistent CTA per SM and net: 256 threads, M tiles of 128 rows.
 //   TMEM (512 columns): fc1 D1 | D2 at 0 | 64, W_ih D1 | D2 at 128 | 320.
 //   smem: A staging (input chunk, later x; hi + lo = 64 KB, reused as the epilogue's transposition scratch) |
-//         W_fc1 chunk (hi + lo = 32 KB) | W_ih (96 KB).
+//         W_fc1 chunk slot(s) (hi + lo = 32 KB each: one when the input fits a 64-wide chunk, else two) | W_ih (96 KB).
+// Inputs wider than one chunk (10v10: 2, 20v20: 4 chunks) are software-pipelined: right after a chunk's MMAs are issued
+// the next chunk's rows are requested into registers and its fc1 weight chunk is staged into the other slot, so both
+// fly under the MMAs; with two chunks both stay resident for the whole kernel.
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -17,8 +20,10 @@
 #define AI_SLAB_W1 (HID * 128)            //  8 KB: [64 rows x 32 floats]
 #define AI_SLAB_W2 (G3 * 128)             // 24 KB: [192 rows x 32 floats]
 #define AI_OFF_W1 (4 * AI_SLAB_A)
-#define AI_OFF_W2 (AI_OFF_W1 + 4 * AI_SLAB_W1)
-#define AI_SMEM_BYTES (AI_OFF_W2 + 4 * AI_SLAB_W2)     // 64 + 32 + 96 = 192 KB
+#define AI_W1_SLOT (4 * AI_SLAB_W1)                    // one fc1 weight chunk, hi + lo: 32 KB
+// one fc1 chunk slot when the input fits one 64-wide chunk, two when it does not (the next chunk is staged under the MMA)
+__host__ __device__ inline int ai_w1_slots(int K1) { return K1 > TC_KC ? 2 : 1; }
+__host__ __device__ inline size_t ai_smem_bytes(int K1) { return AI_OFF_W1 + (size_t)ai_w1_slots(K1) * AI_W1_SLOT + 4 * AI_SLAB_W2; }   // 192 / 224 KB
 #define AI_COL_X1 0
 #define AI_COL_X2 64
 #define AI_COL_G1 128
@@ -39,9 +44,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float b1_s[HID], bih_s[G3];
-    uint8_t *A_hi = tc_smem, *A_lo = tc_smem + 2 * AI_SLAB_A;
-    uint8_t *W1_hi = tc_smem + AI_OFF_W1, *W1_lo = W1_hi + 2 * AI_SLAB_W1;
-    uint8_t *W2_hi = tc_smem + AI_OFF_W2, *W2_lo = W2_hi + 2 * AI_SLAB_W2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, net = blockIdx.y;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
     const float *P = a.params[net];
@@ -51,6 +53,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     const BatchView &bv = a.bv;
     const int K1 = bv.OBS + bv.A;                       // the agent-id columns are a bias gather in the epilogue
     const int nkc1 = (K1 + TC_KC - 1) / TC_KC;
+    const bool two_slots = ai_w1_slots(K1) == 2;
+    uint8_t *A_hi = tc_smem, *A_lo = tc_smem + 2 * AI_SLAB_A;
+    uint8_t *W1_base = tc_smem + AI_OFF_W1;             // slot s: hi at + s * AI_W1_SLOT, lo 2 slabs further
+    uint8_t *W2_hi = W1_base + (two_slots ? 2 : 1) * AI_W1_SLOT, *W2_lo = W2_hi + 2 * AI_SLAB_W2;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
@@ -76,7 +82,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
             split_store_fast(W2_hi, W2_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W2 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
         }
     }
-    auto stage_w1 = [&](int kc) {                       // fc1.weight[:, kc*64 .. +64) (columns >= K1 are zero)
+    auto stage_w1 = [&](int kc, int slot) {             // fc1.weight[:, kc*64 .. +64) (columns >= K1 are zero)
+        uint8_t *W1_hi = W1_base + slot * AI_W1_SLOT, *W1_lo = W1_hi + 2 * AI_SLAB_W1;
         const int kcol = kc * TC_KC + 4 * c4;
         float4 wv[HID / 16];
 #pragma unroll
@@ -95,7 +102,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
             split_store_fast(W1_hi, W1_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W1 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
         }
     };
-    int w1_staged = -1;
+    int slot_chunk0 = -1, slot_chunk1 = -1;             // fc1 chunk held by each slot
+    int step = 0;                                       // running (tile, chunk) counter: slot = step & 1 with two slots
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
         // ---------------------------------------------------------------- x = fc1(input): nkc1 k-chunks into acc 1
         for (int kc = 0; kc < nkc1; ++kc) {
             float4 v[8];
-            if (kc == 0 && have_pre) {
+            if (have_pre) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = pre[i];
             } else {
@@ -153,12 +161,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
                 const int r = rbase + 16 * i;
                 split_store_fast(A_hi, A_lo, a_slab + (uint32_t)r * 128u + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4), v[i]);
             }
-            if (w1_staged != kc) { stage_w1(kc); w1_staged = kc; }
+            const int sl = two_slots ? (step & 1) : 0;
+            if ((sl ? slot_chunk1 : slot_chunk0) != kc) {   // first chunks of the kernel, or the single-slot layout
+                stage_w1(kc, sl);
+                if (sl) slot_chunk1 = kc; else slot_chunk0 = kc;
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tid == 0) {
+                const uint8_t *W1_hi = W1_base + sl * AI_W1_SLOT, *W1_lo = W1_hi + 2 * AI_SLAB_W1;
                 const uint64_t dA_hi = umma_desc_sw128(smem_u32(A_hi)), dA_lo = umma_desc_sw128(smem_u32(A_lo));
                 const uint64_t dW_hi = umma_desc_sw128(smem_u32(W1_hi)), dW_lo = umma_desc_sw128(smem_u32(W1_lo));
                 const int k0 = kc * TC_KC;
@@ -176,13 +189,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
                 }
                 umma_commit(&mma_bar);
             }
-            if (kc == nkc1 - 1) {                       // next tile's first input chunk flies under the rest of this tile
-                have_pre = false;
-                if (mt + (int)gridDim.x < n_mtiles) {
-                    load_in(a.m_begin + (int64_t)(mt + (int)gridDim.x) * TC_M, 0, pre);
-                    have_pre = true;
+            // The next chunk in sequence (this tile's kc + 1, else the next tile's first) is requested now: its rows fly
+            // under this chunk's MMAs (and, for a tile's last chunk, under the rest of the tile), and with two slots
+            // its fc1 weight chunk is staged into the slot the previous chunk's MMAs have released.
+            {
+                const bool same_tile = kc + 1 < nkc1;
+                const bool next_tile = mt + (int)gridDim.x < n_mtiles;
+                have_pre = same_tile || next_tile;
+                if (have_pre) {
+                    const int kcn = same_tile ? kc + 1 : 0;
+                    load_in(same_tile ? m0 : a.m_begin + (int64_t)(mt + (int)gridDim.x) * TC_M, kcn, pre);
+                    if (two_slots) {
+                        const int nsl = (step + 1) & 1;
+                        if ((nsl ? slot_chunk1 : slot_chunk0) != kcn) {
+                            stage_w1(kcn, nsl);
+                            if (nsl) slot_chunk1 = kcn; else slot_chunk0 = kcn;
+                        }
+                    }
                 }
             }
+            ++step;
             wait_mma();
         }
         // ---------------------------------------------------------------- epilogue 1: x = relu(. + b1 + W1[:, K1 + agent])

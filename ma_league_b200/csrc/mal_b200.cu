@@ -644,10 +644,11 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     // cores and most issue slots idle)
     const int t_split = (fused_in && g_time_chunks > 1 && g_overlap && d.TT >= 32) ? d.TT / 2 : d.TT;
     if (fused_in) {
-        static thread_local bool attr = false;
-        if (!attr) {
-            MAL_CUDA(cudaFuncSetAttribute(k_agent_in_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AI_SMEM_BYTES));
-            attr = true;
+        const size_t ai_smem = ai_smem_bytes(bv.OBS + bv.A);
+        static thread_local size_t attr = 0;
+        if (ai_smem > attr) {
+            MAL_CUDA(cudaFuncSetAttribute(k_agent_in_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ai_smem));
+            attr = ai_smem;
         }
         auto launch_in = [&](int tb, int te, cudaStream_t s_) -> int {
             AgentInArgs a;
@@ -657,7 +658,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             const int64_t tiles = ceil_div64(a.m_end - a.m_begin, TC_M);
             int64_t per = sms / 2; if (per < 1) per = 1;
             dim3 grid((unsigned)(tiles < per ? tiles : per), 2);
-            { ProfScope _ps("k_agent_in_tc", s_); k_agent_in_tc<<<grid, TC_THREADS, AI_SMEM_BYTES, s_>>>(a); }
+            { ProfScope _ps("k_agent_in_tc", s_); k_agent_in_tc<<<grid, TC_THREADS, ai_smem, s_>>>(a); }
             MAL_LAUNCH_CHECK("k_agent_in_tc");
             return 0;
         };
