@@ -111,16 +111,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     uint32_t bar_phase = 0;
     const float invR = 1.0f / (float)bv.R, invN = 1.0f / (float)bv.N;
 
+    const int q16 = 16 / bv.N, r16 = 16 - q16 * bv.N;   // a thread's rows are 16 apart: (t, b, n) advance incrementally
     auto load_in = [&](int64_t m0, int kc, float4 (&v)[8]) {   // [obs | last-action one-hot] rows, float4 over the obs part
         const int kcol = kc * TC_KC + 4 * c4;
+        int t, rr, b, n;
+        fast_divmod((int)m0 + rbase, bv.R, invR, t, rr);
+        fast_divmod(rr, bv.N, invN, b, n);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t m = m0 + rbase + 16 * i;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i > 0) {                                // row m = row (m - 16) + 16
+                rr += 16; b += q16; n += r16;
+                if (n >= bv.N) { n -= bv.N; ++b; }
+                if (rr >= bv.R) {                       // next timestep(s): rare, recompute (b, n)
+                    do { rr -= bv.R; ++t; } while (rr >= bv.R);
+                    fast_divmod(rr, bv.N, invN, b, n);
+                }
+            }
             if (m < M && kcol < K1) {
-                int t, rr, b, n;
-                fast_divmod((int)m, bv.R, invR, t, rr);
-                fast_divmod(rr, bv.N, invN, b, n);
                 if (kcol < bv.OBS) {                    // OBS % 4 == 0 (host-checked)
                     v[i] = __ldg(reinterpret_cast<const float4 *>(field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS + kcol));
                 } else if (t > 0) {
