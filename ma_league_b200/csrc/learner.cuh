@@ -394,7 +394,9 @@ __device__ __forceinline__ float tanh_mufu(float x) { return fmaf(2.0f, rcp_appr
 // The gi[t] terms are per-thread cp.async copies running PF steps ahead (one commit group per timestep).
 // Saved gates layout (private to k_gru_fwd4 / k_gru_bwd4): [m][unit][r, z, n, gh_n].
 // =============================================================================================
+#ifndef PDL_LEAD_STEPS
 #define PDL_LEAD_STEPS 6   // timesteps before the end of a recurrence at which its dependent kernel may start its prologue
+#endif
 template <int DBG = 0>   // DBG (probe only): 1 no global stores, 4 cheap gate math, 8 no matvec, 128 libm expf/tanhf gate math
 __global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
     constexpr int PF = 8;
