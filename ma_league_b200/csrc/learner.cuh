@@ -727,7 +727,7 @@ __device__ __forceinline__ float qmix_row(const MixArgs &a, int net, int64_t m, 
     return y;
 }
 
-__global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
+__global__ void __launch_bounds__(256, 4) k_mix_td(MixArgs a) {
     __shared__ float s_stats[8][MIX_NSTAT];
     __shared__ float s_v2[8][MAL_MAX_EMBED + 1];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
             wf = act ? fabsf(a2o[a.N * a.E + lane]) : 0.0f;
             const float v1_t = act ? y1t[a.E + lane] : 0.0f;
             v1 = act ? y1o[a.E + lane] : 0.0f;
-#pragma unroll 4
+#pragma unroll 8
             for (int n = 0; n < a.N; ++n) {
                 const float w1o = act ? fabsf(a2o[n * a.E + lane]) : 0.0f;
                 const float w1t = act ? fabsf(a2t[n * a.E + lane]) : 0.0f;
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
         // gather + fc2 backward: d h_t[row n] = d_chosen[n] * fc2.weight[a_t[n], :]   (consumed by the BPTT kernel)
         auto head_inject = [&](float dq_lane) {
             float *dh = a.dh_head + ((int64_t)t * a.R + (int64_t)b * a.N) * HID;
-#pragma unroll 4
+#pragma unroll 8
             for (int n = 0; n < a.N; ++n) {
                 const float dq = __shfl_sync(0xffffffffu, dq_lane, n);
                 const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w2p + (int64_t)__shfl_sync(0xffffffffu, act_mine, n) * HID) + lane);
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(256) k_mix_td(MixArgs a) {
         }
         if (lane == 0) dv2b += gseed;
         float dq_mine = 0.0f;                 // lane n ends up with d q_tot / d q_n * seed
-#pragma unroll 4
+#pragma unroll 8
         for (int n = 0; n < a.N; ++n) {
             const float a1 = act ? a2o[n * a.E + lane] : 0.0f;
             const float dq = warp_sum(act ? dpre * fabsf(a1) : 0.0f);
