@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MAL_ABI_VERSION 1
+#define MAL_ABI_VERSION 2
 #define MAL_HID 64
 #define MAL_MAX_ACTIONS 32
 #define MAL_MAX_EMBED 32

@@ -14,7 +14,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmal_b200.so")
 SRC = os.path.join(_HERE, "csrc", "mal_b200.cu")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MIXER_VDN, MIXER_QMIX2, MIXER_QMIX1 = 0, 1, 2
 SC_MASK_SUM, SC_LOSS, SC_TD_ABS, SC_Q_TAKEN, SC_TARGET, SC_GRAD_NORM, SC_MASK_COUNT, SC_STATUS = range(8)
