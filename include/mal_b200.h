@@ -184,8 +184,16 @@ int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t o
 /* dense_input != 0: `obs` is the already assembled agent input [rows, obs_dim] with row stride obs_sb
  * (DRQNAgentNetwork.forward(inputs, hidden_state), drqn_agent.py:29-35); obs_dim is then the full input width. */
 
-/* Library options.  "tensor_cores": 1 (default) runs the batched projections on tcgen05 (3xTF32, fp32-accurate),
- * 0 on the fp32 FFMA panel GEMM. */
+/* Library options (process-wide experiment switches; the defaults are the measured best).
+ *   "tensor_cores"  1 (default): batched projections on tcgen05 (3xTF32, fp32-accurate); 0: fp32 FFMA panel GEMM
+ *   "tc_pipelined"  0 / 1 (default, by launch size) / 2 (always): warp-specialised pipelined GEMM kernel
+ *   "reduce_tc"     0 / 1 (default, by rows per CTA) / 2 (always): weight-gradient reductions on tcgen05
+ *   "fuse_agent_in" 1 (default): fc1 + W_ih in one kernel; 0: two grouped GEMM launches
+ *   "overlap"       1 (default): independent kernel chains of the learner step on side streams; 0: one stream
+ *   "pdl"           1 (default): programmatic dependent launch along the main kernel chain; 0: full serialisation
+ *   "time_chunks"   1 (default) / 2: time-chunked forward (input projection of the 2nd half beside the 1st half's recurrence)
+ *   "tc_dbg"        probe switches of tools/gemm_bench.py
+ * Returns non-zero (and sets mal_last_error) for an unknown name. */
 int mal_set_option(const char *name, int value);
 
 /* Unit-test hook: Y = epi(A W^T + bias) on dense operands through the learner's own GEMM kernels
