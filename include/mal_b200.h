@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MAL_ABI_VERSION 2
+#define MAL_ABI_VERSION 3
 #define MAL_HID 64
 #define MAL_MAX_ACTIONS 32
 #define MAL_MAX_EMBED 32
@@ -62,7 +62,12 @@ typedef struct mal_learner_cfg {
     int32_t save_q;                   /* also materialise mac_out / target_mac_out (tests, debugging) */
     int32_t unnormalized;             /* data-parallel mode: mal_learner_backward leaves the gradient WITHOUT the
                                          1/mask.sum() factor so that ranks can all-reduce grads and mask sums first */
+    int32_t freeze_agent;             /* the agent's parameters are frozen (multi_agent_controller.py:74-76, args.freeze_native):
+                                         no agent gradient is computed, its grad slice is zero and left out of the clip norm,
+                                         and clip + RMSprop skip its parameters and square_avg (only the mixer trains) */
+    int32_t agent_kind;               /* MAL_AGENT_RNN (drqn_agent.py) or MAL_AGENT_DQN (dqn_agent.py: fc1 -> ReLU -> fc2) */
 } mal_learner_cfg_t;
+enum { MAL_AGENT_RNN = 0, MAL_AGENT_DQN = 1 };
 
 /* Byte offsets of every intermediate inside the caller-owned workspace (filled by mal_learner_plan).
  * Row index of the [TT*R, .] arrays is m = t*R + b*N + n; of the [B*T, .] arrays m = b*T + t. */
@@ -137,9 +142,11 @@ int mal_learner_backward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg,
  * scratch needs ceil((n_agent+n_mixer)/256) floats. */
 int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                      float *square_avg, float lr, float alpha, float eps, float clip, float *scalars,
-                     float *scratch, const float *denominator, void *stream);
+                     float *scratch, const float *denominator, int64_t n_frozen, void *stream);
 /* denominator: NULL, or a DEVICE pointer to the global mask sum; the gradient is divided by it first (data-parallel
- * mode: grads and mask sums are all-reduced across ranks, then every rank applies the identical update). */
+ * mode: grads and mask sums are all-reduced across ranks, then every rank applies the identical update).
+ * n_frozen: the first n_frozen parameters are frozen (requires_grad = False): their gradient is zeroed and left out
+ * of the norm, and neither they nor their square_avg are touched. */
 
 /* Data-parallel mode, fused exchange: peer_bufs[r] = device pointer of rank r's symmetric buffer holding its UN-normalised
  * gradient [n_agent + n_mixer] followed by `tail` raw statistic sums (element 4 = its mask sum), all peer-mapped into
@@ -149,7 +156,7 @@ int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixe
 int mal_peer_allreduce_clip_rmsprop(const void *const *peer_bufs, int32_t world, float *agent, int64_t n_agent, float *mixer,
                                     int64_t n_mixer, float *grad_out, float *tail_out, int32_t tail, float *square_avg,
                                     float lr, float alpha, float eps, float clip, float *scalars, float *scratch,
-                                    void *stream);
+                                    int64_t n_frozen, void *stream);
 
 /* forward + backward + clip + RMSprop in one call (the whole of q_learner.py:34-105). */
 int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
@@ -184,7 +191,13 @@ int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t o
 /* dense_input != 0: `obs` is the already assembled agent input [rows, obs_dim] with row stride obs_sb
  * (DRQNAgentNetwork.forward(inputs, hidden_state), drqn_agent.py:29-35); obs_dim is then the full input width. */
 
-/* Library options (process-wide experiment switches; the defaults are the measured best).
+/* Launch counters per kernel flavour since process start, for tests that assert which variant the launch heuristics
+ * picked: "linear_tc2" (pipelined tcgen05 GEMM), "linear_tc", "reduce_tc", "reduce_tc_swap", "reduce_ffma",
+ * "agent_in_fused".  Unknown names return 0. */
+uint64_t mal_stat(const char *name);
+
+/* Library options (experiment switches; the defaults are the measured best).  They are PER CALLING THREAD, like the
+ * library's side streams: a second thread driving another learner keeps its own settings.
  *   "tensor_cores"  1 (default): batched projections on tcgen05 (3xTF32, fp32-accurate); 0: fp32 FFMA panel GEMM
  *   "tc_pipelined"  0 / 1 (default, by launch size) / 2 (always): warp-specialised pipelined GEMM kernel
  *   "reduce_tc"     0 / 1 (default, by rows per CTA) / 2 (always): weight-gradient reductions on tcgen05

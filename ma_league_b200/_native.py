@@ -14,9 +14,10 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmal_b200.so")
 SRC = os.path.join(_HERE, "csrc", "mal_b200.cu")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MIXER_VDN, MIXER_QMIX2, MIXER_QMIX1 = 0, 1, 2
+AGENT_RNN, AGENT_DQN = 0, 1
 SC_MASK_SUM, SC_LOSS, SC_TD_ABS, SC_Q_TAKEN, SC_TARGET, SC_GRAD_NORM, SC_MASK_COUNT, SC_STATUS = range(8)
 SC_RAW0 = 8     # raw sums: sum mtd^2, sum |mtd|, sum q_tot*m, sum targets*m, sum m, count
 HID = 64
@@ -41,7 +42,8 @@ class Batch(C.Structure):
 class LearnerCfg(C.Structure):
     _fields_ = [("mixer", C.c_int32), ("double_q", C.c_int32), ("embed", C.c_int32), ("hyper_embed", C.c_int32),
                 ("gamma", C.c_float), ("lr", C.c_float), ("alpha", C.c_float), ("eps", C.c_float),
-                ("clip", C.c_float), ("save_q", C.c_int32), ("unnormalized", C.c_int32)]
+                ("clip", C.c_float), ("save_q", C.c_int32), ("unnormalized", C.c_int32), ("freeze_agent", C.c_int32),
+                ("agent_kind", C.c_int32)]
 
 
 _PLAN_FIELDS = ["total_bytes", "n_agent_params", "n_mixer_params", "x_on", "x_tg", "gi_on", "gi_tg", "h_on", "h_tg",
@@ -68,6 +70,7 @@ _PROTOS = {
     "mal_profile_begin": (C.c_int, []),
     "mal_profile_end": (C.c_int, [C.c_char_p, C.c_int64]),
     "mal_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "mal_stat": (C.c_uint64, [C.c_char_p]),
     "mal_debug_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int32, C.c_void_p]),
@@ -79,10 +82,11 @@ _PROTOS = {
     "mal_learner_backward": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_clip_rmsprop": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
-                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mal_peer_allreduce_clip_rmsprop": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float,
-                                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,
+                                                  C.c_void_p]),
     "mal_learner_step": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_copy_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -28,15 +28,18 @@ struct PeerBufs {
 };
 
 __global__ void __launch_bounds__(256) k_peer_allreduce_grad(const __grid_constant__ PeerBufs peers, int64_t n_total, int tail,
-                                                             float *grad_out, float *tail_out, float *norm_part) {
+                                                             float *grad_out, float *tail_out, float *norm_part,
+                                                             int64_t n_frozen) {
     __shared__ float s_sq[8];
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     float denom = 0.0f;
     for (int r = 0; r < peers.world; ++r) denom += __ldcg(peers.p[r] + n_total + 4);      // global mask.sum()
     float v = 0.0f;
     if (p < n_total) {
-        for (int r = 0; r < peers.world; ++r) v += __ldcg(peers.p[r] + p);
-        v = v / denom;
+        if (p >= n_frozen) {                       // frozen prefix (freeze_agent_weights): no gradient, not in the norm
+            for (int r = 0; r < peers.world; ++r) v += __ldcg(peers.p[r] + p);
+            v = v / denom;
+        }
         grad_out[p] = v;
     }
     if (blockIdx.x == 0 && threadIdx.x < tail) {
@@ -1098,6 +1101,7 @@ struct GradReduceArgs {
     float *norm_part;        // [gridDim.x]
     const float *scalars;    // mask sum
     int unnormalized;        // leave out the 1/mask.sum() factor (data-parallel mode)
+    int64_t n_frozen;        // parameters [0, n_frozen) are frozen: gradient 0 (their partials are not even read)
 };
 
 #define GRED_EPB 64   // gradient elements per block: 256 threads = 64 elements x 4 chunk slices
@@ -1109,7 +1113,7 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ Gra
     const int e = threadIdx.x & (GRED_EPB - 1), slice = threadIdx.x >> 6;   // slice is warp-uniform
     const int64_t p = (int64_t)blockIdx.x * GRED_EPB + e;
     float v = 0.0f;
-    if (p < a.total) {
+    if (p < a.total && p >= a.n_frozen) {
         int si = 0;
         while (si + 1 < a.n && p >= a.s[si + 1].grad_off) ++si;
         const GradSeg &s = a.s[si];
@@ -1143,11 +1147,12 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const __grid_constant__ Gra
 }
 
 // sum of squares of an arbitrary flat gradient (used when mal_clip_rmsprop is called stand-alone)
-__global__ void __launch_bounds__(256) k_sumsq(const float *g, int64_t n, float *norm_part, const float *denominator) {
+__global__ void __launch_bounds__(256) k_sumsq(float *g, int64_t n, float *norm_part, const float *denominator, int64_t n_frozen) {
     __shared__ float s_sq[8];
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const float inv = denominator ? 1.0f / denominator[0] : 1.0f;
-    float v = p < n ? g[p] * inv : 0.0f;
+    if (p < n_frozen && p < n) g[p] = 0.0f;       // frozen prefix: no gradient, not in the norm
+    float v = (p < n && p >= n_frozen) ? g[p] * inv : 0.0f;
     float sq = warp_sum(v * v);
     if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
     __syncthreads();
@@ -1164,7 +1169,7 @@ __global__ void __launch_bounds__(256) k_sumsq(const float *g, int64_t n, float 
 __global__ void __launch_bounds__(256) k_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer,
                                                       float *grad, float *sq, const float *norm_part, int n_part,
                                                       float lr, float alpha, float eps, float clip, float *scalars,
-                                                      const float *denominator) {
+                                                      const float *denominator, int64_t n_frozen) {
     __shared__ float s_red[8];
     __shared__ float s_coef;
     pdl_wait();
@@ -1185,7 +1190,7 @@ __global__ void __launch_bounds__(256) k_clip_rmsprop(float *agent, int64_t n_ag
     __syncthreads();
     const float coef = s_coef;
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (p >= n_agent + n_mixer) return;
+    if (p >= n_agent + n_mixer || p < n_frozen) return;   // frozen parameters: RMSprop skips them (p.grad is None)
     float *param = p < n_agent ? agent + p : mixer + (p - n_agent);
     const float gv = grad[p] * (denominator ? 1.0f / denominator[0] : 1.0f) * coef;
     grad[p] = gv;   // clip_grad_norm_ scales .grad in place

@@ -99,6 +99,29 @@ extern "C" int64_t mal_mixer_param_count(int32_t mixer, int32_t S, int32_t N, in
     return mixer_layout(mixer, S, N, E, HE).total;
 }
 
+// Per-device state is indexed by the device ordinal (a thread may drive several GPUs one after the other).
+#define MAL_MAX_DEV 64
+// Opt `kernel` into `bytes` of dynamic shared memory on the CURRENT device.  `cache` is the call site's per-device
+// high-water mark (static, zero-initialised; a benign race sets the attribute twice).
+template <typename K>
+static int ensure_dyn_smem(K kernel, size_t bytes, size_t *cache) {
+    int dev = 0;
+    MAL_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAL_MAX_DEV) {
+        MAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        return 0;
+    }
+    if (bytes > cache[dev]) {
+        MAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cache[dev] = bytes;
+    }
+    return 0;
+}
+
+// kernel-flavour counters (tests assert which variant the launch heuristics picked): see mal_stat()
+static uint64_t g_stat_tc2 = 0, g_stat_tc1 = 0, g_stat_reduce_tc = 0, g_stat_reduce_tc_swap = 0, g_stat_reduce_ffma = 0,
+                g_stat_agent_in_fused = 0;
+
 static int device_sm_count(int *sms, int *threads_per_sm) {
     static thread_local int c_dev = -1, c_sms = 0, c_tps = 0;
     int dev = 0;
@@ -118,13 +141,15 @@ static int device_sm_count(int *sms, int *threads_per_sm) {
 // and leave most SMs idle).  Fork/join with events only, so the pattern is also capturable into a CUDA graph.
 // ---------------------------------------------------------------------------------------------
 struct SideStreams {
-    int dev = -1;
+    bool ready = false;
     cudaStream_t s[2];
     cudaEvent_t fork_ev[4], join_ev[2];
 };
-static thread_local SideStreams g_side;
-static int g_overlap = 1;
-static int g_pdl = 1;              // programmatic dependent launch on the main kernel chain (prologues overlap the predecessor's tail)
+static thread_local SideStreams g_side[MAL_MAX_DEV];   // one set per (thread, device)
+// mal_set_option switches are PER CALLING THREAD (like the side streams): two learners driven by two threads of one
+// process do not see each other's settings
+static thread_local int g_overlap = 1;
+static thread_local int g_pdl = 1;              // programmatic dependent launch on the main kernel chain (prologues overlap the predecessor's tail)
 static thread_local bool g_defer_stats = false;   // set by mal_learner_step around its forward half
 static thread_local bool g_next_pdl = false;      // the next launch_linear / launch_reduce call may start under its stream predecessor
 static thread_local bool g_in_step = false;       // inside mal_learner_step: the stream predecessors of backward / update are ours
@@ -147,13 +172,15 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 static int side_streams(SideStreams **out) {
     int dev = 0;
     MAL_CUDA(cudaGetDevice(&dev));
-    if (g_side.dev != dev) {
-        for (int i = 0; i < 2; ++i) MAL_CUDA(cudaStreamCreateWithFlags(&g_side.s[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 4; ++i) MAL_CUDA(cudaEventCreateWithFlags(&g_side.fork_ev[i], cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) MAL_CUDA(cudaEventCreateWithFlags(&g_side.join_ev[i], cudaEventDisableTiming));
-        g_side.dev = dev;
+    MAL_REQUIRE(dev >= 0 && dev < MAL_MAX_DEV, "device ordinal %d out of range", dev);
+    SideStreams &ss = g_side[dev];
+    if (!ss.ready) {
+        for (int i = 0; i < 2; ++i) MAL_CUDA(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) MAL_CUDA(cudaEventCreateWithFlags(&ss.fork_ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) MAL_CUDA(cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming));
+        ss.ready = true;
     }
-    *out = &g_side;
+    *out = &ss;
     return 0;
 }
 // `side` starts after everything enqueued on `main` so far
@@ -191,11 +218,8 @@ extern "C" int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst
     a.tiles_per_rec = (int32_t)ceil_div64(bytes, RC_TILE);
     a.n_tiles = (int64_t)a.tiles_per_rec * n;
     const size_t smem = (size_t)RC_STAGES * RC_TILE;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        MAL_CUDA(cudaFuncSetAttribute(k_record_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static size_t attr[MAL_MAX_DEV];
+    if (int rc = ensure_dyn_smem(k_record_copy_tma, smem, attr)) return rc;
     int64_t grid = a.n_tiles < (int64_t)sms * 3 ? a.n_tiles : (int64_t)sms * 3;   // 3 x 64 KB rings per SM
     { ProfScope _ps("k_record_copy_tma", (cudaStream_t)stream); k_record_copy_tma<<<(unsigned)grid, 32, smem, (cudaStream_t)stream>>>(a); }
     MAL_LAUNCH_CHECK("k_record_copy_tma");
@@ -282,11 +306,13 @@ extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents
     if (device_sm_count(&sms, &tps)) return 2;
     const int ctas = (rows + AS_ROWS - 1) / AS_ROWS;
     if (ctas <= 2 * sms) {   // latency-bound regime (rollouts): all weights prefetched into registers
-        if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t attr[MAL_MAX_DEV];
+        if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step, smem, attr)) return rc;
         ProfScope _ps("k_agent_step", (cudaStream_t)stream);
         k_agent_step<<<ctas, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
     } else {
-        if (smem > 48 * 1024) MAL_CUDA(cudaFuncSetAttribute(k_agent_step_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t attr[MAL_MAX_DEV];
+        if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step_stream, smem, attr)) return rc;
         ProfScope _ps("k_agent_step", (cudaStream_t)stream);
         k_agent_step_stream<<<ctas, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
     }
@@ -452,12 +478,24 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
     return v;
 }
 
-static int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
-static int g_tc_dbg = 0;
-static int g_reduce_tc = 1;       // weight-gradient reductions on tcgen05 (k_reduce_tc); 0: fp32 FFMA k_reduce_group
-static int g_time_chunks = 1;     // 2: time-chunked forward (input projection of the 2nd half beside the recurrence of the 1st): measured 0.406 vs 0.400 ms at B=32, off by default
-static int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc); 0: two grouped GEMM launches
-static int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
+static thread_local int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
+static thread_local int g_tc_dbg = 0;
+static thread_local int g_reduce_tc = 1;       // weight-gradient reductions on tcgen05 (k_reduce_tc); 0: fp32 FFMA k_reduce_group
+static thread_local int g_time_chunks = 1;     // 2: time-chunked forward (input projection of the 2nd half beside the recurrence of the 1st): measured 0.406 vs 0.400 ms at B=32, off by default
+static thread_local int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc); 0: two grouped GEMM launches
+static thread_local int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
+
+// Launch counters per kernel flavour since process start (tests check which variant the heuristics picked).
+extern "C" uint64_t mal_stat(const char *name) {
+    if (!name) return 0;
+    if (strcmp(name, "linear_tc2") == 0) return g_stat_tc2;
+    if (strcmp(name, "linear_tc") == 0) return g_stat_tc1;
+    if (strcmp(name, "reduce_tc") == 0) return g_stat_reduce_tc;
+    if (strcmp(name, "reduce_tc_swap") == 0) return g_stat_reduce_tc_swap;
+    if (strcmp(name, "reduce_ffma") == 0) return g_stat_reduce_ffma;
+    if (strcmp(name, "agent_in_fused") == 0) return g_stat_agent_in_fused;
+    return 0;
+}
 extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
@@ -474,11 +512,9 @@ extern "C" int mal_set_option(const char *name, int value) {
 
 template <int AK, int EK>
 static int launch_tc_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag, bool pdl) {
-    static thread_local bool attr = false;
-    if (!attr) {
-        MAL_CUDA(cudaFuncSetAttribute(k_linear_tc<AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        attr = true;
-    }
+    static size_t attr[MAL_MAX_DEV];
+    if (int rc = ensure_dyn_smem(k_linear_tc<AK, EK>, TC_SMEM_BYTES, attr)) return rc;
+    ++g_stat_tc1;
     { ProfScope _ps(tag, st); launch_k(k_linear_tc<AK, EK>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, pdl, g); }
     MAL_LAUNCH_CHECK("k_linear_tc");
     return 0;
@@ -486,11 +522,9 @@ static int launch_tc_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const c
 
 template <int AK, int EK>
 static int launch_tc2_inst(const LinGroup &g, dim3 grid, cudaStream_t st, const char *tag, bool pdl) {
-    static thread_local bool attr = false;
-    if (!attr) {
-        MAL_CUDA(cudaFuncSetAttribute(k_linear_tc2<AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
-        attr = true;
-    }
+    static size_t attr[MAL_MAX_DEV];
+    if (int rc = ensure_dyn_smem(k_linear_tc2<AK, EK>, TC2_SMEM_BYTES, attr)) return rc;
+    ++g_stat_tc2;
     { ProfScope _ps(tag, st); launch_k(k_linear_tc2<AK, EK>, grid, dim3(TC2_THREADS), TC2_SMEM_BYTES, st, pdl, g); }
     MAL_LAUNCH_CHECK("k_linear_tc2");
     return 0;
@@ -575,11 +609,8 @@ static int launch_linear(LinGroup &g, int64_t maxM, int maxK, cudaStream_t st, c
     const int nkc = (maxK + LIN_KC - 1) / LIN_KC;
     const size_t smem = sizeof(float) * ((size_t)LIN_TM * (nkc * LIN_KC + 4) + (size_t)LIN_TN * LIN_LDW);
     MAL_REQUIRE(smem <= 220 * 1024, "inner dimension %d too large for the panel GEMM", maxK);
-    static thread_local size_t attr = 48 * 1024;
-    if (smem > attr) {
-        MAL_CUDA(cudaFuncSetAttribute(k_linear_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static size_t attr[MAL_MAX_DEV];
+    if (int rc = ensure_dyn_smem(k_linear_group, smem, attr)) return rc;
     dim3 grid((unsigned)ceil_div64(maxM, LIN_TM), g.n);
     { ProfScope _ps(tag, st); k_linear_group<<<grid, 256, smem, st>>>(g); }
     MAL_LAUNCH_CHECK("k_linear_group");
@@ -645,11 +676,9 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     const int t_split = (fused_in && g_time_chunks > 1 && g_overlap && d.TT >= 32) ? d.TT / 2 : d.TT;
     if (fused_in) {
         const size_t ai_smem = ai_smem_bytes(bv.OBS + bv.A);
-        static thread_local size_t attr = 0;
-        if (ai_smem > attr) {
-            MAL_CUDA(cudaFuncSetAttribute(k_agent_in_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ai_smem));
-            attr = ai_smem;
-        }
+        static size_t attr[MAL_MAX_DEV];
+        if (int rc = ensure_dyn_smem(k_agent_in_tc, ai_smem, attr)) return rc;
+        ++g_stat_agent_in_fused;
         auto launch_in = [&](int tb, int te, cudaStream_t s_) -> int {
             AgentInArgs a;
             for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.x[net] = x[net]; a.gi[net] = gi[net]; }
@@ -735,11 +764,8 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         const size_t smem = qh_smem_bytes(d.A);
         const int64_t qh_tiles = ceil_div64(d.M1, 64), qh_slots = 3 * (int64_t)sms;      // balanced: every CTA walks the same
         const int64_t qh_grid = ceil_div64(qh_tiles, ceil_div64(qh_tiles, qh_slots));    // number of tiles (+-1), in one wave
-        static thread_local size_t attr = 48 * 1024;
-        if (smem > attr) {
-            MAL_CUDA(cudaFuncSetAttribute(k_q_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
+        static size_t attr[MAL_MAX_DEV];
+        if (int rc = ensure_dyn_smem(k_q_head, smem, attr)) return rc;
         { ProfScope _ps("k_q_head", st); launch_k(k_q_head, dim3((unsigned)qh_grid), dim3(128), smem, st, true, a); }   // predecessor: k_gru_fwd4
         MAL_LAUNCH_CHECK("k_q_head");
     }
@@ -901,17 +927,16 @@ static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, con
     }
     dim3 grid(maxc, tiles);
     if (tc) {
-        static thread_local bool attr = false;
-        if (!attr) {
-            MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
-            MAL_CUDA(cudaFuncSetAttribute(k_reduce_tc<AK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM_BYTES));
-            attr = true;
-        }
+        static size_t attr0[MAL_MAX_DEV], attr1[MAL_MAX_DEV];
+        if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 0>, RT_SMEM_BYTES, attr0)) return rc;
+        if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 1>, RT_SMEM_BYTES, attr1)) return rc;
+        if (swap) ++g_stat_reduce_tc_swap; else ++g_stat_reduce_tc;
         if (swap) { ProfScope _ps(tag_tc, st); launch_k(k_reduce_tc<AK, 1>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g); }
         else { ProfScope _ps(tag_tc, st); launch_k(k_reduce_tc<AK, 0>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g); }
         MAL_LAUNCH_CHECK("k_reduce_tc");
         return 0;
     }
+    ++g_stat_reduce_ffma;
     { ProfScope _ps(tag, st); launch_k(k_reduce_group<AK, DK>, grid, dim3(256), 0, st, g_next_pdl, g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
     return 0;
@@ -985,24 +1010,22 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         r.p[2] = red(d.BT, d.S, d.ld1, d_y1, d.ld1, A_STATE, 0, nullptr, 0, parts + pl.m_l1_w, parts + pl.m_l1_b, pl.nc_m1, pl.rpc_m1);
         if (int rc = launch_reduce(r, s1, "k_reduce_group:mixer")) return rc;
     }
+    const bool frozen = cfg->freeze_agent != 0;   // multi_agent_controller.py:74-76: the agent gets no gradient at all
     // ---- side stream 2: fc2 gradients only need d_chosen and h (both forward products)
-    {
+    if (!frozen) {
         Fc2GradArgs a;
         a.d_chosen = F(plan->d_chosen); a.actions = batch->actions; a.hout = F(plan->h_on);
         a.partW = parts + pl.fc2_w; a.partB = parts + pl.fc2_b;
         a.T = d.T; a.N = d.N; a.A = d.A; a.R = d.R; a.rows = (int64_t)d.T * d.R;
         const size_t smem = sizeof(float) * 8 * ((size_t)d.A * HID + 32);
-        static thread_local size_t attr = 48 * 1024;
-        if (smem > attr) {
-            MAL_CUDA(cudaFuncSetAttribute(k_fc2_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
+        static size_t attr[MAL_MAX_DEV];
+        if (int rc = ensure_dyn_smem(k_fc2_grad, smem, attr)) return rc;
         { ProfScope _ps("k_fc2_grad", s2); k_fc2_grad<<<pl.nc_f2, 256, smem, s2>>>(a); }
         MAL_LAUNCH_CHECK("k_fc2_grad");
     }
 
     // ---- main stream: BPTT recurrence
-    {
+    if (!frozen) {
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
@@ -1011,7 +1034,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads
     if (fork_to(st, s2, ss->fork_ev[2])) return 2;
-    {
+    if (!frozen) {
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.M1, HID, G3, d_g, 4 * HID, A_DENSE, 0, F(plan->x_on), HID, parts + pl.wih_w, parts + pl.wih_b, pl.nc_a, pl.rpc_a);
         // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)
@@ -1019,7 +1042,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
         if (int rc = launch_reduce(r, s2, "k_reduce_group:agent")) return rc;
     }
-    {
+    if (!frozen) {
         LinGroup g; g.n = 1; g.bv = bv;
         g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, F(plan->w_t), G3, 0, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);   // W_ih^T from the forward call
         g_next_pdl = true;                       // stream predecessor: k_gru_bwd4 (W_ih staging flies under its last timesteps)
@@ -1084,6 +1107,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         a.norm_part = parts + pl.norm;
         a.scalars = F(plan->scalars);
         a.unnormalized = cfg->unnormalized ? 1 : 0;
+        a.n_frozen = frozen ? AL.total : 0;
         { ProfScope _ps("k_grad_reduce", st); launch_k(k_grad_reduce, dim3(pl.nblk_norm), dim3(256), 0, st, true, a); }   // stream predecessor: the fc1 reduction
         MAL_LAUNCH_CHECK("k_grad_reduce");
     }
@@ -1092,32 +1116,34 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
 
 static int launch_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                                float *sq, const float *norm_part, int n_part, float lr, float alpha, float eps,
-                               float clip, float *scalars, const float *denominator, cudaStream_t st, bool pdl = false) {
+                               float clip, float *scalars, const float *denominator, int64_t n_frozen, cudaStream_t st, bool pdl = false) {
     const int64_t P = n_agent + n_mixer;
     { ProfScope _ps("k_clip_rmsprop", st); launch_k(k_clip_rmsprop, dim3((unsigned)ceil_div64(P, 256)), dim3(256), 0, st, pdl, agent, n_agent, mixer, n_mixer, grad, sq, norm_part,
-                                                                n_part, lr, alpha, eps, clip, scalars, denominator); }
+                                                                n_part, lr, alpha, eps, clip, scalars, denominator, n_frozen); }
     MAL_LAUNCH_CHECK("k_clip_rmsprop");
     return 0;
 }
 
 extern "C" int mal_clip_rmsprop(float *agent, int64_t n_agent, float *mixer, int64_t n_mixer, float *grad,
                                 float *square_avg, float lr, float alpha, float eps, float clip, float *scalars,
-                                float *scratch, const float *denominator, void *stream) {
+                                float *scratch, const float *denominator, int64_t n_frozen, void *stream) {
     MAL_REQUIRE(agent && grad && square_avg && scalars && scratch && n_agent > 0 && n_mixer >= 0,
                 "mal_clip_rmsprop: bad arguments (scratch needs ceil(P/256) floats)");
+    MAL_REQUIRE(n_frozen >= 0 && n_frozen <= n_agent + n_mixer, "mal_clip_rmsprop: n_frozen out of range");
     MAL_REQUIRE(n_mixer == 0 || mixer, "mal_clip_rmsprop: mixer buffer missing");
     const int64_t P = n_agent + n_mixer;
     const int nb = (int)ceil_div64(P, 256);
-    { ProfScope _ps("k_sumsq", (cudaStream_t)stream); k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch, denominator); }
+    { ProfScope _ps("k_sumsq", (cudaStream_t)stream); k_sumsq<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, P, scratch, denominator, n_frozen); }
     MAL_LAUNCH_CHECK("k_sumsq");
     return launch_clip_rmsprop(agent, n_agent, mixer, n_mixer, grad, square_avg, scratch, nb, lr, alpha, eps, clip,
-                               scalars, denominator, (cudaStream_t)stream);
+                               scalars, denominator, n_frozen, (cudaStream_t)stream);
 }
 
 extern "C" int mal_peer_allreduce_clip_rmsprop(const void *const *peer_bufs, int32_t world, float *agent, int64_t n_agent,
                                                float *mixer, int64_t n_mixer, float *grad_out, float *tail_out, int32_t tail,
                                                float *square_avg, float lr, float alpha, float eps, float clip,
-                                               float *scalars, float *scratch, void *stream) {
+                                               float *scalars, float *scratch, int64_t n_frozen, void *stream) {
+    MAL_REQUIRE(n_frozen >= 0 && n_frozen <= n_agent + n_mixer, "mal_peer_allreduce_clip_rmsprop: n_frozen out of range");
     MAL_REQUIRE(peer_bufs && world >= 1 && world <= PEER_MAX, "mal_peer_allreduce_clip_rmsprop: world size must be in [1, %d]", PEER_MAX);
     MAL_REQUIRE(agent && grad_out && tail_out && square_avg && scalars && scratch && n_agent > 0 && n_mixer >= 0 && tail >= 5 && tail <= 32,
                 "mal_peer_allreduce_clip_rmsprop: bad arguments (scratch needs ceil(P/256) floats, tail >= 5)");
@@ -1131,10 +1157,10 @@ extern "C" int mal_peer_allreduce_clip_rmsprop(const void *const *peer_bufs, int
     const int64_t P = n_agent + n_mixer;
     const int nb = (int)ceil_div64(P, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    { ProfScope _ps("k_peer_allreduce_grad", st); k_peer_allreduce_grad<<<nb, 256, 0, st>>>(pb, P, tail, grad_out, tail_out, scratch); }
+    { ProfScope _ps("k_peer_allreduce_grad", st); k_peer_allreduce_grad<<<nb, 256, 0, st>>>(pb, P, tail, grad_out, tail_out, scratch, n_frozen); }
     MAL_LAUNCH_CHECK("k_peer_allreduce_grad");
     return launch_clip_rmsprop(agent, n_agent, mixer, n_mixer, grad_out, square_avg, scratch, nb, lr, alpha, eps, clip,
-                               scalars, nullptr, st);
+                               scalars, nullptr, n_frozen, st);
 }
 
 extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
@@ -1160,7 +1186,7 @@ extern "C" int mal_learner_step(const mal_batch_t *batch, const mal_learner_cfg_
     float *scalars = reinterpret_cast<float *>(ws + plan->scalars);
     return launch_clip_rmsprop(agent, plan->n_agent_params, mixer, plan->n_mixer_params, grad, square_avg,
                                parts + pl.norm, pl.nblk_norm, cfg->lr, cfg->alpha, cfg->eps, cfg->clip, scalars,
-                               nullptr, (cudaStream_t)stream, true);   // stream predecessor: k_grad_reduce
+                               nullptr, cfg->freeze_agent ? plan->n_agent_params : 0, (cudaStream_t)stream, true);   // stream predecessor: k_grad_reduce
 }
 
 extern "C" int mal_copy_f32(float *dst, const float *src, int64_t n, void *stream) {

@@ -75,7 +75,21 @@ class QLearner(Learner):
         qm = isinstance(self.mixer, QMixer)
         return nat.LearnerCfg(self._mixer_kind(), int(bool(a.double_q)), self.mixer.embed_dim if qm else 0,
                               self.mixer.hypernet_embed if qm else 0, a.gamma, a.lr, a.optim_alpha, a.optim_eps,
-                              a.grad_norm_clip, int(self.save_q), int(self._dp_world() > 1))
+                              a.grad_norm_clip, int(self.save_q), int(self._dp_world() > 1), int(self._agent_frozen()),
+                              getattr(self.mac.agent, "mal_kind", nat.AGENT_RNN))
+
+    def _agent_frozen(self):
+        """`freeze_agent_weights()` (multi_agent_controller.py:74-76, `args.freeze_native`): in the reference a frozen
+        agent gets no gradient, stays out of the clip norm and is skipped by RMSprop, so only the mixer trains
+        (q_learner.py:101-105).  Supported as all-or-nothing per network, like the reference's own switch."""
+        ap = getattr(self.mac.agent, "_mal_params", None) or list(self.mac.parameters())   # cached list (flat.py)
+        n_req = sum(1 for p in ap if p.requires_grad)
+        if 0 < n_req < len(ap):
+            raise nat.MalError("partially frozen agents are not supported: freeze all agent parameters or none")
+        mp = getattr(self.mixer, "_mal_params", None) or list(self.mixer.parameters())
+        if not all(p.requires_grad for p in mp):
+            raise nat.MalError("frozen mixer parameters are not supported by the fused learner step")
+        return len(ap) > 0 and n_req == 0
 
     def _dp_world(self):
         """>1 when `args.data_parallel` is set and a process group exists: the batch given to train() is this rank's
@@ -88,7 +102,10 @@ class QLearner(Learner):
     def _batch_struct(self, batch):
         obs = nat.require_cuda(batch["obs"], "batch")
         # the marshalled struct only depends on where the batch's tensors live: reuse it for a batch seen before
-        ck = (obs.data_ptr(), obs.shape, obs.stride(), batch["filled"].data_ptr(), batch["state"].data_ptr())
+        # (unpacked batches keep one tensor per key, so every key's address is part of the identity)
+        ck = (obs.data_ptr(), obs.shape, obs.stride()) + tuple(
+            (batch[k].data_ptr(), batch[k].stride(0), batch[k].stride(1)) for k in
+            ("actions_onehot", "actions", "avail_actions", "state", "reward", "terminated", "filled"))
         hit = self._bs_cache.get(ck)
         if hit is not None:
             return hit
@@ -126,7 +143,9 @@ class QLearner(Learner):
         cfg = self._cfg()
         key = (bs.B, bs.TT, bs.N, bs.A, bs.OBS, bs.S, cfg.mixer, cfg.save_q, str(dev))
         if key != self._ws_key:
-            nat.check(nat.lib().mal_learner_plan(C.byref(bs), C.byref(cfg), C.byref(self._plan)), "mal_learner_plan")
+            with nat.on_device(dev):     # the chunk layout is sized from the SM count of the learner's device
+                nat.check(nat.lib().mal_learner_plan(C.byref(bs), C.byref(cfg), C.byref(self._plan)),
+                          "mal_learner_plan")
             if self._ws is None or self._ws.numel() < self._plan.total_bytes or self._ws.device != dev:
                 self._ws = th.empty(self._plan.total_bytes, dtype=th.uint8, device=dev)
             self._ws_key = key
@@ -168,7 +187,10 @@ class QLearner(Learner):
         if getattr(self, "_grad_views", None) is None:   # p.grad = views of the flat (clipped) gradient, bound once
             params = self.parameters()
             self._grad_views = list(zip(params, flat_views(self._grad, params)))
+        frozen = cfg.freeze_agent != 0
         for p, g in self._grad_views:
+            if frozen and not p.requires_grad:
+                continue                                  # a frozen parameter keeps p.grad = None, as in the reference
             if p.grad is not g:
                 p.grad = g
 
@@ -269,7 +291,8 @@ class QLearner(Learner):
                                            self._plan.n_mixer_params, nat.ptr(self._grad),
                                            nat.ptr(self.optimiser.flat_sq), a.lr, a.optim_alpha, a.optim_eps,
                                            a.grad_norm_clip, nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
-                                           nat.ptr(denom), st), "mal_clip_rmsprop")
+                                           nat.ptr(denom), self._plan.n_agent_params if cfg.freeze_agent else 0, st),
+                      "mal_clip_rmsprop")
 
     # ---- fused exchange: peer-memory all-reduce inside the optimiser prologue (no NCCL call on the path)
     def _dp_symmetric(self, n_total, dev):
@@ -322,7 +345,8 @@ class QLearner(Learner):
                 ptrs[h], hdl.world_size, nat.ptr(f["agent"]), self._plan.n_agent_params, nat.ptr(f["mixer"]),
                 self._plan.n_mixer_params, nat.ptr(self._grad), nat.ptr(self._grad_store[n_total:]), DP_TAIL,
                 nat.ptr(self.optimiser.flat_sq), a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip,
-                nat.ptr(self.scalars()), nat.ptr(self._dp_scratch), st), "mal_peer_allreduce_clip_rmsprop")
+                nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
+                self._plan.n_agent_params if cfg.freeze_agent else 0, st), "mal_peer_allreduce_clip_rmsprop")
         self._dp_step += 1
 
     def train_from_buffer(self, buffer, batch_size: int, t_env: int, episode_num: int, truncate: bool = False):

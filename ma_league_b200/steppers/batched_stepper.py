@@ -134,7 +134,7 @@ class BatchedEpisodeStepper:
         for tv in views:
             for key, v in tv.items():
                 m = keep_trans if key in ("reward", "terminated") else keep_state
-                v.mul_(m.view((B, TT) + (1,) * (v.dim() - 2)).to(v.dtype))
+                v.masked_fill_(~m.view((B, TT) + (1,) * (v.dim() - 2)), 0)      # (0 * NaN would stay NaN)
             tv["filled"][:, :, 0].copy_(keep_state)
         n_steps = int(steps.sum())
         self.t = int(steps.max())                 # transitions of the longest match (the reference's self.t for one match)

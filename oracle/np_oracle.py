@@ -139,16 +139,19 @@ def unroll(p, obs, actions_onehot):
 # --------------------------------------------------------------------------
 # a5: masked (double-Q) target max   marl/learners/q_learner.py:65-78
 # --------------------------------------------------------------------------
-def masked_target_max(mac_out, target_mac_out_full, avail, double_q: bool):
+def masked_target_max(mac_out, target_mac_out_full, avail, double_q: bool, argmax_override=None):
     """mac_out/target_mac_out_full [B,TT,N,A], avail [B,TT,N,A] int -> (target_max [B,T,N], argmax [B,T,N] int64).
 
-    Ties resolve to the lowest action index (np.argmax == torch.max first occurrence)."""
+    Ties resolve to the lowest action index (np.argmax == torch.max first occurrence); NaN wins the max, as in torch.
+    ``argmax_override`` (tests only, double-Q): use these indices instead of the oracle's own arg-max -- a checker that
+    has verified that an fp32 implementation flipped a genuine near-tie re-evaluates everything downstream of the
+    discrete choice on the implementation's indices ("discrete argmax inside the loss")."""
     tq = target_mac_out_full[:, 1:].copy()
     tq[avail[:, 1:] == 0] = NEG_MASK
     if double_q:
         oq = mac_out.copy()
         oq[avail == 0] = NEG_MASK
-        amax = np.argmax(oq[:, 1:], axis=3)
+        amax = np.argmax(oq[:, 1:], axis=3) if argmax_override is None else np.asarray(argmax_override, dtype=np.int64)
         tmax = np.take_along_axis(tq, amax[..., None], axis=3)[..., 0]
     else:
         amax = np.argmax(tq, axis=3)
@@ -293,7 +296,7 @@ def agent_backward(p, caches, dq_all):
 
 
 def learner_forward_backward(agent_p, target_agent_p, mixer_p, target_mixer_p, batch, *, mixer: str,
-                             double_q: bool, gamma: float, dtype=np.float32):
+                             double_q: bool, gamma: float, dtype=np.float32, argmax_override=None):
     """Everything QLearner.train computes up to and including loss.backward() (q_learner.py:34-103).
 
     ``batch`` is a dict of numpy arrays with the reference's keys/shapes
@@ -313,7 +316,7 @@ def learner_forward_backward(agent_p, target_agent_p, mixer_p, target_mixer_p, b
     mac_out, caches = unroll(ap, obs, onehot)
     chosen = np.take_along_axis(mac_out[:, :-1], actions, axis=3)[..., 0]          # :55
     target_full, _ = unroll(tp, obs, onehot)
-    tmax, amax = masked_target_max(mac_out, target_full, avail, double_q)           # :65-78
+    tmax, amax = masked_target_max(mac_out, target_full, avail, double_q, argmax_override)   # :65-78
 
     if mixer == "qmix":
         q_tot, mc = qmix_forward(mp, chosen, state[:, :-1])                         # :82

@@ -161,3 +161,83 @@ def test_dp_train_two_ranks_equals_full_batch(nccl, fused):
     # replicas stay bit-identical: same reduced gradient, same update on every rank
     for k in ref_a:
         assert np.array_equal(res[0][1][k], res[1][1][k]), k
+
+
+# ---------------------------------------------------------------------------------------------- fused exchange kernel
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("clip", [10.0, 0.05])
+def test_peer_allreduce_kernel_one_device_fake_peers(world, clip):
+    """`mal_peer_allreduce_clip_rmsprop` (k_peer_allreduce_grad + k_clip_rmsprop) takes raw peer pointers, so W "ranks"
+    can live on ONE device: every fake rank's buffer holds the oracle's UN-normalised gradient sum of its batch shard
+    followed by its raw statistic sums.  Checked against the numpy oracle on the full batch: rank-order sums, the global
+    mask-sum normaliser, grad norm, clipped gradient, post-step parameters and square_avg (q_learner.py:98-105)."""
+    import ctypes as C
+    from ma_league_b200 import _native as nat
+    from ma_league_b200.learners.q_learner import DP_TAIL
+    O, params, batch, N = _oracle_case(seed=11, B=8, TT=9, N=3)
+    B = batch["obs"].shape[0]
+    full = O.learner_forward_backward(*params, batch, mixer="qmix", double_q=True, gamma=0.99, dtype=np.float64)
+    n_agent = sum(v.size for v in params[0].values())
+    n_mixer = sum(v.size for v in params[2].values())
+    P = n_agent + n_mixer
+    dev = "cuda:0"
+    bufs, raw_sum = [], np.zeros(DP_TAIL)
+    for r in range(world):
+        lo, hi = r * B // world, (r + 1) * B // world
+        res = O.learner_forward_backward(*params, {k: v[lo:hi] for k, v in batch.items()}, mixer="qmix",
+                                         double_q=True, gamma=0.99, dtype=np.float64)
+        raw = _raw(res, N)
+        raw_sum += raw
+        bufs.append(th.from_numpy(np.concatenate([_flat(res) * raw[4], raw]).astype(np.float32)).to(dev))
+    flat0 = np.concatenate([v.ravel() for v in list(params[0].values()) + list(params[2].values())]).astype(np.float32)
+    agent = th.from_numpy(flat0[:n_agent].copy()).to(dev)
+    mixer = th.from_numpy(flat0[n_agent:].copy()).to(dev)
+    rng = np.random.default_rng(5)
+    sq0 = rng.uniform(0.0, 1e-3, P).astype(np.float32)
+    sq = th.from_numpy(sq0.copy()).to(dev)
+    grad = th.full((P,), 7.0, device=dev)
+    tail = th.zeros(DP_TAIL, device=dev)
+    scalars = th.zeros(64, device=dev)
+    scratch = th.zeros((P + 255) // 256, device=dev)
+    ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    lr, alpha, eps = 5e-4, 0.99, 1e-5
+    nat.check(nat.lib().mal_peer_allreduce_clip_rmsprop(ptrs, world, nat.ptr(agent), n_agent, nat.ptr(mixer), n_mixer,
+                                                        nat.ptr(grad), nat.ptr(tail), DP_TAIL, nat.ptr(sq), lr, alpha,
+                                                        eps, clip, nat.ptr(scalars), nat.ptr(scratch), 0,
+                                                        nat.current_stream(dev)), "mal_peer_allreduce_clip_rmsprop")
+    th.cuda.synchronize()
+    g_ref = _flat(full)                                                  # full-batch gradient (normalised)
+    norm_ref, clipped = O.clip_grad_norm([g_ref], clip)
+    assert (norm_ref > clip) == (clip < 1.0)                             # both branches of the clip are exercised
+    assert_close(tail.cpu().numpy()[:6], raw_sum[:6], 1e-6, "reduced statistic sums")
+    assert abs(float(scalars[nat.SC_GRAD_NORM]) - norm_ref) <= 1e-5 * norm_ref
+    assert_close(grad.cpu().numpy(), clipped[0], 1e-5, "normalised + clipped gradient")
+    p_ref, sq_ref = O.rmsprop_update(flat0.astype(np.float64), clipped[0], sq0.astype(np.float64), lr, alpha, eps)
+    assert_close(np.concatenate([agent.cpu().numpy(), mixer.cpu().numpy()]), p_ref, 1e-6, "post-step parameters")
+    assert_close(np.concatenate([agent.cpu().numpy(), mixer.cpu().numpy()]) - flat0, p_ref - flat0, 2e-4, "update")
+    assert_close(sq.cpu().numpy(), sq_ref, 1e-5, "square_avg")
+    # rank-order summation in fp32: bit-identical to the same loop on the host
+    acc = np.zeros(P, np.float32)
+    den = np.float32(0)
+    for b in bufs:
+        hb = b.cpu().numpy()
+        acc = acc + hb[:P]
+        den = den + hb[P + 4]
+    coef = np.float32(min(np.float32(clip) / (np.float32(scalars[nat.SC_GRAD_NORM].item()) + np.float32(1e-6)), 1.0))
+    assert np.array_equal(grad.cpu().numpy(), (acc / den) * coef)
+    # frozen prefix (freeze_agent_weights): agent slice zeroed, left out of the norm, parameters and square_avg untouched
+    agent2, mixer2 = th.from_numpy(flat0[:n_agent].copy()).to(dev), th.from_numpy(flat0[n_agent:].copy()).to(dev)
+    sq2 = th.from_numpy(sq0.copy()).to(dev)
+    nat.check(nat.lib().mal_peer_allreduce_clip_rmsprop(ptrs, world, nat.ptr(agent2), n_agent, nat.ptr(mixer2), n_mixer,
+                                                        nat.ptr(grad), nat.ptr(tail), DP_TAIL, nat.ptr(sq2), lr, alpha,
+                                                        eps, clip, nat.ptr(scalars), nat.ptr(scratch), n_agent,
+                                                        nat.current_stream(dev)), "mal_peer_allreduce_clip_rmsprop")
+    th.cuda.synchronize()
+    norm_m, clipped_m = O.clip_grad_norm([g_ref[n_agent:]], clip)
+    assert abs(float(scalars[nat.SC_GRAD_NORM]) - norm_m) <= 1e-5 * norm_m
+    assert np.array_equal(agent2.cpu().numpy(), flat0[:n_agent]) and np.array_equal(sq2.cpu().numpy()[:n_agent], sq0[:n_agent])
+    assert not grad[:n_agent].any()
+    assert_close(grad.cpu().numpy()[n_agent:], clipped_m[0], 1e-5, "mixer gradient with a frozen agent")
+    pm_ref, _ = O.rmsprop_update(flat0[n_agent:].astype(np.float64), clipped_m[0], sq0[n_agent:].astype(np.float64), lr, alpha, eps)
+    assert_close(mixer2.cpu().numpy(), pm_ref, 1e-6, "mixer parameters with a frozen agent")

@@ -26,8 +26,16 @@ def test_ring_fixture_on_device():
         for k, v in buf.data.transition_data.items():
             assert np.array_equal(v.cpu().numpy(), g["buf%d.%s" % (i, k)]), (i, k)       # bit-exact buffer contents
         if buf.can_sample(4):
+            # sample() must sit at the same position of numpy's legacy stream as the reference's np.random.choice
+            # (replay_buffer.py:52): predict the draw, rewind, sample, and compare ids AND the stream position after
+            st0 = np.random.get_state()
+            predicted = np.random.choice(buf.episodes_in_buffer, 4, replace=False)
+            st1 = np.random.get_state()
+            np.random.set_state(st0)
             smp = buf.sample(4)
-            assert np.array_equal(np.asarray(g["smp%d.ids" % i]), g["smp%d.ids" % i])
+            assert np.array_equal(predicted, g["smp%d.ids" % i]), (i, predicted)
+            after = np.random.get_state()
+            assert after[2] == st1[2] and np.array_equal(after[1], st1[1])      # exactly one choice() was consumed
             for k, v in smp.data.transition_data.items():
                 assert np.array_equal(v.cpu().numpy(), g["smp%d.%s" % (i, k)]), (i, k)
             assert int(smp.max_t_filled()) == int(g["smp%d.max_t" % i])
@@ -109,3 +117,54 @@ def test_train_from_buffer_equals_sample_truncate_train():
                 assert_close(x[k], y[k], 1e-5, k)
         for k, v in ref[2].items():
             assert abs(variant[2][k] - v) <= 1e-5 * max(1.0, abs(v)), (k, variant[2][k], v)
+
+
+def test_train_from_buffer_against_oracle():
+    """SURVEY.md 8(f3) against the ORACLE (not against the repo's own sample -> truncate -> train): the fused input
+    pipeline samples with numpy's stream (ids predicted from the same state), gathers into its staging batch and trains
+    over the full sequence length with the padding masked; the oracle runs the reference's sequence
+    (ma_experiment.py:231-241: sample -> max_t_filled -> truncate -> train) on the SAME episode ids in fp64."""
+    from oracle import np_oracle as O
+    from tests.gpu_helpers import seeded_system, np_params, np_batch
+    from tests.helpers import assert_close
+    clip = 0.5
+    s = seeded_system(3, 6, 14, "qmix", True, seed=33, buffer_size=24, learner_log_interval=0, clip=clip)
+    gen = th.Generator().manual_seed(78)
+    for _ in range(4):      # 24 episodes, none of full length: the truncation bound is < max_seq_length
+        data, lens = synth_episode_data(6, 14, 3, 9, 32, 48, gen, var_len=True, device="cuda")
+        lens = th.clamp(lens, max=10)
+        data["terminated"].zero_()
+        data["terminated"][th.arange(6), lens - 1] = 1
+        eb = fill_episode_batch(M.EpisodeBatch(s.scheme, s.groups, 6, 14, preprocess=s.pre, device="cuda"), data, lens)
+        s.buf.insert_episode_batch(eb)
+    host_buf = np_batch(s.buf)
+    L = s.learner
+    a = s.args
+    for variant in ("masked", "truncate"):
+        p_agent, p_tagent = np_params(s.mac.agent), np_params(L.target_mac.agent)
+        p_mixer, p_tmixer = np_params(L.mixer), np_params(L.target_mixer)
+        sq0 = L.optimiser.flat_sq.cpu().numpy().astype(np.float64)
+        np.random.seed(9)
+        ids = np.random.choice(s.buf.episodes_in_buffer, 6, replace=False)
+        np.random.seed(9)
+        b = L.train_from_buffer(s.buf, 6, t_env=0, episode_num=0, truncate=(variant == "truncate"))
+        th.cuda.synchronize()
+        smp = {k: v[ids] for k, v in host_buf.items()}
+        mt = O.max_t_filled(smp["filled"])
+        assert mt < 14 and b.max_seq_length == (mt if variant == "truncate" else 14)
+        smp = {k: v[:, :mt] for k, v in smp.items()}
+        ref = O.learner_forward_backward(p_agent, p_tagent, p_mixer, p_tmixer, smp, mixer="qmix", double_q=True,
+                                         gamma=a.gamma, dtype=np.float64)
+        g_ref = np.concatenate([v.ravel() for v in list(ref["agent_grads"].values()) + list(ref["mixer_grads"].values())])
+        norm, (g_clip,) = O.clip_grad_norm([g_ref], clip)
+        assert norm > clip
+        st = {k: v[0] for k, v in s.logger.stats.items()}
+        assert abs(st["home_qlearner_loss"] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+        assert abs(st["home_qlearner_grad_norm"] - norm) <= 1e-5 * norm
+        assert_close(L._grad.cpu().numpy(), g_clip, 1e-5, "clipped gradient (%s)" % variant)
+        p0 = np.concatenate([v.ravel() for v in list(p_agent.values()) + list(p_mixer.values())]).astype(np.float64)
+        p_ref, sq_ref = O.rmsprop_update(p0, g_clip, sq0, a.lr, a.optim_alpha, a.optim_eps)
+        p_new = np.concatenate([v.ravel() for v in list(np_params(s.mac.agent).values()) + list(np_params(L.mixer).values())])
+        assert_close(p_new, p_ref, 1e-6, "post-step parameters (%s)" % variant)
+        assert_close(p_new - p0, p_ref - p0, 2e-4, "parameter update (%s)" % variant)
+        assert_close(L.optimiser.flat_sq.cpu().numpy(), sq_ref, 1e-5, "square_avg (%s)" % variant)

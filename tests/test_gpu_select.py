@@ -118,6 +118,13 @@ def test_mac_select_actions_fixture():
     acts, _ = s.mac.select_actions(eb, 0, 0, bs=[0, 2], u=th.from_numpy(g["t0.u"])[[0, 2]],
                                    e=th.from_numpy(g["t0.e"]).view(bs, N, A)[[0, 2]].reshape(-1, A))
     assert acts.shape == (2, N)
+    # a subset of environments sees exactly the actions the full call gave those rows (same draws, same Q-values)
+    assert np.array_equal(acts.cpu().numpy(), g["t0.actions"][[0, 2]])
+    s.mac.init_hidden(bs)
+    acts1, greedy1 = s.mac.select_actions(eb, 0, 0, bs=slice(1, 3), u=th.from_numpy(g["t0.u"])[1:3],
+                                          e=th.from_numpy(g["t0.e"]).view(bs, N, A)[1:3].reshape(-1, A))
+    assert np.array_equal(acts1.cpu().numpy(), g["t0.actions"][1:3])
+    assert np.array_equal(greedy1.cpu().numpy(), g["t0.greedy"][1:3])
 
 
 def test_agent_and_mixer_modules_standalone():
