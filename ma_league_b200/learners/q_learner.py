@@ -62,6 +62,8 @@ class QLearner(Learner):
         self._graph_cap = 32
         self._graph_captures_left = 64   # a capture costs ~10 ms: batches whose addresses never repeat stay eager
         self._bs_cache = {}
+        self.n_graph_replays = self.n_graph_captures = self.n_eager_steps = 0   # accounting (bench.py reports them)
+        self.dp_profile = None   # set to [] to collect (start, end) CUDA events around the data-parallel exchange
 
     def parameters(self):
         return list(self.mac.parameters()) + list(self.mixer.parameters())
@@ -238,17 +240,21 @@ class QLearner(Learner):
             graph, n_kernels = entry
             graph.replay()
             nat.lib().mal_count_launches(n_kernels)
+            self.n_graph_replays += 1
             return True
         if entry is False:                      # first sighting: eager
             if len(self._graphs) >= self._graph_cap:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = None
             self._step_eager(bs, cfg, f, dev)
+            self.n_eager_steps += 1
             return False
         if self._graph_captures_left <= 0:
             self._step_eager(bs, cfg, f, dev)
+            self.n_eager_steps += 1
             return False
         self._graph_captures_left -= 1
+        self.n_graph_captures += 1
         # second sighting: capture (the capture stream becomes torch's current stream, which the C ABI call reads)
         lib = nat.lib()
         graph = th.cuda.CUDAGraph()
@@ -283,6 +289,9 @@ class QLearner(Learner):
                                                nat.ptr(f["mixer"]), nat.ptr(self._ws), nat.ptr(self._grad), st),
                       "mal_learner_backward")
         self._grad_store[n_total:n_total + DP_RAW].copy_(self.scalars()[nat.SC_RAW0:nat.SC_RAW0 + DP_RAW])
+        if self.dp_profile is not None:
+            ev0 = th.cuda.Event(enable_timing=True)
+            ev0.record()
         dist.all_reduce(self._grad_store, op=dist.ReduceOp.SUM)
         denom = self._grad_store[n_total + 4:]            # global mask.sum()
         a = self.args
@@ -293,6 +302,10 @@ class QLearner(Learner):
                                            a.grad_norm_clip, nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
                                            nat.ptr(denom), self._plan.n_agent_params if cfg.freeze_agent else 0, st),
                       "mal_clip_rmsprop")
+        if self.dp_profile is not None:
+            ev1 = th.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.dp_profile.append((ev0, ev1))
 
     # ---- fused exchange: peer-memory all-reduce inside the optimiser prologue (no NCCL call on the path)
     def _dp_symmetric(self, n_total, dev):
@@ -338,6 +351,9 @@ class QLearner(Learner):
                                                nat.ptr(f["mixer"]), nat.ptr(self._ws), nat.ptr(half), st),
                       "mal_learner_backward")
         half[n_total:n_total + DP_RAW].copy_(self.scalars()[nat.SC_RAW0:nat.SC_RAW0 + DP_RAW])
+        if self.dp_profile is not None:
+            ev0 = th.cuda.Event(enable_timing=True)
+            ev0.record()
         hdl.barrier(channel=0)                           # every rank's half h is complete (and half h^1 is free again)
         a = self.args
         with nat.on_device(dev):
@@ -347,6 +363,10 @@ class QLearner(Learner):
                 nat.ptr(self.optimiser.flat_sq), a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip,
                 nat.ptr(self.scalars()), nat.ptr(self._dp_scratch),
                 self._plan.n_agent_params if cfg.freeze_agent else 0, st), "mal_peer_allreduce_clip_rmsprop")
+        if self.dp_profile is not None:
+            ev1 = th.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.dp_profile.append((ev0, ev1))
         self._dp_step += 1
 
     def train_from_buffer(self, buffer, batch_size: int, t_env: int, episode_num: int, truncate: bool = False):
@@ -409,7 +429,14 @@ class QLearner(Learner):
                    targets=self._ws_f32(p.targets, B * T).view(B, T, 1),
                    td=self._ws_f32(p.td, B * T).view(B, T, 1),
                    hout=self._ws_f32(p.h_on, TT * B * N * nat.HID).view(TT, B * N, nat.HID),
+                   x=self._ws_f32(p.x_on, TT * B * N * nat.HID).view(TT, B * N, nat.HID),
                    scalars=self.scalars())
+        if isinstance(self.mixer, QMixer):
+            E, HE = self.mixer.embed_dim, self.mixer.hypernet_embed
+            two = self._mixer_kind() == nat.MIXER_QMIX2
+            ld1, ld2 = (2 * HE + 2 * E) if two else 2 * E, E * N + E
+            out["a2"] = self._ws_f32(p.a2_on, B * T * ld2).view(B * T, ld2)     # a1 | af (pre-abs)
+            out["y1"] = self._ws_f32(p.y1_on, B * T * ld1).view(B * T, ld1)     # [h1 | hf |] b1 | v1
         if self.save_q:
             out["mac_out"] = self._ws_f32(p.mac_out, B * TT * N * A).view(B, TT, N, A)
             out["target_mac_out"] = self._ws_f32(p.target_mac_out, B * TT * N * A).view(B, TT, N, A)

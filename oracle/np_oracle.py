@@ -117,7 +117,7 @@ def drqn_step(p, inp, h):
     n = np.tanh(gi[:, 2 * Hh:] + r * gh[:, 2 * Hh:])
     h_new = n + z * (h - n)  # == (1-z)*n + z*h, the form torch's CPU gru_cell evaluates
     q = h_new @ p["fc2.weight"].T + p["fc2.bias"]
-    cache = dict(inp=inp, x=x, h_prev=h, r=r, z=z, n=n, ghn=gh[:, 2 * Hh:], h=h_new)
+    cache = dict(inp=inp, x=x, x_pre=x_pre, h_prev=h, r=r, z=z, n=n, ghn=gh[:, 2 * Hh:], h=h_new)
     return q, h_new, cache
 
 
@@ -163,11 +163,12 @@ def masked_target_max(mac_out, target_mac_out_full, avail, double_q: bool, argma
 # a6: mixers   marl/modules/mixers/qmix.py:41-59, marl/modules/mixers/vdn.py:9-10
 # --------------------------------------------------------------------------
 def _hyper(mp, name, s):
-    """Evaluate a 1- or 2-layer hypernet branch; returns (out, hidden_or_None)."""
+    """Evaluate a 1- or 2-layer hypernet branch; returns (out, hidden_or_None, hidden_pre_activation_or_None)."""
     if name + ".0.weight" in mp:
-        hid = np.maximum(s @ mp[name + ".0.weight"].T + mp[name + ".0.bias"], 0)
-        return hid @ mp[name + ".2.weight"].T + mp[name + ".2.bias"], hid
-    return s @ mp[name + ".weight"].T + mp[name + ".bias"], None
+        pre = s @ mp[name + ".0.weight"].T + mp[name + ".0.bias"]
+        hid = np.maximum(pre, 0)
+        return hid @ mp[name + ".2.weight"].T + mp[name + ".2.bias"], hid, pre
+    return s @ mp[name + ".weight"].T + mp[name + ".bias"], None, None
 
 
 def qmix_forward(mp, agent_qs, states):
@@ -176,33 +177,44 @@ def qmix_forward(mp, agent_qs, states):
     E = mp["hyper_b_1.weight"].shape[0]
     s = states.reshape(B * T, -1)
     q = agent_qs.reshape(B * T, N)
-    a1, h1 = _hyper(mp, "hyper_w_1", s)
+    a1, h1, h1_pre = _hyper(mp, "hyper_w_1", s)
     w1 = np.abs(a1).reshape(B * T, N, E)
     b1 = s @ mp["hyper_b_1.weight"].T + mp["hyper_b_1.bias"]
     pre = np.einsum("mn,mne->me", q, w1) + b1
     hidden = np.where(pre > 0, pre, np.expm1(np.minimum(pre, 0)))  # F.elu, alpha=1
-    af, hf = _hyper(mp, "hyper_w_final", s)
+    af, hf, hf_pre = _hyper(mp, "hyper_w_final", s)
     wf = np.abs(af)
-    v1 = np.maximum(s @ mp["V.0.weight"].T + mp["V.0.bias"], 0)
+    v1_pre = s @ mp["V.0.weight"].T + mp["V.0.bias"]
+    v1 = np.maximum(v1_pre, 0)
     v = v1 @ mp["V.2.weight"].T + mp["V.2.bias"]
     y = (hidden * wf).sum(axis=1, keepdims=True) + v
-    cache = dict(s=s, q=q, a1=a1, h1=h1, w1=w1, b1=b1, pre=pre, hidden=hidden, af=af, hf=hf, wf=wf, v1=v1)
+    cache = dict(s=s, q=q, a1=a1, h1=h1, w1=w1, b1=b1, pre=pre, hidden=hidden, af=af, hf=hf, wf=wf, v1=v1,
+                 h1_pre=h1_pre, hf_pre=hf_pre, v1_pre=v1_pre)
     return y.reshape(B, T, 1), cache
 
 
-def qmix_backward(mp, cache, g):
-    """g = dL/dq_tot [B,T,1] -> (grads dict keyed like the state_dict, dq [B,T,N])."""
+def qmix_backward(mp, cache, g, discrete=None):
+    """g = dL/dq_tot [B,T,1] -> (grads dict keyed like the state_dict, dq [B,T,N]).
+
+    ``discrete`` (tests only): dict with any of ``a1_sign`` [M,N*E], ``af_sign`` [M,E], ``h1_mask`` / ``hf_mask`` [M,HE],
+    ``v1_mask`` [M,E] -- the derivative of abs / ReLU at these elements is taken from the caller instead of from the
+    oracle's own pre-activations (see learner_forward_backward)."""
     c = cache
     M, N, E = c["w1"].shape
     g = g.reshape(M, 1)
     grads = OrderedDict()
+    discrete = discrete or {}
+    sign_a1 = discrete.get("a1_sign", np.sign(c["a1"])).astype(c["a1"].dtype)
+    sign_af = discrete.get("af_sign", np.sign(c["af"])).astype(c["af"].dtype)
+    hid_mask = {"hyper_w_1": discrete.get("h1_mask"), "hyper_w_final": discrete.get("hf_mask")}
+    v1_mask = discrete.get("v1_mask", c["v1"] > 0)
     # y = sum_e hidden*wf + v
     dhidden = g * c["wf"]
     dwf = g * c["hidden"]
     # V = Linear(S,E)-ReLU-Linear(E,1)
     grads["V.2.weight"] = (g * c["v1"]).sum(axis=0, keepdims=True)
     grads["V.2.bias"] = g.sum(axis=0)
-    dv1 = (g @ mp["V.2.weight"]) * (c["v1"] > 0)
+    dv1 = (g @ mp["V.2.weight"]) * v1_mask
     grads["V.0.weight"] = dv1.T @ c["s"]
     grads["V.0.bias"] = dv1.sum(axis=0)
     # elu
@@ -211,14 +223,14 @@ def qmix_backward(mp, cache, g):
     dw1 = c["q"][:, :, None] * dpre[:, None, :]
     grads["hyper_b_1.weight"] = dpre.T @ c["s"]
     grads["hyper_b_1.bias"] = dpre.sum(axis=0)
-    da1 = (dw1 * np.sign(c["a1"]).reshape(M, N, E)).reshape(M, N * E)
-    daf = dwf * np.sign(c["af"])
+    da1 = (dw1 * sign_a1.reshape(M, N, E)).reshape(M, N * E)
+    daf = dwf * sign_af
 
     def hyper_back(name, dout, hid):
         if hid is not None:
             grads[name + ".2.weight"] = dout.T @ hid
             grads[name + ".2.bias"] = dout.sum(axis=0)
-            dh = (dout @ mp[name + ".2.weight"]) * (hid > 0)
+            dh = (dout @ mp[name + ".2.weight"]) * (hid > 0 if hid_mask[name] is None else hid_mask[name])
             grads[name + ".0.weight"] = dh.T @ c["s"]
             grads[name + ".0.bias"] = dh.sum(axis=0)
         else:
@@ -262,8 +274,9 @@ def td_loss(q_tot, target_q_tot, rewards, term, mask, gamma):
 # --------------------------------------------------------------------------
 # a4+a8: full learner step forward + backward   marl/learners/q_learner.py:34-105
 # --------------------------------------------------------------------------
-def agent_backward(p, caches, dq_all):
-    """BPTT through the unroll.  dq_all [B,TT,N,A] = dL/d mac_out.  Returns grads keyed like the state_dict."""
+def agent_backward(p, caches, dq_all, x_mask=None):
+    """BPTT through the unroll.  dq_all [B,TT,N,A] = dL/d mac_out.  Returns grads keyed like the state_dict.
+    ``x_mask`` (tests only) [TT,R,H] bool: ReLU derivative of fc1's output taken from the caller."""
     Hh = p["gru.weight_hh"].shape[1]
     g = OrderedDict((k, np.zeros_like(v)) for k, v in p.items())
     TT = len(caches)
@@ -289,19 +302,27 @@ def agent_backward(p, caches, dq_all):
         g["gru.weight_hh"] += dgh.T @ c["h_prev"]
         g["gru.bias_hh"] += dgh.sum(axis=0)
         dh_next = dh * c["z"] + dgh @ Whh
-        dx = (dgi @ Wih) * (c["x"] > 0)
+        dx = (dgi @ Wih) * (c["x"] > 0 if x_mask is None else x_mask[t])
         g["fc1.weight"] += dx.T @ c["inp"]
         g["fc1.bias"] += dx.sum(axis=0)
     return g
 
 
 def learner_forward_backward(agent_p, target_agent_p, mixer_p, target_mixer_p, batch, *, mixer: str,
-                             double_q: bool, gamma: float, dtype=np.float32, argmax_override=None):
+                             double_q: bool, gamma: float, dtype=np.float32, argmax_override=None, discrete=None):
     """Everything QLearner.train computes up to and including loss.backward() (q_learner.py:34-103).
 
     ``batch`` is a dict of numpy arrays with the reference's keys/shapes
     (state, obs, actions, avail_actions, reward, terminated, actions_onehot, filled), already truncated in time.
-    ``mixer`` in {"qmix", "vdn"}.  Returns a dict of intermediates and gradients."""
+    ``mixer`` in {"qmix", "vdn"}.  Returns a dict of intermediates and gradients.
+
+    ``argmax_override`` / ``discrete`` (tests only): the loss contains DISCRETE choices -- the double-Q arg-max, the ReLU
+    derivatives of fc1 / the hypernet hidden layers / V, and sign() from abs() of the hypernet outputs.  An fp32
+    implementation may legitimately take the other branch where the fp64 pre-activation lies within rounding distance of
+    the discontinuity (a handful of the 10^7 elements of a full-size batch; one flipped element moves a weight-gradient
+    tensor by ~1e-4 norm-wise).  A checker that has VERIFIED that every differing choice sits on such a near-tie passes the
+    implementation's choices here and compares everything downstream at the 1e-5 tolerance.
+    ``discrete`` keys: ``x_mask`` [TT,R,H] and the keys of qmix_backward."""
     cast = lambda d: OrderedDict((k, v.astype(dtype)) for k, v in d.items()) if d is not None else None
     ap, tp, mp, tmp = cast(agent_p), cast(target_agent_p), cast(mixer_p), cast(target_mixer_p)
     obs = batch["obs"].astype(dtype)
@@ -329,13 +350,13 @@ def learner_forward_backward(agent_p, target_agent_p, mixer_p, target_mixer_p, b
     loss, td, mtd, targets, g = td_loss(q_tot, tq_tot, rewards, term, mask, gamma)  # :86-98
 
     if mixer == "qmix":
-        mixer_grads, dchosen = qmix_backward(mp, mc, g)
+        mixer_grads, dchosen = qmix_backward(mp, mc, g, discrete)
         dchosen = dchosen.reshape(chosen.shape)
     else:
         mixer_grads, dchosen = OrderedDict(), np.broadcast_to(g, chosen.shape).copy()
     dmac = np.zeros_like(mac_out)
     np.put_along_axis(dmac[:, :-1], actions, dchosen[..., None], axis=3)
-    agent_grads = agent_backward(ap, caches, dmac)
+    agent_grads = agent_backward(ap, caches, dmac, (discrete or {}).get("x_mask"))
     hout = np.stack([c["h"] for c in caches], axis=0)  # [TT, R, H]
     msum = mask.sum(dtype=dtype)
     n_agents = obs.shape[2]
@@ -345,7 +366,11 @@ def learner_forward_backward(agent_p, target_agent_p, mixer_p, target_mixer_p, b
         target_mean=(targets * mask).sum(dtype=dtype) / (msum * n_agents),
         mask_sum=msum, trained_steps=int(np.count_nonzero(np.broadcast_to(mask, td.shape))),
     )
-    return dict(mac_out=mac_out, target_mac_out=target_full, hout=hout, chosen=chosen, target_max=tmax,
+    # pre-activations at the discontinuities (ReLU inputs, abs inputs): see `discrete`
+    pre = dict(x=np.stack([c["x_pre"] for c in caches], axis=0))      # [TT, R, H]
+    if mixer == "qmix":
+        pre.update(a1=mc["a1"], af=mc["af"], h1=mc["h1_pre"], hf=mc["hf_pre"], v1=mc["v1_pre"])
+    return dict(pre=pre, mac_out=mac_out, target_mac_out=target_full, hout=hout, chosen=chosen, target_max=tmax,
                 argmax=amax, q_tot=q_tot, target_q_tot=tq_tot, targets=targets, td=td, mask=mask, loss=loss,
                 dq_tot=g, dchosen=dchosen, agent_grads=agent_grads, mixer_grads=mixer_grads, stats=stats)
 

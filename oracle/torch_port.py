@@ -24,8 +24,8 @@ import torch.nn.functional as F
 from torch.distributions import Categorical
 
 
-def to_params(np_dict, requires_grad=True):
-    return OrderedDict((k, th.tensor(np.asarray(v), dtype=th.float32, requires_grad=requires_grad))
+def to_params(np_dict, requires_grad=True, device="cpu"):
+    return OrderedDict((k, th.tensor(np.asarray(v), dtype=th.float32, device=device, requires_grad=requires_grad))
                        for k, v in np_dict.items())
 
 
@@ -35,7 +35,7 @@ def agent_step(p, batch, t, h):
     B, _, N, _ = obs.shape
     parts = [obs[:, t]]
     parts.append(th.zeros_like(onehot[:, t]) if t == 0 else onehot[:, t - 1])
-    parts.append(th.eye(N).unsqueeze(0).expand(B, -1, -1))
+    parts.append(th.eye(N, device=obs.device).unsqueeze(0).expand(B, -1, -1))
     inp = th.cat([x.reshape(B * N, -1) for x in parts], dim=1)
     x = F.relu(F.linear(inp, p["fc1.weight"], p["fc1.bias"]))
     h = th.gru_cell(x, h.reshape(-1, x.shape[1]), p["gru.weight_ih"], p["gru.weight_hh"], p["gru.bias_ih"],
@@ -46,7 +46,7 @@ def agent_step(p, batch, t, h):
 
 def unroll(p, batch):
     B, TT, N, _ = batch["obs"].shape
-    h = th.zeros(1, p["gru.weight_hh"].shape[1]).unsqueeze(0).expand(B, N, -1)
+    h = th.zeros(1, p["gru.weight_hh"].shape[1], device=batch["obs"].device).unsqueeze(0).expand(B, N, -1)
     outs = []
     for t in range(TT):
         q, h = agent_step(p, batch, t, h)
@@ -78,11 +78,13 @@ class TorchPortLearner:
     """Stateful CPU learner: parameters, target copies and a stock torch RMSprop."""
 
     def __init__(self, agent_p, target_agent_p, mixer_p, target_mixer_p, *, mixer, double_q, gamma, lr, alpha, eps,
-                 clip):
-        self.ap = to_params(agent_p)
-        self.tp = to_params(target_agent_p)
-        self.mp = to_params(mixer_p) if mixer == "qmix" else OrderedDict()
-        self.tmp = to_params(target_mixer_p) if mixer == "qmix" else OrderedDict()
+                 clip, device="cpu"):
+        # device="cuda": the same ATen op sequence in PyTorch eager on the GPU ("just run pymarl on the GPU",
+        # BASELINE.md section 3 optional bar) -- a reported baseline, never part of the product path
+        self.ap = to_params(agent_p, device=device)
+        self.tp = to_params(target_agent_p, device=device)
+        self.mp = to_params(mixer_p, device=device) if mixer == "qmix" else OrderedDict()
+        self.tmp = to_params(target_mixer_p, device=device) if mixer == "qmix" else OrderedDict()
         self.mixer, self.double_q, self.gamma, self.clip = mixer, double_q, gamma, clip
         self.params = list(self.ap.values()) + list(self.mp.values())
         self.opt = th.optim.RMSprop(self.params, lr=lr, alpha=alpha, eps=eps)

@@ -165,6 +165,6 @@ def test_train_from_buffer_against_oracle():
         p0 = np.concatenate([v.ravel() for v in list(p_agent.values()) + list(p_mixer.values())]).astype(np.float64)
         p_ref, sq_ref = O.rmsprop_update(p0, g_clip, sq0, a.lr, a.optim_alpha, a.optim_eps)
         p_new = np.concatenate([v.ravel() for v in list(np_params(s.mac.agent).values()) + list(np_params(L.mixer).values())])
-        assert_close(p_new, p_ref, 1e-6, "post-step parameters (%s)" % variant)
-        assert_close(p_new - p0, p_ref - p0, 2e-4, "parameter update (%s)" % variant)
+        assert_close(p_new, p_ref, 1e-5, "post-step parameters (%s)" % variant)
+        assert_close(p_new - p0, p_ref - p0, 1e-3, "parameter update (%s)" % variant)
         assert_close(L.optimiser.flat_sq.cpu().numpy(), sq_ref, 1e-5, "square_avg (%s)" % variant)
