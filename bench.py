@@ -823,7 +823,7 @@ def main():
                 line["gpu_eager_baseline"] = {"value": v, "unit": UNIT, "ms_per_step": ms, "kind": "port on cuda", "sample": sample}
             except Exception as ex:
                 line["gpu_eager_baseline"] = {"error": repr(ex)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         th.distributed.barrier()
         th.distributed.destroy_process_group()

@@ -1,0 +1,234 @@
+// GRU recurrences of the learner step (q_learner.py:49-51, 60-62 and their autograd transposes).
+// One batch row (chain) per CTA, 64 threads, several CTAs per SM; thread = hidden unit for the gate math, the
+// saved-state ring and the stores.  Everything that does not depend on h_{t-1} was hoisted into the batched GEMMs
+// (gi = W_ih x + b_ih); what remains per timestep is gh = W_hh h_{t-1} with W_hh resident in REGISTERS, the gate math
+// (MUFU ex2/rcp sigmoid and tanh), one h / d(gates) exchange through shared memory and ONE barrier between the two warps.
+// gi[t] (forward) and saved gates / h_{t-1} / head seed (backward) stream through per-thread cp.async rings PF steps
+// ahead.  Saved gates layout (private to these two kernels): [m][unit][r, z, n, gh_n].
+//
+// Register-tiled matvec.  With one thread per output every lane needs the whole h_{t-1} (64 floats) resp. d(gates) vector
+// (192 floats) in its own registers: 16 resp. 48 broadcast LDS.128 per thread-step, each writing 512 B of registers per
+// warp -- operand delivery, not the FMA pipe, set the pace of the backward kernel (measured r2: 742 -> 648 cycles per
+// step at 160 chains, 2 866 -> 2 414 at 1 280 with the tiling below; two lanes per unit with half of K each move the same
+// bytes and gained nothing, and neither did one persistent 128-thread CTA per SM owning all of its chains).
+// A thread owns a U x (K/S) tile with U = S (still 192 weights in registers):
+//     forward   U = S = 2: units (2g, 2g+1) x half of the 64 columns          ->  8 LDS.128 + 96 FFMA2 per thread-step
+//     backward  U = S = 4: columns (4g .. 4g+3) x a quarter of the 192 rows   -> 12 LDS.128 + 96 FFMA2
+// and the S partial sums per output meet in a transposing xor-shuffle reduction after which lane p of a group holds the
+// complete sum of ITS unit / column.  The S sub-ranges of the shared operand are shifted by 16 bytes against each other
+// so that the S addresses of one LDS.128 fall into different banks.  fp32 throughout (FFMA2 = two fp32 FMAs per
+// instruction; it issues at half rate, i.e. the same FMA-pipe time as FFMA in half the issue slots).
+#pragma once
+#include "learner.cuh"
+
+#define GT_PAD 4                           // floats between consecutive K sub-ranges of a shared operand row
+
+template <int DBG = 0>
+__global__ void __launch_bounds__(64, 4) k_gru_fwd7(GruFwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int KC = HID / 2;            // columns per lane
+    constexpr int HROW = HID + GT_PAD;
+    __shared__ __align__(16) float h_s[2][HROW];
+    __shared__ float st_s[PF][3][HID];
+    __shared__ float pdl_anchor_s[HID];
+    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
+    const int ug = i >> 1, part = i & 1;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const float *P = net ? a.params[1] : a.params[0];
+    const float *gi = net ? a.gi[1] : a.gi[0];
+    float *hout = net ? a.hout[1] : a.hout[0];
+    float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
+    const int t0 = a.t0, t1 = a.t1;
+
+    float anchor = 0.0f;
+    unsigned long long w[2][3][KC / 2];    // packed pairs of W_hh[g*64 + 2*ug + u][part*32 + 2j, +1]
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + 2 * ug + u) * HID + part * KC);
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const float4 v = __ldg(wr + q);
+                w[u][g][2 * q] = pack2(v.x, v.y); w[u][g][2 * q + 1] = pack2(v.z, v.w);
+                anchor += v.x;
+            }
+        }
+    const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
+    // step constants are loaded BEFORE the dependency wait; the shared store of a value that depends on every load pins them above it (ptxas sinks free-standing loads below the wait)
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;
+    pdl_wait();
+    float hprev = t0 > 0 ? hout[((int64_t)(t0 - 1) * a.R + row) * HID + i] : 0.0f;   // init_hidden: zeros
+    const int hpos = i + (i >= KC ? GT_PAD : 0);
+    h_s[0][hpos] = hprev; h_s[1][hpos] = 0.0f;
+    const int64_t tstride = (int64_t)a.R * G3;
+    const float *p_g = gi + (int64_t)row * G3 + i;
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        if (t0 + p < t1) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], p_g + (int64_t)(t0 + p) * tstride + g * HID);
+        }
+        cp_async_commit();
+    }
+    __syncthreads();
+
+    for (int tt = t0; tt < t1; tt += 2) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int t = tt + p;
+            if (t >= t1) break;
+            const int buf = p;                   // == (t - t0) & 1
+            const int slot = (t - t0) % PF;
+            if (t + PDL_LEAD_STEPS == t1) pdl_trigger();
+            cp_async_wait<PF - 1>();             // this thread's group of step t has landed
+            const float g_r = st_s[slot][0][i], g_z = st_s[slot][1][i], g_n = st_s[slot][2][i];
+            if (t + PF < t1) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g) cp_async4(&st_s[slot][g][i], p_g + (int64_t)(t + PF) * tstride + g * HID);
+            }
+            cp_async_commit();
+            const float4 *hp = reinterpret_cast<const float4 *>(h_s[buf] + part * (KC + GT_PAD));
+            unsigned long long s[2][3];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) s[u][g] = 0ull;
+#pragma unroll
+            for (int q = 0; q < ((DBG & 8) ? 1 : KC / 4); ++q) {
+                const float4 hv = hp[q];
+                const unsigned long long hxy = pack2(hv.x, hv.y), hzw = pack2(hv.z, hv.w);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        s[u][g] = fma2(w[u][g][2 * q], hxy, s[u][g]);
+                        s[u][g] = fma2(w[u][g][2 * q + 1], hzw, s[u][g]);
+                    }
+            }
+            // transposing reduction over the lane pair: lane `part` ends with the complete sums of unit 2*ug + part
+            float x[3];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                float a0, a1, c0, c1;
+                unpack2(s[0][g], a0, a1); unpack2(s[1][g], c0, c1);
+                const float p0 = a0 + a1, p1 = c0 + c1;          // this lane's partial for units 2ug, 2ug+1
+                const float mine = part ? p1 : p0, other = part ? p0 : p1;
+                x[g] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+            }
+            const float xr = x[0] + (g_r + b_r), xz = x[1] + (g_z + b_z), ghn = x[2] + b_n;
+            const float rr = sigmoid_mufu(xr), zz = sigmoid_mufu(xz);
+            const float nn = tanh_mufu(g_n + rr * ghn);
+            const float hn = nn + zz * (hprev - nn);
+            hprev = hn;
+            h_s[buf ^ 1][hpos] = hn;
+            if (!(DBG & 1)) {
+                const int64_t m = (int64_t)t * a.R + row;
+                hout[m * HID + i] = hn;
+                if (gates) gates[m * HID + i] = make_float4(rr, zz, nn, ghn);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64, 4) k_gru_bwd7(GruBwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int JC = G3 / 4;             // rows j of W_hh per lane (48)
+    constexpr int DSEG = JC + GT_PAD;      // padded quarter of the d(gates) operand
+    __shared__ __align__(16) float dg_s[2][4 * DSEG];   // d gi_r | d gi_z | d gh_n of the previous step, in four shifted quarters
+    __shared__ __align__(16) float4 g4_s[PF][HID];
+    __shared__ float hp_s[PF][HID], dh_s[PF][HID];
+    __shared__ float pdl_anchor_s[HID];
+    const int k = threadIdx.x, row = blockIdx.x;
+    const int kg = k >> 2, part = k & 3;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const int T = a.TT - 1;
+
+    float anchor = 0.0f;
+    for (int idx = k; idx < 2 * 4 * DSEG; idx += HID) (&dg_s[0][0])[idx] = 0.0f;
+    unsigned long long wT[4][JC / 2];      // packed pairs (W_hh[48*part + 2j][4kg + c], W_hh[48*part + 2j + 1][4kg + c])
+#pragma unroll
+    for (int j = 0; j < JC / 2; ++j) {
+        const int jj = part * JC + 2 * j;
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)jj * HID + 4 * kg));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)(jj + 1) * HID + 4 * kg));
+        wT[0][j] = pack2(w0.x, w1.x); wT[1][j] = pack2(w0.y, w1.y); wT[2][j] = pack2(w0.z, w1.z); wT[3][j] = pack2(w0.w, w1.w);
+        anchor += w0.x + w1.y;
+    }
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[k]) = anchor;   // pins the loads above the wait (see k_gru_fwd7)
+
+    pdl_wait();                                  // W_hh is a step constant; gates / h / dh_head come from the predecessors
+    const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
+    auto fetch = [&](int i, int slot) {          // step i <-> t = TT-1-i
+        const int t = a.TT - 1 - i;
+        const int64_t m = (int64_t)t * a.R + row;
+        cp_async16(&g4_s[slot][k], gates4 + m * HID + k);
+        cp_async4(&hp_s[slot][k], a.hout + (t > 0 ? (m - a.R) * HID + k : 0), t > 0 ? 4 : 0);    // h_{-1} = 0
+        cp_async4(&dh_s[slot][k], a.dh_head + (t < T ? m * HID + k : 0), t < T ? 4 : 0);          // no q at t = T
+    };
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        if (p < a.TT) fetch(p, p);
+        cp_async_commit();
+    }
+    float carry = 0.0f;
+    // position of logical element e of [drp | dzp | dghn] inside the shifted-quarter layout
+    auto dpos = [&](int e) { return e + (e / JC) * GT_PAD; };
+    const int pos_r = dpos(k), pos_z = dpos(HID + k), pos_n = dpos(2 * HID + k);
+    __syncthreads();
+
+    for (int i0 = 0; i0 < a.TT; i0 += 2) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int i = i0 + p;
+            if (i >= a.TT) break;
+            const int buf = p;
+            const int slot = i % PF;
+            if (i + PDL_LEAD_STEPS == a.TT) pdl_trigger();
+            cp_async_wait<PF - 1>();
+            const float4 g4 = g4_s[slot][k];
+            const float hp = hp_s[slot][k], dhh = dh_s[slot][k];
+            if (i + PF < a.TT) fetch(i + PF, slot);
+            cp_async_commit();
+            const float4 *dp = reinterpret_cast<const float4 *>(dg_s[buf] + part * DSEG);
+            unsigned long long s[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int u = 0; u < JC / 4; ++u) {
+                const float4 d = dp[u];
+                const unsigned long long dxy = pack2(d.x, d.y), dzw = pack2(d.z, d.w);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    s[c] = fma2(wT[c][2 * u], dxy, s[c]);
+                    s[c] = fma2(wT[c][2 * u + 1], dzw, s[c]);
+                }
+            }
+            // transposing reduction over the lane quad: lane `part` ends with the complete sum of column 4*kg + part
+            float pc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { float lo, hi; unpack2(s[c], lo, hi); pc[c] = lo + hi; }
+            const bool b0 = part & 1, b1 = part & 2;
+            // stage 1 (xor 1): lanes with bit0 = 0 keep columns {0, 2}, the others {1, 3}
+            const float k0 = b0 ? pc[1] : pc[0], k1 = b0 ? pc[3] : pc[2];
+            const float g0 = b0 ? pc[0] : pc[1], g1 = b0 ? pc[2] : pc[3];
+            const float q0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 1);
+            const float q1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 1);
+            // stage 2 (xor 2): lanes with bit1 = 0 keep the first of the pair, the others the second
+            const float keep = b1 ? q1 : q0, give = b1 ? q0 : q1;
+            const float dh = (keep + __shfl_xor_sync(0xffffffffu, give, 2)) + (carry + dhh);
+            const float rr = g4.x, zz = g4.y, nn = g4.z, ghn = g4.w;
+            const float dn = dh * (1.0f - zz);
+            const float dz = dh * (hp - nn);
+            const float dnp = dn * (1.0f - nn * nn);
+            const float dzp = dz * zz * (1.0f - zz);
+            const float drp = dnp * ghn * rr * (1.0f - rr);
+            const float dghn = dnp * rr;
+            carry = dh * zz;
+            float *sm = dg_s[buf ^ 1];
+            sm[pos_r] = drp; sm[pos_z] = dzp; sm[pos_n] = dghn;
+            float *dg = a.d_g + ((int64_t)(a.TT - 1 - i) * a.R + row) * 4 * HID + k;
+            dg[0] = drp; dg[HID] = dzp; dg[2 * HID] = dnp; dg[3 * HID] = dghn;
+            __syncthreads();
+        }
+    }
+}

@@ -387,112 +387,10 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 __device__ __forceinline__ float sigmoid_mufu(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_mufu(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 
-// =============================================================================================
-// GRU recurrence, forward, v4: ONE batch row per CTA, 64 threads (thread = hidden unit), several CTAs per SM.
-// grid (R, nets).  Thread i keeps the three gate rows r/z/n of W_hh for unit i in registers (192 weights), so a
-// timestep is: 16 broadcast LDS.128 of h_{t-1}, 192 FMAs, both sigmoids + the candidate tanh + the blend (h_{t-1} of
-// the unit stays in a register), one h store, one float4 store of the saved gates, and ONE barrier between the two
-// warps (h is double-buffered in shared memory).  No shuffles, no redundant gate math: the kernel is bound by
-// instruction issue on the SMs that host ceil(rows / SMs) rows, so the instruction count per row-step is what counts.
-// The gi[t] terms are per-thread cp.async copies running PF steps ahead (one commit group per timestep).
-// Saved gates layout (private to k_gru_fwd4 / k_gru_bwd4): [m][unit][r, z, n, gh_n].
-// =============================================================================================
 #ifndef PDL_LEAD_STEPS
 #define PDL_LEAD_STEPS 6   // timesteps before the end of a recurrence at which its dependent kernel may start its prologue
 #endif
-template <int DBG = 0>   // DBG (probe only): 1 no global stores, 4 cheap gate math, 8 no matvec, 128 libm expf/tanhf gate math
-__global__ void __launch_bounds__(64, 4) k_gru_fwd4(GruFwdArgs a) {
-    constexpr int PF = 8;
-    __shared__ __align__(16) float h_s[2][HID];
-    __shared__ float st_s[PF][3][HID];
-    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
-    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
-    const float *P = net ? a.params[1] : a.params[0];
-    const float *gi = net ? a.gi[1] : a.gi[0];
-    float *hout = net ? a.hout[1] : a.hout[0];
-    float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
-
-    const int t0 = a.t0, t1 = a.t1;
-    __shared__ float pdl_anchor_s[HID];
-    float anchor = 0.0f;
-    unsigned long long w[3][HID / 2];   // packed pairs (W_hh[g*64+i][2j], W_hh[g*64+i][2j+1]) for FFMA2
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + i) * HID);
-#pragma unroll
-        for (int u = 0; u < HID / 4; ++u) {
-            const float4 v = __ldg(wr + u);
-            w[g][2 * u] = pack2(v.x, v.y); w[g][2 * u + 1] = pack2(v.z, v.w);
-            anchor += v.x;
-        }
-    }
-    const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
-    // The weights above are step constants and are loaded BEFORE the dependency wait (they fly under the predecessor's
-    // tail); gi / hout come from the predecessor.  The shared store of a value that depends on every load pins the
-    // loads above the wait (ptxas sinks free-standing loads below it).
-    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;
-    pdl_wait();
-    float hprev = t0 > 0 ? hout[((int64_t)(t0 - 1) * a.R + row) * HID + i] : 0.0f;   // init_hidden: zeros
-    h_s[0][i] = hprev; h_s[1][i] = 0.0f;
-    const int64_t tstride = (int64_t)a.R * G3;
-    const float *p_g = gi + (int64_t)row * G3 + i;
-#pragma unroll
-    for (int p = 0; p < PF; ++p) {
-        if (t0 + p < t1) {
-#pragma unroll
-            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], p_g + (int64_t)(t0 + p) * tstride + g * HID);
-        }
-        cp_async_commit();
-    }
-    __syncthreads();
-
-    for (int tt = t0; tt < t1; tt += 2) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int t = tt + p;
-            if (t >= t1) break;
-            const int buf = p;                   // == (t - t0) & 1
-            const int slot = (t - t0) % PF;
-            if (t + PDL_LEAD_STEPS == t1) pdl_trigger();   // late: dependents parked at their wait would take issue slots from this latency-bound loop
-            cp_async_wait<PF - 1>();             // this thread's group of step t has landed
-            const float g_r = st_s[slot][0][i], g_z = st_s[slot][1][i], g_n = st_s[slot][2][i];
-            if (t + PF < t1) {
-#pragma unroll
-                for (int g = 0; g < 3; ++g) cp_async4(&st_s[slot][g][i], p_g + (int64_t)(t + PF) * tstride + g * HID);
-            }
-            cp_async_commit();
-            const float4 *hp = reinterpret_cast<const float4 *>(h_s[buf]);
-            unsigned long long s[3] = {pack2(g_r + b_r, 0.0f), pack2(g_z + b_z, 0.0f), pack2(b_n, 0.0f)};
-#pragma unroll
-            for (int u = 0; u < ((DBG & 8) ? 2 : HID / 4); ++u) {
-                const float4 hv = hp[u];
-                const unsigned long long hxy = pack2(hv.x, hv.y), hzw = pack2(hv.z, hv.w);
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    s[g] = fma2(w[g][2 * u], hxy, s[g]);
-                    s[g] = fma2(w[g][2 * u + 1], hzw, s[g]);
-                }
-            }
-            float sa, sb;
-            unpack2(s[0], sa, sb); const float xr = sa + sb;
-            unpack2(s[1], sa, sb); const float xz = sa + sb;
-            unpack2(s[2], sa, sb); const float ghn = sa + sb;
-            const float rr = (DBG & 4) ? 0.5f * xr : (DBG & 128) ? sigmoid_fast(xr) : sigmoid_mufu(xr);
-            const float zz = (DBG & 4) ? 0.5f * xz : (DBG & 128) ? sigmoid_fast(xz) : sigmoid_mufu(xz);
-            const float xn = g_n + rr * ghn;
-            const float nn = (DBG & 4) ? 0.1f * xn : (DBG & 128) ? tanhf(xn) : tanh_mufu(xn);
-            const float hn = nn + zz * (hprev - nn);
-            hprev = hn;
-            h_s[buf ^ 1][i] = hn;
-            if (!(DBG & 1)) {
-                const int64_t m = (int64_t)t * a.R + row;
-                hout[m * HID + i] = hn;
-                if (gates) gates[m * HID + i] = make_float4(rr, zz, nn, ghn);
-            }
-            __syncthreads();
-        }
-    }
-}
+// (the recurrence kernels k_gru_fwd7 / k_gru_bwd7 live in gru_rec.cuh)
 
 // out[c][r] = in[r][c] for up to three small weight matrices (grid: 32x32 tiles, problem); see mal_plan_t.w_t
 struct TransArgs {
@@ -925,93 +823,6 @@ struct GruBwdArgs {
     float *d_g;                // [TT*R,256]: d gi_r | d gi_z | d gi_n | d gh_n
     int TT, R, d_in, n_actions;
 };
-
-// =============================================================================================
-// GRU recurrence, backward, v4 (same one-row-per-CTA, thread = unit layout as k_gru_fwd4).  grid R, 64 threads.
-// Thread k keeps column k of W_hh (192 weights) in registers:  d h_{t-1}[k] = d h_t[k] z[k] + sum_j d gh[j] W_hh[j][k]
-// is 48 broadcast LDS.128 + 192 FMAs per timestep, then the element-wise gate derivatives of unit k, 3 shared stores
-// (next step's d gh), 4 global stores (the d_g row) and one barrier between the two warps.
-// Saved gates, h_{t-1} and the fc2/gather injection stream through a PF-deep per-thread cp.async ring.
-// =============================================================================================
-__global__ void __launch_bounds__(64, 4) k_gru_bwd4(GruBwdArgs a) {
-    constexpr int PF = 8;
-    __shared__ __align__(16) float dg_s[2][G3];   // d gi_r | d gi_z | d gh_n of the previous step
-    __shared__ __align__(16) float4 g4_s[PF][HID];
-    __shared__ float hp_s[PF][HID], dh_s[PF][HID];
-    const int k = threadIdx.x, row = blockIdx.x;
-    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
-    const int T = a.TT - 1;
-
-    __shared__ float pdl_anchor_s[HID];
-    float anchor = 0.0f;
-    for (int idx = k; idx < 2 * G3; idx += HID) (&dg_s[0][0])[idx] = 0.0f;
-    unsigned long long wT[G3 / 2];   // packed pairs (W_hh[2j][k], W_hh[2j+1][k]) for FFMA2
-#pragma unroll
-    for (int j = 0; j < G3 / 2; ++j)
-    {
-        const float w0 = __ldg(a.params + L.w_hh + (int64_t)(2 * j) * HID + k), w1 = __ldg(a.params + L.w_hh + (int64_t)(2 * j + 1) * HID + k);
-        wT[j] = pack2(w0, w1);
-        anchor += w0 + w1;
-    }
-    *reinterpret_cast<volatile float *>(&pdl_anchor_s[k]) = anchor;   // pins the loads above the wait (see k_gru_fwd4)
-
-    pdl_wait();                                  // W_hh is a step constant; gates / h / dh_head come from the predecessors
-    const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
-    auto fetch = [&](int i, int slot) {          // step i <-> t = TT-1-i
-        const int t = a.TT - 1 - i;
-        const int64_t m = (int64_t)t * a.R + row;
-        cp_async16(&g4_s[slot][k], gates4 + m * HID + k);
-        cp_async4(&hp_s[slot][k], a.hout + (t > 0 ? (m - a.R) * HID + k : 0), t > 0 ? 4 : 0);    // h_{-1} = 0
-        cp_async4(&dh_s[slot][k], a.dh_head + (t < T ? m * HID + k : 0), t < T ? 4 : 0);          // no q at t = T
-    };
-#pragma unroll
-    for (int p = 0; p < PF; ++p) {
-        if (p < a.TT) fetch(p, p);
-        cp_async_commit();
-    }
-    float carry = 0.0f;
-    __syncthreads();
-
-    for (int i0 = 0; i0 < a.TT; i0 += 2) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int i = i0 + p;
-            if (i >= a.TT) break;
-            const int buf = p;
-            const int slot = i % PF;
-            if (i + PDL_LEAD_STEPS == a.TT) pdl_trigger();
-            cp_async_wait<PF - 1>();
-            const float4 g4 = g4_s[slot][k];
-            const float hp = hp_s[slot][k], dhh = dh_s[slot][k];
-            if (i + PF < a.TT) fetch(i + PF, slot);
-            cp_async_commit();
-            const float4 *dp = reinterpret_cast<const float4 *>(dg_s[buf]);
-            unsigned long long s01 = pack2(carry, 0.0f), s23 = pack2(dhh, 0.0f);
-#pragma unroll
-            for (int u = 0; u < G3 / 4; ++u) {
-                const float4 d = dp[u];
-                s01 = fma2(wT[2 * u], pack2(d.x, d.y), s01);
-                s23 = fma2(wT[2 * u + 1], pack2(d.z, d.w), s23);
-            }
-            float s0, s1, s2, s3;
-            unpack2(s01, s0, s1); unpack2(s23, s2, s3);
-            const float dh = (s0 + s1) + (s2 + s3);
-            const float rr = g4.x, zz = g4.y, nn = g4.z, ghn = g4.w;
-            const float dn = dh * (1.0f - zz);
-            const float dz = dh * (hp - nn);
-            const float dnp = dn * (1.0f - nn * nn);
-            const float dzp = dz * zz * (1.0f - zz);
-            const float drp = dnp * ghn * rr * (1.0f - rr);
-            const float dghn = dnp * rr;
-            carry = dh * zz;
-            float *sm = dg_s[buf ^ 1];
-            sm[k] = drp; sm[HID + k] = dzp; sm[2 * HID + k] = dghn;
-            float *dg = a.d_g + ((int64_t)(a.TT - 1 - i) * a.R + row) * 4 * HID + k;
-            dg[0] = drp; dg[HID] = dzp; dg[2 * HID] = dnp; dg[3 * HID] = dghn;
-            __syncthreads();
-        }
-    }
-}
 
 // =============================================================================================
 // fc2 gradients:  dW2[a, :] = sum_m [a_m == a] d_chosen[m] h_m ,  db2[a] = sum_m [a_m == a] d_chosen[m]

@@ -7,6 +7,7 @@
 #include "replay.cuh"
 #include "actsel.cuh"
 #include "learner.cuh"
+#include "gru_rec.cuh"
 #include "tc_gemm.cuh"
 #include "agent_in_gemm.cuh"
 #include "tc_reduce.cuh"
@@ -627,13 +628,15 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
     return p;
 }
 
-static void launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool pdl) {
+static int launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_fwd", st);
-    launch_k(k_gru_fwd4<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);      // one batch row per CTA, thread = hidden unit
+    launch_k(k_gru_fwd7<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);      // one batch row per CTA
+    return 0;
 }
-static void launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
+static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_bwd", st);
-    launch_k(k_gru_bwd4, dim3(a.R), dim3(HID), 0, st, pdl, a);
+    launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
+    return 0;
 }
 
 extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, const mal_plan_t *plan,
@@ -742,12 +745,12 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         a.t0 = 0; a.t1 = t_split;
-        launch_gru_fwd(a, 2, st, fused_in && t_split == d.TT);   // stream predecessor: k_agent_in_tc
+        if (launch_gru_fwd(a, 2, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
         MAL_LAUNCH_CHECK("k_gru_fwd");
         if (t_split < d.TT) {
             if (join_from(st, ss->s[1], ss->join_ev[1])) return 2;    // second half of gi is ready
             a.t0 = t_split; a.t1 = d.TT;
-            launch_gru_fwd(a, 2, st, false);
+            if (launch_gru_fwd(a, 2, st, false)) return 2;
             MAL_LAUNCH_CHECK("k_gru_fwd");
         }
     }
@@ -766,7 +769,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         const int64_t qh_grid = ceil_div64(qh_tiles, ceil_div64(qh_tiles, qh_slots));    // number of tiles (+-1), in one wave
         static size_t attr[MAL_MAX_DEV];
         if (int rc = ensure_dyn_smem(k_q_head, smem, attr)) return rc;
-        { ProfScope _ps("k_q_head", st); launch_k(k_q_head, dim3((unsigned)qh_grid), dim3(128), smem, st, true, a); }   // predecessor: k_gru_fwd4
+        { ProfScope _ps("k_q_head", st); launch_k(k_q_head, dim3((unsigned)qh_grid), dim3(128), smem, st, true, a); }   // predecessor: k_gru_fwd7
         MAL_LAUNCH_CHECK("k_q_head");
     }
     // mixer hypernetworks                                                   qmix.py:41-59
@@ -1029,7 +1032,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        launch_gru_bwd(a, st, g_in_step);        // inside a step the stream predecessor is k_mix_td
+        if (launch_gru_bwd(a, st, g_in_step)) return 2;        // inside a step the stream predecessor is k_mix_td
         MAL_LAUNCH_CHECK("k_gru_bwd");
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads
@@ -1045,7 +1048,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     if (!frozen) {
         LinGroup g; g.n = 1; g.bv = bv;
         g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, F(plan->w_t), G3, 0, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);   // W_ih^T from the forward call
-        g_next_pdl = true;                       // stream predecessor: k_gru_bwd4 (W_ih staging flies under its last timesteps)
+        g_next_pdl = true;                       // stream predecessor: k_gru_bwd7 (W_ih staging flies under its last timesteps)
         int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx");
         g_next_pdl = false;
         if (rc) return rc;

@@ -1,7 +1,7 @@
 // Stand-alone timing + cross-check harness for the GRU recurrence kernels of learner.cuh (not product code).
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/gru_bench tools/gru_bench.cu
-// Checks k_gru_fwd4 / k_gru_bwd4 against an fp64 CPU recurrence on the first rows, then times them.
-#include "../ma_league_b200/csrc/learner.cuh"
+// Checks k_gru_fwd7 / k_gru_bwd7 against an fp64 CPU recurrence on the first rows, then times them.
+#include "../ma_league_b200/csrc/gru_rec.cuh"
 #include <vector>
 #include <random>
 #include <cstdlib>
@@ -19,7 +19,7 @@ template <typename F> static float time_us(F f, int reps = 20) {
 
 int main(int argc, char **argv) {
     const int R = argc > 1 ? atoi(argv[1]) : 160, TT = argc > 2 ? atoi(argv[2]) : 201;
-    const int d_in = 64, A = 11, NCHK = 3;
+    const int d_in = 64, A = 11; const int NCHK = argc > 3 ? atoi(argv[3]) : 3;
     const AgentLayout L = agent_layout(d_in, A);
     std::mt19937 rng(1);
     std::uniform_real_distribution<float> U(-0.125f, 0.125f);
@@ -41,9 +41,12 @@ int main(int argc, char **argv) {
     GruBwdArgs ba; ba.params = dP0; ba.hout = h[0]; ba.gates = gates; ba.dh_head = ddhh; ba.d_g = dg; ba.TT = TT; ba.R = R;
     ba.d_in = d_in; ba.n_actions = A;
 
-    const float fus = time_us([&] { k_gru_fwd4<0><<<dim3(R, 2), HID>>>(fa); });
-    const float bus = time_us([&] { k_gru_bwd4<<<R, HID>>>(ba); });
-    printf("k_gru_fwd4 grid %dx2: %7.1f us  %5.0f cycles/step    k_gru_bwd4 grid %d: %7.1f us  %5.0f cycles/step   (%s)\n", R, fus,
+    const int variant = 7;
+    auto fwd = [&] { k_gru_fwd7<0><<<dim3(R, 2), HID>>>(fa); };
+    auto bwd = [&] { k_gru_bwd7<<<R, HID>>>(ba); };
+    const float fus = time_us(fwd);
+    const float bus = time_us(bwd);
+    printf("variant %d  fwd grid %dx2: %7.1f us  %5.0f cycles/step    bwd grid %d: %7.1f us  %5.0f cycles/step   (%s)\n", variant, R, fus,
            fus * 1965 / TT, R, bus, bus * 1965 / TT, cudaGetErrorString(cudaGetLastError()));
 
     // ---- fp64 reference on rows 0..NCHK-1 of the online net

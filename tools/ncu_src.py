@@ -8,7 +8,12 @@ rows = list(csv.reader(open(sys.argv[1])))
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
-data = rows[hdr_i + 1:]
+data = []
+for r in rows[hdr_i + 1:]:
+    if r and r[0] in ("Address", "Kernel Name"):      # the next section / kernel of a multi-kernel export
+        break
+    if len(r) >= len(hdr):
+        data.append(r)
 ci = {n: i for i, n in enumerate(hdr)}
 samp = ci["# Samples"]
 stall_cols = [(n, i) for n, i in ci.items() if n.startswith("stall_") and "Not Issued" not in n]

@@ -73,7 +73,7 @@ with open(os.path.join(OUT, tag + "_full.csv"), "w") as f:
             return x * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         traffic[k].append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
 tj = {k: int(sum(v) / len(v)) for k, v in traffic.items()}
-alias = {"k_gru_fwd4": "k_gru_fwd", "k_gru_bwd4": "k_gru_bwd"}
+alias = {"k_gru_fwd4": "k_gru_fwd", "k_gru_bwd4": "k_gru_bwd", "k_gru_fwd7": "k_gru_fwd", "k_gru_bwd7": "k_gru_bwd"}
 for k, a in alias.items():
     if k in tj:
         tj[a] = tj[k]
