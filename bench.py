@@ -610,10 +610,12 @@ def run_dp_leg(a, rank, world, device):
         th.cuda.synchronize(device)
         ex_us = statistics.median([e0.elapsed_time(e1) * 1e3 for e0, e1 in learner.dp_profile])
         learner.dp_profile = None
+        nat.lib().mal_set_option(b"overlap", 0)             # kernels timed alone (no queueing behind side-stream neighbours)
         nat.profile_begin()
         for i in range(K):
             learner.train(shard, t_env=i, episode_num=0)
         prof = nat.profile_end()
+        nat.lib().mal_set_option(b"overlap", 1)
         kb = kernel_bytes(d, "qmix", B)
         tot = sum(v[1] for v in prof.values())
         kern = [{"kernel": k, "us_per_launch": round(v[1] / v[0] * 1e3, 2), "share": round(v[1] / tot, 4),

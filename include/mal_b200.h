@@ -117,6 +117,8 @@ uint64_t mal_launch_count(void);
 void mal_count_launches(uint64_t n);
 int mal_profile_begin(void);
 int mal_profile_end(char *out, int64_t out_len);
+/* same, but one line per launch in issue order: "<name> <start_us> <end_us>\n" relative to the first recorded launch */
+int mal_profile_end_timeline(char *out, int64_t out_len);
 
 /* Parameter counts in state_dict order (drqn_agent.py:21-23, qmix.py:16-39). */
 int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions);
@@ -190,6 +192,39 @@ int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t o
                    void *stream);
 /* dense_input != 0: `obs` is the already assembled agent input [rows, obs_dim] with row stride obs_sb
  * (DRQNAgentNetwork.forward(inputs, hidden_state), drqn_agent.py:29-35); obs_dim is then the full input width. */
+
+/* One rollout timestep of `bs` lock-step matches in ONE launch: the loop body of EpisodeStepper.run / SelfPlayStepper.run
+ * (steppers/episode_stepper.py:110-142,177-186; steppers/self_play_stepper.py:64-106) for one team --
+ *   EpisodeBatch.update(pre_transition_data, ts=t)   state / avail_actions / obs from the environment + filled = 1
+ *   EpisodeBatch.update(post_transition_data, ts=t-1) reward / terminated of the previous step (when prev_reward != NULL)
+ *   BasicMAC.select_actions(batch, t_ep=t, ...)       mal_agent_step + epsilon-greedy on the environment's obs / avail
+ *   EpisodeBatch.update({"actions": ...}, ts=t)       actions + the derived actions_onehot
+ * All `*_t` pointers address element [0, t] of the batch field (`*_tm1`: [0, t-1]); strides are batch strides in elements
+ * of the field's dtype.  `alive` (optional, [bs] bytes): matches that have already ended select on a dummy avail row (no
+ * ValueError from their all-zero rows); what they write past their end is cleared by the caller after the loop. */
+typedef struct mal_rollout_io {
+    int32_t state_dim;
+    const float *env_state; int64_t env_state_sb;         /* [bs,S]      env.get_state()          */
+    const int32_t *env_avail; int64_t env_avail_sb;       /* [bs,N,A]    env.get_avail_actions()  */
+    const float *env_obs; int64_t env_obs_sb;             /* [bs,N,OBS]  env.get_obs()            */
+    const uint8_t *alive;                                 /* [bs] or NULL */
+    const float *prev_reward;                             /* [bs] or NULL (t == 0) */
+    const uint8_t *prev_done;                             /* [bs] */
+    float *state_t; int64_t state_sb;
+    int32_t *avail_t; int64_t avail_sb;
+    float *obs_t; int64_t obs_sb;
+    int64_t *filled_t; int64_t filled_sb;
+    int64_t *actions_t; int64_t actions_sb;
+    float *onehot_t; int64_t onehot_sb;
+    const float *onehot_tm1; int64_t onehot_tm1_sb;       /* actions_onehot[:, t-1] (agent input), NULL at t == 0 */
+    float *reward_tm1; int64_t reward_sb;
+    uint8_t *term_tm1; int64_t term_sb;
+} mal_rollout_io_t;
+
+/* `sel` is required (sel->avail / avail_sb are ignored: the environment's avail rows of `io` are used). */
+int mal_rollout_step(const float *agent, int32_t bs, int32_t n_agents, int32_t obs_dim, int32_t n_actions,
+                     const mal_rollout_io_t *io, const float *h_in, float *h_out, float *q, const mal_select_t *sel,
+                     void *stream);
 
 /* Launch counters per kernel flavour since process start, for tests that assert which variant the launch heuristics
  * picked: "linear_tc2" (pipelined tcgen05 GEMM), "linear_tc", "reduce_tc", "reduce_tc_swap", "reduce_ffma",

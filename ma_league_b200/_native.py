@@ -62,6 +62,17 @@ class Select(C.Structure):
                 ("actions", C.c_void_p), ("greedy", C.c_void_p), ("status", C.c_void_p)]
 
 
+class RolloutIO(C.Structure):
+    _fields_ = [("state_dim", C.c_int32),
+                ("env_state", C.c_void_p), ("env_state_sb", C.c_int64), ("env_avail", C.c_void_p), ("env_avail_sb", C.c_int64),
+                ("env_obs", C.c_void_p), ("env_obs_sb", C.c_int64), ("alive", C.c_void_p), ("prev_reward", C.c_void_p),
+                ("prev_done", C.c_void_p), ("state_t", C.c_void_p), ("state_sb", C.c_int64), ("avail_t", C.c_void_p),
+                ("avail_sb", C.c_int64), ("obs_t", C.c_void_p), ("obs_sb", C.c_int64), ("filled_t", C.c_void_p),
+                ("filled_sb", C.c_int64), ("actions_t", C.c_void_p), ("actions_sb", C.c_int64), ("onehot_t", C.c_void_p),
+                ("onehot_sb", C.c_int64), ("onehot_tm1", C.c_void_p), ("onehot_tm1_sb", C.c_int64),
+                ("reward_tm1", C.c_void_p), ("reward_sb", C.c_int64), ("term_tm1", C.c_void_p), ("term_sb", C.c_int64)]
+
+
 _PROTOS = {
     "mal_version": (C.c_int, []),
     "mal_last_error": (C.c_char_p, []),
@@ -69,6 +80,7 @@ _PROTOS = {
     "mal_count_launches": (None, [C.c_uint64]),
     "mal_profile_begin": (C.c_int, []),
     "mal_profile_end": (C.c_int, [C.c_char_p, C.c_int64]),
+    "mal_profile_end_timeline": (C.c_int, [C.c_char_p, C.c_int64]),
     "mal_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "mal_stat": (C.c_uint64, [C.c_char_p]),
     "mal_debug_linear": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
@@ -93,6 +105,8 @@ _PROTOS = {
     "mal_agent_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.POINTER(Select), C.c_void_p]),
+    "mal_rollout_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(RolloutIO), C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.POINTER(Select), C.c_void_p]),
     "mal_mixer_forward": (C.c_int, [C.c_int32] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "mal_eps_greedy_select": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Select),
@@ -157,6 +171,17 @@ def profile_end():
     for line in buf.value.decode().splitlines():
         name, n, ms = line.rsplit(" ", 2)
         out[name] = (int(n), float(ms))
+    return out
+
+
+def profile_end_timeline():
+    """[(kernel name, start_us, end_us)] per launch since profile_begin(), relative to the first launch."""
+    buf = C.create_string_buffer(1 << 18)
+    check(lib().mal_profile_end_timeline(buf, len(buf)), "mal_profile_end_timeline")
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, a, b = line.rsplit(" ", 2)
+        out.append((name, float(a), float(b)))
     return out
 
 

@@ -43,6 +43,88 @@ class BasicMAC(MultiAgentController):
         agent_outs = self.forward(ep_batch, t_ep, test_mode=test_mode)
         return self.action_selector.select(agent_outs[bs], avail_actions[bs], t_env, test_mode, u=u, e=e)
 
+    def rollout_step(self, ep_batch, t_ep, t_env, pre, prev=None, alive=None, test_mode=False, u=None, e=None):
+        """One timestep of the rollout loop around `select_actions` in ONE launch (steppers/episode_stepper.py:110-142,
+        177-186): `ep_batch.update(pre, ts=t_ep)` (state / avail_actions / obs from the environment, device tensors
+        [bs, ...]), `ep_batch.update({"reward", "terminated"}, ts=t_ep-1)` for `prev = (reward [bs] f32, done [bs] bool)`,
+        `select_actions(ep_batch, t_ep, t_env)` and `ep_batch.update({"actions": ...}, ts=t_ep)` incl. the one-hot.
+        `alive` [bs] bool: matches that have ended select on a dummy avail row.  Returns (actions, is_greedy) like
+        `select_actions`.  Needs a packed device batch and the fused agent (`_fusable()`); callers fall back to the
+        separate calls otherwise."""
+        if not self._fusable():
+            raise nat.MalError("rollout_step needs the fused recurrent agent path")
+        if self.hidden_states is None:
+            raise HiddenStateNotInitialized()
+        tv = ep_batch.data.transition_data
+        obs_all = nat.require_cuda(tv["obs"], "ep_batch")
+        B, TT, N, OBS = obs_all.shape
+        A = self.n_actions
+        dev = obs_all.device
+        state, avail, obs = pre["state"], pre["avail_actions"], pre["obs"]
+        if state.dtype != th.float32 or obs.dtype != th.float32 or avail.dtype != th.int32:
+            raise nat.MalError("pre-transition data must be float32 state / obs and int32 avail_actions")
+        if state.stride(-1) != 1 or not obs[0].is_contiguous() or not avail[0].is_contiguous():
+            raise nat.MalError("pre-transition rows must be contiguous")
+        sel = self.action_selector
+        eps = sel._epsilon(t_env, test_mode)
+        out = th.empty(2, B, N, dtype=th.long, device=dev)                       # actions | greedy
+        status = th.zeros(1, dtype=th.int32, device=dev) if sel.validate else None
+        s, keep = make_select_struct(avail, eps, out[0], out[1], status, u, e)
+        io = nat.RolloutIO()
+        io.state_dim = state.shape[-1]
+        io.env_state, io.env_state_sb = state.data_ptr(), state.stride(0)
+        io.env_avail, io.env_avail_sb = avail.data_ptr(), avail.stride(0)
+        io.env_obs, io.env_obs_sb = obs.data_ptr(), obs.stride(0)
+        if alive is not None:
+            alive = alive if alive.dtype == th.bool else alive != 0
+            io.alive = alive.data_ptr()
+        fld = {}
+        for key in ("state", "avail_actions", "obs", "filled", "actions", "actions_onehot", "reward", "terminated"):
+            v = tv[key]
+            fld[key] = (v.data_ptr(), v.element_size(), v.stride(0), v.stride(1))
+
+        def at(key, t):
+            p, es, sb, st = fld[key]
+            return p + es * st * t, sb
+        io.state_t, io.state_sb = at("state", t_ep)
+        io.avail_t, io.avail_sb = at("avail_actions", t_ep)
+        io.obs_t, io.obs_sb = at("obs", t_ep)
+        io.filled_t, io.filled_sb = at("filled", t_ep)
+        io.actions_t, io.actions_sb = at("actions", t_ep)
+        io.onehot_t, io.onehot_sb = at("actions_onehot", t_ep)
+        if t_ep > 0:
+            io.onehot_tm1, io.onehot_tm1_sb = at("actions_onehot", t_ep - 1)
+        if prev is not None:
+            if t_ep == 0:
+                raise nat.MalError("there is no previous step at t_ep = 0")
+            reward, done = prev
+            reward = reward if reward.dtype == th.float32 else reward.float()
+            done = done if done.dtype == th.bool else done != 0
+            io.prev_reward, io.prev_done = reward.data_ptr(), done.data_ptr()
+            io.reward_tm1, io.reward_sb = at("reward", t_ep - 1)
+            io.term_tm1, io.term_sb = at("terminated", t_ep - 1)
+            keep += [reward, done]
+        rows = B * N
+        h_in = self.hidden_states
+        if h_in.dim() == 3 and h_in.stride(0) == 0 and h_in.stride(1) == 0:      # fresh init_hidden(): zeros
+            h_ptr = None
+        else:
+            h_in = h_in.reshape(rows, nat.HID)
+            if not h_in.is_contiguous():
+                h_in = h_in.contiguous()
+            h_ptr = h_in.data_ptr()
+        buf = th.empty(rows * (A + nat.HID), dtype=th.float32, device=dev)       # q | h_out, one allocation
+        q = buf[:rows * A].view(B, N, A)
+        h_out = buf[rows * A:].view(rows, nat.HID)
+        flat = self.agent.flat_params()
+        with nat.on_device(dev):
+            nat.check(nat.lib().mal_rollout_step(flat.data_ptr(), B, N, OBS, A, C.byref(io), h_ptr, h_out.data_ptr(),
+                                                 q.data_ptr(), C.byref(s), nat.current_stream(dev)), "mal_rollout_step")
+        self.hidden_states = h_out
+        if status is not None and int(status.item()) != 0:
+            raise ValueError("Expected at least one available action per agent (Categorical probs are all zero)")
+        return out[0], out[1]
+
     def forward(self, ep_batch, t, test_mode=False):
         if self._fusable():
             return self._step(ep_batch, t, None)

@@ -50,6 +50,25 @@ __device__ __forceinline__ float torch_exponential1(float r) {                  
     return -1.0f * lg;
 }
 
+// Rollout-step fusion (steppers/episode_stepper.py:110-142,177-186): besides selecting actions the launch also performs
+// the EpisodeBatch.update calls around select_actions -- the environment's pre-transition data of step t, the previous
+// step's reward / terminated, and the selected actions + their one-hot -- straight into the episode records.
+struct RolloutIO {
+    int enabled;
+    int S;
+    const float *env_state; int64_t env_state_sb;     // [bs,S]
+    const uint8_t *alive;                              // [bs] or NULL: matches that have ended select on a dummy avail row
+    const float *prev_reward; const uint8_t *prev_done;   // [bs] outcome of step t-1, NULL at t = 0
+    float *state_t; int64_t state_sb;                 // episode batch fields at time index t: &field[0, t], batch strides in elements
+    int32_t *avail_t; int64_t avail_sb;
+    float *obs_t; int64_t obs_sb;
+    long long *filled_t; int64_t filled_sb;
+    long long *actions_t; int64_t actions_sb;
+    float *onehot_t; int64_t onehot_sb;
+    float *reward_tm1; int64_t reward_sb;             // &reward[0, t-1]
+    uint8_t *term_tm1; int64_t term_sb;
+};
+
 struct SelectArgs {
     const int32_t *avail;
     int64_t avail_sb;
@@ -63,10 +82,14 @@ struct SelectArgs {
     int32_t *status;
 };
 
-// One warp selects for one row.  qv = this lane's Q-value (lane < A).
-__device__ __forceinline__ void select_row(const SelectArgs &s, int row, int A, int lane, float qv) {
+// One warp selects for one row.  qv = this lane's Q-value (lane < A).  With `io` the avail row, the chosen action and
+// its one-hot also go into the episode batch at time index t.
+__device__ __forceinline__ void select_row(const SelectArgs &s, int row, int A, int lane, float qv, const RolloutIO *io = nullptr) {
     const bool valid = lane < A;
-    const int av = valid ? s.avail[(int64_t)(row / s.N) * s.avail_sb + (int64_t)(row % s.N) * A + lane] : 0;
+    const int b = row / s.N, n = row - b * s.N;
+    int av = valid ? s.avail[(int64_t)b * s.avail_sb + (int64_t)n * A + lane] : 0;
+    if (io && valid) io->avail_t[(int64_t)b * io->avail_sb + (int64_t)n * A + lane] = av;
+    if (io && io->alive && !io->alive[b]) av = (lane == 0) ? 1 : 0;       // an ended match: any valid row (its data is cleared later)
     // greedy branch: masked_q[avail == 0] = -inf ; max(dim=2)[1]
     float gv = (valid && av != 0) ? qv : -INFINITY;
     int gi = lane;
@@ -80,13 +103,39 @@ __device__ __forceinline__ void select_row(const SelectArgs &s, int row, int A, 
     float rv = valid ? (avf / tot) / ev : -INFINITY;
     int ri = lane;
     warp_argmax(rv, ri);
+    int act = 0;
     if (lane == 0) {
         float uu = (s.rng_mode == 0) ? s.u[row]
                                      : torch_uniform01(torch_philox_uniform(s.seed, s.offset_u, s.grid_u, (uint64_t)row));
         const long long pick_random = (uu < s.epsilon) ? 1 : 0;
-        s.actions[row] = pick_random * ri + (1 - pick_random) * gi;
+        act = (int)(pick_random * ri + (1 - pick_random) * gi);
+        s.actions[row] = act;
         s.greedy[row] = 1 - pick_random;
         if (!(tot > 0.0f) && s.status) atomicExch(s.status, 1);
+    }
+    if (io) {
+        act = __shfl_sync(0xffffffffu, act, 0);
+        if (lane == 0) io->actions_t[(int64_t)b * io->actions_sb + n] = act;
+        if (valid) io->onehot_t[(int64_t)b * io->onehot_sb + (int64_t)n * A + lane] = (lane == act) ? 1.0f : 0.0f;   // OneHot, transforms.py:16-19
+    }
+}
+
+// Per-match part of the fused rollout step (rows r0 .. r0+AS_ROWS-1 of this CTA; the row with n == 0 acts for its match):
+// state / filled at t, reward / terminated at t-1.
+__device__ __forceinline__ void rollout_match_fields(const RolloutIO &io, int r0, int rows, int N, int tid, int nthreads) {
+    for (int r = 0; r < AS_ROWS; ++r) {
+        const int row = r0 + r;
+        if (row >= rows) break;
+        const int b = row / N;
+        if (row - b * N != 0) continue;
+        for (int k = tid; k < io.S; k += nthreads) io.state_t[(int64_t)b * io.state_sb + k] = io.env_state[(int64_t)b * io.env_state_sb + k];
+        if (tid == 0) {
+            io.filled_t[(int64_t)b * io.filled_sb] = 1;
+            if (io.prev_reward) {
+                io.reward_tm1[(int64_t)b * io.reward_sb] = io.prev_reward[b];
+                io.term_tm1[(int64_t)b * io.term_sb] = io.prev_done[b] ? 1 : 0;
+            }
+        }
     }
 }
 
@@ -132,6 +181,7 @@ struct AgentStepArgs {
     float *h_out, *q;
     int do_select;
     SelectArgs sel;
+    RolloutIO io;
 };
 
 // Latency plan: a CTA needs every weight exactly once, and nothing but the inputs depends on anything, so ALL
@@ -199,11 +249,15 @@ __global__ void __launch_bounds__(AS_THREADS, 1) k_agent_step(AgentStepArgs a) {
         if (row < a.rows) {
             const int b = row / a.N, n = row - b * a.N;
             if (a.dense) v = a.obs[(int64_t)row * a.obs_sb + k];
-            else if (k < a.OBS) v = a.obs[(int64_t)b * a.obs_sb + (int64_t)n * a.OBS + k];
+            else if (k < a.OBS) {
+                v = a.obs[(int64_t)b * a.obs_sb + (int64_t)n * a.OBS + k];
+                if (a.io.enabled) a.io.obs_t[(int64_t)b * a.io.obs_sb + (int64_t)n * a.OBS + k] = v;   // pre-transition update of step t
+            }
             else if (a.onehot) v = a.onehot[(int64_t)b * a.onehot_sb + (int64_t)n * a.A + (k - a.OBS)];
         }
         in_s[r * ldin + k] = v;
     }
+    if (a.io.enabled) rollout_match_fields(a.io, r0, a.rows, a.N, tid, AS_THREADS);
     for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
         int r = idx >> 6, row = r0 + r;
         h_s[idx] = (a.h_in && row < a.rows) ? a.h_in[(int64_t)row * HID + (idx & 63)] : 0.0f;
@@ -291,7 +345,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) k_agent_step(AgentStepArgs a) {
     // ---- epsilon-greedy selection: one warp per row
     {
         int row = r0 + warp;
-        if (row < a.rows) select_row(a.sel, row, a.A, lane, lane < a.A ? q_s[warp * 32 + lane] : 0.0f);
+        if (row < a.rows) select_row(a.sel, row, a.A, lane, lane < a.A ? q_s[warp * 32 + lane] : 0.0f, a.io.enabled ? &a.io : nullptr);
     }
 }
 
@@ -319,11 +373,15 @@ __global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs 
         if (row < a.rows) {
             const int b = row / a.N, n = row - b * a.N;
             if (a.dense) v = a.obs[(int64_t)row * a.obs_sb + k];
-            else if (k < a.OBS) v = a.obs[(int64_t)b * a.obs_sb + (int64_t)n * a.OBS + k];
+            else if (k < a.OBS) {
+                v = a.obs[(int64_t)b * a.obs_sb + (int64_t)n * a.OBS + k];
+                if (a.io.enabled) a.io.obs_t[(int64_t)b * a.io.obs_sb + (int64_t)n * a.OBS + k] = v;   // pre-transition update of step t
+            }
             else if (a.onehot) v = a.onehot[(int64_t)b * a.onehot_sb + (int64_t)n * a.A + (k - a.OBS)];
         }
         in_s[r * ldin + k] = v;
     }
+    if (a.io.enabled) rollout_match_fields(a.io, r0, a.rows, a.N, tid, AS_THREADS);
     for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
         int r = idx >> 6, row = r0 + r;
         h_s[idx] = (a.h_in && row < a.rows) ? a.h_in[(int64_t)row * HID + (idx & 63)] : 0.0f;
@@ -410,6 +468,6 @@ __global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs 
     // ---- epsilon-greedy selection: one warp per row
     {
         int row = r0 + warp;
-        if (row < a.rows) select_row(a.sel, row, a.A, lane, lane < a.A ? q_s[warp * 32 + lane] : 0.0f);
+        if (row < a.rows) select_row(a.sel, row, a.A, lane, lane < a.A ? q_s[warp * 32 + lane] : 0.0f, a.io.enabled ? &a.io : nullptr);
     }
 }

@@ -95,6 +95,26 @@ extern "C" int mal_profile_end(char *out, int64_t out_len) {
     return 0;
 }
 
+// Like mal_profile_end, but one line per LAUNCH in issue order: "<name> <start_us> <end_us>\n" relative to the first
+// recorded launch (events on different streams share the device's clock): the overlapped timeline of a step.
+extern "C" int mal_profile_end_timeline(char *out, int64_t out_len) {
+    g_prof_on = false;
+    MAL_REQUIRE(out && out_len > 0, "mal_profile_end_timeline: bad buffer");
+    MAL_CUDA(cudaDeviceSynchronize());
+    int64_t pos = 0;
+    out[0] = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        float t0 = 0.f, t1 = 0.f;
+        MAL_CUDA(cudaEventElapsedTime(&t0, g_prof_ev[0][0], g_prof_ev[i][0]));
+        MAL_CUDA(cudaEventElapsedTime(&t1, g_prof_ev[0][0], g_prof_ev[i][1]));
+        int w = snprintf(out + pos, (size_t)(out_len - pos), "%s %.3f %.3f\n", g_prof_name[i], t0 * 1e3, t1 * 1e3);
+        if (w < 0 || pos + w >= out_len) break;
+        pos += w;
+    }
+    g_prof_n = 0;
+    return 0;
+}
+
 extern "C" int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions) { return agent_layout(d_in, n_actions).total; }
 extern "C" int64_t mal_mixer_param_count(int32_t mixer, int32_t S, int32_t N, int32_t E, int32_t HE) {
     return mixer_layout(mixer, S, N, E, HE).total;
@@ -285,6 +305,28 @@ extern "C" int mal_eps_greedy_select(const float *q, int64_t q_ld, int32_t rows,
     return 0;
 }
 
+static int launch_agent_step(AgentStepArgs &a, int Kin, cudaStream_t stream) {
+    const size_t smem = sizeof(float) * (size_t)(AS_ROWS * (Kin + 1) + AS_ROWS * HID * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
+    MAL_REQUIRE(smem <= 200 * 1024 && Kin <= 32 * AS_FC1_MAXK, "mal_agent_step: input width %d too large (max %d)", Kin,
+                32 * AS_FC1_MAXK);
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    const int ctas = (a.rows + AS_ROWS - 1) / AS_ROWS;
+    if (ctas <= 2 * sms) {   // latency-bound regime (rollouts): all weights prefetched into registers
+        static size_t attr[MAL_MAX_DEV];
+        if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step, smem, attr)) return rc;
+        ProfScope _ps("k_agent_step", stream);
+        k_agent_step<<<ctas, AS_THREADS, smem, stream>>>(a);
+    } else {
+        static size_t attr[MAL_MAX_DEV];
+        if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step_stream, smem, attr)) return rc;
+        ProfScope _ps("k_agent_step", stream);
+        k_agent_step_stream<<<ctas, AS_THREADS, smem, stream>>>(a);
+    }
+    MAL_LAUNCH_CHECK("k_agent_step");
+    return 0;
+}
+
 extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t obs_dim, int32_t n_actions,
                               int32_t dense_input, const float *obs, int64_t obs_sb, const float *last_onehot,
                               int64_t onehot_sb, const float *h_in, float *h_out, float *q, const mal_select_t *sel,
@@ -293,32 +335,42 @@ extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents
     MAL_REQUIRE(n_actions >= 1 && n_actions <= MAL_MAX_ACTIONS, "n_actions must be in [1, %d]", MAL_MAX_ACTIONS);
     MAL_REQUIRE(n_agents >= 1 && obs_dim >= 1, "mal_agent_step: bad dims");
     AgentStepArgs a;
+    memset(&a, 0, sizeof(a));
     a.params = agent; a.rows = rows; a.N = n_agents; a.OBS = obs_dim; a.A = n_actions;
     a.dense = dense_input ? 1 : 0;
     a.obs = obs; a.obs_sb = obs_sb; a.onehot = dense_input ? nullptr : last_onehot; a.onehot_sb = onehot_sb;
     a.h_in = h_in; a.h_out = h_out; a.q = q; a.do_select = sel ? 1 : 0;
-    memset(&a.sel, 0, sizeof(a.sel));
     if (sel) if (int rc = fill_select(sel, rows, n_agents, n_actions, &a.sel)) return rc;
-    const int Kin = dense_input ? obs_dim : obs_dim + n_actions;
-    const size_t smem = sizeof(float) * (size_t)(AS_ROWS * (Kin + 1) + AS_ROWS * HID * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
-    MAL_REQUIRE(smem <= 200 * 1024 && Kin <= 32 * AS_FC1_MAXK, "mal_agent_step: input width %d too large (max %d)", Kin,
-                32 * AS_FC1_MAXK);
-    int sms, tps;
-    if (device_sm_count(&sms, &tps)) return 2;
-    const int ctas = (rows + AS_ROWS - 1) / AS_ROWS;
-    if (ctas <= 2 * sms) {   // latency-bound regime (rollouts): all weights prefetched into registers
-        static size_t attr[MAL_MAX_DEV];
-        if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step, smem, attr)) return rc;
-        ProfScope _ps("k_agent_step", (cudaStream_t)stream);
-        k_agent_step<<<ctas, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
-    } else {
-        static size_t attr[MAL_MAX_DEV];
-        if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step_stream, smem, attr)) return rc;
-        ProfScope _ps("k_agent_step", (cudaStream_t)stream);
-        k_agent_step_stream<<<ctas, AS_THREADS, smem, (cudaStream_t)stream>>>(a);
-    }
-    MAL_LAUNCH_CHECK("k_agent_step");
-    return 0;
+    return launch_agent_step(a, dense_input ? obs_dim : obs_dim + n_actions, (cudaStream_t)stream);
+}
+
+extern "C" int mal_rollout_step(const float *agent, int32_t bs, int32_t n_agents, int32_t obs_dim, int32_t n_actions,
+                                const mal_rollout_io_t *io, const float *h_in, float *h_out, float *q, const mal_select_t *sel,
+                                void *stream) {
+    MAL_REQUIRE(agent && io && sel && h_out && q && bs > 0, "mal_rollout_step: bad arguments");
+    MAL_REQUIRE(n_actions >= 1 && n_actions <= MAL_MAX_ACTIONS, "n_actions must be in [1, %d]", MAL_MAX_ACTIONS);
+    MAL_REQUIRE(n_agents >= 1 && obs_dim >= 1 && io->state_dim >= 1, "mal_rollout_step: bad dims");
+    MAL_REQUIRE(io->env_state && io->env_avail && io->env_obs && io->state_t && io->avail_t && io->obs_t && io->filled_t &&
+                    io->actions_t && io->onehot_t, "mal_rollout_step: environment / batch pointers missing");
+    MAL_REQUIRE(!io->prev_reward || (io->prev_done && io->reward_tm1 && io->term_tm1), "mal_rollout_step: previous-step fields missing");
+    AgentStepArgs a;
+    memset(&a, 0, sizeof(a));
+    const int rows = bs * n_agents;
+    a.params = agent; a.rows = rows; a.N = n_agents; a.OBS = obs_dim; a.A = n_actions; a.dense = 0;
+    a.obs = io->env_obs; a.obs_sb = io->env_obs_sb; a.onehot = io->onehot_tm1; a.onehot_sb = io->onehot_tm1_sb;
+    a.h_in = h_in; a.h_out = h_out; a.q = q; a.do_select = 1;
+    mal_select_t s2 = *sel;
+    s2.avail = io->env_avail; s2.avail_sb = io->env_avail_sb;
+    if (int rc = fill_select(&s2, rows, n_agents, n_actions, &a.sel)) return rc;
+    RolloutIO &r = a.io;
+    r.enabled = 1; r.S = io->state_dim;
+    r.env_state = io->env_state; r.env_state_sb = io->env_state_sb; r.alive = io->alive;
+    r.prev_reward = io->prev_reward; r.prev_done = io->prev_done;
+    r.state_t = io->state_t; r.state_sb = io->state_sb; r.avail_t = io->avail_t; r.avail_sb = io->avail_sb;
+    r.obs_t = io->obs_t; r.obs_sb = io->obs_sb; r.filled_t = (long long *)io->filled_t; r.filled_sb = io->filled_sb;
+    r.actions_t = (long long *)io->actions_t; r.actions_sb = io->actions_sb; r.onehot_t = io->onehot_t; r.onehot_sb = io->onehot_sb;
+    r.reward_tm1 = io->reward_tm1; r.reward_sb = io->reward_sb; r.term_tm1 = io->term_tm1; r.term_sb = io->term_sb;
+    return launch_agent_step(a, obs_dim + n_actions, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ from ..components.episode_batch import EpisodeBatch
 
 
 class BatchedEpisodeStepper:
-    def __init__(self, args, logger, env, log_start_t=0, sync_every=1):
+    def __init__(self, args, logger, env, log_start_t=0, sync_every=1, fuse=True):
         self.args = args
         self.logger = logger
         self.env = env
@@ -35,6 +35,7 @@ class BatchedEpisodeStepper:
         self.t_env = 0
         self.log_start_t = log_start_t
         self.sync_every = max(1, int(sync_every))
+        self.fuse = bool(fuse)
         self.home_mac = self.away_mac = None
         self.home_batch = self.away_batch = None
         self.new_batch_fn = None
@@ -75,8 +76,9 @@ class BatchedEpisodeStepper:
         self.env.reset()
         self.t = 0
 
-    def run(self, test_mode=False):
-        """Run B matches to their ends.  Returns (home_batch, env_info) or (home_batch, away_batch, env_info)."""
+    def run(self, test_mode=False, draws=None):
+        """Run B matches to their ends.  Returns (home_batch, env_info) or (home_batch, away_batch, env_info).
+        `draws` (tests): callable (team, t) -> (u [B, N], e [B*N, A]) of injected random draws for the selector."""
         if self.home_mac is None:
             raise RuntimeError("MultiAgentControllerNotInitialized")     # exceptions/runner_exceptions.py
         self.reset()
@@ -91,33 +93,52 @@ class BatchedEpisodeStepper:
         steps = th.zeros(B, dtype=th.long, device=dev)
         env_info = {}
         views = [bt.data.transition_data for bt in batches]        # strided views into the packed episode records
+        # one launch per team and timestep when the controller offers the fused rollout step (pre-transition update +
+        # previous step's reward / terminated + act-select + actions / one-hot), else the separate calls
+        fused = [self.fuse and hasattr(m, "rollout_step") and m._fusable() and bt._layout is not None
+                 for m, bt in zip(macs, batches)]
+        prev_rewards, prev_done = None, None
         t = 0
         while True:
-            # every match writes index t unconditionally (a match that has ended still selects on valid inputs: the
-            # selector rejects all-zero avail rows); what lies past a match's end is cleared once, after the loop
-            for k, tv in enumerate(views):
-                pre = self.env.observe(k)
-                tv["state"][:, t].copy_(pre["state"])
-                tv["avail_actions"][:, t].copy_(pre["avail_actions"])
-                tv["obs"][:, t].copy_(pre["obs"])
             acts = []
-            for mac, batch, tv in zip(macs, batches, views):
-                a, _ = mac.select_actions(batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+            for k, (mac, batch, tv) in enumerate(zip(macs, batches, views)):
+                pre = self.env.observe(k)
+                kw = {}
+                if draws is not None:
+                    kw["u"], kw["e"] = draws(k, t)
+                if fused[k]:
+                    # every match writes index t unconditionally; a match that has ended selects on a dummy avail row and
+                    # what lies past its end is cleared once, after the loop
+                    a, _ = mac.rollout_step(batch, t, self.t_env, pre, prev=(prev_rewards[k], prev_done) if t > 0 else None,
+                                            alive=running_prev, test_mode=test_mode, **kw)
+                else:
+                    tv["state"][:, t].copy_(pre["state"])
+                    avail = pre["avail_actions"]
+                    if t > 0:                                        # ended matches: a valid dummy row (never all-zero)
+                        avail = avail.clone()
+                        avail[:, :, 0] |= (~running_prev).to(avail.dtype).view(B, 1)
+                    tv["avail_actions"][:, t].copy_(avail)
+                    tv["obs"][:, t].copy_(pre["obs"])
+                    a, _ = mac.select_actions(batch, t_ep=t, t_env=self.t_env, test_mode=test_mode, **kw)
+                    tv["actions"][:, t].copy_(a.view_as(tv["actions"][:, t]))
+                    for key, (new_key, transforms) in batch.preprocess.items():       # actions -> actions_onehot
+                        v = tv[key][:, t]
+                        for tr in transforms:
+                            v = tr.transform(v)
+                        tv[new_key][:, t].copy_(v)
+                    if t > 0:
+                        tv["reward"][:, t - 1, 0].copy_(prev_rewards[k])
+                        tv["terminated"][:, t - 1, 0].copy_(prev_done)
                 acts.append(a)
-                tv["actions"][:, t].copy_(a.view_as(tv["actions"][:, t]))
-                for key, (new_key, transforms) in batch.preprocess.items():       # actions -> actions_onehot
-                    v = tv[key][:, t]
-                    for tr in transforms:
-                        v = tr.transform(v)
-                    tv[new_key][:, t].copy_(v)
             if t == self.episode_limit:
                 break
+            # NB the environment keeps being stepped for matches that have already ended (lock-step batch); their
+            # outcome is ignored: `running` masks it out of the returns and the data is cleared below
             rewards, done, env_info = self.env.step(acts)
-            for k, tv in enumerate(views):
-                tv["reward"][:, t, 0].copy_(rewards[k])
-                tv["terminated"][:, t, 0].copy_(done)
+            for k in range(len(macs)):
                 returns[k] += rewards[k] * running
             steps += running
+            prev_rewards, prev_done = rewards, done
             running_prev = running
             running = running & ~done
             t += 1

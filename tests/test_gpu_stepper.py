@@ -78,3 +78,60 @@ def test_training_mode_advances_t_env_and_feeds_the_buffer():
     L = int(env.lengths[0])
     a = batch["actions"][0, :L, :, 0].sum(-1).float()
     assert th.allclose(batch["reward"][0, :L, 0], env._noise[0, 0, :L] + 0.01 * a)
+
+
+@pytest.mark.parametrize("n_teams", [1, 2])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_rollout_against_the_reference_loop_oracle(n_teams, fuse):
+    """SURVEY.md 8(f1) against an ORACLE: oracle/rollout_oracle.py restates EpisodeStepper.run (steppers/episode_stepper.py:
+    86-186) and SelfPlayStepper.run (self_play_stepper.py:44-147) for one match on numpy.  B lock-step matches on the
+    device -- through the fused one-launch rollout step and through the separate update / select_actions calls -- must
+    leave, match by match, exactly the episode batch the reference loop leaves, with exploration on (injected draws)."""
+    from oracle import rollout_oracle as RO
+    from tests.gpu_helpers import np_params
+    args, scheme, groups, pre, home, away = _system(3)
+    macs = [home, away][:n_teams]
+    B, T_ENV = 5, 25000                                           # epsilon = 0.525: random and greedy picks both occur
+    env = SyntheticVecEnv(B, N, A, OBS, S, LIMIT, n_teams=n_teams, seed=11, device=DEV, min_len=3)
+    gen = th.Generator().manual_seed(5)
+    U = [[th.rand(B, N, generator=gen) for _ in range(LIMIT + 1)] for _ in range(n_teams)]
+    E = [[th.empty(B * N, A).exponential_(generator=gen) for _ in range(LIMIT + 1)] for _ in range(n_teams)]
+    st = BatchedEpisodeStepper(args, None, env, sync_every=1, fuse=fuse)
+    st.initialize(scheme, groups, pre, home, away if n_teams == 2 else None)
+    st.t_env = T_ENV
+    out = st.run(test_mode=False, draws=lambda k, t: (U[k][t], E[k][t]))
+    batches, info = out[:-1], out[-1]
+    lens = env.lengths.cpu().numpy()
+    assert st.t_env == T_ENV + int(lens.sum()) and len(set(lens.tolist())) > 1
+    n_random = 0
+    for b in range(B):
+        penv = RO.PlaybackEnv(env._obs[:, b].cpu().numpy(), env._state[:, b].cpu().numpy(), env._avail[:, b].cpu().numpy(),
+                              env._noise[:, b].cpu().numpy(), lens[b], LIMIT)
+        omacs = [RO.OracleMAC(np_params(m.agent), N, A, dtype=np.float64,
+                              draws=(lambda t, k=k: (U[k][t][b].numpy(), E[k][t].view(B, N, A)[b].numpy())))
+                 for k, m in enumerate(macs)]
+        ref_batches, ref_returns, ref_steps = RO.run_episode(penv, omacs, (N, A, OBS, S), t_env=T_ENV, test_mode=False)
+        assert ref_steps == lens[b] == int(info["episode_steps"][b])
+        for k in range(n_teams):
+            for key, ref in ref_batches[k].items():
+                got = batches[k][key][b].cpu().numpy()
+                if key == "reward":
+                    assert np.allclose(got, ref, rtol=1e-6, atol=1e-6), (key, b, k)
+                else:
+                    assert np.array_equal(got, ref), (key, b, k)              # bit-exact: indices, masks, copied floats
+            assert abs(float(info["episode_returns"][k][b]) - float(ref_returns[k])) <= 1e-5 * max(1.0, abs(float(ref_returns[k])))
+            u = np.stack([U[k][t][b].numpy() for t in range(lens[b] + 1)])
+            n_random += int((u < 0.525).sum())
+    assert n_random > 0
+
+
+def test_fused_rollout_step_is_one_launch_per_team_and_timestep():
+    from ma_league_b200 import _native as nat
+    args, scheme, groups, pre, home, away = _system(4)
+    env = SyntheticVecEnv(4, N, A, OBS, S, LIMIT, n_teams=2, seed=2, device=DEV, min_len=LIMIT)
+    st = BatchedEpisodeStepper(args, None, env, sync_every=4)
+    st.initialize(scheme, groups, pre, home, away)
+    home.action_selector.validate = away.action_selector.validate = False
+    n0 = nat.lib().mal_launch_count()
+    st.run(test_mode=True)
+    assert nat.lib().mal_launch_count() - n0 == 2 * (LIMIT + 1)
