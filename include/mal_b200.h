@@ -122,6 +122,7 @@ int mal_profile_end_timeline(char *out, int64_t out_len);
 
 /* Parameter counts in state_dict order (drqn_agent.py:21-23, qmix.py:16-39). */
 int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions);
+int64_t mal_agent_param_count_kind(int32_t agent_kind, int32_t d_in, int32_t n_actions);   /* MAL_AGENT_DQN: dqn_agent.py:24-25 */
 int64_t mal_mixer_param_count(int32_t mixer, int32_t state_dim, int32_t n_agents, int32_t embed, int32_t hyper_embed);
 
 int mal_learner_plan(const mal_batch_t *batch, const mal_learner_cfg_t *cfg, mal_plan_t *plan);
@@ -192,6 +193,12 @@ int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents, int32_t o
                    void *stream);
 /* dense_input != 0: `obs` is the already assembled agent input [rows, obs_dim] with row stride obs_sb
  * (DRQNAgentNetwork.forward(inputs, hidden_state), drqn_agent.py:29-35); obs_dim is then the full input width. */
+
+/* The same for the feed-forward DQNAgentNetwork (marl/modules/agents/dqn_agent.py:9-37: q = fc2(relu(fc1(inputs))), the
+ * hidden state is passed through untouched); flat parameters fc1.weight | fc1.bias | fc2.weight | fc2.bias. */
+int mal_dqn_step(const float *agent, int32_t rows, int32_t n_agents, int32_t obs_dim, int32_t n_actions,
+                 int32_t dense_input, const float *obs, int64_t obs_sb, const float *last_onehot, int64_t onehot_sb,
+                 float *q, const mal_select_t *sel, void *stream);
 
 /* One rollout timestep of `bs` lock-step matches in ONE launch: the loop body of EpisodeStepper.run / SelfPlayStepper.run
  * (steppers/episode_stepper.py:110-142,177-186; steppers/self_play_stepper.py:64-106) for one team --

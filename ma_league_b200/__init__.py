@@ -11,9 +11,9 @@ from .components.transforms import OneHot
 from .components.action_selectors import EpsilonGreedyActionSelector, REGISTRY as action_REGISTRY
 from .controllers import BasicMAC, EnsembleMAC, REGISTRY as mac_REGISTRY
 from .learners import QLearner, REGISTRY as learner_REGISTRY
-from .modules.agents import DRQNAgentNetwork, REGISTRY as agent_REGISTRY
+from .modules.agents import DRQNAgentNetwork, DQNAgentNetwork, REGISTRY as agent_REGISTRY
 from .modules.mixers import QMixer, VDNMixer
 
 __all__ = ["EpisodeBatch", "ReplayBuffer", "OneHot", "EpsilonGreedyActionSelector", "BasicMAC", "QLearner",
-           "EnsembleMAC", "DRQNAgentNetwork", "QMixer", "VDNMixer", "mac_REGISTRY", "learner_REGISTRY", "agent_REGISTRY",
+           "EnsembleMAC", "DRQNAgentNetwork", "DQNAgentNetwork", "QMixer", "VDNMixer", "mac_REGISTRY", "learner_REGISTRY", "agent_REGISTRY",
            "action_REGISTRY"]

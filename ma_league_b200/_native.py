@@ -87,6 +87,9 @@ _PROTOS = {
                                    C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int32, C.c_void_p]),
     "mal_agent_param_count": (C.c_int64, [C.c_int32, C.c_int32]),
+    "mal_agent_param_count_kind": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "mal_dqn_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                               C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Select), C.c_void_p]),
     "mal_mixer_param_count": (C.c_int64, [C.c_int32] * 5),
     "mal_learner_plan": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan)]),
     "mal_learner_forward": (C.c_int, [C.POINTER(Batch), C.POINTER(LearnerCfg), C.POINTER(Plan), C.c_void_p,

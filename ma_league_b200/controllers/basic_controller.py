@@ -16,6 +16,7 @@ from ..components.action_selectors import make_select_struct
 from ..exceptions import HiddenStateNotInitialized
 from ..modules.agents import REGISTRY as agent_REGISTRY
 from ..modules.agents.drqn_agent import DRQNAgentNetwork
+from ..modules.agents.dqn_agent import DQNAgentNetwork
 from .multi_agent_controller import MultiAgentController
 
 
@@ -51,7 +52,7 @@ class BasicMAC(MultiAgentController):
         `alive` [bs] bool: matches that have ended select on a dummy avail row.  Returns (actions, is_greedy) like
         `select_actions`.  Needs a packed device batch and the fused agent (`_fusable()`); callers fall back to the
         separate calls otherwise."""
-        if not self._fusable():
+        if not self._rollout_fusable():
             raise nat.MalError("rollout_step needs the fused recurrent agent path")
         if self.hidden_states is None:
             raise HiddenStateNotInitialized()
@@ -135,6 +136,12 @@ class BasicMAC(MultiAgentController):
         return agent_outs.view(ep_batch.batch_size, self.n_agents, -1)
 
     def init_hidden(self, batch_size):
+        if isinstance(self.agent, DQNAgentNetwork):
+            # The reference's expand() of the 3-D placeholder (basic_controller.py:59-60 on dqn_agent.py:27-32) raises a
+            # RuntimeError, i.e. the "dqn" agent cannot be rolled out or trained there; here the placeholder is a
+            # [bs, N, 1] zero tensor that nothing reads (dqn_agent.py:34-37 passes it through).
+            self.hidden_states = th.zeros(batch_size, self.n_agents, 1, device=self.args.device)
+            return
         self.hidden_states = self.agent.init_hidden().unsqueeze(0).expand(batch_size, self.n_agents, -1)
 
     def update_trained_steps(self, update):
@@ -192,8 +199,11 @@ class BasicMAC(MultiAgentController):
     def _fusable(self):
         cls = type(self)
         return (cls._build_inputs is BasicMAC._build_inputs and cls._compute_agent_outputs is BasicMAC._compute_agent_outputs
-                and isinstance(self.agent, DRQNAgentNetwork) and self.args.obs_last_action and self.args.obs_agent_id
-                and self.agent_output_type == "q")
+                and isinstance(self.agent, (DRQNAgentNetwork, DQNAgentNetwork)) and self.args.obs_last_action
+                and self.args.obs_agent_id and self.agent_output_type == "q")
+
+    def _rollout_fusable(self):
+        return self._fusable() and isinstance(self.agent, DRQNAgentNetwork)
 
     def _step(self, ep_batch, t, select_struct):
         if self.hidden_states is None:
@@ -212,6 +222,14 @@ class BasicMAC(MultiAgentController):
             last_ptr, last_sb = oh.data_ptr() + 4 * (t - 1) * oh.stride(1), oh.stride(0)
         rows = B * N
         dev = obs_all.device
+        if isinstance(self.agent, DQNAgentNetwork):      # feed-forward agent: no hidden state to read or write
+            q = th.empty(B, N, A, dtype=th.float32, device=dev)
+            flat = self.agent.flat_params()
+            with nat.on_device(dev):
+                nat.check(nat.lib().mal_dqn_step(
+                    flat.data_ptr(), rows, N, OBS, A, 0, obs_ptr, obs_all.stride(0), last_ptr, last_sb, q.data_ptr(),
+                    C.byref(select_struct) if select_struct is not None else None, nat.current_stream(dev)), "mal_dqn_step")
+            return q
         h_in = self.hidden_states
         if h_in.dim() == 3 and h_in.stride(0) == 0 and h_in.stride(1) == 0:   # fresh init_hidden(): zeros
             h_ptr = None

@@ -173,6 +173,7 @@ __device__ __forceinline__ float warp_fold8(const float (&v)[8], int lane) {
 
 struct AgentStepArgs {
     const float *params;
+    int kind;                                   // MAL_AGENT_RNN | MAL_AGENT_DQN (feed-forward: no hidden state; stream kernel only)
     int rows, N, OBS, A;
     int dense;                                  // 1: obs is the full [rows, d_in] agent input (row stride obs_sb)
     const float *obs; int64_t obs_sb;
@@ -353,7 +354,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) k_agent_step(AgentStepArgs a) {
 // instead of being parked in 255 registers per thread.
 __global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs a) {
     extern __shared__ float as_smem[];
-    const AgentLayout L = agent_layout(a.dense ? a.OBS : a.OBS + a.A + a.N, a.A);
+    const AgentLayout L = agent_layout(a.dense ? a.OBS : a.OBS + a.A + a.N, a.A, a.kind);
+    const bool rnn = a.kind == MAL_AGENT_RNN;
     const int Kin = a.dense ? a.OBS : a.OBS + a.A;
     const int ldin = Kin + 1;
     float *in_s = as_smem;                       // [8][ldin]
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs 
     if (a.io.enabled) rollout_match_fields(a.io, r0, a.rows, a.N, tid, AS_THREADS);
     for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
         int r = idx >> 6, row = r0 + r;
-        h_s[idx] = (a.h_in && row < a.rows) ? a.h_in[(int64_t)row * HID + (idx & 63)] : 0.0f;
+        h_s[idx] = (rnn && a.h_in && row < a.rows) ? a.h_in[(int64_t)row * HID + (idx & 63)] : 0.0f;
     }
     __syncthreads();
 
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs 
     __syncthreads();
 
     // ---- gi = W_ih x + b_ih ; gh = W_hh h + b_hh   (384 weight rows of 64)
-    {
+    if (rnn) {
         float xv[8][2], hv[8][2];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -430,7 +432,10 @@ __global__ void __launch_bounds__(AS_THREADS) k_agent_step_stream(AgentStepArgs 
     }
     __syncthreads();
 
-    // ---- gate math: r,z,n ; h' = n + z (h - n)
+    // ---- gate math: r,z,n ; h' = n + z (h - n)        (DQN: q = fc2(relu(fc1(.))), dqn_agent.py:34-37)
+    if (!rnn) {
+        for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) hn_s[idx] = x_s[idx];
+    } else
     for (int idx = tid; idx < AS_ROWS * HID; idx += AS_THREADS) {
         int r = idx >> 6, i = idx & 63, row = r0 + r;
         const float *g = g_s + r * 2 * G3;

@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) k_transpose_w(TransArgs a) {
 struct HeadArgs {
     const float *params[2];
     const float *hout[2];
-    int B, TT, N, A, R, d_in, double_q;
+    int B, TT, N, A, R, d_in, double_q, kind;
     mal_field_t actions, avail;
     float *mac_out, *target_mac_out;   // [B,TT,N,A] or null
     float *chosen, *target_max;        // [B,T,N]
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
     extern __shared__ __align__(16) float4 qh_smem[];        // hs_s [QH_HS_F4] | w2_s [2][w2_pitch] | q_s [2][64*qpitch] | av_s [64*qpitch]
     __shared__ float b2_s[2][MAL_MAX_ACTIONS];
     float4 *hs_s = qh_smem;
-    const AgentLayout L = agent_layout(a.d_in, a.A);
+    const AgentLayout L = agent_layout(a.d_in, a.A, a.kind);
     const int tid = threadIdx.x;
     const int Apad = (a.A + 3) & ~3, w2_pitch = qh_w2_pitch(a.A), qpitch = qh_q_pitch(a.A);
     float *w2_all = reinterpret_cast<float *>(qh_smem + QH_HS_F4);
@@ -590,7 +590,8 @@ __global__ void __launch_bounds__(128, 3) k_q_head(HeadArgs a) {
 // =============================================================================================
 #define MIX_NSTAT 6   // sum mtd^2, sum |mtd|, sum q_tot*m, sum targets*m, sum m, count(m != 0)
 struct MixArgs {
-    int mixer, B, T, N, E, HE, S, R, A, d_in;
+    int mixer, B, T, N, E, HE, S, R, A, d_in, kind;
+    const float *relu_src;             // feed-forward agent: x = relu(fc1) [TT*R,64]; the head seed is multiplied by (x > 0)
     const float *y1[2], *a2[2];        // online, target
     const float *mparams[2];
     const float *agent;                // online agent parameters (fc2.weight for the dh injection)
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(256, 4) k_mix_td(MixArgs a) {
     const int ld1 = two ? 2 * a.HE + 2 * a.E : 2 * a.E;
     const int ld2 = a.E * a.N + a.E;
     const int yo = two ? 2 * a.HE : 0;                    // column of [b1 | v1] inside a y1 row
-    const float *w2p = a.agent + agent_layout(a.d_in, a.A).fc2_w;
+    const float *w2p = a.agent + agent_layout(a.d_in, a.A, a.kind).fc2_w;
     const bool act = lane < a.E;
     float st[MIX_NSTAT] = {0, 0, 0, 0, 0, 0};
     float dv2w = 0, dv2b = 0;
@@ -702,11 +703,17 @@ __global__ void __launch_bounds__(256, 4) k_mix_td(MixArgs a) {
         // gather + fc2 backward: d h_t[row n] = d_chosen[n] * fc2.weight[a_t[n], :]   (consumed by the BPTT kernel)
         auto head_inject = [&](float dq_lane) {
             float *dh = a.dh_head + ((int64_t)t * a.R + (int64_t)b * a.N) * HID;
+            const float *xr = a.relu_src ? a.relu_src + ((int64_t)t * a.R + (int64_t)b * a.N) * HID : nullptr;
 #pragma unroll 8
             for (int n = 0; n < a.N; ++n) {
                 const float dq = __shfl_sync(0xffffffffu, dq_lane, n);
                 const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w2p + (int64_t)__shfl_sync(0xffffffffu, act_mine, n) * HID) + lane);
-                reinterpret_cast<float2 *>(dh + (int64_t)n * HID)[lane] = make_float2(dq * w2.x, dq * w2.y);
+                float2 v = make_float2(dq * w2.x, dq * w2.y);
+                if (xr) {                                     // d relu(fc1): the seed becomes d(fc1 pre-activation)
+                    const float2 xv = reinterpret_cast<const float2 *>(xr + (int64_t)n * HID)[lane];
+                    v.x = xv.x > 0.0f ? v.x : 0.0f; v.y = xv.y > 0.0f ? v.y : 0.0f;
+                }
+                reinterpret_cast<float2 *>(dh + (int64_t)n * HID)[lane] = v;
             }
         };
         if (a.mixer == MAL_MIXER_VDN) {

@@ -116,6 +116,7 @@ extern "C" int mal_profile_end_timeline(char *out, int64_t out_len) {
 }
 
 extern "C" int64_t mal_agent_param_count(int32_t d_in, int32_t n_actions) { return agent_layout(d_in, n_actions).total; }
+extern "C" int64_t mal_agent_param_count_kind(int32_t kind, int32_t d_in, int32_t n_actions) { return agent_layout(d_in, n_actions, kind).total; }
 extern "C" int64_t mal_mixer_param_count(int32_t mixer, int32_t S, int32_t N, int32_t E, int32_t HE) {
     return mixer_layout(mixer, S, N, E, HE).total;
 }
@@ -312,7 +313,7 @@ static int launch_agent_step(AgentStepArgs &a, int Kin, cudaStream_t stream) {
     int sms, tps;
     if (device_sm_count(&sms, &tps)) return 2;
     const int ctas = (a.rows + AS_ROWS - 1) / AS_ROWS;
-    if (ctas <= 2 * sms) {   // latency-bound regime (rollouts): all weights prefetched into registers
+    if (ctas <= 2 * sms && a.kind == MAL_AGENT_RNN) {   // latency-bound regime (rollouts): all weights prefetched into registers
         static size_t attr[MAL_MAX_DEV];
         if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step, smem, attr)) return rc;
         ProfScope _ps("k_agent_step", stream);
@@ -340,6 +341,24 @@ extern "C" int mal_agent_step(const float *agent, int32_t rows, int32_t n_agents
     a.dense = dense_input ? 1 : 0;
     a.obs = obs; a.obs_sb = obs_sb; a.onehot = dense_input ? nullptr : last_onehot; a.onehot_sb = onehot_sb;
     a.h_in = h_in; a.h_out = h_out; a.q = q; a.do_select = sel ? 1 : 0;
+    if (sel) if (int rc = fill_select(sel, rows, n_agents, n_actions, &a.sel)) return rc;
+    return launch_agent_step(a, dense_input ? obs_dim : obs_dim + n_actions, (cudaStream_t)stream);
+}
+
+// DQNAgentNetwork.forward (dqn_agent.py:34-37: q = fc2(relu(fc1(inputs))), no hidden state) through BasicMAC's input
+// assembly, with the optional epsilon-greedy tail; same argument meaning as mal_agent_step.
+extern "C" int mal_dqn_step(const float *agent, int32_t rows, int32_t n_agents, int32_t obs_dim, int32_t n_actions,
+                            int32_t dense_input, const float *obs, int64_t obs_sb, const float *last_onehot,
+                            int64_t onehot_sb, float *q, const mal_select_t *sel, void *stream) {
+    MAL_REQUIRE(agent && obs && q && rows > 0, "mal_dqn_step: bad arguments");
+    MAL_REQUIRE(n_actions >= 1 && n_actions <= MAL_MAX_ACTIONS, "n_actions must be in [1, %d]", MAL_MAX_ACTIONS);
+    MAL_REQUIRE(n_agents >= 1 && obs_dim >= 1, "mal_dqn_step: bad dims");
+    AgentStepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.params = agent; a.kind = MAL_AGENT_DQN; a.rows = rows; a.N = n_agents; a.OBS = obs_dim; a.A = n_actions;
+    a.dense = dense_input ? 1 : 0;
+    a.obs = obs; a.obs_sb = obs_sb; a.onehot = dense_input ? nullptr : last_onehot; a.onehot_sb = onehot_sb;
+    a.h_in = nullptr; a.h_out = nullptr; a.q = q; a.do_select = sel ? 1 : 0;
     if (sel) if (int rc = fill_select(sel, rows, n_agents, n_actions, &a.sel)) return rc;
     return launch_agent_step(a, dense_input ? obs_dim : obs_dim + n_actions, (cudaStream_t)stream);
 }
@@ -377,7 +396,7 @@ extern "C" int mal_rollout_step(const float *agent, int32_t bs, int32_t n_agents
 // learner: planning
 // ---------------------------------------------------------------------------------------------
 struct Dims {
-    int B, TT, T, N, A, OBS, S, R, E, HE, d_in, mixer, two;
+    int B, TT, T, N, A, OBS, S, R, E, HE, d_in, mixer, two, kind;
     int64_t M1, BT;
     int ld1, ld2;
 };
@@ -390,6 +409,8 @@ static int get_dims(const mal_batch_t *b, const mal_learner_cfg_t *c, Dims *d) {
     MAL_REQUIRE(c->mixer == MAL_MIXER_VDN || c->mixer == MAL_MIXER_QMIX2 || c->mixer == MAL_MIXER_QMIX1,
                 "Mixer %d not recognised.", c->mixer);
     d->B = b->B; d->TT = b->TT; d->T = b->TT - 1; d->N = b->N; d->A = b->A; d->OBS = b->OBS; d->S = b->S;
+    MAL_REQUIRE(c->agent_kind == MAL_AGENT_RNN || c->agent_kind == MAL_AGENT_DQN, "agent kind %d not recognised", c->agent_kind);
+    d->kind = c->agent_kind;
     d->R = b->B * b->N; d->d_in = b->OBS + b->A + b->N; d->mixer = c->mixer;
     d->E = c->embed; d->HE = c->hyper_embed; d->two = (c->mixer == MAL_MIXER_QMIX2);
     if (c->mixer != MAL_MIXER_VDN) {
@@ -461,7 +482,7 @@ static PartLayout part_layout(const Dims &d, int sms) {
     }
     int64_t nm = ceil_div64(d.BT, 8); if (nm > (int64_t)sms * 4) nm = (int64_t)sms * 4; if (nm < 1) nm = 1;
     p.nblk_mix = (int)nm;
-    const int64_t P = agent_layout(d.d_in, d.A).total + mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
+    const int64_t P = agent_layout(d.d_in, d.A, d.kind).total + mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
     p.nblk_norm = (int)ceil_div64(P, GRED_EPB);
     int64_t o = 0;
     auto take = [&](int64_t n) { int64_t r = o; o += align_up64(n, 64); return r; };
@@ -492,7 +513,7 @@ extern "C" int mal_learner_plan(const mal_batch_t *batch, const mal_learner_cfg_
     memset(plan, 0, sizeof(*plan));
     int64_t o = 0;
     auto take = [&](int64_t n_elems, int64_t elem) { int64_t r = o; o += align_up64(n_elems * elem, 256); return r; };
-    plan->n_agent_params = agent_layout(d.d_in, d.A).total;
+    plan->n_agent_params = agent_layout(d.d_in, d.A, d.kind).total;
     plan->n_mixer_params = mixer_layout(d.mixer, d.S, d.N, d.E, d.HE).total;
     plan->scalars = take(64, 4);
     plan->x_on = take(d.M1 * HID, 4);   plan->x_tg = take(d.M1 * HID, 4);
@@ -705,7 +726,8 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *ws = (uint8_t *)workspace;
     auto F = [&](int64_t off) { return reinterpret_cast<float *>(ws + off); };
-    const AgentLayout AL = agent_layout(d.d_in, d.A);
+    const AgentLayout AL = agent_layout(d.d_in, d.A, d.kind);
+    const bool dqn = d.kind == MAL_AGENT_DQN;       // feed-forward agent: h := x = relu(fc1(.)), no gi / recurrence
     const MixerLayout ML = mixer_layout(d.mixer, d.S, d.N, d.E, d.HE);
     const BatchView bv = make_view(batch, d);
     float *scalars = F(plan->scalars);
@@ -723,7 +745,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
 
     // x = relu(fc1([obs | last action | agent id])) and gi = W_ih x + b_ih for every (t,b,n), both nets
     //                                                  basic_controller.py:80-92, drqn_agent.py:30-31, GRUCell input half
-    const bool fused_in = g_use_tc && g_fuse_agent_in && d.M1 < (1 << 24) && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 &&
+    const bool fused_in = !dqn && g_use_tc && g_fuse_agent_in && d.M1 < (1 << 24) && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 &&
                           (bv.obs.st & 3) == 0 && aligned16(bv.obs.ptr);
     // time-chunked forward: the recurrence over the first half of the timesteps runs while the input projection of the
     // second half is still being computed on a side stream (the recurrence is latency-bound and leaves the tensor
@@ -756,11 +778,11 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         LinGroup g; g.n = 2; g.bv = bv;
         for (int net = 0; net < 2; ++net)
             g.p[net] = lin(d.M1, d.OBS + d.A, HID, A_AGENT_IN, 0, nullptr, 0, ap[net] + AL.fc1_w, d.d_in, 0,
-                           ap[net] + AL.fc1_b, EPI_FC1, nullptr, 0, x[net], HID);
+                           ap[net] + AL.fc1_b, EPI_FC1, nullptr, 0, dqn ? hh[net] : x[net], HID);   // DQN: the "hidden state" IS relu(fc1)
         if (int rc = launch_linear(g, d.M1, d.OBS + d.A, st, "k_linear_group:fc1")) return rc;
     }
     // gi = W_ih x + b_ih
-    {
+    if (!dqn) {
         LinGroup g; g.n = 2; g.bv = bv;
         for (int net = 0; net < 2; ++net)
             g.p[net] = lin(d.M1, HID, G3, A_DENSE, 0, x[net], HID, ap[net] + AL.w_ih, HID, 0, ap[net] + AL.b_ih,
@@ -777,7 +799,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         TransArgs ta;
         memset(&ta, 0, sizeof(ta));
         float *wt = F(plan->w_t);
-        ta.in[0] = agent + AL.w_ih; ta.out[0] = wt; ta.rows[0] = G3; ta.cols[0] = HID; ta.n = 1;
+        ta.in[0] = agent + (dqn ? AL.fc1_w : AL.w_ih); ta.out[0] = wt; ta.rows[0] = dqn ? 1 : G3; ta.cols[0] = dqn ? 1 : HID; ta.n = 1;
         if (d.mixer == MAL_MIXER_QMIX2) {
             ta.in[1] = mixer + ML.w1b_w; ta.out[1] = wt + (int64_t)HID * G3; ta.rows[1] = d.E * d.N; ta.cols[1] = d.HE;
             ta.in[2] = mixer + ML.wfb_w; ta.out[2] = ta.out[1] + (int64_t)d.HE * d.E * d.N; ta.rows[2] = d.E; ta.cols[2] = d.HE;
@@ -792,7 +814,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         MAL_LAUNCH_CHECK("k_transpose_w");
     }
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
-    {
+    if (!dqn) {
         GruFwdArgs a;
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
@@ -810,7 +832,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     {
         HeadArgs a;
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.hout[net] = hh[net]; }
-        a.B = d.B; a.TT = d.TT; a.N = d.N; a.A = d.A; a.R = d.R; a.d_in = d.d_in; a.double_q = cfg->double_q;
+        a.B = d.B; a.TT = d.TT; a.N = d.N; a.A = d.A; a.R = d.R; a.d_in = d.d_in; a.double_q = cfg->double_q; a.kind = d.kind;
         a.actions = batch->actions; a.avail = batch->avail;
         a.mac_out = cfg->save_q ? F(plan->mac_out) : nullptr;
         a.target_mac_out = cfg->save_q ? F(plan->target_mac_out) : nullptr;
@@ -859,7 +881,8 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         MixArgs a;
         memset(&a, 0, sizeof(a));
         a.mixer = d.mixer; a.B = d.B; a.T = d.T; a.N = d.N; a.E = d.E; a.HE = d.HE; a.S = d.S;
-        a.R = d.R; a.A = d.A; a.d_in = d.d_in; a.agent = agent;
+        a.R = d.R; a.A = d.A; a.d_in = d.d_in; a.agent = agent; a.kind = d.kind;
+        a.relu_src = dqn ? hh[0] : nullptr;          // DQN: the head seed is d x: masked by relu'(x) right here
         for (int net = 0; net < 2; ++net) { a.y1[net] = y1[net]; a.a2[net] = a2[net]; a.mparams[net] = mp[net]; }
         a.chosen = F(plan->chosen); a.target_max = F(plan->target_max); a.mask = F(plan->mask);
         a.reward = batch->reward; a.terminated = batch->terminated; a.filled = batch->filled; a.actions = batch->actions;
@@ -1032,7 +1055,8 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *ws = (uint8_t *)workspace;
     auto F = [&](int64_t off) { return reinterpret_cast<float *>(ws + off); };
-    const AgentLayout AL = agent_layout(d.d_in, d.A);
+    const AgentLayout AL = agent_layout(d.d_in, d.A, d.kind);
+    const bool dqn = d.kind == MAL_AGENT_DQN;
     const MixerLayout ML = mixer_layout(d.mixer, d.S, d.N, d.E, d.HE);
     const BatchView bv = make_view(batch, d);
     const PartLayout pl = part_layout(d, sms);
@@ -1080,7 +1104,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
 
     // ---- main stream: BPTT recurrence
-    if (!frozen) {
+    if (!frozen && !dqn) {
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
@@ -1089,7 +1113,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads
     if (fork_to(st, s2, ss->fork_ev[2])) return 2;
-    if (!frozen) {
+    if (!frozen && !dqn) {
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.M1, HID, G3, d_g, 4 * HID, A_DENSE, 0, F(plan->x_on), HID, parts + pl.wih_w, parts + pl.wih_b, pl.nc_a, pl.rpc_a);
         // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)
@@ -1097,7 +1121,13 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         r.p[2] = red(d.M1, HID, 64, d_g + 3 * HID, 4 * HID, A_DENSE, d.R, F(plan->h_on), HID, parts + pl.whhb_w, parts + pl.whhb_b, pl.nc_a, pl.rpc_a);
         if (int rc = launch_reduce(r, s2, "k_reduce_group:agent")) return rc;
     }
-    if (!frozen) {
+    if (!frozen && dqn) {
+        // feed-forward agent: d x (masked by relu' in k_mix_td) is the head seed of the rows t < T; fc1 gradients from it
+        RedGroup r; r.n = 1; r.bv = bv;
+        r.p[0] = red((int64_t)d.T * d.R, d.d_in, HID, F(plan->dh_head), HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
+        if (int rc = launch_reduce(r, st, "k_reduce_group:agent")) return rc;
+    }
+    if (!frozen && !dqn) {
         LinGroup g; g.n = 1; g.bv = bv;
         g.p[0] = lin(d.M1, G3, HID, A_DENSE, 0, d_g, 4 * HID, F(plan->w_t), G3, 0, nullptr, EPI_MASKPOS, F(plan->x_on), HID, d_x, HID);   // W_ih^T from the forward call
         g_next_pdl = true;                       // stream predecessor: k_gru_bwd7 (W_ih staging flies under its last timesteps)
@@ -1124,12 +1154,14 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         };
         seg(AL.fc1_w, (int64_t)HID * d.d_in, parts + pl.fc1_w, pl.nc_f1, (int64_t)HID * d.d_in);
         seg(AL.fc1_b, HID, parts + pl.fc1_b, pl.nc_f1, HID);
-        seg(AL.w_ih, (int64_t)G3 * HID, parts + pl.wih_w, pl.nc_a, (int64_t)G3 * HID);
-        seg(AL.w_hh, 128 * HID, parts + pl.whha_w, pl.nc_a, 128 * HID);
-        seg(AL.w_hh + 128 * HID, 64 * HID, parts + pl.whhb_w, pl.nc_a, 64 * HID);
-        seg(AL.b_ih, G3, parts + pl.wih_b, pl.nc_a, G3);
-        seg(AL.b_hh, 128, parts + pl.whha_b, pl.nc_a, 128);
-        seg(AL.b_hh + 128, 64, parts + pl.whhb_b, pl.nc_a, 64);
+        if (!dqn) {
+            seg(AL.w_ih, (int64_t)G3 * HID, parts + pl.wih_w, pl.nc_a, (int64_t)G3 * HID);
+            seg(AL.w_hh, 128 * HID, parts + pl.whha_w, pl.nc_a, 128 * HID);
+            seg(AL.w_hh + 128 * HID, 64 * HID, parts + pl.whhb_w, pl.nc_a, 64 * HID);
+            seg(AL.b_ih, G3, parts + pl.wih_b, pl.nc_a, G3);
+            seg(AL.b_hh, 128, parts + pl.whha_b, pl.nc_a, 128);
+            seg(AL.b_hh + 128, 64, parts + pl.whhb_b, pl.nc_a, 64);
+        }
         seg(AL.fc2_w, (int64_t)d.A * HID, parts + pl.fc2_w, pl.nc_f2, (int64_t)d.A * HID);
         seg(AL.fc2_b, d.A, parts + pl.fc2_b, pl.nc_f2, d.A);
         const int64_t o = AL.total;

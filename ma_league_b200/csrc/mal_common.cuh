@@ -50,16 +50,20 @@ struct AgentLayout {   // drqn_agent.py:21-23
     int d_in, n_actions;
     int64_t fc1_w, fc1_b, w_ih, w_hh, b_ih, b_hh, fc2_w, fc2_b, total;
 };
-__host__ __device__ inline AgentLayout agent_layout(int d_in, int n_actions) {
+// kind MAL_AGENT_RNN: fc1 | gru | fc2 (drqn_agent.py:21-23); MAL_AGENT_DQN: fc1 | fc2 (dqn_agent.py:24-25)
+__host__ __device__ inline AgentLayout agent_layout(int d_in, int n_actions, int kind = MAL_AGENT_RNN) {
     AgentLayout L;
     L.d_in = d_in; L.n_actions = n_actions;
     int64_t o = 0;
     L.fc1_w = o; o += (int64_t)HID * d_in;
     L.fc1_b = o; o += HID;
-    L.w_ih = o;  o += (int64_t)G3 * HID;
-    L.w_hh = o;  o += (int64_t)G3 * HID;
-    L.b_ih = o;  o += G3;
-    L.b_hh = o;  o += G3;
+    L.w_ih = L.w_hh = L.b_ih = L.b_hh = -1;
+    if (kind == MAL_AGENT_RNN) {
+        L.w_ih = o;  o += (int64_t)G3 * HID;
+        L.w_hh = o;  o += (int64_t)G3 * HID;
+        L.b_ih = o;  o += G3;
+        L.b_hh = o;  o += G3;
+    }
     L.fc2_w = o; o += (int64_t)n_actions * HID;
     L.fc2_b = o; o += n_actions;
     L.total = o;

@@ -429,7 +429,9 @@ class QLearner(Learner):
                    targets=self._ws_f32(p.targets, B * T).view(B, T, 1),
                    td=self._ws_f32(p.td, B * T).view(B, T, 1),
                    hout=self._ws_f32(p.h_on, TT * B * N * nat.HID).view(TT, B * N, nat.HID),
-                   x=self._ws_f32(p.x_on, TT * B * N * nat.HID).view(TT, B * N, nat.HID),
+                   # relu(fc1): its own array for the recurrent agent, the "hidden state" itself for the feed-forward one
+                   x=self._ws_f32(p.h_on if getattr(self.mac.agent, "mal_kind", nat.AGENT_RNN) == nat.AGENT_DQN else p.x_on,
+                                  TT * B * N * nat.HID).view(TT, B * N, nat.HID),
                    scalars=self.scalars())
         if isinstance(self.mixer, QMixer):
             E, HE = self.mixer.embed_dim, self.mixer.hypernet_embed

@@ -1,5 +1,6 @@
 from .agent_network import AgentNetwork
+from .dqn_agent import DQNAgentNetwork
 from .drqn_agent import DRQNAgentNetwork
 
-# reference registry: marl/modules/agents/__init__.py:5-8 ("dqn" is outside the hot path)
-REGISTRY = {"rnn": DRQNAgentNetwork}
+# reference registry: marl/modules/agents/__init__.py:5-8
+REGISTRY = {"rnn": DRQNAgentNetwork, "dqn": DQNAgentNetwork}

@@ -12,6 +12,8 @@ from .agent_network import AgentNetwork
 
 
 class DRQNAgentNetwork(AgentNetwork):
+    mal_kind = nat.AGENT_RNN
+
     def __init__(self, input_shape, args):
         super().__init__(input_shape, args)
         if args.rnn_hidden_dim != nat.HID:

@@ -95,7 +95,7 @@ class BatchedEpisodeStepper:
         views = [bt.data.transition_data for bt in batches]        # strided views into the packed episode records
         # one launch per team and timestep when the controller offers the fused rollout step (pre-transition update +
         # previous step's reward / terminated + act-select + actions / one-hot), else the separate calls
-        fused = [self.fuse and hasattr(m, "rollout_step") and m._fusable() and bt._layout is not None
+        fused = [self.fuse and hasattr(m, "rollout_step") and m._rollout_fusable() and bt._layout is not None
                  for m, bt in zip(macs, batches)]
         prev_rewards, prev_done = None, None
         t = 0

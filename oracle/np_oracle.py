@@ -121,11 +121,37 @@ def drqn_step(p, inp, h):
     return q, h_new, cache
 
 
+def dqn_agent_param_shapes(d_in: int, n_actions: int, hidden: int = H_DEFAULT) -> "OrderedDict[str, tuple]":
+    """Keys/shapes of DQNAgentNetwork.state_dict(), marl/modules/agents/dqn_agent.py:24-25."""
+    return OrderedDict([("fc1.weight", (hidden, d_in)), ("fc1.bias", (hidden,)),
+                        ("fc2.weight", (n_actions, hidden)), ("fc2.bias", (n_actions,))])
+
+
+def dqn_step(p, inp, h=None):
+    """DQNAgentNetwork.forward, marl/modules/agents/dqn_agent.py:34-37: q = fc2(relu(fc1(inputs))); the hidden state is
+    passed through untouched.  The cache mirrors drqn_step's (h := x, the activation fc2 reads)."""
+    x_pre = inp @ p["fc1.weight"].T + p["fc1.bias"]
+    x = np.maximum(x_pre, 0)
+    q = x @ p["fc2.weight"].T + p["fc2.bias"]
+    return q, h, dict(inp=inp, x=x, x_pre=x_pre, h=x)
+
+
+def is_dqn(p):
+    return "gru.weight_hh" not in p
+
+
 def unroll(p, obs, actions_onehot):
     """QLearner.train's time loop, marl/learners/q_learner.py:46-52 (and :58-62 for the target net).
 
     Returns mac_out [B,TT,N,A] and the per-step caches."""
     B, TT, N, _ = obs.shape
+    if is_dqn(p):
+        outs, caches = [], []
+        for t in range(TT):
+            q, _, c = dqn_step(p, build_inputs(obs, actions_onehot, t))
+            outs.append(q.reshape(B, N, -1))
+            caches.append(c)
+        return np.stack(outs, axis=1), caches
     Hh = p["gru.weight_hh"].shape[1]
     h = np.zeros((B * N, Hh), dtype=obs.dtype)  # init_hidden: basic_controller.py:59-60, drqn_agent.py:25-27
     outs, caches = [], []
@@ -277,10 +303,20 @@ def td_loss(q_tot, target_q_tot, rewards, term, mask, gamma):
 def agent_backward(p, caches, dq_all, x_mask=None):
     """BPTT through the unroll.  dq_all [B,TT,N,A] = dL/d mac_out.  Returns grads keyed like the state_dict.
     ``x_mask`` (tests only) [TT,R,H] bool: ReLU derivative of fc1's output taken from the caller."""
-    Hh = p["gru.weight_hh"].shape[1]
     g = OrderedDict((k, np.zeros_like(v)) for k, v in p.items())
     TT = len(caches)
     R = caches[0]["h"].shape[0]
+    if is_dqn(p):                                   # feed-forward agent: no recurrence, every step independent
+        for t in range(TT):
+            c = caches[t]
+            dq = dq_all[:, t].reshape(R, -1)
+            g["fc2.weight"] += dq.T @ c["x"]
+            g["fc2.bias"] += dq.sum(axis=0)
+            dx = (dq @ p["fc2.weight"]) * (c["x"] > 0 if x_mask is None else x_mask[t])
+            g["fc1.weight"] += dx.T @ c["inp"]
+            g["fc1.bias"] += dx.sum(axis=0)
+        return g
+    Hh = p["gru.weight_hh"].shape[1]
     dh_next = np.zeros((R, Hh), dtype=caches[0]["h"].dtype)
     Whh, Wih = p["gru.weight_hh"], p["gru.weight_ih"]
     for t in range(TT - 1, -1, -1):

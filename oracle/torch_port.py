@@ -38,6 +38,8 @@ def agent_step(p, batch, t, h):
     parts.append(th.eye(N, device=obs.device).unsqueeze(0).expand(B, -1, -1))
     inp = th.cat([x.reshape(B * N, -1) for x in parts], dim=1)
     x = F.relu(F.linear(inp, p["fc1.weight"], p["fc1.bias"]))
+    if "gru.weight_ih" not in p:                    # DQNAgentNetwork (dqn_agent.py:34-37): no recurrence
+        return F.linear(x, p["fc2.weight"], p["fc2.bias"]).view(B, N, -1), h
     h = th.gru_cell(x, h.reshape(-1, x.shape[1]), p["gru.weight_ih"], p["gru.weight_hh"], p["gru.bias_ih"],
                     p["gru.bias_hh"])
     q = F.linear(h, p["fc2.weight"], p["fc2.bias"])
@@ -46,7 +48,7 @@ def agent_step(p, batch, t, h):
 
 def unroll(p, batch):
     B, TT, N, _ = batch["obs"].shape
-    h = th.zeros(1, p["gru.weight_hh"].shape[1], device=batch["obs"].device).unsqueeze(0).expand(B, N, -1)
+    h = th.zeros(1, p["fc1.weight"].shape[0], device=batch["obs"].device).unsqueeze(0).expand(B, N, -1)
     outs = []
     for t in range(TT):
         q, h = agent_step(p, batch, t, h)

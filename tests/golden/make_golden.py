@@ -93,16 +93,25 @@ def sd_to_np(sd, prefix):
     return {prefix + k: v.detach().numpy().copy() for k, v in sd.items()}
 
 
-def learner_case(R, name, *, B, TT, N, A, OBS, S, mixer, double_q, hypernet_layers=2, seed=0, clip=10.0, steps=2):
+def learner_case(R, name, *, B, TT, N, A, OBS, S, mixer, double_q, hypernet_layers=2, seed=0, clip=10.0, steps=2,
+                 agent="rnn"):
     th.manual_seed(seed)
     np.random.seed(seed)
     gen = th.Generator().manual_seed(seed + 1)
     args = make_args(N, A, S, mixer, double_q, hypernet_layers, clip)
+    args.agent, args.batch_size = agent, B
     scheme, groups, pre = make_scheme(R, N, A, OBS, S)
     buf = R.ReplayBuffer(scheme, groups, B, TT, preprocess=pre, device="cpu")
     mac = R.mac["basic"](buf.scheme, groups, args)
     learner = R.learner["q"](mac, buf.scheme, NullLogger(), args, name="home")
     learner.build_optimizer()
+    if agent == "dqn":
+        # The reference's BasicMAC.init_hidden crashes for this agent (basic_controller.py:59-60 expands the 3-D
+        # placeholder of dqn_agent.py:27-32 with three sizes -> RuntimeError), so QLearner.train cannot run with it as
+        # shipped.  The placeholder is never read (dqn_agent.py:34-37 passes it through), so the harness -- not the
+        # reference's files -- replaces that one call; everything else is the reference's own code.
+        for m in (mac, learner.target_mac):
+            m.init_hidden = (lambda bs, m=m: setattr(m, "hidden_states", th.zeros(bs, N, 1)))
     # make the target network differ from the online one (as after some training)
     with th.no_grad():
         for p in learner.target_mac.parameters():
@@ -114,6 +123,8 @@ def learner_case(R, name, *, B, TT, N, A, OBS, S, mixer, double_q, hypernet_laye
     out = {"meta": np.array([B, TT, N, A, OBS, S, int(mixer == "qmix"), int(double_q), hypernet_layers, steps],
                             dtype=np.int64),
            "hyper": np.array([args.gamma, args.lr, args.optim_alpha, args.optim_eps, clip], dtype=np.float64)}
+    if agent != "rnn":
+        out["agent_kind"] = np.int64(1)
     out.update({"batch." + k: v for k, v in batch_to_np(eb).items()})
     out.update(sd_to_np(mac.agent.state_dict(), "agent0."))
     out.update(sd_to_np(learner.target_mac.agent.state_dict(), "tagent0."))
@@ -292,8 +303,31 @@ def replay_case(R, name, seed=3):
     print(name, "ok", log)
 
 
+def dqn_agent_case(R, name, *, rows, d_in, A, seed=0):
+    """DQNAgentNetwork.forward(inputs, hidden_states) (marl/modules/agents/dqn_agent.py:34-37) and its state_dict."""
+    from marl.modules.agents import REGISTRY as agent_REGISTRY
+    th.manual_seed(seed)
+    args = SN(rnn_hidden_dim=64, n_actions=A, device=th.device("cpu"), batch_size=rows)
+    net = agent_REGISTRY["dqn"](d_in, args)
+    x = th.randn(rows, d_in)
+    hidden = net.init_hidden()
+    with th.no_grad():
+        q, h_out = net(x, hidden)
+    assert h_out is hidden
+    out = {"meta": np.array([rows, d_in, A], dtype=np.int64), "x": x.numpy(), "q": q.numpy(),
+           "hidden_shape": np.array(hidden.shape, dtype=np.int64)}
+    out.update(sd_to_np(net.state_dict(), "agent."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok")
+
+
 def main():
     R = ref_imports()
+    if "--only-new" in sys.argv:      # fixtures added in round 2 (the earlier ones are reproduced bit-identically by a full run)
+        dqn_agent_case(R, "dqn_agent", rows=12, d_in=25, A=9)
+        learner_case(R, "learner_qmix_dqn", B=3, TT=7, N=3, A=9, OBS=12, S=14, mixer="qmix", double_q=True, seed=4,
+                     agent="dqn")
+        return
     learner_case(R, "learner_qmix_3v3", B=4, TT=9, N=3, A=9, OBS=12, S=14, mixer="qmix", double_q=True)
     learner_case(R, "learner_vdn_2v2", B=3, TT=6, N=2, A=8, OBS=10, S=9, mixer="vdn", double_q=True, seed=1)
     learner_case(R, "learner_qmix_nodouble", B=2, TT=5, N=4, A=10, OBS=7, S=11, mixer="qmix", double_q=False,
@@ -301,6 +335,8 @@ def main():
     select_case(R, "select_eps_greedy", bs=6, N=5, A=11)
     mac_step_case(R, "mac_select_actions", bs=3, N=4, A=10, OBS=9, S=6)
     replay_case(R, "replay_ring")
+    dqn_agent_case(R, "dqn_agent", rows=12, d_in=25, A=9)
+    learner_case(R, "learner_qmix_dqn", B=3, TT=7, N=3, A=9, OBS=12, S=14, mixer="qmix", double_q=True, seed=4, agent="dqn")
 
 
 if __name__ == "__main__":

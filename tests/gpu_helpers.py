@@ -43,7 +43,8 @@ class SN(dict):
 def system_from_golden(g, device="cuda"):
     B, TT, N, A, OBS, S, is_qmix, double_q, layers, steps = [int(x) for x in g["meta"]]
     gamma, lr, alpha, eps, clip = [float(x) for x in g["hyper"]]
-    sysm = build_system(N, A, OBS, S, B, TT, "qmix" if is_qmix else "vdn", bool(double_q), device, layers, clip)
+    over = dict(agent="dqn") if int(g.get("agent_kind", 0)) == 1 else {}
+    sysm = build_system(N, A, OBS, S, B, TT, "qmix" if is_qmix else "vdn", bool(double_q), device, layers, clip, **over)
     sysm.mac.agent.load_state_dict(to_sd(sub(g, "agent0."), device))
     sysm.learner.target_mac.agent.load_state_dict(to_sd(sub(g, "tagent0."), device))
     if is_qmix:

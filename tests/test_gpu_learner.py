@@ -8,7 +8,7 @@ from tests.gpu_helpers import system_from_golden, seeded_system, np_params, np_b
 from tests.helpers import load_golden, assert_close, rel_err, sub
 
 pytestmark = pytest.mark.gpu
-CASES = ["learner_qmix_3v3", "learner_vdn_2v2", "learner_qmix_nodouble"]
+CASES = ["learner_qmix_3v3", "learner_vdn_2v2", "learner_qmix_nodouble", "learner_qmix_dqn"]
 TOL = 1e-5   # north_star: 1e-5 relative (fp32) on Q-values, mixer outputs, loss and gradients
 
 
@@ -464,3 +464,15 @@ def test_frozen_agent_trains_only_the_mixer():
     next(iter(s.mac.parameters())).requires_grad = True
     with pytest.raises(Exception):
         L.train(s.batch, t_env=9, episode_num=9)
+
+
+@pytest.mark.parametrize("N,B,TT,mixer", [(5, 32, 201, "qmix"), (3, 4, 9, "vdn"), (10, 6, 12, "qmix")])
+def test_dqn_agent_learner_against_oracle(N, B, TT, mixer):
+    """the feed-forward DQNAgentNetwork (dqn_agent.py:9-37) behind the "dqn" registry key through the
+    same learner step (fc1 GEMM -> Q head -> mixer / TD -> fc2 / fc1 gradients, no recurrence), against the fp64 oracle
+    (pinned to the reference by tests/golden/learner_qmix_dqn.npz), incl. the metric's B=32, T=200 shape."""
+    s = seeded_system(N, B, TT, mixer, True, seed=70 + N, agent="dqn")
+    assert type(s.mac.agent).__name__ == "DQNAgentNetwork" and list(s.mac.agent.state_dict()) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    _check_against_oracle_full(s, mixer)
+    s.learner.train(s.batch, 0, 0)                       # the full step (clip + RMSprop) runs on this agent too
+    th.cuda.synchronize()

@@ -200,3 +200,39 @@ def test_ensemble_mac_matches_oracle_per_agent():
     a1, _ = plain.select_actions(eb, 0, 0, test_mode=True)
     a2, _ = base.select_actions(eb, 0, 0, test_mode=True)
     assert th.equal(a1, a2)
+
+
+def test_dqn_agent_forward_fixture_and_select_actions():
+    """DQNAgentNetwork.forward against the reference fixture (dqn_agent.py:34-37), and BasicMAC with agent="dqn":
+    forward / select_actions against the numpy oracle over three steps (greedy and exploring picks, injected draws)."""
+    from tests.gpu_helpers import np_params, np_batch
+    from ma_league_b200.synthetic import synth_episode_data, fill_episode_batch
+    g = load_golden("dqn_agent")
+    rows, d_in, A = [int(x) for x in g["meta"]]
+    args = make_args(3, A, 10, device=DEV, agent="dqn", batch_size=rows)
+    net = M.agent_REGISTRY["dqn"](d_in, args)
+    net.load_state_dict(to_sd(sub(g, "agent."), DEV))
+    hidden = net.init_hidden()
+    assert tuple(hidden.shape) == tuple(int(x) for x in g["hidden_shape"])
+    q, h_out = net(th.from_numpy(g["x"]).to(DEV), hidden)
+    assert h_out is hidden                                # passed through untouched
+    assert_close(q.cpu().numpy(), g["q"], 1e-5, "dqn q vs reference fixture")
+    # through the controller
+    N, A, OBS, S, B, TT = 4, 10, 40, 64, 5, 6
+    s = build_system(N, A, OBS, S, B, TT, "vdn", True, DEV, agent="dqn")
+    gen = th.Generator().manual_seed(9)
+    data, lens = synth_episode_data(B, TT, N, A, OBS, S, gen, var_len=False, device=DEV)
+    eb = fill_episode_batch(M.EpisodeBatch(s.scheme, s.groups, B, TT, preprocess=s.pre, device=DEV), data, lens)
+    nb, p = np_batch(eb), np_params(s.mac.agent)
+    with pytest.raises(Exception):
+        s.mac.forward(eb, 0)                              # HiddenStateNotInitialized, as for the recurrent agent
+    s.mac.init_hidden(B)
+    for t in range(3):
+        u, e = th.rand(B, N, generator=gen), th.empty(B * N, A).exponential_(generator=gen)
+        q_ref, _, _ = O.dqn_step({k: v.astype(np.float64) for k, v in p.items()}, O.build_inputs(nb["obs"], nb["actions_onehot"], t).astype(np.float64))
+        q = s.mac.forward(eb, t)
+        assert_close(q.cpu().numpy(), q_ref.reshape(B, N, A), 1e-5, "dqn q t=%d" % t)
+        acts, greedy = s.mac.select_actions(eb, t_ep=t, t_env=30000, u=u, e=e)
+        ra, rg = O.eps_greedy_select(q_ref.reshape(B, N, A), nb["avail_actions"][:, t], s.mac.action_selector.epsilon, u.numpy(), e.numpy())
+        assert np.array_equal(acts.cpu().numpy(), ra) and np.array_equal(greedy.cpu().numpy(), rg)
+        assert 0 < int(rg.sum()) < rg.size                # both branches taken

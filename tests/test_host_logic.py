@@ -115,7 +115,7 @@ def test_records_are_aligned_and_views_alias_storage():
 
 def test_registries_and_schedule():
     assert set(M.mac_REGISTRY) == {"basic", "ensemble"} and set(M.learner_REGISTRY) == {"q"}
-    assert set(M.agent_REGISTRY) == {"rnn"} and set(M.action_REGISTRY) == {"epsilon_greedy"}
+    assert set(M.agent_REGISTRY) == {"rnn", "dqn"} and set(M.action_REGISTRY) == {"epsilon_greedy"}
     s = DecayThenFlatSchedule(1.0, 0.05, 50000, decay="linear")
     for t in (0, 1, 25000, 49999, 50000, 10 ** 7):
         assert s.eval(t) == O.epsilon_linear(1.0, 0.05, 50000, t)

@@ -5,7 +5,7 @@ import pytest
 from oracle import np_oracle as O
 from tests.helpers import load_golden, sub, assert_close, rel_err
 
-LEARNER_CASES = ["learner_qmix_3v3", "learner_vdn_2v2", "learner_qmix_nodouble"]
+LEARNER_CASES = ["learner_qmix_3v3", "learner_vdn_2v2", "learner_qmix_nodouble", "learner_qmix_dqn"]
 
 
 def _run(g, dtype):
@@ -149,3 +149,14 @@ def test_torch_port_two_steps_match_reference(case):
         assert np.array_equal(v.detach().numpy(), g["agentK." + k]), k      # same ops -> bit-identical on this host
     for k, v in L.mp.items():
         assert np.array_equal(v.detach().numpy(), g["mixerK." + k]), k
+
+
+def test_dqn_agent_forward_matches_reference():
+    """DQNAgentNetwork.forward (marl/modules/agents/dqn_agent.py:34-37) and its state_dict layout."""
+    g = load_golden("dqn_agent")
+    rows, d_in, A = [int(x) for x in g["meta"]]
+    p = sub(g, "agent.")
+    assert list(p) == list(O.dqn_agent_param_shapes(d_in, A)) and all(p[k].shape == v for k, v in O.dqn_agent_param_shapes(d_in, A).items())
+    q, h, _ = O.dqn_step(p, g["x"])
+    assert h is None and rel_err(q, g["q"]) < 1e-6
+    assert list(g["hidden_shape"]) == [rows, 1, 1]               # dqn_agent.py:27-32: a placeholder, passed through
