@@ -244,6 +244,7 @@ uint64_t mal_stat(const char *name);
  *   "tc_pipelined"  0 / 1 (default, by launch size) / 2 (always): warp-specialised pipelined GEMM kernel
  *   "reduce_tc"     0 / 1 (default, by rows per CTA) / 2 (always): weight-gradient reductions on tcgen05
  *   "fuse_agent_in" 1 (default): fc1 + W_ih in one kernel; 0: two grouped GEMM launches
+ *   "actsel_lat"    1 (default): rollout-sized act-select launches use the mma.sync latency kernel; 0: the lanes-along-k kernel
  *   "overlap"       1 (default): independent kernel chains of the learner step on side streams; 0: one stream
  *   "pdl"           1 (default): programmatic dependent launch along the main kernel chain; 0: full serialisation
  *   "time_chunks"   1 (default) / 2: time-chunked forward (input projection of the 2nd half beside the 1st half's recurrence)

@@ -306,6 +306,7 @@ extern "C" int mal_eps_greedy_select(const float *q, int64_t q_ld, int32_t rows,
     return 0;
 }
 
+static thread_local int g_actsel_lat = 1;    // 1: mma.sync latency kernel for rollout-sized launches; 0: lanes-along-k register kernel
 static int launch_agent_step(AgentStepArgs &a, int Kin, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (size_t)(AS_ROWS * (Kin + 1) + AS_ROWS * HID * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
     MAL_REQUIRE(smem <= 200 * 1024 && Kin <= 32 * AS_FC1_MAXK, "mal_agent_step: input width %d too large (max %d)", Kin,
@@ -313,7 +314,13 @@ static int launch_agent_step(AgentStepArgs &a, int Kin, cudaStream_t stream) {
     int sms, tps;
     if (device_sm_count(&sms, &tps)) return 2;
     const int ctas = (a.rows + AS_ROWS - 1) / AS_ROWS;
-    if (ctas <= 2 * sms && a.kind == MAL_AGENT_RNN) {   // latency-bound regime (rollouts): all weights prefetched into registers
+    if (ctas <= sms && a.kind == MAL_AGENT_RNN && g_actsel_lat) {   // rollouts: latency is what counts
+        const size_t smem_l = sizeof(float) * (size_t)(AS_ROWS * (((Kin + 7) & ~7) + 4) + AS_ROWS * 68 * 3 + AS_ROWS * 2 * G3 + AS_ROWS * 32);
+        static size_t attr[MAL_MAX_DEV];
+        if (smem_l > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step_lat, smem_l, attr)) return rc;
+        ProfScope _ps("k_agent_step", stream);
+        k_agent_step_lat<<<ctas, AL_THREADS, smem_l, stream>>>(a);
+    } else if (ctas <= 2 * sms && a.kind == MAL_AGENT_RNN) {   // all weights prefetched into registers
         static size_t attr[MAL_MAX_DEV];
         if (smem > 48 * 1024) if (int rc = ensure_dyn_smem(k_agent_step, smem, attr)) return rc;
         ProfScope _ps("k_agent_step", stream);
@@ -579,6 +586,7 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
+    if (strcmp(name, "actsel_lat") == 0) { g_actsel_lat = value ? 1 : 0; return 0; }
     if (strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
