@@ -310,79 +310,102 @@ def run_ours(a, rank, world, device):
                         "under hbm_kernels"}
 
     # ---------------- e2e: batch in pinned host memory, H2D + train + D2H every step
+    # The host keeps the sampled batches as compact WIRE records (EpisodeBatch.to_wire: no derivable fields, narrow flags);
+    # every step copies its wire batch H2D (copy stream, double-buffered), expands it on the device into the staging batch
+    # (EpisodeBatch.load_wire, one launch), trains, and reads the loss back.  `full_records` = the same loop shipping the
+    # full packed records (the round-1 method), for comparison.
     n_pin = nb if B * rb * nb < 2 ** 31 else 2         # bound pinned host memory on the big workloads
-    pinned = [p_._storage.cpu().pin_memory() for p_ in parents[:n_pin]]
+    wb = parents[0].wire_bytes()
     stage = [M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=device) for _ in range(2)]
     copy_stream = th.cuda.Stream(device=device)
-    ready = [th.cuda.Event(), th.cuda.Event()]
-    consumed = [th.cuda.Event(), th.cuda.Event()]
-
-    def prefetch(i):
-        slot = i % 2
-        with th.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            stage[slot]._storage.copy_(pinned[i % n_pin], non_blocking=True)
-            ready[slot].record(copy_stream)
-
     out_ring = [th.empty(8, dtype=th.float32).pin_memory() for _ in range(2)]
-    done = [th.cuda.Event(), th.cuda.Event()]
 
-    def e2e_steps(k, t0, pipelined):
-        """Every step: H2D of its record batch (copy stream, double-buffered), train, D2H of its loss/statistics.
-        pipelined: the host waits for step i's result after it has enqueued step i+1 (a training loop that logs the
-        previous step's loss); otherwise it synchronises on every step before enqueueing the next one."""
-        prefetch(t0)
-        cur = th.cuda.current_stream(device)
-        last = float("nan")
-        for i in range(t0, t0 + k):
+    def e2e_variant(use_wire):
+        if use_wire:
+            pinned = [p_.to_wire().cpu().pin_memory() for p_ in parents[:n_pin]]
+            land = [th.empty(B, wb, dtype=th.uint8, device=device) for _ in range(2)]
+        else:
+            pinned = [p_._storage.cpu().pin_memory() for p_ in parents[:n_pin]]
+            land = [st_._storage for st_ in stage]
+        ready = [th.cuda.Event(), th.cuda.Event()]
+        consumed = [th.cuda.Event(), th.cuda.Event()]
+        done = [th.cuda.Event(), th.cuda.Event()]
+
+        def prefetch(i):
             slot = i % 2
-            if i + 1 < t0 + k:
-                prefetch(i + 1)
-            cur.wait_event(ready[slot])
-            learner.train(stage[slot], t_env=i, episode_num=0)
-            consumed[slot].record()
-            out_ring[slot].copy_(learner.scalars()[:8], non_blocking=True)
-            done[slot].record()
-            if not pipelined:
-                done[slot].synchronize()           # this step's loss is on the host
-                last = float(out_ring[slot][1])
-            elif i > t0:
-                done[slot ^ 1].synchronize()       # the previous step's loss is on the host
-                last = float(out_ring[slot ^ 1][1])
-        done[(t0 + k - 1) % 2].synchronize()
-        return float(out_ring[(t0 + k - 1) % 2][1]) if pipelined else last
+            with th.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                land[slot].copy_(pinned[i % n_pin], non_blocking=True)
+                ready[slot].record(copy_stream)
 
-    for c in consumed:
-        c.record()
-    # the H2D copy alone (pinned -> device on the copy stream): the e2e step cannot be shorter than this
-    hs, he = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    with th.cuda.stream(copy_stream):
-        stage[0]._storage.copy_(pinned[0], non_blocking=True)
-        hs.record(copy_stream)
-        for _ in range(8):
-            stage[0]._storage.copy_(pinned[0], non_blocking=True)
-        he.record(copy_stream)
-    copy_stream.synchronize()
-    h2d_ms = hs.elapsed_time(he) / 8
-    res = {}
-    k_e2e = max(a.steps, 100) if B * rb < 64 * 2 ** 20 else a.steps      # a longer window for the small (sub-ms) steps
-    for pipelined in (False, True):
-        e2e_steps(max(a.warmup, 3), 0, pipelined)
-        barrier(world, device)
-        t0 = time.perf_counter()
-        last_loss = e2e_steps(k_e2e, 100, pipelined)
-        barrier(world, device)
-        res[pipelined] = dist_max(time.perf_counter() - t0, world, device)
-    e2e_s = res[True]
-    e2e = {"value": world * transitions * k_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * rb,
-           "d2h_bytes_per_step": 32, "ms_per_step": e2e_s / k_e2e * 1e3, "steps": k_e2e,
-           "h2d_copy_alone_ms": round(h2d_ms, 4), "h2d_gbs": round(B * rb / (h2d_ms * 1e-3) / 1e9, 1),
-           "how": "pinned host batch -> double-buffered H2D on a copy stream -> QLearner.train -> loss D2H; every "
-                  "step's loss is read on the host, one step behind the enqueue (the host enqueues step i+1, then "
-                  "waits for step i's result)",
-           "sync_every_step": {"value": world * transitions * k_e2e / res[False], "ms_per_step": res[False] / k_e2e * 1e3,
-                               "how": "same, but the host synchronises on each step's loss before enqueueing the next step"}}
-    assert np.isfinite(last_loss)
+        def e2e_steps(k, t0, pipelined):
+            """Every step: H2D of its batch (copy stream, double-buffered), [unpack,] train, D2H of its loss/statistics.
+            pipelined: the host waits for step i's result after it has enqueued step i+1 (a training loop that logs the
+            previous step's loss); otherwise it synchronises on every step before enqueueing the next one."""
+            prefetch(t0)
+            cur = th.cuda.current_stream(device)
+            last = float("nan")
+            for i in range(t0, t0 + k):
+                slot = i % 2
+                if i + 1 < t0 + k:
+                    prefetch(i + 1)
+                cur.wait_event(ready[slot])
+                if use_wire:
+                    stage[slot].load_wire(land[slot])
+                learner.train(stage[slot], t_env=i, episode_num=0)
+                consumed[slot].record()
+                out_ring[slot].copy_(learner.scalars()[:8], non_blocking=True)
+                done[slot].record()
+                if not pipelined:
+                    done[slot].synchronize()           # this step's loss is on the host
+                    last = float(out_ring[slot][1])
+                elif i > t0:
+                    done[slot ^ 1].synchronize()       # the previous step's loss is on the host
+                    last = float(out_ring[slot ^ 1][1])
+            done[(t0 + k - 1) % 2].synchronize()
+            return float(out_ring[(t0 + k - 1) % 2][1]) if pipelined else last
+
+        for c in consumed:
+            c.record()
+        # the H2D copy alone (pinned -> device on the copy stream): the e2e step cannot be shorter than this
+        hs, he = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        with th.cuda.stream(copy_stream):
+            land[0].copy_(pinned[0], non_blocking=True)
+            hs.record(copy_stream)
+            for _ in range(8):
+                land[0].copy_(pinned[0], non_blocking=True)
+            he.record(copy_stream)
+        copy_stream.synchronize()
+        h2d_ms = hs.elapsed_time(he) / 8
+        res = {}
+        k_e2e = max(a.steps, 100) if B * rb < 64 * 2 ** 20 else a.steps      # a longer window for the small (sub-ms) steps
+        last_loss = float("nan")
+        for pipelined in (False, True):
+            e2e_steps(max(a.warmup, 3), 0, pipelined)
+            barrier(world, device)
+            t0 = time.perf_counter()
+            last_loss = e2e_steps(k_e2e, 100, pipelined)
+            barrier(world, device)
+            res[pipelined] = dist_max(time.perf_counter() - t0, world, device)
+        assert np.isfinite(last_loss)
+        nbytes = B * (wb if use_wire else rb)
+        return {"value": world * transitions * k_e2e / res[True], "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                "d2h_bytes_per_step": 32, "ms_per_step": res[True] / k_e2e * 1e3, "steps": k_e2e,
+                "h2d_copy_alone_ms": round(h2d_ms, 4), "h2d_gbs": round(nbytes / (h2d_ms * 1e-3) / 1e9, 1),
+                "sync_every_step": {"value": world * transitions * k_e2e / res[False], "ms_per_step": res[False] / k_e2e * 1e3,
+                                    "how": "same, but the host synchronises on each step's loss before enqueueing the next step"}}
+
+    e2e = e2e_variant(True)
+    e2e["how"] = ("pinned host batch as compact wire records (EpisodeBatch.to_wire: %d of %d bytes per episode) -> double-buffered "
+                  "H2D on a copy stream -> EpisodeBatch.load_wire (device unpack, one launch) -> QLearner.train -> loss D2H; "
+                  "every step's loss is read on the host, one step behind the enqueue (the host enqueues step i+1, then "
+                  "waits for step i's result)" % (wb, rb))
+    try:
+        full = e2e_variant(False)
+        e2e["full_records"] = {k: full[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "h2d_copy_alone_ms", "h2d_gbs")}
+        e2e["full_records"]["how"] = "the same loop shipping the full packed records (no unpack launch)"
+    except Exception as ex:
+        e2e["full_records"] = {"error": repr(ex)}
 
     extra = {}
     # ---------------- M1': the learner-side input pipeline (sample + truncate + train), ma_experiment.py:231-241
@@ -430,17 +453,26 @@ def run_ours(a, rank, world, device):
     try:
         from ma_league_b200.steppers import BatchedEpisodeStepper, SyntheticVecEnv
         env = SyntheticVecEnv(B, N, A, OBS, S, TT - 1, n_teams=1, seed=3, device=device, min_len=TT - 1)
-        stp = BatchedEpisodeStepper(args, None, env, sync_every=50)
-        stp.initialize(scheme, groups, pre, mac)
-        stp.run(test_mode=False)
-        th.cuda.synchronize(device)
-        w0 = time.perf_counter()
-        stp.run(test_mode=False)
-        th.cuda.synchronize(device)
-        dt = time.perf_counter() - w0
-        extra["rollout_loop_bs%d" % B] = {"agent_steps_per_s": round(B * N * (TT - 1) / dt, 1),
-                                          "env_steps_per_s": round(B * (TT - 1) / dt, 1), "ms_per_timestep": round(dt / (TT - 1) * 1e3, 4),
-                                          "what": "BatchedEpisodeStepper.run: pre-transition update + fused act-select + post-transition update per step"}
+        roll = {}
+        for fuse, validate in ((True, False), (True, True), (False, False)):
+            mac.action_selector.validate = validate
+            stp = BatchedEpisodeStepper(args, None, env, sync_every=50, fuse=fuse)
+            stp.initialize(scheme, groups, pre, mac)
+            stp.run(test_mode=False)
+            th.cuda.synchronize(device)
+            l0 = lib.mal_launch_count()
+            w0 = time.perf_counter()
+            stp.run(test_mode=False)
+            th.cuda.synchronize(device)
+            dt = time.perf_counter() - w0
+            roll["%s_validate_%s" % ("fused_step" if fuse else "separate_calls", "default" if validate else "off")] = {
+                "agent_steps_per_s": round(B * N * (TT - 1) / dt, 1), "env_steps_per_s": round(B * (TT - 1) / dt, 1),
+                "ms_per_timestep": round(dt / (TT - 1) * 1e3, 4), "our_launches_per_timestep": round((lib.mal_launch_count() - l0) / TT, 2)}
+        mac.action_selector.validate = True
+        roll["what"] = ("BatchedEpisodeStepper.run over %d timesteps: fused_step = ONE launch per timestep (pre-transition update + "
+                        "previous reward/terminated + act-select + actions/one-hot), separate_calls = update / select_actions / "
+                        "update; the synthetic environment's own step (3 small torch ops) is inside the timed loop" % (TT - 1))
+        extra["rollout_loop_bs%d" % B] = roll
     except Exception as ex:                                  # the extra leg must never take the headline down
         extra["rollout_loop_error"] = repr(ex)
 

@@ -281,6 +281,21 @@ int mal_select_philox_advance(int32_t rows, int32_t n_actions, uint64_t *advance
 int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst_ids, const void *src, int64_t src_stride,
                     const int64_t *src_ids, int32_t n, int64_t bytes, void *stream);
 
+/* Compact wire form of an episode batch for the host <-> device path of a host-resident replay buffer
+ * (`buffer_cpu_only`: runs/train/ma_experiment.py:238-239 moves the sampled batch to the device every step).  The wire
+ * record of an episode holds, per stored step, state f32 | obs f32 | reward f32 | actions u8 [N] | avail bitmask u32 [N] |
+ * flags u8 (bit 0 filled, bit 1 terminated); `actions_onehot` and `filled` are re-derived on the device (OneHot,
+ * transforms.py:16-19: written for filled steps).  mal_wire_pack sets *status (device int, may be NULL) to 1 when a value
+ * does not fit the encoding (actions outside [0, 255], avail flags other than 0 / 1, a one-hot row that is not the
+ * OneHot of its action or all-zero); n_actions <= 32. */
+typedef struct mal_wire_layout {
+    int64_t record_bytes;             /* per episode, multiple of 128 */
+    int64_t off_state, off_obs, off_reward, off_actions, off_avail, off_flags;
+} mal_wire_layout_t;
+int mal_wire_layout(int32_t TT, int32_t N, int32_t OBS, int32_t S, mal_wire_layout_t *out);
+int mal_wire_pack(const mal_batch_t *batch, void *wire, const mal_wire_layout_t *layout, int32_t *status, void *stream);
+int mal_wire_unpack(const mal_batch_t *batch, const void *wire, const mal_wire_layout_t *layout, void *stream);
+
 /* EpisodeBatch.max_t_filled, episode_batch.py:240-242: out[0] = max_b sum_t filled[b,t]. */
 int mal_max_t_filled(const int64_t *filled, int64_t sb, int64_t st, int32_t B, int32_t TT, int32_t *out,
                      void *stream);

@@ -73,6 +73,11 @@ class RolloutIO(C.Structure):
                 ("reward_tm1", C.c_void_p), ("reward_sb", C.c_int64), ("term_tm1", C.c_void_p), ("term_sb", C.c_int64)]
 
 
+class WireLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("record_bytes", "off_state", "off_obs", "off_reward", "off_actions", "off_avail",
+                                         "off_flags")]
+
+
 _PROTOS = {
     "mal_version": (C.c_int, []),
     "mal_last_error": (C.c_char_p, []),
@@ -117,6 +122,9 @@ _PROTOS = {
     "mal_select_philox_advance": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     "mal_record_copy": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                   C.c_int64, C.c_void_p]),
+    "mal_wire_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(WireLayout)]),
+    "mal_wire_pack": (C.c_int, [C.POINTER(Batch), C.c_void_p, C.POINTER(WireLayout), C.c_void_p, C.c_void_p]),
+    "mal_wire_unpack": (C.c_int, [C.POINTER(Batch), C.c_void_p, C.POINTER(WireLayout), C.c_void_p]),
     "mal_max_t_filled": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_PROTOS)

@@ -8,6 +8,7 @@ kernels read each field through (pointer, batch stride, time stride).
 """
 from __future__ import annotations
 
+import ctypes as C
 from types import SimpleNamespace as SN
 
 import numpy as np
@@ -299,6 +300,62 @@ class EpisodeBatch:
             out._storage = self._storage.view(self.batch_size, rb).index_select(0, ids_t.to(dev)).reshape(-1)
         out._bind_views()
         return out
+
+    # ------------------------------------------------------------------ compact wire form (host <-> device path)
+    def _wire_batch_struct(self):
+        """(mal_batch_t of this packed device batch, wire layout) for the hot-path scheme of ma_experiment.py:99-118."""
+        tv = self.data.transition_data
+        need = ("state", "obs", "actions", "avail_actions", "reward", "terminated", "actions_onehot", "filled")
+        if self._layout is None or set(tv) != set(need) or self.data.episode_data:
+            raise nat.MalError("the wire form covers packed batches with exactly the hot-path scheme %s" % (need,))
+        obs = nat.require_cuda(tv["obs"], "batch")
+        B, TT, N, OBS = obs.shape
+        A, S = tv["avail_actions"].shape[-1], tv["state"].shape[-1]
+        b = nat.Batch(B, TT, N, A, OBS, S)
+        b.obs = nat.field_of(obs, N * OBS)
+        b.onehot = nat.field_of(tv["actions_onehot"], N * A)
+        b.actions = nat.field_of(tv["actions"], N)
+        b.avail = nat.field_of(tv["avail_actions"], N * A)
+        b.state = nat.field_of(tv["state"], S)
+        b.reward = nat.field_of(tv["reward"], 1)
+        b.terminated = nat.field_of(tv["terminated"], 1)
+        b.filled = nat.field_of(tv["filled"], 1)
+        wl = nat.WireLayout()
+        nat.check(nat.lib().mal_wire_layout(TT, N, OBS, S, C.byref(wl)), "mal_wire_layout")
+        return b, wl
+
+    def wire_bytes(self):
+        """Bytes per episode of the compact wire record."""
+        return int(self._wire_batch_struct()[1].record_bytes)
+
+    def to_wire(self, out=None, check=True):
+        """This (device-resident, packed) batch as compact wire records: uint8 [batch_size, wire_bytes] on the device.
+        The wire form drops what the device can re-derive (`actions_onehot`, `filled` as a bit) and narrows 0/1 flags and
+        action indices: 26 % fewer bytes at 5v5.  It is what a host-resident replay buffer
+        (`buffer_cpu_only`) should keep in pinned memory and ship per learner step; `load_wire` restores the batch bit for
+        bit.  `check=True` raises ValueError (one device sync) if a value does not fit the encoding."""
+        b, wl = self._wire_batch_struct()
+        dev = self._storage.device
+        if out is None:
+            out = th.empty(self.batch_size, wl.record_bytes, dtype=th.uint8, device=dev)
+        status = th.zeros(1, dtype=th.int32, device=dev) if check else None
+        with nat.on_device(dev):
+            nat.check(nat.lib().mal_wire_pack(C.byref(b), nat.ptr(out), C.byref(wl), nat.ptr(status), nat.current_stream(dev)),
+                      "mal_wire_pack")
+        if check and int(status.item()) != 0:
+            raise ValueError("batch does not fit the wire encoding (actions in [0, 255], 0/1 avail flags, one-hot = OneHot(actions) on filled steps)")
+        return out
+
+    def load_wire(self, wire):
+        """Overwrite this packed device batch with the episodes of `wire` (uint8 [batch_size, wire_bytes] on the same device,
+        e.g. the H2D copy of pinned host wire records): one unpack launch, bit-exact inverse of `to_wire`."""
+        b, wl = self._wire_batch_struct()
+        dev = self._storage.device
+        if wire.device != dev or wire.dtype != th.uint8 or wire.numel() != self.batch_size * wl.record_bytes or not wire.is_contiguous():
+            raise nat.MalError("wire buffer must be a contiguous uint8 [batch_size, %d] tensor on %s" % (wl.record_bytes, dev))
+        with nat.on_device(dev):
+            nat.check(nat.lib().mal_wire_unpack(C.byref(b), nat.ptr(wire), C.byref(wl), nat.current_stream(dev)), "mal_wire_unpack")
+        return self
 
     def max_t_filled(self):
         """episode_batch.py:240-242; returns a 1-element long tensor like the reference."""

@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(256) k_fc2_grad(Fc2GradArgs a) {
     for (int e = lane; e < ld; e += 32) acc[e] = 0.0f;
     __syncwarp();
     const int64_t stride = (int64_t)gridDim.x * 8;
-    constexpr int U = 4;                                      // rows in flight per warp
+    constexpr int U = 8;                                      // rows in flight per warp
     for (int64_t m0 = (int64_t)blockIdx.x * 8 + warp; m0 < a.rows; m0 += U * stride) {
         float d[U];
         int act[U];

@@ -248,6 +248,47 @@ extern "C" int mal_record_copy(void *dst, int64_t dst_stride, const int64_t *dst
     return 0;
 }
 
+extern "C" int mal_wire_layout(int32_t TT, int32_t N, int32_t OBS, int32_t S, mal_wire_layout_t *out) {
+    MAL_REQUIRE(out && TT > 0 && N > 0 && OBS > 0 && S > 0, "mal_wire_layout: bad arguments");
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t r = o; o += align_up64(bytes, 16); return r; };
+    out->off_state = take((int64_t)TT * S * 4);
+    out->off_obs = take((int64_t)TT * N * OBS * 4);
+    out->off_reward = take((int64_t)TT * 4);
+    out->off_avail = take((int64_t)TT * N * 4);
+    out->off_actions = take((int64_t)TT * N);
+    out->off_flags = take(TT);
+    out->record_bytes = align_up64(o, 128);
+    return 0;
+}
+
+static int launch_wire(const mal_batch_t *b, void *wire, const mal_wire_layout_t *wl, int32_t *status, bool pack, void *stream) {
+    MAL_REQUIRE(b && wire && wl, "mal_wire: null argument");
+    MAL_REQUIRE(b->B >= 1 && b->TT >= 1 && b->N >= 1 && b->A >= 1 && b->A <= 32 && b->OBS >= 1 && b->S >= 1, "mal_wire: bad dims (n_actions <= 32)");
+    MAL_REQUIRE((reinterpret_cast<uintptr_t>(wire) & 15) == 0 && (wl->record_bytes & 15) == 0, "mal_wire: the wire buffer must be 16-byte aligned");
+    WireArgs a;
+    a.B = b->B; a.TT = b->TT; a.N = b->N; a.A = b->A; a.OBS = b->OBS; a.S = b->S;
+    a.obs = b->obs; a.onehot = b->onehot; a.actions = b->actions; a.avail = b->avail; a.state = b->state;
+    a.reward = b->reward; a.terminated = b->terminated; a.filled = b->filled;
+    a.wire = (uint8_t *)wire; a.record_bytes = wl->record_bytes; a.off_state = wl->off_state; a.off_obs = wl->off_obs;
+    a.off_reward = wl->off_reward; a.off_actions = wl->off_actions; a.off_avail = wl->off_avail; a.off_flags = wl->off_flags;
+    a.status = status;
+    int sms, tps;
+    if (device_sm_count(&sms, &tps)) return 2;
+    int64_t grid = ceil_div64((int64_t)b->B * b->TT, 8); if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pack) { ProfScope _ps("k_wire_pack", st); k_wire<true><<<(unsigned)grid, 256, 0, st>>>(a); }
+    else { ProfScope _ps("k_wire_unpack", st); k_wire<false><<<(unsigned)grid, 256, 0, st>>>(a); }
+    MAL_LAUNCH_CHECK("k_wire");
+    return 0;
+}
+extern "C" int mal_wire_pack(const mal_batch_t *batch, void *wire, const mal_wire_layout_t *layout, int32_t *status, void *stream) {
+    return launch_wire(batch, wire, layout, status, true, stream);
+}
+extern "C" int mal_wire_unpack(const mal_batch_t *batch, const void *wire, const mal_wire_layout_t *layout, void *stream) {
+    return launch_wire(batch, const_cast<void *>(wire), layout, nullptr, false, stream);
+}
+
 extern "C" int mal_max_t_filled(const int64_t *filled, int64_t sb, int64_t st, int32_t B, int32_t TT, int32_t *out,
                                 void *stream) {
     MAL_REQUIRE(filled && out && B > 0 && TT > 0, "mal_max_t_filled: bad arguments");
@@ -473,9 +514,12 @@ static PartLayout part_layout(const Dims &d, int sms) {
     memset(&p, 0, sizeof(p));
     chunking(d.M1, tiles_of(G3, HID) + tiles_of(128, HID) + tiles_of(64, HID), sms, &p.nc_a, &p.rpc_a);
     chunking(d.M1, tiles_of(HID, d.d_in), sms, &p.nc_f1, &p.rpc_f1);
-    {   // k_fc2_grad: one partial per CTA, 8 warps x >= 4 rows each, at most one CTA per SM
-        int64_t nb = ceil_div64((int64_t)d.T * d.R, 32);
-        if (nb > sms) nb = sms;
+    {   // k_fc2_grad: one partial per CTA, 8 warps x >= 32 rows each; the kernel is HBM-bound on the h rows, so large batches
+        // fill every SM with as many CTAs as their [8][A*64+32]-float accumulators allow (<= 4)
+        const int64_t smem = (int64_t)sizeof(float) * 8 * ((int64_t)d.A * HID + 32);
+        int64_t per_sm = (200 * 1024) / smem; if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
+        int64_t nb = ceil_div64((int64_t)d.T * d.R, 256);
+        if (nb > sms * per_sm) nb = sms * per_sm;
         if (nb < 1) nb = 1;
         p.nc_f2 = (int)nb; p.rpc_f2 = 0;
     }

@@ -91,3 +91,90 @@ __global__ void k_max_t_filled(const int64_t *filled, int64_t sb, int64_t st, in
     __syncthreads();
     if (threadIdx.x == 0) out[0] = best;
 }
+
+// =============================================================================================
+// Compact wire records for the host <-> device path of a host-resident replay buffer (`buffer_cpu_only`: the sampled
+// batch crosses PCIe on every learner step, runs/train/ma_experiment.py:238-239 `batch.to(args.device)`).
+// The packed episode record carries two fields that are pure functions of others -- `actions_onehot` (f32 [N,A] per
+// step, OneHot of `actions`, transforms.py:16-19) and `filled` (i64) -- and three that are far wider than their content
+// (`actions` i64, `avail_actions` i32 [N,A] of 0/1 flags, `terminated`).  The wire record ships
+//     state f32 | obs f32 | reward f32 | actions u8 [N] | avail bitmask u32 [N] | flags u8 (bit 0 filled, bit 1 terminated)
+// per stored step (26 % fewer bytes at 5v5, 30 % at 20v20) and k_wire_unpack re-expands it on the device into the full
+// record (bit-exact round trip for 0/1 avail flags, actions < 256, filled / terminated in {0, 1}; the packer reports
+// anything else through `status`).  One warp per (episode, step); HBM-bound, algorithmic bytes = wire + full record.
+// =============================================================================================
+struct WireArgs {
+    int B, TT, N, A, OBS, S;
+    mal_field_t obs, onehot, actions, avail, state, reward, terminated, filled;   // the full (packed-record) batch
+    uint8_t *wire;
+    int64_t record_bytes, off_state, off_obs, off_reward, off_actions, off_avail, off_flags;
+    int *status;                                       // pack: set to 1 when a value does not fit the wire encoding
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_wire(WireArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)a.B * a.TT;
+    for (int64_t w = (int64_t)blockIdx.x * 8 + warp; w < total; w += (int64_t)gridDim.x * 8) {
+        const int b = (int)(w / a.TT), t = (int)(w - (int64_t)b * a.TT);
+        uint8_t *rec = a.wire + (int64_t)b * a.record_bytes;
+        float *w_state = reinterpret_cast<float *>(rec + a.off_state) + (int64_t)t * a.S;
+        float *w_obs = reinterpret_cast<float *>(rec + a.off_obs) + (int64_t)t * a.N * a.OBS;
+        float *w_reward = reinterpret_cast<float *>(rec + a.off_reward) + t;
+        uint8_t *w_act = rec + a.off_actions + (int64_t)t * a.N;
+        uint32_t *w_avail = reinterpret_cast<uint32_t *>(rec + a.off_avail) + (int64_t)t * a.N;
+        uint8_t *w_flags = rec + a.off_flags + t;
+        float *f_state = const_cast<float *>(field_ptr<float>(a.state, b, t));
+        float *f_obs = const_cast<float *>(field_ptr<float>(a.obs, b, t));
+        float *f_onehot = const_cast<float *>(field_ptr<float>(a.onehot, b, t));
+        long long *f_act = const_cast<long long *>(field_ptr<long long>(a.actions, b, t));
+        int *f_avail = const_cast<int *>(field_ptr<int>(a.avail, b, t));
+        float *f_reward = const_cast<float *>(field_ptr<float>(a.reward, b, t));
+        unsigned char *f_term = const_cast<unsigned char *>(field_ptr<unsigned char>(a.terminated, b, t));
+        long long *f_filled = const_cast<long long *>(field_ptr<long long>(a.filled, b, t));
+        if (PACK) {
+            for (int k = lane; k < a.S; k += 32) w_state[k] = f_state[k];
+            for (int k = lane; k < a.N * a.OBS; k += 32) w_obs[k] = f_obs[k];
+            const long long fl = *f_filled;                 // every lane: same address, one broadcast load
+            const unsigned char tm = *f_term;
+            bool bad = (fl != 0 && fl != 1) || tm > 1;
+            for (int n = lane; n < a.N; n += 32) {
+                const long long act = f_act[n];
+                bad = bad || act < 0 || act > 255;
+                w_act[n] = (uint8_t)act;
+                uint32_t bits = 0;
+                for (int j = 0; j < a.A; ++j) {
+                    const int av = f_avail[n * a.A + j];
+                    bad = bad || (av != 0 && av != 1);
+                    bits |= (av != 0 ? 1u : 0u) << j;
+                    // the wire drops actions_onehot: the unpacker writes OneHot(action) on filled steps and zeros elsewhere,
+                    // which is what EpisodeBatch.update leaves (episode_batch.py:163-166, 183-195) -- anything else is reported
+                    const float oh = f_onehot[n * a.A + j];
+                    bad = bad || oh != ((fl != 0 && j == act) ? 1.0f : 0.0f);
+                }
+                w_avail[n] = bits;
+            }
+            if (lane == 0) {
+                *w_reward = *f_reward;
+                *w_flags = (uint8_t)((fl != 0 ? 1 : 0) | (tm != 0 ? 2 : 0));
+            }
+            if (bad && a.status) atomicExch(a.status, 1);
+        } else {
+            const uint8_t flags = *w_flags;
+            const bool filled = flags & 1;
+            for (int k = lane; k < a.S; k += 32) f_state[k] = w_state[k];
+            for (int k = lane; k < a.N * a.OBS; k += 32) f_obs[k] = w_obs[k];
+            for (int e = lane; e < a.N * a.A; e += 32) {
+                const int n = e / a.A, j = e - n * a.A;
+                f_avail[e] = (int)((w_avail[n] >> j) & 1u);
+                f_onehot[e] = (filled && j == (int)w_act[n]) ? 1.0f : 0.0f;
+            }
+            for (int n = lane; n < a.N; n += 32) f_act[n] = (long long)w_act[n];
+            if (lane == 0) {
+                *f_reward = *w_reward;
+                *f_term = (flags >> 1) & 1;
+                *f_filled = filled ? 1 : 0;
+            }
+        }
+    }
+}

@@ -168,3 +168,34 @@ def test_train_from_buffer_against_oracle():
         assert_close(p_new, p_ref, 1e-5, "post-step parameters (%s)" % variant)
         assert_close(p_new - p0, p_ref - p0, 1e-3, "parameter update (%s)" % variant)
         assert_close(L.optimiser.flat_sq.cpu().numpy(), sq_ref, 1e-5, "square_avg (%s)" % variant)
+
+
+@pytest.mark.parametrize("N,B,TT", [(5, 32, 201), (3, 4, 7), (20, 3, 5), (26, 2, 4)])
+def test_wire_records_round_trip_bit_exact(N, B, TT):
+    """Compact wire form of an episode batch (host <-> device path of a host-resident replay buffer): pack -> (host) ->
+    unpack restores every field bit for bit, incl. variable-length episodes; values that do not fit are reported."""
+    A, OBS, S = 6 + N, 8 + 8 * N, 16 * N
+    scheme, groups, pre = make_scheme(N, A, OBS, S)
+    gen = th.Generator().manual_seed(N)
+    data, lens = synth_episode_data(B, TT, N, A, OBS, S, gen, var_len=True, device=DEV)
+    eb = fill_episode_batch(M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=DEV), data, lens)
+    wire = eb.to_wire()
+    rb, wb = eb._layout.record_bytes, eb.wire_bytes()
+    assert wire.shape == (B, wb) and wb < 0.8 * rb                        # at least 20 % fewer bytes on the wire
+    host = wire.cpu().pin_memory()                                         # what a host-resident buffer keeps
+    out = M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=DEV)
+    out._storage.fill_(0xAB)                                               # every field must be overwritten
+    out.load_wire(host.to(DEV, non_blocking=True))
+    for k, v in eb.data.transition_data.items():
+        assert th.equal(out[k], v), k
+    assert int(out.max_t_filled()) == int(eb.max_t_filled())
+    # the learner sees the same batch: identical loss statistics after one forward
+    bad = M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=DEV)
+    bad._storage.copy_(eb._storage)
+    bad["avail_actions"][0, 0, 0, 1] = 7                                   # not a 0/1 flag
+    with pytest.raises(ValueError):
+        bad.to_wire()
+    bad._storage.copy_(eb._storage)
+    bad["actions_onehot"][0, 0, 0].zero_()                                 # a filled step without its one-hot
+    with pytest.raises(ValueError):
+        bad.to_wire()
