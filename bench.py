@@ -395,17 +395,19 @@ def run_ours(a, rank, world, device):
                 "sync_every_step": {"value": world * transitions * k_e2e / res[False], "ms_per_step": res[False] / k_e2e * 1e3,
                                     "how": "same, but the host synchronises on each step's loss before enqueueing the next step"}}
 
-    e2e = e2e_variant(True)
-    e2e["how"] = ("pinned host batch as compact wire records (EpisodeBatch.to_wire: %d of %d bytes per episode) -> double-buffered "
-                  "H2D on a copy stream -> EpisodeBatch.load_wire (device unpack, one launch) -> QLearner.train -> loss D2H; "
-                  "every step's loss is read on the host, one step behind the enqueue (the host enqueues step i+1, then "
-                  "waits for step i's result)" % (wb, rb))
-    try:
-        full = e2e_variant(False)
-        e2e["full_records"] = {k: full[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "h2d_copy_alone_ms", "h2d_gbs")}
-        e2e["full_records"]["how"] = "the same loop shipping the full packed records (no unpack launch)"
-    except Exception as ex:
-        e2e["full_records"] = {"error": repr(ex)}
+    how_common = ("double-buffered H2D on a copy stream -> %sQLearner.train -> loss D2H; every step's loss is read on the host, one "
+                  "step behind the enqueue (the host enqueues step i+1, then waits for step i's result)")
+    ev = {"wire_records": e2e_variant(True), "full_records": e2e_variant(False)}
+    ev["wire_records"]["how"] = ("pinned host batch as compact wire records (EpisodeBatch.to_wire: %d of %d bytes per episode) -> " % (wb, rb)) + \
+        how_common % "EpisodeBatch.load_wire (device unpack, one launch) -> "
+    ev["full_records"]["how"] = "pinned host batch as full packed records -> " + how_common % ""
+    # both are public-API paths; the headline is the faster one on THIS run (the wire form wins when the H2D copy is the
+    # bottleneck, i.e. several GPUs sharing the host's PCIe / memory bandwidth; the extra unpack launch loses when it is not)
+    best = max(ev, key=lambda k: ev[k]["value"])
+    e2e = dict(ev[best])
+    e2e["path"] = best
+    other = "full_records" if best == "wire_records" else "wire_records"
+    e2e["alternative"] = dict(ev[other], path=other)
 
     extra = {}
     # ---------------- M1': the learner-side input pipeline (sample + truncate + train), ma_experiment.py:231-241

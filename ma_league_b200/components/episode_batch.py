@@ -304,6 +304,9 @@ class EpisodeBatch:
     # ------------------------------------------------------------------ compact wire form (host <-> device path)
     def _wire_batch_struct(self):
         """(mal_batch_t of this packed device batch, wire layout) for the hot-path scheme of ma_experiment.py:99-118."""
+        cached = getattr(self, "_wire_cache", None)
+        if cached is not None and cached[0] == self._storage.data_ptr():
+            return cached[1], cached[2]
         tv = self.data.transition_data
         need = ("state", "obs", "actions", "avail_actions", "reward", "terminated", "actions_onehot", "filled")
         if self._layout is None or set(tv) != set(need) or self.data.episode_data:
@@ -322,6 +325,7 @@ class EpisodeBatch:
         b.filled = nat.field_of(tv["filled"], 1)
         wl = nat.WireLayout()
         nat.check(nat.lib().mal_wire_layout(TT, N, OBS, S, C.byref(wl)), "mal_wire_layout")
+        self._wire_cache = (self._storage.data_ptr(), b, wl)       # the views are fixed once the record array exists
         return b, wl
 
     def wire_bytes(self):
