@@ -211,6 +211,8 @@ def run_ours(a, rank, world, device):
         nat.check(lib.mal_set_option(k.encode(), int(v)), "mal_set_option")
     d = workload_dims(a.workload)
     N, A, OBS, S, B, TT = d["N"], d["A"], d["OBS"], d["S"], d["B"], d["TT"]
+    if a.buffer_size <= B:                              # sample() of a buffer holding exactly one batch returns views of the buffer itself
+        a.buffer_size = B + max(B // 2, 1)
     th.manual_seed(1000 + rank)
     np.random.seed(1000 + rank)
     B_global = B
@@ -314,6 +316,10 @@ def run_ours(a, rank, world, device):
     # every step copies its wire batch H2D (copy stream, double-buffered), expands it on the device into the staging batch
     # (EpisodeBatch.load_wire, one launch), trains, and reads the loss back.  `full_records` = the same loop shipping the
     # full packed records (the round-1 method), for comparison.
+    if a.learner_only:                                  # profiling runs (tools/profile_round.sh): the learner step only
+        return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "config": {"workload": workload_string(a.workload)}, "learner_only": True,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern}
     n_pin = nb if B * rb * nb < 2 ** 31 else 2         # bound pinned host memory on the big workloads
     wb = parents[0].wire_bytes()
     stage = [M.EpisodeBatch(scheme, groups, B, TT, preprocess=pre, device=device) for _ in range(2)]
@@ -806,6 +812,7 @@ def main():
     ap.add_argument("--workload", default="qmix_5v5_b32")
     ap.add_argument("--buffer-size", dest="buffer_size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--learner-only", dest="learner_only", action="store_true", help="profiling runs: value + per-kernel table only")
     ap.add_argument("--dp", action="store_true", help="data-parallel mode (config 5): the batch is split over the ranks, "
                     "gradients meet in the fused peer-memory all-reduce (strong scaling)")
     ap.add_argument("--dp-nccl", dest="dp_nccl", action="store_true", help="with --dp: exchange through NCCL all_reduce instead")

@@ -232,3 +232,233 @@ __global__ void __launch_bounds__(64, 4) k_gru_bwd7(GruBwdArgs a) {
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 128-thread variants: ONE chain per CTA spread over all four sub-partitions of its SM (one warp each), so that the FMA
+// phase of a timestep is 48 FFMA2 per warp instead of 96 and an SM that hosts three chains (320 chains over 148 SMs)
+// has three warps on EVERY sub-partition instead of two chains sharing two of them.
+//     forward   U = 2 units x K/4 = 16 columns per lane   ->  4 LDS.128 + 48 FFMA2, two xor-shuffle stages
+//     backward  U = 4 columns x 192/8 = 24 rows per lane  ->  6 LDS.128 + 48 FFMA2, three xor-shuffle stages
+// The last shuffle stage is a butterfly: two lanes end with the same complete sum and do the gate math redundantly (no
+// extra latency); the lower one of the pair ("owner") stores.  The per-step operands (gi / saved gates, h_{t-1}, head
+// seed) arrive through a CTA-wide cp.async ring of 16-byte pieces: step s + PF - 1 is requested at step s into the slot
+// that step s - 1 used (everybody is past that step's barrier), and the issuing threads wait for step s + 1's group
+// before the barrier that ends step s, which publishes it.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DBG = 0>
+__global__ void __launch_bounds__(128, 3) k_gru_fwd8(GruFwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int KC = HID / 4;            // columns per lane
+    constexpr int SEG = KC + GT_PAD;
+    __shared__ __align__(16) float h_s[2][4 * SEG];
+    __shared__ __align__(16) float st_s[PF][G3];
+    __shared__ float pdl_anchor_s[128];
+    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
+    const int grp = i >> 2, part = i & 3;
+    const int unit = 2 * grp + (part & 1);           // the unit this lane finishes (lanes part and part ^ 2 both do)
+    const bool owner = part < 2;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const float *P = net ? a.params[1] : a.params[0];
+    const float *gi = net ? a.gi[1] : a.gi[0];
+    float *hout = net ? a.hout[1] : a.hout[0];
+    float4 *gates = net == 0 ? reinterpret_cast<float4 *>(a.gates) : nullptr;
+    const int t0 = a.t0, t1 = a.t1;
+
+    float anchor = 0.0f;
+    unsigned long long w[2][3][KC / 2];    // packed pairs of W_hh[g*64 + 2*grp + u][part*16 + 2j, +1]
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + 2 * grp + u) * HID + part * KC);
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const float4 v = __ldg(wr + q);
+                w[u][g][2 * q] = pack2(v.x, v.y); w[u][g][2 * q + 1] = pack2(v.z, v.w);
+                anchor += v.x;
+            }
+        }
+    const float b_r = __ldg(P + L.b_hh + unit), b_z = __ldg(P + L.b_hh + HID + unit), b_n = __ldg(P + L.b_hh + 2 * HID + unit);
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;   // pins the loads above the wait (see k_gru_fwd7)
+    pdl_wait();
+    float hprev = t0 > 0 ? hout[((int64_t)(t0 - 1) * a.R + row) * HID + unit] : 0.0f;   // init_hidden: zeros
+    const int hpos = unit + (unit / KC) * GT_PAD;
+    if (owner) { h_s[0][hpos] = hprev; h_s[1][hpos] = 0.0f; }
+    const int64_t tstride = (int64_t)a.R * G3;
+    const float *p_g = gi + (int64_t)row * G3 + 4 * i;          // threads 0..47: 16-byte piece i of the 768-byte gi row
+    const bool loader = i < G3 / 4;
+#pragma unroll
+    for (int p = 0; p < PF - 1; ++p) {
+        if (loader && t0 + p < t1) cp_async16(&st_s[p][4 * i], p_g + (int64_t)(t0 + p) * tstride);
+        cp_async_commit();
+    }
+    cp_async_wait<PF - 2>();
+    __syncthreads();
+
+    for (int tt = t0; tt < t1; tt += 2) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int t = tt + p;
+            if (t >= t1) break;
+            const int buf = p;                   // == (t - t0) & 1
+            const int s = t - t0;
+            const int slot = s % PF;
+            if (t + PDL_LEAD_STEPS == t1) pdl_trigger();
+            const float g_r = st_s[slot][unit], g_z = st_s[slot][HID + unit], g_n = st_s[slot][2 * HID + unit];
+            if (loader && t + PF - 1 < t1) cp_async16(&st_s[(s + PF - 1) % PF][4 * i], p_g + (int64_t)(t + PF - 1) * tstride);
+            cp_async_commit();
+            const float4 *hp = reinterpret_cast<const float4 *>(h_s[buf] + part * SEG);
+            unsigned long long acc[2][3];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) acc[u][g] = 0ull;
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const float4 hv = hp[q];
+                const unsigned long long hxy = pack2(hv.x, hv.y), hzw = pack2(hv.z, hv.w);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        acc[u][g] = fma2(w[u][g][2 * q], hxy, acc[u][g]);
+                        acc[u][g] = fma2(w[u][g][2 * q + 1], hzw, acc[u][g]);
+                    }
+            }
+            // transposing reduction over the lane quad: xor 1 hands each lane its unit, xor 2 completes the sum
+            float x[3];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                float a0, a1, c0, c1;
+                unpack2(acc[0][g], a0, a1); unpack2(acc[1][g], c0, c1);
+                const float p0 = a0 + a1, p1 = c0 + c1;
+                const float mine = (part & 1) ? p1 : p0, other = (part & 1) ? p0 : p1;
+                const float y = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+                x[g] = y + __shfl_xor_sync(0xffffffffu, y, 2);
+            }
+            const float xr = x[0] + (g_r + b_r), xz = x[1] + (g_z + b_z), ghn = x[2] + b_n;
+            const float rr = sigmoid_mufu(xr), zz = sigmoid_mufu(xz);
+            const float nn = tanh_mufu(g_n + rr * ghn);
+            const float hn = nn + zz * (hprev - nn);
+            hprev = hn;
+            if (owner) {
+                h_s[buf ^ 1][hpos] = hn;
+                if (!(DBG & 1)) {
+                    const int64_t m = (int64_t)t * a.R + row;
+                    hout[m * HID + unit] = hn;
+                    if (gates) gates[m * HID + unit] = make_float4(rr, zz, nn, ghn);
+                }
+            }
+            cp_async_wait<PF - 2>();             // step t + 1's operands have landed (issuing threads); the barrier publishes them
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 3) k_gru_bwd8(GruBwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int JC = G3 / 8;             // rows j of W_hh per lane (24)
+    constexpr int DSEG = JC + GT_PAD;      // padded eighth of the d(gates) operand
+    __shared__ __align__(16) float dg_s[2][8 * DSEG];   // d gi_r | d gi_z | d gh_n of the previous step, in eight shifted pieces
+    __shared__ __align__(16) float4 g4_s[PF][HID];
+    __shared__ __align__(16) float hp_s[PF][HID];
+    __shared__ __align__(16) float dh_s[PF][HID];
+    __shared__ float pdl_anchor_s[128];
+    const int k = threadIdx.x, row = blockIdx.x;
+    const int grp = k >> 3, part = k & 7;
+    const int col = 4 * grp + (part & 3);            // the column this lane finishes (lanes part and part ^ 4 both do)
+    const bool owner = part < 4;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const int T = a.TT - 1;
+
+    float anchor = 0.0f;
+    for (int idx = k; idx < 2 * 8 * DSEG; idx += 128) (&dg_s[0][0])[idx] = 0.0f;
+    unsigned long long wT[4][JC / 2];      // packed pairs (W_hh[24*part + 2j][4grp + c], W_hh[24*part + 2j + 1][4grp + c])
+#pragma unroll
+    for (int j = 0; j < JC / 2; ++j) {
+        const int jj = part * JC + 2 * j;
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)jj * HID + 4 * grp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)(jj + 1) * HID + 4 * grp));
+        wT[0][j] = pack2(w0.x, w1.x); wT[1][j] = pack2(w0.y, w1.y); wT[2][j] = pack2(w0.z, w1.z); wT[3][j] = pack2(w0.w, w1.w);
+        anchor += w0.x + w1.y;
+    }
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[k]) = anchor;   // pins the loads above the wait (see k_gru_fwd7)
+
+    pdl_wait();                                  // W_hh is a step constant; gates / h / dh_head come from the predecessors
+    const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
+    auto fetch = [&](int i, int slot) {          // step i <-> t = TT-1-i; threads 0..63 gates, 64..79 h_{t-1}, 80..95 head seed
+        const int t = a.TT - 1 - i;
+        const int64_t m = (int64_t)t * a.R + row;
+        if (k < 64) cp_async16(&g4_s[slot][k], gates4 + m * HID + k);
+        else if (k < 80) cp_async16(&hp_s[slot][4 * (k - 64)], a.hout + (t > 0 ? (m - a.R) * HID + 4 * (k - 64) : 0), t > 0 ? 16 : 0);   // h_{-1} = 0
+        else if (k < 96) cp_async16(&dh_s[slot][4 * (k - 80)], a.dh_head + (t < T ? m * HID + 4 * (k - 80) : 0), t < T ? 16 : 0);        // no q at t = T
+    };
+#pragma unroll
+    for (int p = 0; p < PF - 1; ++p) {
+        if (p < a.TT) fetch(p, p);
+        cp_async_commit();
+    }
+    float carry = 0.0f;
+    // position of logical element e of [drp | dzp | dghn] inside the shifted-piece layout
+    auto dpos = [&](int e) { return e + (e / JC) * GT_PAD; };
+    const int pos_r = dpos(col), pos_z = dpos(HID + col), pos_n = dpos(2 * HID + col);
+    cp_async_wait<PF - 2>();
+    __syncthreads();
+
+    for (int i0 = 0; i0 < a.TT; i0 += 2) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int i = i0 + p;
+            if (i >= a.TT) break;
+            const int buf = p;
+            const int slot = i % PF;
+            if (i + PDL_LEAD_STEPS == a.TT) pdl_trigger();
+            const float4 g4 = g4_s[slot][col];
+            const float hp = hp_s[slot][col], dhh = dh_s[slot][col];
+            if (i + PF - 1 < a.TT) fetch(i + PF - 1, (i + PF - 1) % PF);
+            cp_async_commit();
+            const float4 *dp = reinterpret_cast<const float4 *>(dg_s[buf] + part * DSEG);
+            unsigned long long s[4][2];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[c][0] = s[c][1] = 0ull;
+#pragma unroll
+            for (int u = 0; u < JC / 4; ++u) {
+                const float4 d = dp[u];
+                const unsigned long long dxy = pack2(d.x, d.y), dzw = pack2(d.z, d.w);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    s[c][0] = fma2(wT[c][2 * u], dxy, s[c][0]);
+                    s[c][1] = fma2(wT[c][2 * u + 1], dzw, s[c][1]);
+                }
+            }
+            // transposing reduction over the lane octet: xor 1 and xor 2 hand each lane its column, xor 4 completes the sum
+            float pc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { float l0, h0, l1, h1; unpack2(s[c][0], l0, h0); unpack2(s[c][1], l1, h1); pc[c] = (l0 + h0) + (l1 + h1); }
+            const bool b0 = part & 1, b1 = part & 2;
+            const float k0 = b0 ? pc[1] : pc[0], k1 = b0 ? pc[3] : pc[2];
+            const float g0 = b0 ? pc[0] : pc[1], g1 = b0 ? pc[2] : pc[3];
+            const float q0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 1);
+            const float q1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 1);
+            const float keep = b1 ? q1 : q0, give = b1 ? q0 : q1;
+            const float v2 = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+            const float dh = (v2 + __shfl_xor_sync(0xffffffffu, v2, 4)) + (carry + dhh);
+            const float rr = g4.x, zz = g4.y, nn = g4.z, ghn = g4.w;
+            const float dn = dh * (1.0f - zz);
+            const float dz = dh * (hp - nn);
+            const float dnp = dn * (1.0f - nn * nn);
+            const float dzp = dz * zz * (1.0f - zz);
+            const float drp = dnp * ghn * rr * (1.0f - rr);
+            const float dghn = dnp * rr;
+            carry = dh * zz;
+            if (owner) {
+                float *sm = dg_s[buf ^ 1];
+                sm[pos_r] = drp; sm[pos_z] = dzp; sm[pos_n] = dghn;
+                float *dg = a.d_g + ((int64_t)(a.TT - 1 - i) * a.R + row) * 4 * HID + col;
+                dg[0] = drp; dg[HID] = dzp; dg[2 * HID] = dnp; dg[3 * HID] = dghn;
+            }
+            cp_async_wait<PF - 2>();
+            __syncthreads();
+        }
+    }
+}

@@ -28,12 +28,35 @@
 // SWAP = 1 computes the transposed tile dW^T[k, n] (MMA rows <- 128 columns of A, MMA columns <- 64 columns of dY): for
 // narrow outputs with a wide inner dimension (fc1: Nout = 64, K = d_in up to 246) this fills the 128-row operand
 // instead of padding half of it, and halves the number of tiles.
-template <int AK, int SWAP>
+//
+// MNM = 1 (default): the operands are handed to the tensor core in MN-MAJOR form, i.e. exactly as they lie in memory
+// (the contraction index m is the slow one): a 32-row block is staged as [32-column slab][m row][128 bytes] straight
+// from the registers the coalesced float4 loads landed in.  No scratch, no column-wise read-back, no __syncwarp; a
+// k-step (8 rows of m) is 1 KB further into every slab.
+// For MN-major TF32 operands the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1;
+// with type 2 the MMA reads zeros -- decoded with tools/mn_probe.cu, which makes the tensor core report the shared-memory
+// offset it fetches for every (mn, k)): atoms of 4 m rows x 128 bytes, the 32-byte granule index XOR-ed with (m & 3),
+// SBO = 512 B between 4-row groups, LBO = the slab stride between 32-column groups.
+// MNM = 0 keeps the round-1 in-shared-memory transposition into K-major tiles (mal_set_option "reduce_mn" = 0) for A/B checks.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // next 32-column slab of the MN dimension
+    d |= (uint64_t)(512 >> 4) << 32;                      // next group of four m rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                               // SWIZZLE_128B_BASE32B
+    return d;
+}
+// byte offset of 16-byte piece c (0..7) of m row kr inside one [32 m rows x 32 columns] MN-major slab
+__device__ __forceinline__ uint32_t mn_off(int kr, int c) { return (uint32_t)kr * 128u + (uint32_t)((c ^ ((kr & 3) << 1)) << 4); }
+#define RT_SLAB (RT_BM * 128)             // 4 KB: [32 m rows x 32 columns] of one operand piece (MN-major staging)
+
+template <int AK, int SWAP, int MNM>
 __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ RedGroup g) {
     extern __shared__ __align__(1024) uint8_t rt_smem[];
     __shared__ __align__(8) uint64_t st_bar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bsum_s[8][RT_NT];
+    __shared__ __align__(16) float bsum_s[8][RT_NT];
     int pi = 0;
     while (pi + 1 < g.n && (int)blockIdx.y >= g.p[pi + 1].tile0) ++pi;
     const RedProb p = g.p[pi];
@@ -140,7 +163,8 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         return v;
     };
     float4 py[4], pa[2];                              // wide rows (32 float4 each) / narrow rows (16 float4 each)
-    auto load_block = [&](int j) {
+    float4 qy[4], qa[2];                              // MNM: second register set (block j+1 is requested before block j is staged)
+    auto load_block_into = [&](int j, float4 (&py)[4], float4 (&pa)[2]) {
         const int64_t mm = mb + (int64_t)j * RT_BM;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                 // warp w owns rows 4w .. 4w+3 (one 16-byte piece of every operand row)
@@ -154,13 +178,15 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             pa[i] = SWAP ? load_dy4(m, n0 + 4 * c) : load_a4(m, k0 + 4 * c);
         }
     };
+    auto load_block = [&](int j) { load_block_into(j, py, pa); };
 
     const int q = warp & 3, half = warp >> 2;         // accumulator ownership: TMEM lane quarter q, columns half*32 .. +32
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
     float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // column sums of dY (bias gradient) over this warp's rows: columns lane + 32 i
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24) |
+                           (MNM ? ((1u << 15) | (1u << 16)) : 0u);       // bits 15 / 16: A / B operand MN-major
     bool fresh = true;                                // the next MMA overwrites the TMEM accumulators
     auto fold = [&](int j) {                          // all MMAs up to block j -> register accumulators
         mbar_wait(&st_bar[j & 1], (uint32_t)((j >> 1) & 1));
@@ -175,56 +201,111 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    if (nblk > 0) load_block(0);
-    for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        uint8_t *Ah = rt_smem + (size_t)s * RT_STAGE, *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
-        // ---- raw rows (coalesced) -> the warp's private scratch; only this warp reads them back: __syncwarp suffices
-        float *ry = rawY + warp * (4 * RT_NT), *ra = rawA + warp * (4 * RT_KT);
+    if (MNM) {
+        float4 bs4 = make_float4(0.f, 0.f, 0.f, 0.f);     // column sums of dY over this thread's rows: columns 4 lane .. +3 (wide) / 4 (lane & 15) .. +3 (narrow)
+        auto add4 = [&](const float4 &v) { bs4.x += v.x; bs4.y += v.y; bs4.z += v.z; bs4.w += v.w; };
+        auto body = [&](int j, float4 (&cy)[4], float4 (&ca)[2], float4 (&ny)[4], float4 (&na)[2]) {
+            const int s = j & 1;
+            uint8_t *Ah = rt_smem + (size_t)s * RT_STAGE, *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
+            if (j + 1 < nblk) load_block_into(j + 1, ny, na);                    // flies under the staging + MMAs of block j
+            if (j >= 2) mbar_wait(&st_bar[s], (uint32_t)(((j - 2) >> 1) & 1));   // the MMAs of block j-2 released this stage
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<float4 *>(ry)[i * 32 + lane] = py[i];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) reinterpret_cast<float4 *>(ra)[(2 * i + (lane >> 4)) * 16 + (lane & 15)] = pa[i];
-        __syncwarp();
-        if (j + 1 < nblk) load_block(j + 1);                             // flies under the transposition + MMAs
-        if (j >= 2) mbar_wait(&st_bar[s], (uint32_t)(((j - 2) >> 1) & 1));   // the MMAs of block j-2 released this stage
-        // ---- transpose + split: the warp's four rows are 16-byte piece `warp` of every operand row
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int n = lane + 32 * i;
-            const float4 v = make_float4(ry[n], ry[RT_NT + n], ry[2 * RT_NT + n], ry[3 * RT_NT + n]);
-            if (!SWAP) bsum[i] += (v.x + v.y) + (v.z + v.w);
-            split_store_fast(Ah, Al, (uint32_t)n * 128u + (uint32_t)((warp ^ (n & 7)) << 4), v);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int k = lane + 32 * i;
-            const float4 v = make_float4(ra[k], ra[RT_KT + k], ra[2 * RT_KT + k], ra[3 * RT_KT + k]);
-            if (SWAP) bsum[i] += (v.x + v.y) + (v.z + v.w);
-            split_store_fast(Bh, Bl, (uint32_t)k * 128u + (uint32_t)((warp ^ (k & 7)) << 4), v);
-        }
-        __syncwarp();                                                    // scratch is rewritten by the next block
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 0) {
-            const uint64_t dAh = umma_desc_sw128(smem_u32(Ah)), dAl = umma_desc_sw128(smem_u32(Al));
-            const uint64_t dBh = umma_desc_sw128(smem_u32(Bh)), dBl = umma_desc_sw128(smem_u32(Bl));
-#pragma unroll
-            for (int ks = 0; ks < RT_BM / 8; ++ks) {
-                const uint64_t o = (uint64_t)((ks * 32) >> 4);
-                const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
-                umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
-                umma_tf32(tmem_base + RT_KT, dAl + o, dBh + o, idesc, first);
-                umma_tf32(tmem_base + RT_KT, dAh + o, dBl + o, idesc, 1u);
+            for (int i = 0; i < 4; ++i) {                                        // wide operand: row m = 4 warp + i, columns 4 lane .. +3
+                const int kr = 4 * warp + i;
+                if (!SWAP) add4(cy[i]);
+                split_store_fast(Ah, Al, (uint32_t)(lane >> 3) * RT_SLAB + mn_off(kr, lane & 7), cy[i]);
             }
-            umma_commit(&st_bar[s]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {                                        // narrow operand: rows 4 warp + 2 i + (lane >> 4)
+                const int kr = 4 * warp + 2 * i + (lane >> 4), c = lane & 15;
+                if (SWAP) add4(ca[i]);
+                split_store_fast(Bh, Bl, (uint32_t)(c >> 3) * RT_SLAB + mn_off(kr, c & 7), ca[i]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                const uint64_t dAh = umma_desc_mn_sw128(smem_u32(Ah), RT_SLAB), dAl = umma_desc_mn_sw128(smem_u32(Al), RT_SLAB);
+                const uint64_t dBh = umma_desc_mn_sw128(smem_u32(Bh), RT_SLAB), dBl = umma_desc_mn_sw128(smem_u32(Bl), RT_SLAB);
+#pragma unroll
+                for (int ks = 0; ks < RT_BM / 8; ++ks) {
+                    const uint64_t o = (uint64_t)((ks * 1024) >> 4);             // eight m rows = one atom further
+                    const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + RT_KT, dAl + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + RT_KT, dAh + o, dBl + o, idesc, 1u);
+                }
+                umma_commit(&st_bar[s]);
+            }
+            fresh = false;
+            if ((j % RT_FLUSH) == RT_FLUSH - 1 || j == nblk - 1) {
+                fold(j);
+                fresh = true;
+            }
+        };
+        if (nblk > 0) load_block_into(0, py, pa);
+        for (int j = 0; j < nblk; j += 2) {
+            body(j, py, pa, qy, qa);
+            if (j + 1 < nblk) body(j + 1, qy, qa, py, pa);
         }
-        fresh = false;
-        if ((j % RT_FLUSH) == RT_FLUSH - 1 || j == nblk - 1) {
-            fold(j);
-            fresh = true;
+        if (SWAP) {                                       // lanes c and c + 16 hold the same narrow columns
+            bs4.x += __shfl_xor_sync(0xffffffffu, bs4.x, 16); bs4.y += __shfl_xor_sync(0xffffffffu, bs4.y, 16);
+            bs4.z += __shfl_xor_sync(0xffffffffu, bs4.z, 16); bs4.w += __shfl_xor_sync(0xffffffffu, bs4.w, 16);
+        }
+        if (want_bias && (!SWAP || lane < 16)) *reinterpret_cast<float4 *>(&bsum_s[warp][4 * lane]) = bs4;
+    } else {
+        if (nblk > 0) load_block(0);
+        for (int j = 0; j < nblk; ++j) {
+            const int s = j & 1;
+            uint8_t *Ah = rt_smem + (size_t)s * RT_STAGE, *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
+            // ---- raw rows (coalesced) -> the warp's private scratch; only this warp reads them back: __syncwarp suffices
+            float *ry = rawY + warp * (4 * RT_NT), *ra = rawA + warp * (4 * RT_KT);
+    #pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4 *>(ry)[i * 32 + lane] = py[i];
+    #pragma unroll
+            for (int i = 0; i < 2; ++i) reinterpret_cast<float4 *>(ra)[(2 * i + (lane >> 4)) * 16 + (lane & 15)] = pa[i];
+            __syncwarp();
+            if (j + 1 < nblk) load_block(j + 1);                             // flies under the transposition + MMAs
+            if (j >= 2) mbar_wait(&st_bar[s], (uint32_t)(((j - 2) >> 1) & 1));   // the MMAs of block j-2 released this stage
+            // ---- transpose + split: the warp's four rows are 16-byte piece `warp` of every operand row
+    #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = lane + 32 * i;
+                const float4 v = make_float4(ry[n], ry[RT_NT + n], ry[2 * RT_NT + n], ry[3 * RT_NT + n]);
+                if (!SWAP) bsum[i] += (v.x + v.y) + (v.z + v.w);
+                split_store_fast(Ah, Al, (uint32_t)n * 128u + (uint32_t)((warp ^ (n & 7)) << 4), v);
+            }
+    #pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int k = lane + 32 * i;
+                const float4 v = make_float4(ra[k], ra[RT_KT + k], ra[2 * RT_KT + k], ra[3 * RT_KT + k]);
+                if (SWAP) bsum[i] += (v.x + v.y) + (v.z + v.w);
+                split_store_fast(Bh, Bl, (uint32_t)k * 128u + (uint32_t)((warp ^ (k & 7)) << 4), v);
+            }
+            __syncwarp();                                                    // scratch is rewritten by the next block
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                const uint64_t dAh = umma_desc_sw128(smem_u32(Ah)), dAl = umma_desc_sw128(smem_u32(Al));
+                const uint64_t dBh = umma_desc_sw128(smem_u32(Bh)), dBl = umma_desc_sw128(smem_u32(Bl));
+    #pragma unroll
+                for (int ks = 0; ks < RT_BM / 8; ++ks) {
+                    const uint64_t o = (uint64_t)((ks * 32) >> 4);
+                    const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + RT_KT, dAl + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + RT_KT, dAh + o, dBl + o, idesc, 1u);
+                }
+                umma_commit(&st_bar[s]);
+            }
+            fresh = false;
+            if ((j % RT_FLUSH) == RT_FLUSH - 1 || j == nblk - 1) {
+                fold(j);
+                fresh = true;
+            }
         }
     }
     // ---- partials: partW[chunk][n][k]; TMEM lane = wide-operand row, columns = narrow-operand rows
@@ -247,8 +328,10 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         }
     }
     if (want_bias) {
+        if (!MNM) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bsum_s[warp][lane + 32 * i] = bsum[i];
+            for (int i = 0; i < 4; ++i) bsum_s[warp][lane + 32 * i] = bsum[i];
+        }
         __syncthreads();
         if (tid < (SWAP ? RT_KT : RT_NT) && n0 + tid < p.Nout) {
             float sacc = 0.0f;

@@ -1,6 +1,7 @@
 // Stand-alone timing + cross-check harness for the GRU recurrence kernels of learner.cuh (not product code).
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/gru_bench tools/gru_bench.cu
-// Checks k_gru_fwd7 / k_gru_bwd7 against an fp64 CPU recurrence on the first rows, then times them.
+//   tools/gru_bench [R] [TT] [rows checked] [variant 7|8]
+// Checks k_gru_fwd7/8 / k_gru_bwd7/8 against an fp64 CPU recurrence on the first rows, then times them.
 #include "../ma_league_b200/csrc/gru_rec.cuh"
 #include <vector>
 #include <random>
@@ -41,9 +42,9 @@ int main(int argc, char **argv) {
     GruBwdArgs ba; ba.params = dP0; ba.hout = h[0]; ba.gates = gates; ba.dh_head = ddhh; ba.d_g = dg; ba.TT = TT; ba.R = R;
     ba.d_in = d_in; ba.n_actions = A;
 
-    const int variant = 7;
-    auto fwd = [&] { k_gru_fwd7<0><<<dim3(R, 2), HID>>>(fa); };
-    auto bwd = [&] { k_gru_bwd7<<<R, HID>>>(ba); };
+    const int variant = argc > 4 ? atoi(argv[4]) : 8;
+    auto fwd = [&] { if (variant == 7) k_gru_fwd7<0><<<dim3(R, 2), HID>>>(fa); else k_gru_fwd8<0><<<dim3(R, 2), 128>>>(fa); };
+    auto bwd = [&] { if (variant == 7) k_gru_bwd7<<<R, HID>>>(ba); else k_gru_bwd8<<<R, 128>>>(ba); };
     const float fus = time_us(fwd);
     const float bus = time_us(bwd);
     printf("variant %d  fwd grid %dx2: %7.1f us  %5.0f cycles/step    bwd grid %d: %7.1f us  %5.0f cycles/step   (%s)\n", variant, R, fus,
