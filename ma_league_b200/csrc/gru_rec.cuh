@@ -19,6 +19,7 @@
 // so that the S addresses of one LDS.128 fall into different banks.  fp32 throughout (FFMA2 = two fp32 FMAs per
 // instruction; it issues at half rate, i.e. the same FMA-pipe time as FFMA in half the issue slots).
 #pragma once
+#include <type_traits>
 #include "learner.cuh"
 
 #define GT_PAD 4                           // floats between consecutive K sub-ranges of a shared operand row
@@ -461,4 +462,261 @@ __global__ void __launch_bounds__(128, 3) k_gru_bwd8(GruBwdArgs a) {
             __syncthreads();
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 9 = the 64-thread layout of variant 7 with the per-step instruction count cut down.  The source-level profile
+// of variant 7 (profiles/r02_gru7_source_summary.txt) shows a single warp per sub-partition issuing one instruction every
+// ~4.4 cycles, FMA or not: 96 FFMA2 and ~100 other instructions per step, ~40 of them ring-slot / address / boundary
+// arithmetic.  Here the time loop is unrolled over the PF ring slots (slot and h buffer are compile-time constants, so
+// every shared-memory access has an immediate offset), the global pointers advance by a constant per step, and the
+// steady-state loop carries no boundary predicates (the last <= 2 PF - 1 steps run in a guarded tail).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DBG = 0>
+__global__ void __launch_bounds__(64, 4) k_gru_fwd9(GruFwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int KC = HID / 2;            // columns per lane
+    constexpr int HROW = HID + GT_PAD;
+    __shared__ __align__(16) float h_s[2][HROW];
+    __shared__ float st_s[PF][3][HID];
+    __shared__ float pdl_anchor_s[HID];
+    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
+    const int ug = i >> 1, part = i & 1;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const float *P = net ? a.params[1] : a.params[0];
+    const float *gi = net ? a.gi[1] : a.gi[0];
+    float *hout = net ? a.hout[1] : a.hout[0];
+    const bool save_gates = net == 0;
+    const int t0 = a.t0, n = a.t1 - a.t0;
+
+    float anchor = 0.0f;
+    unsigned long long w[2][3][KC / 2];    // packed pairs of W_hh[g*64 + 2*ug + u][part*32 + 2j, +1]
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + 2 * ug + u) * HID + part * KC);
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const float4 v = __ldg(wr + q);
+                w[u][g][2 * q] = pack2(v.x, v.y); w[u][g][2 * q + 1] = pack2(v.z, v.w);
+                anchor += v.x;
+            }
+        }
+    const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;   // pins the loads above the wait (see k_gru_fwd7)
+    pdl_wait();
+    const int64_t hstride = (int64_t)a.R * HID, tstride = (int64_t)a.R * G3;
+    float *hdst = hout + ((int64_t)t0 * a.R + row) * HID + i;                 // h of the current step
+    float4 *gdst = reinterpret_cast<float4 *>(a.gates) + ((int64_t)t0 * a.R + row) * HID + i;
+    float hprev = t0 > 0 ? *(hdst - hstride) : 0.0f;                           // init_hidden: zeros
+    const int hpos = i + (i >= KC ? GT_PAD : 0);
+    h_s[0][hpos] = hprev; h_s[1][hpos] = 0.0f;
+    const float *gsrc = gi + ((int64_t)t0 * a.R + row) * G3 + i;              // gi row of the next step to request
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        if (p < n) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], gsrc + g * HID);
+        }
+        cp_async_commit();
+        gsrc += tstride;
+    }
+    __syncthreads();
+    const float4 *hp0 = reinterpret_cast<const float4 *>(h_s[0] + part * (KC + GT_PAD));
+    const float4 *hp1 = reinterpret_cast<const float4 *>(h_s[1] + part * (KC + GT_PAD));
+
+    // one timestep; SLOT / BUF are compile-time, `more` = the step PF ahead exists (always true in the steady-state loop)
+    auto step = [&](auto slot_c, auto buf_c, bool more) {
+        constexpr int SLOT = decltype(slot_c)::value, BUF = decltype(buf_c)::value;
+        cp_async_wait<PF - 1>();             // this thread's group of this step has landed
+        const float g_r = st_s[SLOT][0][i], g_z = st_s[SLOT][1][i], g_n = st_s[SLOT][2][i];
+        if (more) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) cp_async4(&st_s[SLOT][g][i], gsrc + g * HID);
+        }
+        cp_async_commit();
+        gsrc += tstride;
+        const float4 *hp = BUF ? hp1 : hp0;
+        float4 hv[KC / 4];
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) hv[q] = hp[q];
+        unsigned long long s[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) s[u][g] = 0ull;
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) {
+            const unsigned long long hxy = pack2(hv[q].x, hv[q].y), hzw = pack2(hv[q].z, hv[q].w);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) s[u][g] = fma2(w[u][g][2 * q], hxy, s[u][g]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) s[u][g] = fma2(w[u][g][2 * q + 1], hzw, s[u][g]);
+        }
+        float x[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float a0, a1, c0, c1;
+            unpack2(s[0][g], a0, a1); unpack2(s[1][g], c0, c1);
+            const float p0 = a0 + a1, p1 = c0 + c1;
+            const float mine = part ? p1 : p0, other = part ? p0 : p1;
+            x[g] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+        }
+        const float xr = x[0] + (g_r + b_r), xz = x[1] + (g_z + b_z), ghn = x[2] + b_n;
+        const float rr = sigmoid_mufu(xr), zz = sigmoid_mufu(xz);
+        const float nn = tanh_mufu(g_n + rr * ghn);
+        const float hn = nn + zz * (hprev - nn);
+        hprev = hn;
+        h_s[BUF ^ 1][hpos] = hn;
+        if (!(DBG & 1)) {
+            *hdst = hn;
+            if (save_gates) *gdst = make_float4(rr, zz, nn, ghn);
+        }
+        hdst += hstride; gdst += hstride;
+        __syncthreads();
+    };
+    using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+    int sdone = 0;
+    for (; sdone + 2 * PF <= n; sdone += PF) {       // steady state: every prefetch target exists
+        step(std::integral_constant<int, 0>{}, I0{}, true); step(std::integral_constant<int, 1>{}, I1{}, true);
+        step(std::integral_constant<int, 2>{}, I0{}, true); step(std::integral_constant<int, 3>{}, I1{}, true);
+        step(std::integral_constant<int, 4>{}, I0{}, true); step(std::integral_constant<int, 5>{}, I1{}, true);
+        step(std::integral_constant<int, 6>{}, I0{}, true); step(std::integral_constant<int, 7>{}, I1{}, true);
+    }
+    pdl_trigger();                                   // at most 2 PF - 1 steps left: the dependent kernel may start its prologue
+    // guarded tail (sdone is a multiple of PF, so slots and buffers line up with the unrolled order)
+#define GRU9_TAIL(S, B) if (sdone + S < n) step(std::integral_constant<int, S>{}, B{}, sdone + S + PF < n)
+    for (; sdone < n; sdone += PF) {
+        GRU9_TAIL(0, I0); GRU9_TAIL(1, I1); GRU9_TAIL(2, I0); GRU9_TAIL(3, I1);
+        GRU9_TAIL(4, I0); GRU9_TAIL(5, I1); GRU9_TAIL(6, I0); GRU9_TAIL(7, I1);
+    }
+#undef GRU9_TAIL
+}
+
+__global__ void __launch_bounds__(64, 4) k_gru_bwd9(GruBwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int JC = G3 / 4;             // rows j of W_hh per lane (48)
+    constexpr int DSEG = JC + GT_PAD;      // padded quarter of the d(gates) operand
+    __shared__ __align__(16) float dg_s[2][4 * DSEG];   // d gi_r | d gi_z | d gh_n of the previous step, in four shifted quarters
+    __shared__ __align__(16) float4 g4_s[PF][HID];
+    __shared__ float hp_s[PF][HID], dh_s[PF][HID];
+    __shared__ float pdl_anchor_s[HID];
+    const int k = threadIdx.x, row = blockIdx.x;
+    const int kg = k >> 2, part = k & 3;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const int n = a.TT;
+
+    float anchor = 0.0f;
+    for (int idx = k; idx < 2 * 4 * DSEG; idx += HID) (&dg_s[0][0])[idx] = 0.0f;
+    unsigned long long wT[4][JC / 2];      // packed pairs (W_hh[48*part + 2j][4kg + c], W_hh[48*part + 2j + 1][4kg + c])
+#pragma unroll
+    for (int j = 0; j < JC / 2; ++j) {
+        const int jj = part * JC + 2 * j;
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)jj * HID + 4 * kg));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)(jj + 1) * HID + 4 * kg));
+        wT[0][j] = pack2(w0.x, w1.x); wT[1][j] = pack2(w0.y, w1.y); wT[2][j] = pack2(w0.z, w1.z); wT[3][j] = pack2(w0.w, w1.w);
+        anchor += w0.x + w1.y;
+    }
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[k]) = anchor;   // pins the loads above the wait (see k_gru_fwd7)
+
+    pdl_wait();                                  // W_hh is a step constant; gates / h / dh_head come from the predecessors
+    // step s <-> t = TT-1-s; every pointer is that of the NEXT step to request and walks backwards by one timestep
+    const int64_t hstride = (int64_t)a.R * HID;
+    const int64_t m_last = (int64_t)(a.TT - 1) * a.R + row;
+    const float4 *gsrc = reinterpret_cast<const float4 *>(a.gates) + m_last * HID + k;
+    const float *hsrc = a.hout + (m_last - a.R) * HID + k;          // h_{t-1}; not dereferenced at t = 0
+    const float *dsrc = a.dh_head + m_last * HID + k;               // not dereferenced at t = TT-1 (no q there)
+    float *dgdst = a.d_g + m_last * 4 * HID + k;
+    // generic request of step s into `slot` (prologue and tail: with the sequence-boundary guards)
+    auto fetch_guarded = [&](int s, int slot) {
+        const int t = n - 1 - s;
+        cp_async16(&g4_s[slot][k], gsrc);
+        cp_async4(&hp_s[slot][k], t > 0 ? hsrc : a.hout, t > 0 ? 4 : 0);          // h_{-1} = 0
+        cp_async4(&dh_s[slot][k], t < n - 1 ? dsrc : a.dh_head, t < n - 1 ? 4 : 0);
+    };
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        if (p < n) fetch_guarded(p, p);
+        cp_async_commit();
+        gsrc -= hstride; hsrc -= hstride; dsrc -= hstride;
+    }
+    float carry = 0.0f;
+    auto dpos = [&](int e) { return e + (e / JC) * GT_PAD; };
+    const int pos_r = dpos(k), pos_z = dpos(HID + k), pos_n = dpos(2 * HID + k);
+    __syncthreads();
+    const float4 *dp0 = reinterpret_cast<const float4 *>(dg_s[0] + part * DSEG);
+    const float4 *dp1 = reinterpret_cast<const float4 *>(dg_s[1] + part * DSEG);
+    const bool b0 = part & 1, b1 = part & 2;
+
+    // one step; MODE 0: steady state (the step PF ahead exists and is away from both sequence ends), 1: guarded request, 2: none
+    auto step = [&](auto slot_c, auto buf_c, int mode, int s) {
+        constexpr int SLOT = decltype(slot_c)::value, BUF = decltype(buf_c)::value;
+        cp_async_wait<PF - 1>();
+        const float4 g4 = g4_s[SLOT][k];
+        const float hp = hp_s[SLOT][k], dhh = dh_s[SLOT][k];
+        if (mode == 0) {
+            cp_async16(&g4_s[SLOT][k], gsrc);
+            cp_async4(&hp_s[SLOT][k], hsrc);
+            cp_async4(&dh_s[SLOT][k], dsrc);
+        } else if (mode == 1) fetch_guarded(s + PF, SLOT);
+        cp_async_commit();
+        gsrc -= hstride; hsrc -= hstride; dsrc -= hstride;
+        const float4 *dp = BUF ? dp1 : dp0;
+        float4 d[JC / 4];
+#pragma unroll
+        for (int u = 0; u < JC / 4; ++u) d[u] = dp[u];
+        unsigned long long acc[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = 0ull;
+#pragma unroll
+        for (int u = 0; u < JC / 4; ++u) {
+            const unsigned long long dxy = pack2(d[u].x, d[u].y), dzw = pack2(d[u].z, d[u].w);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c][0] = fma2(wT[c][2 * u], dxy, acc[c][0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c][1] = fma2(wT[c][2 * u + 1], dzw, acc[c][1]);
+        }
+        float pc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { float l0, h0, l1, h1; unpack2(acc[c][0], l0, h0); unpack2(acc[c][1], l1, h1); pc[c] = (l0 + h0) + (l1 + h1); }
+        const float k0 = b0 ? pc[1] : pc[0], k1 = b0 ? pc[3] : pc[2];
+        const float g0 = b0 ? pc[0] : pc[1], g1 = b0 ? pc[2] : pc[3];
+        const float q0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 1);
+        const float q1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 1);
+        const float keep = b1 ? q1 : q0, give = b1 ? q0 : q1;
+        const float dh = (keep + __shfl_xor_sync(0xffffffffu, give, 2)) + (carry + dhh);
+        const float rr = g4.x, zz = g4.y, nn = g4.z, ghn = g4.w;
+        const float dn = dh * (1.0f - zz);
+        const float dz = dh * (hp - nn);
+        const float dnp = dn * (1.0f - nn * nn);
+        const float dzp = dz * zz * (1.0f - zz);
+        const float drp = dnp * ghn * rr * (1.0f - rr);
+        const float dghn = dnp * rr;
+        carry = dh * zz;
+        float *sm = dg_s[BUF ^ 1];
+        sm[pos_r] = drp; sm[pos_z] = dzp; sm[pos_n] = dghn;
+        dgdst[0] = drp; dgdst[HID] = dzp; dgdst[2 * HID] = dnp; dgdst[3 * HID] = dghn;
+        dgdst -= 4 * hstride;
+        __syncthreads();
+    };
+    using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+    int sdone = 0;
+    for (; sdone + 2 * PF + 1 <= n; sdone += PF) {   // steady state: steps s + PF stay >= 1 timestep away from t = 0
+        step(std::integral_constant<int, 0>{}, I0{}, 0, 0); step(std::integral_constant<int, 1>{}, I1{}, 0, 0);
+        step(std::integral_constant<int, 2>{}, I0{}, 0, 0); step(std::integral_constant<int, 3>{}, I1{}, 0, 0);
+        step(std::integral_constant<int, 4>{}, I0{}, 0, 0); step(std::integral_constant<int, 5>{}, I1{}, 0, 0);
+        step(std::integral_constant<int, 6>{}, I0{}, 0, 0); step(std::integral_constant<int, 7>{}, I1{}, 0, 0);
+    }
+    pdl_trigger();
+#define GRU9_TAIL(S, B) if (sdone + S < n) step(std::integral_constant<int, S>{}, B{}, sdone + S + PF < n ? 1 : 2, sdone + S)
+    for (; sdone < n; sdone += PF) {
+        GRU9_TAIL(0, I0); GRU9_TAIL(1, I1); GRU9_TAIL(2, I0); GRU9_TAIL(3, I1);
+        GRU9_TAIL(4, I0); GRU9_TAIL(5, I1); GRU9_TAIL(6, I0); GRU9_TAIL(7, I1);
+    }
+#undef GRU9_TAIL
 }

@@ -605,8 +605,8 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
 
 static thread_local int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
 static thread_local int g_tc_dbg = 0;
-static thread_local int g_gru_variant = 7;     // recurrences: 8 = one chain per 128-thread CTA (a warp on every sub-partition); 7 = 64-thread CTAs
-static thread_local int g_reduce_mn = 1;       // k_reduce_tc operands MN-major straight from the loads (0: round-1 transposition into K-major tiles)
+static thread_local int g_gru_variant = 9;     // recurrences: 9 = 64-thread CTAs, time loop unrolled over the ring slots; 7 = the same before the trimming; 8 = one chain per 128-thread CTA
+static thread_local int g_reduce_mn = 3;       // k_reduce_tc operands MN-major straight from the loads (0: round-1 transposition into K-major tiles)
 static thread_local int g_reduce_tc = 1;       // weight-gradient reductions on tcgen05 (k_reduce_tc); 0: fp32 FFMA k_reduce_group
 static thread_local int g_time_chunks = 1;     // 2: time-chunked forward (input projection of the 2nd half beside the recurrence of the 1st): measured 0.406 vs 0.400 ms at B=32, off by default
 static thread_local int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc); 0: two grouped GEMM launches
@@ -627,8 +627,8 @@ extern "C" int mal_set_option(const char *name, int value) {
     MAL_REQUIRE(name, "mal_set_option: null name");
     if (strcmp(name, "tensor_cores") == 0) { g_use_tc = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_dbg") == 0) { g_tc_dbg = value; return 0; }
-    if (strcmp(name, "gru_variant") == 0) { g_gru_variant = value == 7 ? 7 : 8; return 0; }
-    if (strcmp(name, "reduce_mn") == 0) { g_reduce_mn = value != 0; return 0; }
+    if (strcmp(name, "gru_variant") == 0) { g_gru_variant = (value == 7 || value == 8) ? value : 9; return 0; }
+    if (strcmp(name, "reduce_mn") == 0) { g_reduce_mn = value < 0 ? 0 : (value > 3 ? 3 : value); return 0; }   // 0 K-major transposition, 1 MN-major from registers, 2 MN-major cp.async pipeline, 3 the same with 512 threads
     if (strcmp(name, "reduce_tc") == 0) { g_reduce_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "time_chunks") == 0) { g_time_chunks = value; return 0; }
     if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
@@ -760,12 +760,14 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
 static int launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_fwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_fwd7<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);      // one batch row per CTA
+    else if (g_gru_variant == 9) launch_k(k_gru_fwd9<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);
     else launch_k(k_gru_fwd8<0>, dim3(a.R, nets), dim3(128), 0, st, pdl, a);
     return 0;
 }
 static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_bwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
+    else if (g_gru_variant == 9) launch_k(k_gru_bwd9, dim3(a.R), dim3(HID), 0, st, pdl, a);
     else launch_k(k_gru_bwd8, dim3(a.R), dim3(128), 0, st, pdl, a);
     return 0;
 }
@@ -1063,14 +1065,25 @@ static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, con
     }
     dim3 grid(maxc, tiles);
     if (tc) {
-        static size_t attr0[MAL_MAX_DEV], attr1[MAL_MAX_DEV], attr2[MAL_MAX_DEV], attr3[MAL_MAX_DEV];
+        static size_t attr0[MAL_MAX_DEV], attr1[MAL_MAX_DEV], attr2[MAL_MAX_DEV], attr3[MAL_MAX_DEV], attr4[MAL_MAX_DEV], attr5[MAL_MAX_DEV];
         if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 0, 0>, RT_SMEM_BYTES, attr0)) return rc;
         if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 1, 0>, RT_SMEM_BYTES, attr1)) return rc;
         if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 0, 1>, RT_SMEM_BYTES, attr2)) return rc;
         if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 1, 1>, RT_SMEM_BYTES, attr3)) return rc;
+        if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 0, 2>, RT_SMEM_BYTES_PIPE, attr4)) return rc;
+        if (int rc = ensure_dyn_smem(k_reduce_tc<AK, 1, 2>, RT_SMEM_BYTES_PIPE, attr5)) return rc;
         if (swap) ++g_stat_reduce_tc_swap; else ++g_stat_reduce_tc;
         ProfScope _ps(tag_tc, st);
-        if (g_reduce_mn) {          // operands staged MN-major, as they lie in memory (no transposition)
+        if (g_reduce_mn == 3) {     // 512-thread MN-major cp.async pipeline
+            static size_t attr6[MAL_MAX_DEV], attr7[MAL_MAX_DEV];
+            if (int rc = ensure_dyn_smem(k_reduce_tc3<AK, 0>, RT_SMEM_BYTES_PIPE, attr6)) return rc;
+            if (int rc = ensure_dyn_smem(k_reduce_tc3<AK, 1>, RT_SMEM_BYTES_PIPE, attr7)) return rc;
+            if (swap) launch_k(k_reduce_tc3<AK, 1>, grid, dim3(RT3_THREADS), RT_SMEM_BYTES_PIPE, st, g_next_pdl, g);
+            else launch_k(k_reduce_tc3<AK, 0>, grid, dim3(RT3_THREADS), RT_SMEM_BYTES_PIPE, st, g_next_pdl, g);
+        } else if (g_reduce_mn == 2) {     // MN-major operands fed by a four-stage cp.async pipeline
+            if (swap) launch_k(k_reduce_tc<AK, 1, 2>, grid, dim3(256), RT_SMEM_BYTES_PIPE, st, g_next_pdl, g);
+            else launch_k(k_reduce_tc<AK, 0, 2>, grid, dim3(256), RT_SMEM_BYTES_PIPE, st, g_next_pdl, g);
+        } else if (g_reduce_mn) {   // MN-major operands staged from registers (one block prefetched)
             if (swap) launch_k(k_reduce_tc<AK, 1, 1>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g);
             else launch_k(k_reduce_tc<AK, 0, 1>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g);
         } else if (swap) launch_k(k_reduce_tc<AK, 1, 0>, grid, dim3(256), RT_SMEM_BYTES, st, g_next_pdl, g);

@@ -24,6 +24,9 @@
 #define RT_RAW_A (RT_BM * RT_KT * 4)      //  8 KB
 #define RT_SMEM_BYTES (2 * RT_STAGE + RT_RAW_Y + RT_RAW_A)   // 120 KB
 #define RT_FLUSH 8                        // blocks between TMEM -> register folds (256 rows)
+#define RT_NS 4                           // MNM = 2: operand stages (blocks j+1, j+2 are in flight while block j is split and multiplied)
+#define RT_AHEAD 2
+#define RT_SMEM_BYTES_PIPE (RT_NS * RT_STAGE)                 // 192 KB
 
 // SWAP = 1 computes the transposed tile dW^T[k, n] (MMA rows <- 128 columns of A, MMA columns <- 64 columns of dY): for
 // narrow outputs with a wide inner dimension (fc1: Nout = 64, K = d_in up to 246) this fills the 128-row operand
@@ -54,7 +57,7 @@ __device__ __forceinline__ uint32_t mn_off(int kr, int c) { return (uint32_t)kr 
 template <int AK, int SWAP, int MNM>
 __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ RedGroup g) {
     extern __shared__ __align__(1024) uint8_t rt_smem[];
-    __shared__ __align__(8) uint64_t st_bar[2];
+    __shared__ __align__(8) uint64_t st_bar[RT_NS];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bsum_s[8][RT_NT];
     int pi = 0;
@@ -83,8 +86,8 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        mbar_init(&st_bar[0], 1);
-        mbar_init(&st_bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < RT_NS; ++i) mbar_init(&st_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -188,8 +191,9 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24) |
                            (MNM ? ((1u << 15) | (1u << 16)) : 0u);       // bits 15 / 16: A / B operand MN-major
     bool fresh = true;                                // the next MMA overwrites the TMEM accumulators
+    constexpr int NSTAGE = MNM == 2 ? RT_NS : 2;
     auto fold = [&](int j) {                          // all MMAs up to block j -> register accumulators
-        mbar_wait(&st_bar[j & 1], (uint32_t)((j >> 1) & 1));
+        mbar_wait(&st_bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t d1[32], d2[32];
         const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
@@ -201,7 +205,129 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    if (MNM) {
+    if (MNM == 2) {
+        // ---- asynchronous pipeline: the raw fp32 rows of block j + RT_AHEAD are requested with cp.async (16-byte pieces,
+        //      zero fill past the edges) straight into the hi tiles of a free stage; when block j's own pieces have landed
+        //      the thread that requested them rounds them to TF32 in place and writes the remainders into the lo tiles.
+        float4 bs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto add4 = [&](const float4 &v) { bs4.x += v.x; bs4.y += v.y; bs4.z += v.z; bs4.w += v.w; };
+        auto issue_dy = [&](uint8_t *dst, int64_t m, int n) {              // dY[m, n .. n+3] -> dst
+            if (m < me && n < p.Nout) {
+                const float *src = p.dY + m * p.ldy + n;
+                if (y_vec && n + 4 <= p.Nout) { cp_async16(dst, src); return; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * e, n + e < p.Nout ? src + e : p.dY, n + e < p.Nout ? 4 : 0);
+            } else cp_async16(dst, p.dY, 0);
+        };
+        auto issue_a = [&](uint8_t *dst, int64_t m, int k) {               // A[m, k .. k+3] through the fused loaders -> dst
+            if (!(m < me && k < p.K)) { cp_async16(dst, p.dY, 0); return; }
+            if (AK == A_DENSE) {
+                if (m < p.shift) { cp_async16(dst, p.dY, 0); return; }
+                const float *src = p.A + (m - p.shift) * p.lda + k;
+                if (a_vec && k + 4 <= p.K) { cp_async16(dst, src); return; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * e, k + e < p.K ? src + e : p.dY, k + e < p.K ? 4 : 0);
+            } else if (AK == A_STATE) {
+                int b, t;
+                if (fast_ok) fast_divmod((int)m, bv.T, invT, b, t);
+                else { b = (int)((unsigned)m / (unsigned)bv.T); t = (int)m - b * bv.T; }
+                const float *src = field_ptr<float>(bv.state, b, t + p.shift) + k;
+                if (s_vec && k + 4 <= p.K) { cp_async16(dst, src); return; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * e, k + e < p.K ? src + e : p.dY, k + e < p.K ? 4 : 0);
+            } else {   // [obs | last-action one-hot | agent-id one-hot]
+                int t, rr, b, n;
+                if (fast_ok) { fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, n); }
+                else { t = (int)((unsigned)m / (unsigned)bv.R); rr = (int)m - t * bv.R; b = rr / bv.N; n = rr - b * bv.N; }
+                const float *ob = field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
+                if (o_vec && k + 4 <= bv.OBS) { cp_async16(dst, ob + k); return; }
+                const float *oh = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int kk = k + e;
+                    if (kk < bv.OBS) cp_async4(dst + 4 * e, ob + kk);
+                    else if (kk < bv.OBS + bv.A) cp_async4(dst + 4 * e, oh ? oh + (kk - bv.OBS) : p.dY, oh ? 4 : 0);
+                    else *reinterpret_cast<float *>(dst + 4 * e) = (kk < p.K && kk - bv.OBS - bv.A == n) ? 1.0f : 0.0f;   // computed, not loaded
+                }
+            }
+        };
+        auto stage_base = [&](int j) { return rt_smem + (size_t)(j % RT_NS) * RT_STAGE; };
+        auto issue_block = [&](int j) {
+            uint8_t *Ah = stage_base(j), *Bh = Ah + 2 * RT_OP_A;
+            const int64_t mm = mb + (int64_t)j * RT_BM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int kr = 4 * warp + i;
+                uint8_t *dst = Ah + (uint32_t)(lane >> 3) * RT_SLAB + mn_off(kr, lane & 7);
+                if (SWAP) issue_a(dst, mm + kr, k0 + 4 * lane); else issue_dy(dst, mm + kr, n0 + 4 * lane);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int kr = 4 * warp + 2 * i + (lane >> 4), c = lane & 15;
+                uint8_t *dst = Bh + (uint32_t)(c >> 3) * RT_SLAB + mn_off(kr, c & 7);
+                if (SWAP) issue_dy(dst, mm + kr, n0 + 4 * c); else issue_a(dst, mm + kr, k0 + 4 * c);
+            }
+        };
+#pragma unroll
+        for (int jj = 0; jj < RT_AHEAD; ++jj) {
+            if (jj < nblk) issue_block(jj);
+            cp_async_commit();
+        }
+        for (int j = 0; j < nblk; ++j) {
+            const int s = j % RT_NS;
+            uint8_t *Ah = stage_base(j), *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
+            const int ja = j + RT_AHEAD;
+            if (ja < nblk) {
+                if (ja >= RT_NS) mbar_wait(&st_bar[ja % RT_NS], (uint32_t)(((ja / RT_NS) - 1) & 1));   // the MMAs of block ja - RT_NS released that stage
+                issue_block(ja);
+            }
+            cp_async_commit();
+            cp_async_wait<RT_AHEAD>();                                       // this thread's pieces of block j have landed
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int kr = 4 * warp + i;
+                const uint32_t off = (uint32_t)(lane >> 3) * RT_SLAB + mn_off(kr, lane & 7);
+                const float4 v = *reinterpret_cast<const float4 *>(Ah + off);
+                if (!SWAP) add4(v);
+                split_store_fast(Ah, Al, off, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int kr = 4 * warp + 2 * i + (lane >> 4), c = lane & 15;
+                const uint32_t off = (uint32_t)(c >> 3) * RT_SLAB + mn_off(kr, c & 7);
+                const float4 v = *reinterpret_cast<const float4 *>(Bh + off);
+                if (SWAP) add4(v);
+                split_store_fast(Bh, Bl, off, v);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                const uint64_t dAh = umma_desc_mn_sw128(smem_u32(Ah), RT_SLAB), dAl = umma_desc_mn_sw128(smem_u32(Al), RT_SLAB);
+                const uint64_t dBh = umma_desc_mn_sw128(smem_u32(Bh), RT_SLAB), dBl = umma_desc_mn_sw128(smem_u32(Bl), RT_SLAB);
+#pragma unroll
+                for (int ks = 0; ks < RT_BM / 8; ++ks) {
+                    const uint64_t o = (uint64_t)((ks * 1024) >> 4);
+                    const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + RT_KT, dAl + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + RT_KT, dAh + o, dBl + o, idesc, 1u);
+                }
+                umma_commit(&st_bar[s]);
+            }
+            fresh = false;
+            if ((j % RT_FLUSH) == RT_FLUSH - 1 || j == nblk - 1) {
+                fold(j);
+                fresh = true;
+            }
+        }
+        if (SWAP) {
+            bs4.x += __shfl_xor_sync(0xffffffffu, bs4.x, 16); bs4.y += __shfl_xor_sync(0xffffffffu, bs4.y, 16);
+            bs4.z += __shfl_xor_sync(0xffffffffu, bs4.z, 16); bs4.w += __shfl_xor_sync(0xffffffffu, bs4.w, 16);
+        }
+        if (want_bias && (!SWAP || lane < 16)) *reinterpret_cast<float4 *>(&bsum_s[warp][4 * lane]) = bs4;
+    } else if (MNM) {
         float4 bs4 = make_float4(0.f, 0.f, 0.f, 0.f);     // column sums of dY over this thread's rows: columns 4 lane .. +3 (wide) / 4 (lane & 15) .. +3 (narrow)
         auto add4 = [&](const float4 &v) { bs4.x += v.x; bs4.y += v.y; bs4.z += v.z; bs4.w += v.w; };
         auto body = [&](int j, float4 (&cy)[4], float4 (&ca)[2], float4 (&ny)[4], float4 (&na)[2]) {
@@ -337,6 +463,261 @@ __global__ void __launch_bounds__(256, 1) k_reduce_tc(const __grid_constant__ Re
             float sacc = 0.0f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) sacc += bsum_s[w][tid];
+            p.partB[(int64_t)chunk * p.Nout + n0 + tid] = sacc;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+}
+
+// =====================================================================================================================
+// k_reduce_tc3: the MN-major pipeline (MNM = 2 above) rebuilt around what its profile showed (profiles/
+// r02_reduce_notes.txt): with 8 warps per SM the kernel was bound by INSTRUCTION ISSUE of two warps per sub-partition --
+// ~380 instructions per warp and 32-row block (cvt.rna.tf32 expands to ~5 instructions, 64-bit address arithmetic and
+// multi-way branches in the loaders), one instruction every ~4 cycles per warp, 2 470 cycles per block against 384 cycles of
+// MMA and a shared-memory / DRAM time well below that.  Here:
+//   * 512 threads (4 warps per sub-partition): a thread owns 2 + 1 sixteen-byte pieces per block instead of 4 + 2;
+//   * everything that does not change from block to block is computed once: piece offsets, column validity, the vector /
+//     scalar decision of a piece, and for plain row-major operands the global pointer, which then advances by a constant;
+//   * the common pieces are ONE predicated cp.async (or a 16-byte zero store); the TF32 split is 2 integer + 1 FADD per value.
+// Same stages, descriptors, MMA order, fold cadence and partial layout as k_reduce_tc<.., 2>.
+// =====================================================================================================================
+#define RT3_THREADS 512
+#define RT3_WARPS 16
+
+__device__ __forceinline__ void cp_async16_plain(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4_plain(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int AK, int SWAP>
+__global__ void __launch_bounds__(RT3_THREADS, 1) k_reduce_tc3(const __grid_constant__ RedGroup g) {
+    extern __shared__ __align__(1024) uint8_t rt_smem[];
+    __shared__ __align__(8) uint64_t st_bar[RT_NS];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bsum_s[RT3_WARPS][RT_NT];
+    int pi = 0;
+    while (pi + 1 < g.n && (int)blockIdx.y >= g.p[pi + 1].tile0) ++pi;
+    const RedProb &p = g.p[pi];
+    const BatchView &bv = g.bv;
+    const int chunk = blockIdx.x;
+    if (chunk >= p.n_chunks) return;
+    const int tile = blockIdx.y - p.tile0;
+    const int n_narrow = SWAP ? (p.Nout + RT_KT - 1) / RT_KT : p.n_ktiles;
+    const int wt = tile / n_narrow, st_ = tile - wt * n_narrow;
+    const int n0 = SWAP ? st_ * RT_KT : wt * RT_NT;      // first dY column of this tile
+    const int k0 = SWAP ? wt * RT_NT : st_ * RT_KT;      // first A column of this tile
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t mb = p.M0 + (int64_t)chunk * p.rows_per_chunk;
+    int64_t me = mb + p.rows_per_chunk;
+    if (me > p.M) me = p.M;
+    const int nblk = me > mb ? (int)((me - mb + RT_BM - 1) / RT_BM) : 0;
+    const bool want_bias = p.partB && (SWAP ? wt == 0 : st_ == 0);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < RT_NS; ++i) mbar_init(&st_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();
+
+    // ---- this thread's three pieces: wide rows 2 warp, 2 warp + 1 (piece = lane), narrow row 2 warp + (lane >> 4) (piece = lane & 15)
+    const int cw = (SWAP ? k0 : n0) + 4 * lane;          // first column of the wide pieces (A column if SWAP, else dY column)
+    const int cn = (SWAP ? n0 : k0) + 4 * (lane & 15);   // first column of the narrow piece
+    const int krn = 2 * warp + (lane >> 4);
+    const uint32_t offw0 = (uint32_t)(lane >> 3) * RT_SLAB + mn_off(2 * warp, lane & 7);
+    const uint32_t offw1 = (uint32_t)(lane >> 3) * RT_SLAB + mn_off(2 * warp + 1, lane & 7);
+    const uint32_t offn = (uint32_t)((lane & 15) >> 3) * RT_SLAB + mn_off(krn, lane & 7);
+    // per-piece class: 0 = always zero (column past the edge), 1 = one 16-byte copy, 2 = element-wise assembly
+    const bool y_vec = ((p.ldy & 3) == 0) && ((p.Nout & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dY) & 15) == 0);
+    auto a_class = [&](int k) -> int {
+        if (k >= p.K) return 0;
+        if (AK == A_DENSE) return (((p.lda & 3) == 0) && ((p.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0)) ? 1 : 2;
+        if (AK == A_STATE) return ((bv.state.sb & 3) == 0 && (bv.state.st & 3) == 0 && (p.K & 3) == 0 &&
+                                   ((reinterpret_cast<uintptr_t>(bv.state.ptr) & 15) == 0)) ? 1 : 2;
+        return ((bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 && (bv.obs.st & 3) == 0 && ((reinterpret_cast<uintptr_t>(bv.obs.ptr) & 15) == 0) &&
+                k + 4 <= bv.OBS) ? 1 : 2;
+    };
+    auto y_class = [&](int nn) -> int { return nn >= p.Nout ? 0 : (y_vec ? 1 : 2); };
+    const int cls_w = SWAP ? a_class(cw) : y_class(cw);
+    const int cls_n = SWAP ? y_class(cn) : a_class(cn);
+    const bool fast_ok = p.M < (1 << 24);
+    const float invR = 1.0f / (float)(bv.R > 0 ? bv.R : 1), invN = 1.0f / (float)(bv.N > 0 ? bv.N : 1);
+    const float invT = 1.0f / (float)(bv.T > 0 ? bv.T : 1);
+
+    // source of dY[m, n ..] / A[m, k ..]; `ok` = the row exists (and, for shifted dense operands, has a predecessor)
+    auto y_src = [&](int64_t m, int nn, bool &ok) -> const float * { ok = m < me; return p.dY + m * p.ldy + nn; };
+    auto a_row = [&](int64_t m, bool &ok, int &agent, const float *&oh) -> const float * {   // row base (column 0)
+        agent = 0; oh = nullptr;
+        ok = m < me;
+        const int64_t mc = ok ? m : mb;                                        // keep the address arithmetic in range
+        if (AK == A_DENSE) { ok = ok && mc >= p.shift; return p.A + (mc >= p.shift ? mc - p.shift : 0) * p.lda; }
+        if (AK == A_STATE) {
+            int b, t;
+            if (fast_ok) fast_divmod((int)mc, bv.T, invT, b, t);
+            else { b = (int)((unsigned)mc / (unsigned)bv.T); t = (int)mc - b * bv.T; }
+            return field_ptr<float>(bv.state, b, t + p.shift);
+        }
+        int t, rr, b, n;
+        if (fast_ok) { fast_divmod((int)mc, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, n); }
+        else { t = (int)((unsigned)mc / (unsigned)bv.R); rr = (int)mc - t * bv.R; b = rr / bv.N; n = rr - b * bv.N; }
+        agent = n;
+        oh = t > 0 ? field_ptr<float>(bv.onehot, b, t - 1) + (int64_t)n * bv.A : nullptr;
+        return field_ptr<float>(bv.obs, b, t) + (int64_t)n * bv.OBS;
+    };
+    auto zero16 = [&](uint8_t *dst) { *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f); };
+    auto issue_y = [&](uint8_t *dst, int64_t m, int nn, int cls) {
+        bool ok;
+        const float *src = y_src(m, nn, ok);
+        if (cls == 1 && ok) cp_async16_plain(dst, src);
+        else if (cls == 2 && ok) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (nn + e < p.Nout) cp_async4_plain(dst + 4 * e, src + e); else *reinterpret_cast<float *>(dst + 4 * e) = 0.0f;
+            }
+        } else zero16(dst);
+    };
+    auto issue_a = [&](uint8_t *dst, int64_t m, int k, int cls) {
+        bool ok; int agent; const float *oh;
+        const float *src = a_row(m, ok, agent, oh);
+        if (cls == 1 && ok) cp_async16_plain(dst, src + k);
+        else if (cls == 2 && ok) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int kk = k + e;
+                float *d = reinterpret_cast<float *>(dst + 4 * e);
+                if (kk >= p.K) *d = 0.0f;
+                else if (AK != A_AGENT_IN || kk < bv.OBS) cp_async4_plain(d, src + kk);
+                else if (kk < bv.OBS + bv.A) { if (oh) cp_async4_plain(d, oh + (kk - bv.OBS)); else *d = 0.0f; }
+                else *d = (kk - bv.OBS - bv.A == agent) ? 1.0f : 0.0f;               // agent-id one-hot: computed, not loaded
+            }
+        } else zero16(dst);
+    };
+    auto stage_base = [&](int j) { return rt_smem + (size_t)(j % RT_NS) * RT_STAGE; };
+    auto issue_block = [&](int j) {
+        uint8_t *Ah = stage_base(j), *Bh = Ah + 2 * RT_OP_A;
+        const int64_t mm = mb + (int64_t)j * RT_BM;
+        if (SWAP) {
+            issue_a(Ah + offw0, mm + 2 * warp, cw, cls_w);
+            issue_a(Ah + offw1, mm + 2 * warp + 1, cw, cls_w);
+            issue_y(Bh + offn, mm + krn, cn, cls_n);
+        } else {
+            issue_y(Ah + offw0, mm + 2 * warp, cw, cls_w);
+            issue_y(Ah + offw1, mm + 2 * warp + 1, cw, cls_w);
+            issue_a(Bh + offn, mm + krn, cn, cls_n);
+        }
+    };
+
+    const int q = warp & 3, cg = warp >> 2;             // accumulator ownership: TMEM lane quarter q, columns 16 cg .. +16
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(RT_KT >> 3) << 17) | ((uint32_t)(RT_NT >> 4) << 24);
+    bool fresh = true;
+    auto fold = [&](int j) {
+        mbar_wait(&st_bar[j % RT_NS], (uint32_t)((j / RT_NS) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t d1[32], d2[32];
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16);
+        tmem_ld16_nowait(tl, d1);
+        tmem_ld16_nowait(tl + RT_KT, d2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] += __uint_as_float(d1[c]) + __uint_as_float(d2[c]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    float4 bs4 = make_float4(0.f, 0.f, 0.f, 0.f);       // column sums of dY over this thread's rows
+    auto add4 = [&](const float4 &v) { bs4.x += v.x; bs4.y += v.y; bs4.z += v.z; bs4.w += v.w; };
+
+#pragma unroll
+    for (int jj = 0; jj < RT_AHEAD; ++jj) {
+        if (jj < nblk) issue_block(jj);
+        cp_async_commit();
+    }
+    for (int j = 0; j < nblk; ++j) {
+        const int s = j % RT_NS;
+        uint8_t *Ah = stage_base(j), *Al = Ah + RT_OP_A, *Bh = Al + RT_OP_A, *Bl = Bh + RT_OP_B;
+        const int ja = j + RT_AHEAD;
+        if (ja < nblk) {
+            if (ja >= RT_NS) mbar_wait(&st_bar[ja % RT_NS], (uint32_t)(((ja / RT_NS) - 1) & 1));   // the MMAs of block ja - RT_NS released that stage
+            issue_block(ja);
+        }
+        cp_async_commit();
+        cp_async_wait<RT_AHEAD>();                       // this thread's pieces of block j have landed
+        {
+            const float4 v0 = *reinterpret_cast<const float4 *>(Ah + offw0);
+            const float4 v1 = *reinterpret_cast<const float4 *>(Ah + offw1);
+            const float4 v2 = *reinterpret_cast<const float4 *>(Bh + offn);
+            if (!SWAP) { add4(v0); add4(v1); } else add4(v2);
+            split_store_fast(Ah, Al, offw0, v0);
+            split_store_fast(Ah, Al, offw1, v1);
+            split_store_fast(Bh, Bl, offn, v2);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const uint64_t dAh = umma_desc_mn_sw128(smem_u32(Ah), RT_SLAB), dAl = umma_desc_mn_sw128(smem_u32(Al), RT_SLAB);
+            const uint64_t dBh = umma_desc_mn_sw128(smem_u32(Bh), RT_SLAB), dBl = umma_desc_mn_sw128(smem_u32(Bl), RT_SLAB);
+#pragma unroll
+            for (int ks = 0; ks < RT_BM / 8; ++ks) {
+                const uint64_t o = (uint64_t)((ks * 1024) >> 4);
+                const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
+                umma_tf32(tmem_base + RT_KT, dAl + o, dBh + o, idesc, first);
+                umma_tf32(tmem_base + RT_KT, dAh + o, dBl + o, idesc, 1u);
+            }
+            umma_commit(&st_bar[s]);
+        }
+        fresh = false;
+        if ((j % RT_FLUSH) == RT_FLUSH - 1 || j == nblk - 1) {
+            fold(j);
+            fresh = true;
+        }
+    }
+    // ---- partials: partW[chunk][n][k]; TMEM lane = wide-operand row, columns = narrow-operand rows
+    if (!SWAP) {
+        const int n = n0 + q * 32 + lane;
+        if (n < p.Nout) {
+            float *pw = p.partW + ((int64_t)chunk * p.Nout + n) * p.K + k0 + cg * 16;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (k0 + cg * 16 + c < p.K) pw[c] = acc[c];
+        }
+    } else {
+        const int k = k0 + q * 32 + lane;
+        if (k < p.K) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int n = n0 + cg * 16 + c;
+                if (n < p.Nout) p.partW[((int64_t)chunk * p.Nout + n) * p.K + k] = acc[c];
+            }
+        }
+    }
+    if (want_bias) {
+        if (SWAP) {                                      // lanes c and c + 16 hold the same narrow columns
+            bs4.x += __shfl_xor_sync(0xffffffffu, bs4.x, 16); bs4.y += __shfl_xor_sync(0xffffffffu, bs4.y, 16);
+            bs4.z += __shfl_xor_sync(0xffffffffu, bs4.z, 16); bs4.w += __shfl_xor_sync(0xffffffffu, bs4.w, 16);
+        }
+        if (!SWAP || lane < 16) *reinterpret_cast<float4 *>(&bsum_s[warp][4 * lane]) = bs4;
+        __syncthreads();
+        if (tid < (SWAP ? RT_KT : RT_NT) && n0 + tid < p.Nout) {
+            float sacc = 0.0f;
+#pragma unroll
+            for (int w = 0; w < RT3_WARPS; ++w) sacc += bsum_s[w][tid];
             p.partB[(int64_t)chunk * p.Nout + n0 + tid] = sacc;
         }
     }
