@@ -111,6 +111,7 @@ def kernel_bytes(d, mixer, B=None):
         "k_gru_bwd": M1 * (256 + 64 + 64 + 256) * f,
         "k_linear_group:dx": M1 * (192 + 64 + 64) * f,
         "k_reduce_group:agent_dense": M1 * (256 + 64 + 64) * f,
+        "k_reduce_gru": M1 * (256 + 64 + 64) * f,
         "k_reduce_group:agent_fc1": M1 * (64 + (OBS + A)) * f,
         "k_fc2_grad": T * R * (64 * f + 12),
     }

@@ -512,7 +512,9 @@ static int tiles_of(int Nout, int K) {   // 128 x 64 output tiles of the tensor-
 static PartLayout part_layout(const Dims &d, int sms) {
     PartLayout p;
     memset(&p, 0, sizeof(p));
-    chunking(d.M1, tiles_of(G3, HID) + tiles_of(128, HID) + tiles_of(64, HID), sms, &p.nc_a, &p.rpc_a);
+    // dense agent reductions: the fused k_reduce_gru handles a whole row chunk on one CTA -> one chunk per SM once every
+    // chunk is long (>= 1024 rows), half as many below that (fewer partials for k_grad_reduce to gather at B = 32)
+    chunking(d.M1, d.M1 >= (int64_t)sms * 1024 ? 1 : 2, sms, &p.nc_a, &p.rpc_a);
     chunking(d.M1, tiles_of(HID, d.d_in), sms, &p.nc_f1, &p.rpc_f1);
     {   // k_fc2_grad: one partial per CTA, 8 warps x >= 32 rows each; the kernel is HBM-bound on the h rows, so large batches
         // fill every SM with as many CTAs as their [8][A*64+32]-float accumulators allow (<= 4)
@@ -1190,7 +1192,22 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads
     if (fork_to(st, s2, ss->fork_ev[2])) return 2;
-    if (!frozen && !dqn) {
+    const bool fused_gru_red = g_use_tc && g_reduce_tc && g_reduce_mn >= 3 && (g_reduce_tc == 2 || pl.rpc_a >= 256);
+    if (!frozen && !dqn && fused_gru_red) {
+        // W_ih, W_hh, b_ih, b_hh gradients: one [x | h_{t-1}]^T . d_g split-M GEMM per row chunk
+        ReduceGruArgs ra;
+        ra.x = F(plan->x_on); ra.hout = F(plan->h_on); ra.d_g = d_g;
+        ra.wih_w = parts + pl.wih_w; ra.wih_b = parts + pl.wih_b;
+        ra.whha_w = parts + pl.whha_w; ra.whha_b = parts + pl.whha_b;
+        ra.whhb_w = parts + pl.whhb_w; ra.whhb_b = parts + pl.whhb_b;
+        ra.M1 = d.M1; ra.rows_per_chunk = pl.rpc_a; ra.n_chunks = pl.nc_a; ra.R = d.R;
+        static size_t attr[MAL_MAX_DEV];
+        if (int rc = ensure_dyn_smem(k_reduce_gru, RG_SMEM_BYTES, attr)) return rc;
+        ++g_stat_reduce_tc;
+        { ProfScope _ps("k_reduce_gru", s2); launch_k(k_reduce_gru, dim3(pl.nc_a), dim3(RT3_THREADS), RG_SMEM_BYTES, s2, false, ra); }
+        MAL_LAUNCH_CHECK("k_reduce_gru");
+    }
+    if (!frozen && !dqn && !fused_gru_red) {
         RedGroup r; r.n = 3; r.bv = bv;
         r.p[0] = red(d.M1, HID, G3, d_g, 4 * HID, A_DENSE, 0, F(plan->x_on), HID, parts + pl.wih_w, parts + pl.wih_b, pl.nc_a, pl.rpc_a);
         // W_hh: rows pair with h_{t-1} = hout shifted by R rows (zero for t == 0)

@@ -726,3 +726,196 @@ __global__ void __launch_bounds__(RT3_THREADS, 1) k_reduce_tc3(const __grid_cons
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
 }
+
+// =====================================================================================================================
+// k_reduce_gru: the W_ih / W_hh / b_ih / b_hh gradients of the GRU in ONE split-M GEMM per 32-row block,
+//     D[128 x 256] += [x | h_{t-1}]^T [32 x 128]  .  d_g [32 x 256]          (d_g = d gi_r | d gi_z | d gi_n | d gh_n)
+// instead of four 128 x 64 tiles on four CTAs.  The generic tiles above are bound by SHARED-MEMORY bandwidth, not by the
+// tensor pipe or HBM (tools/mma_chain_probe.cu: an M128 x N64 x K8 TF32 MMA takes 53 cycles while reading 6 KB of operands,
+// i.e. ~115 B/clk of the 128 B/clk an SM has, and every operand byte is also written and re-read once by the 3xTF32
+// split); the fused shape reads 12 KB per 132-cycle MMA, stages d_g / x / h once instead of once per tile and touches every
+// row from HBM exactly once.  Three quarters of D are used: x rows x (r, z, n) columns -> W_ih, h rows x (r, z) and
+// x (gh_n) columns -> W_hh.
+//   hi operands = the raw fp32 rows where cp.async lands them (the tensor core drops the 13 low mantissa bits itself),
+//   lo operands = v - trunc(v), written by the thread that requested the piece; both biases this leaves (|lo| slightly
+//   larger, lo.lo dropped) are proportional to every product with the same sign and factor (< 5e-7), i.e. a relative
+//   error of the SUM of that size, immune to cancellation.
+//   16-row blocks; smem: five hi stages (24 KB each: block j-1 still being read by the tensor core, block j, blocks j+1 .. j+3
+//   landing) + two lo stages, so that block j is split while block j-1 is multiplied; TMEM: D1 | D2 = 256 + 256 columns.
+// =====================================================================================================================
+#define RG_BM 16                                         // rows (m) per block: two K = 8 MMA steps
+#define RG_SLAB (RG_BM * 128)                            // 2 KB: [16 m rows x 32 columns]
+#define RG_STAGE (12 * RG_SLAB)                          // 24 KB: xh (4 slabs) | d_g (8 slabs)
+#define RG_NHI 5                                         // hi stages: block j (multiplied), j-1 (still being read), j+1 .. j+3 (landing)
+#define RG_NLO 2
+#define RG_AHEAD 3
+#define RG_FLUSH 16                                      // blocks between TMEM -> register folds (256 rows)
+#define RG_SMEM_BYTES ((RG_NHI + RG_NLO) * RG_STAGE)     // 168 KB
+struct ReduceGruArgs {
+    const float *x, *hout, *d_g;      // [M1, 64], [M1, 64] (h_t; h_{t-1} = row m - R, zero for m < R), [M1, 256]
+    float *wih_w, *wih_b;             // [n_chunks][192][64], [n_chunks][192]
+    float *whha_w, *whha_b;           // [n_chunks][128][64], [n_chunks][128]
+    float *whhb_w, *whhb_b;           // [n_chunks][64][64],  [n_chunks][64]
+    int64_t M1, rows_per_chunk;
+    int n_chunks, R;
+};
+
+__global__ void __launch_bounds__(RT3_THREADS, 1) k_reduce_gru(const __grid_constant__ ReduceGruArgs a) {
+    extern __shared__ __align__(1024) uint8_t rt_smem[];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int chunk = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t mb = (int64_t)chunk * a.rows_per_chunk;
+    int64_t me = mb + a.rows_per_chunk;
+    if (me > a.M1) me = a.M1;
+    const int nblk = me > mb ? (int)((me - mb + RG_BM - 1) / RG_BM) : 0;
+    uint8_t *lo_base = rt_smem + RG_NHI * RG_STAGE;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();
+
+    // ---- this thread's three pieces of a block: row `warp`; xh piece `lane` (x: lanes 0-15, h: 16-31), d_g pieces `lane`, `lane + 32`
+    const uint32_t off_xh = (uint32_t)(lane >> 3) * RG_SLAB + mn_off(warp, lane & 7);
+    const uint32_t off_g0 = (uint32_t)(4 + (lane >> 3)) * RG_SLAB + mn_off(warp, lane & 7);
+    const uint32_t off_g1 = off_g0 + 4 * RG_SLAB;
+    const bool is_h = lane >= 16;
+    const float *src_xh = (is_h ? a.hout - (int64_t)a.R * HID : a.x) + (mb + warp) * HID + 4 * (lane & 15);
+    const float *src_g = a.d_g + (mb + warp) * (4 * HID) + 4 * lane;
+    int64_t m_next = mb + warp;                          // this thread's row of the next block to request
+    auto zero16 = [&](uint8_t *dst) { *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f); };
+    auto issue_block = [&](int j) {
+        uint8_t *hi = rt_smem + (size_t)(j % RG_NHI) * RG_STAGE;
+        const bool ok = m_next < me;
+        if (ok && !(is_h && m_next < a.R)) cp_async16_plain(hi + off_xh, src_xh); else zero16(hi + off_xh);
+        if (ok) {
+            cp_async16_plain(hi + off_g0, src_g);
+            cp_async16_plain(hi + off_g1, src_g + 2 * HID);
+        } else { zero16(hi + off_g0); zero16(hi + off_g1); }
+        m_next += RG_BM; src_xh += RG_BM * HID; src_g += RG_BM * 4 * HID;
+    };
+
+    const int q = warp & 3, cg = warp >> 2;              // TMEM lane quarter q (xh column 32 q + lane), d_g columns 64 cg .. +64
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    bool fresh = true;
+    auto wait_block = [&](int j) {                       // the MMAs of block j (and of every earlier block) are complete
+        mbar_wait(&mma_bar[j & 1], (uint32_t)((j >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    auto fold = [&]() {                                  // TMEM -> register accumulators (16 columns at a time)
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint32_t d1[32], d2[32];
+            tmem_ld16_nowait(tl + 16 * h, d1);
+            tmem_ld16_nowait(tl + 256 + 16 * h, d2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[16 * h + c] += __uint_as_float(d1[c]) + __uint_as_float(d2[c]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    float4 bs0 = make_float4(0.f, 0.f, 0.f, 0.f), bs1 = bs0;   // column sums of d_g: columns 4 lane .. +3 and 128 + 4 lane .. +3
+    auto lo_of = [&](const float4 &v) {
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        return l;
+    };
+
+#pragma unroll
+    for (int jj = 0; jj < RG_AHEAD; ++jj) {
+        if (jj < nblk) issue_block(jj);
+        cp_async_commit();
+    }
+    for (int j = 0; j < nblk; ++j) {
+        uint8_t *hi = rt_smem + (size_t)(j % RG_NHI) * RG_STAGE;
+        uint8_t *lo = lo_base + (size_t)(j & 1) * RG_STAGE;
+        // block j-2 is done: its hi stage (the one block j+3 lands in) and this lo stage are free; the tensor pipe
+        // still holds block j-1 while this block is split
+        if (j >= 2) wait_block(j - 2);
+        if (j + RG_AHEAD < nblk) issue_block(j + RG_AHEAD);
+        cp_async_commit();
+        cp_async_wait<RG_AHEAD>();                       // this thread's pieces of block j have landed
+        {
+            const float4 vx = *reinterpret_cast<const float4 *>(hi + off_xh);
+            const float4 g0 = *reinterpret_cast<const float4 *>(hi + off_g0);
+            const float4 g1 = *reinterpret_cast<const float4 *>(hi + off_g1);
+            bs0.x += g0.x; bs0.y += g0.y; bs0.z += g0.z; bs0.w += g0.w;
+            bs1.x += g1.x; bs1.y += g1.y; bs1.z += g1.z; bs1.w += g1.w;
+            *reinterpret_cast<float4 *>(lo + off_xh) = lo_of(vx);
+            *reinterpret_cast<float4 *>(lo + off_g0) = lo_of(g0);
+            *reinterpret_cast<float4 *>(lo + off_g1) = lo_of(g1);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const uint64_t dAh = umma_desc_mn_sw128(smem_u32(hi), RG_SLAB), dAl = umma_desc_mn_sw128(smem_u32(lo), RG_SLAB);
+            const uint64_t dBh = umma_desc_mn_sw128(smem_u32(hi + 4 * RG_SLAB), RG_SLAB), dBl = umma_desc_mn_sw128(smem_u32(lo + 4 * RG_SLAB), RG_SLAB);
+#pragma unroll
+            for (int ks = 0; ks < RG_BM / 8; ++ks) {
+                const uint64_t o = (uint64_t)((ks * 1024) >> 4);
+                const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                umma_tf32(tmem_base, dAh + o, dBh + o, idesc, first);
+                umma_tf32(tmem_base + 256, dAl + o, dBh + o, idesc, first);
+                umma_tf32(tmem_base + 256, dAh + o, dBl + o, idesc, 1u);
+            }
+            umma_commit(&mma_bar[j & 1]);
+        }
+        fresh = false;
+        if ((j % RG_FLUSH) == RG_FLUSH - 1 && j + 1 < nblk) {   // the accumulation so far leaves the tensor core's truncating adder
+            wait_block(j);
+            fold();
+            fresh = true;
+        }
+    }
+    if (nblk > 0) { wait_block(nblk - 1); fold(); }
+    // ---- partials.  TMEM lane = xh column: lanes 0-63 -> W_ih[n][k = lane], lanes 64-127 -> W_hh[n][k = lane - 64]
+    {
+        const int r = q * 32 + lane, k = r & 63;
+        const bool hrow = r >= 64;
+        float *dst = nullptr;                            // &part[chunk][n = first column of this warp's group][k]
+        if (!hrow && cg < 3) dst = a.wih_w + ((int64_t)chunk * G3 + 64 * cg) * HID + k;
+        else if (hrow && cg < 2) dst = a.whha_w + ((int64_t)chunk * 128 + 64 * cg) * HID + k;
+        else if (hrow && cg == 3) dst = a.whhb_w + (int64_t)chunk * 64 * HID + k;
+        if (dst) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) dst[(int64_t)c * HID] = acc[c];
+        }
+    }
+    // ---- bias partials: column sums of d_g over the chunk (cross-warp sum through the free shared memory)
+    __syncthreads();
+    float *bsum = reinterpret_cast<float *>(rt_smem);    // [16 warps][256]
+    *reinterpret_cast<float4 *>(bsum + warp * 256 + 4 * lane) = bs0;
+    *reinterpret_cast<float4 *>(bsum + warp * 256 + 128 + 4 * lane) = bs1;
+    __syncthreads();
+    if (tid < 256) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < RT3_WARPS; ++w) s += bsum[w * 256 + tid];
+        if (tid < G3) a.wih_b[(int64_t)chunk * G3 + tid] = s;
+        if (tid < 128) a.whha_b[(int64_t)chunk * 128 + tid] = s;
+        if (tid >= G3) a.whhb_b[(int64_t)chunk * 64 + tid - G3] = s;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
