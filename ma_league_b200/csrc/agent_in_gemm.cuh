@@ -24,6 +24,9 @@
 // one fc1 chunk slot when the input fits one 64-wide chunk, two when it does not (the next chunk is staged under the MMA)
 __host__ __device__ inline int ai_w1_slots(int K1) { return K1 > TC_KC ? 2 : 1; }
 __host__ __device__ inline size_t ai_smem_bytes(int K1) { return AI_OFF_W1 + (size_t)ai_w1_slots(K1) * AI_W1_SLOT + 4 * AI_SLAB_W2; }   // 192 / 224 KB
+#define AI_THREADS 512                    // 16 warps: four per sub-partition hide the load / TMEM / shared-memory latencies of the staging and epilogue phases (r2: 256 threads left ~20 K of a tile's 23 K cycles to those phases)
+#define AI_RSTEP (AI_THREADS / 16)        // rows between two staging pieces of a thread (32)
+#define AI_RPT (TC_M / AI_RSTEP)          // staging rows per thread (4)
 #define AI_COL_X1 0
 #define AI_COL_X2 64
 #define AI_COL_G1 128
@@ -39,7 +42,7 @@ struct AgentInArgs {
     BatchView bv;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_constant__ AgentInArgs a) {
+__global__ void __launch_bounds__(AI_THREADS, 1) k_agent_in_tc(const __grid_constant__ AgentInArgs a) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
@@ -68,27 +71,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     }
     if (tid < HID) b1_s[tid] = __ldg(P + L.fc1_b + tid);
     if (tid < G3) bih_s[tid] = __ldg(P + L.b_ih + tid);
-    const int c4 = tid & 15, rbase = tid >> 4;          // staging map: float4 column c4 of a 64-wide chunk, rows rbase + 16 i
+    const int c4 = tid & 15, rbase = tid >> 4;          // staging map: float4 column c4 of a 64-wide chunk, rows rbase + AI_RSTEP i
     const uint32_t a_slab = (uint32_t)(c4 >> 3) * AI_SLAB_A;
     // W_ih [192 x 64], resident for the whole kernel (all twelve loads of a thread in flight before the first split)
     {
-        float4 wv[G3 / 16];
+        float4 wv[G3 / AI_RSTEP];
 #pragma unroll
-        for (int i = 0; i < G3 / 16; ++i)
-            wv[i] = __ldg(reinterpret_cast<const float4 *>(P + L.w_ih + (int64_t)(rbase + 16 * i) * HID + 4 * c4));
+        for (int i = 0; i < G3 / AI_RSTEP; ++i)
+            wv[i] = __ldg(reinterpret_cast<const float4 *>(P + L.w_ih + (int64_t)(rbase + AI_RSTEP * i) * HID + 4 * c4));
 #pragma unroll
-        for (int i = 0; i < G3 / 16; ++i) {
-            const int j = rbase + 16 * i;
+        for (int i = 0; i < G3 / AI_RSTEP; ++i) {
+            const int j = rbase + AI_RSTEP * i;
             split_store_fast(W2_hi, W2_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W2 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
         }
     }
     auto stage_w1 = [&](int kc, int slot) {             // fc1.weight[:, kc*64 .. +64) (columns >= K1 are zero)
         uint8_t *W1_hi = W1_base + slot * AI_W1_SLOT, *W1_lo = W1_hi + 2 * AI_SLAB_W1;
         const int kcol = kc * TC_KC + 4 * c4;
-        float4 wv[HID / 16];
+        float4 wv[HID / AI_RSTEP];
 #pragma unroll
-        for (int i = 0; i < HID / 16; ++i) {
-            const float *wr = P + L.fc1_w + (int64_t)(rbase + 16 * i) * a.d_in + kcol;
+        for (int i = 0; i < HID / AI_RSTEP; ++i) {
+            const float *wr = P + L.fc1_w + (int64_t)(rbase + AI_RSTEP * i) * a.d_in + kcol;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kcol < K1) v.x = __ldg(wr);             // d_in is not a multiple of 4 in general: scalar loads
             if (kcol + 1 < K1) v.y = __ldg(wr + 1);
@@ -97,8 +100,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
             wv[i] = v;
         }
 #pragma unroll
-        for (int i = 0; i < HID / 16; ++i) {
-            const int j = rbase + 16 * i;
+        for (int i = 0; i < HID / AI_RSTEP; ++i) {
+            const int j = rbase + AI_RSTEP * i;
             split_store_fast(W1_hi, W1_lo, (uint32_t)(c4 >> 3) * AI_SLAB_W1 + (uint32_t)j * 128u + (uint32_t)(((c4 & 7) ^ (j & 7)) << 4), wv[i]);
         }
     };
@@ -111,19 +114,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     uint32_t bar_phase = 0;
     const float invR = 1.0f / (float)bv.R, invN = 1.0f / (float)bv.N;
 
-    const int q16 = 16 / bv.N, r16 = 16 - q16 * bv.N;   // a thread's rows are 16 apart: (t, b, n) advance incrementally
-    auto load_in = [&](int64_t m0, int kc, float4 (&v)[8]) {   // [obs | last-action one-hot] rows, float4 over the obs part
+    const int q16 = AI_RSTEP / bv.N, r16 = AI_RSTEP - q16 * bv.N;   // a thread's rows are AI_RSTEP apart: (t, b, n) advance incrementally
+    auto load_in = [&](int64_t m0, int kc, float4 (&v)[AI_RPT]) {   // [obs | last-action one-hot] rows, float4 over the obs part
         const int kcol = kc * TC_KC + 4 * c4;
         int t, rr, b, n;
         fast_divmod((int)m0 + rbase, bv.R, invR, t, rr);
         fast_divmod(rr, bv.N, invN, b, n);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int64_t m = m0 + rbase + 16 * i;
+        for (int i = 0; i < AI_RPT; ++i) {
+            const int64_t m = m0 + rbase + AI_RSTEP * i;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i > 0) {                                // row m = row (m - 16) + 16
-                rr += 16; b += q16; n += r16;
-                if (n >= bv.N) { n -= bv.N; ++b; }
+            if (i > 0) {                                // row m = row (m - AI_RSTEP) + AI_RSTEP
+                rr += AI_RSTEP; b += q16; n += r16;
+                while (n >= bv.N) { n -= bv.N; ++b; }
                 if (rr >= bv.R) {                       // next timestep(s): rare, recompute (b, n)
                     do { rr -= bv.R; ++t; } while (rr >= bv.R);
                     fast_divmod(rr, bv.N, invN, b, n);
@@ -151,23 +154,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
     const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(G3 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-    float4 pre[8];
+    float4 pre[AI_RPT];
     bool have_pre = false;
     for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
         const int64_t m0 = a.m_begin + (int64_t)mt * TC_M;
         if (mt + (int)gridDim.x >= n_mtiles) pdl_trigger();   // last tile of this CTA: the recurrence may be scheduled and load W_hh
         // ---------------------------------------------------------------- x = fc1(input): nkc1 k-chunks into acc 1
         for (int kc = 0; kc < nkc1; ++kc) {
-            float4 v[8];
+            float4 v[AI_RPT];
             if (have_pre) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = pre[i];
+                for (int i = 0; i < AI_RPT; ++i) v[i] = pre[i];
             } else {
                 load_in(m0, kc, v);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
+            for (int i = 0; i < AI_RPT; ++i) {
+                const int r = rbase + AI_RSTEP * i;
                 split_store_fast(A_hi, A_lo, a_slab + (uint32_t)r * 128u + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4), v[i]);
             }
             const int sl = two_slots ? (step & 1) : 0;
@@ -221,34 +224,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
             wait_mma();
         }
         // ---------------------------------------------------------------- epilogue 1: x = relu(. + b1 + W1[:, K1 + agent])
-        // lane = row (TMEM lane quarter warp & 3); warps 0-3 take columns 0-31, warps 4-7 columns 32-63.  x goes to global
+        // lane = row (TMEM lane quarter warp & 3); warp group warp >> 2 takes columns 16 (warp >> 2) .. +16.  x goes to global
         // (backward) and, split hi/lo, into the A staging of the second MMA (the input chunk there is consumed).
         {
-            const int q = warp & 3, half = warp >> 2;
+            const int q = warp & 3, cgp = warp >> 2;
             const int r = q * 32 + lane;
             const int64_t m = m0 + r;
             uint32_t d1[32], d2[32];
-            const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
-            tmem_ld32_nowait(tl + AI_COL_X1, d1);
-            tmem_ld32_nowait(tl + AI_COL_X2, d2);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cgp * 16);
+            tmem_ld16_nowait(tl + AI_COL_X1, d1);
+            tmem_ld16_nowait(tl + AI_COL_X2, d2);
             int agent = 0;
             if (m < M) { int t, rr, b; fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, agent); }
             const float *wid = P + L.fc1_w + K1 + agent;          // fc1.weight[n, K1 + agent]
-            float *xrow = a.x[net] + m * HID + half * 32;
+            float wa[16];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int e = 0; e < 16; ++e) wa[e] = __ldg(wid + (int64_t)(cgp * 16 + e) * a.d_in);   // in flight under the TMEM load
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float *xrow = a.x[net] + m * HID + cgp * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
                 float4 xv;
                 float *xp = &xv.x;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int n = half * 32 + 4 * c + e;
-                    float s = (__uint_as_float(d1[4 * c + e]) + __uint_as_float(d2[4 * c + e])) + b1_s[n];
-                    if (m < M) s += __ldg(wid + (int64_t)n * a.d_in);
+                    const int n = cgp * 16 + 4 * c + e;
+                    const float s = (__uint_as_float(d1[4 * c + e]) + __uint_as_float(d2[4 * c + e])) + b1_s[n] + wa[4 * c + e];
                     xp[e] = m < M ? fmaxf(s, 0.0f) : 0.0f;
                 }
                 if (m < M) *reinterpret_cast<float4 *>(xrow + 4 * c) = xv;
-                const int cc = half * 8 + c;                      // 16-byte chunk of the 64-float row: slab cc >> 3
+                const int cc = cgp * 4 + c;                       // 16-byte chunk of the 64-float row: slab cc >> 3
                 split_store_fast(A_hi, A_lo, (uint32_t)(cc >> 3) * AI_SLAB_A + (uint32_t)r * 128u + (uint32_t)(((cc & 7) ^ (r & 7)) << 4), xv);
             }
         }
@@ -277,17 +282,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_agent_in_tc(const __grid_cons
             const int q = warp & 3;
             const int64_t mw = m0 + q * 32;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-            float4 *stg = reinterpret_cast<float4 *>(A_hi) + warp * 256;      // the x operand is consumed: 4 KB per warp
+            float4 *stg = reinterpret_cast<float4 *>(A_hi) + warp * 256;      // the x operand is consumed: 4 KB per warp (16 warps = the 64 KB of A staging)
             TcEpi e;
             e.Y = a.gi[net]; e.aux = nullptr; e.W = nullptr; e.ldy = G3; e.ld_aux = 0; e.ldw = 0;
             e.M = (int)M; e.Nout = G3; e.K = 0; e.R = bv.R; e.N = bv.N; e.relu = false; e.vec_ok = true;
 #pragma unroll 1
-            for (int c0 = (warp >> 2) * 32; c0 < G3; c0 += 64) {
+            for (int c0 = (warp >> 2) * 16; c0 < G3; c0 += 64) {
                 uint32_t d1[32], d2[32];
-                tmem_ld32_nowait(tlane + (uint32_t)(AI_COL_G1 + c0), d1);
-                tmem_ld32_nowait(tlane + (uint32_t)(AI_COL_G2 + c0), d2);
+                tmem_ld16_nowait(tlane + (uint32_t)(AI_COL_G1 + c0), d1);
+                tmem_ld16_nowait(tlane + (uint32_t)(AI_COL_G2 + c0), d2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_epilogue_group<TCE_BIAS_ACT>(e, stg, d1, d2, 32, c0, mw, lane, bih_s, false);
+                tc_epilogue_group<TCE_BIAS_ACT>(e, stg, d1, d2, 16, c0, mw, lane, bih_s, false);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(128, 3) k_gru_bwd8(GruBwdArgs a) {
 // every shared-memory access has an immediate offset), the global pointers advance by a constant per step, and the
 // steady-state loop carries no boundary predicates (the last <= 2 PF - 1 steps run in a guarded tail).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int DBG = 0>
+template <int DBG = 0, int PACKED = 1>
 __global__ void __launch_bounds__(64, 4) k_gru_fwd9(GruFwdArgs a) {
     constexpr int PF = 8;
     constexpr int KC = HID / 2;            // columns per lane
@@ -541,31 +541,60 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd9(GruFwdArgs a) {
         float4 hv[KC / 4];
 #pragma unroll
         for (int q = 0; q < KC / 4; ++q) hv[q] = hp[q];
-        unsigned long long s[2][3];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int g = 0; g < 3; ++g) s[u][g] = 0ull;
-#pragma unroll
-        for (int q = 0; q < KC / 4; ++q) {
-            const unsigned long long hxy = pack2(hv[q].x, hv[q].y), hzw = pack2(hv[q].z, hv[q].w);
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int g = 0; g < 3; ++g) s[u][g] = fma2(w[u][g][2 * q], hxy, s[u][g]);
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int g = 0; g < 3; ++g) s[u][g] = fma2(w[u][g][2 * q + 1], hzw, s[u][g]);
-        }
         float x[3];
+        if (PACKED) {
+            unsigned long long s[2][3];
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            float a0, a1, c0, c1;
-            unpack2(s[0][g], a0, a1); unpack2(s[1][g], c0, c1);
-            const float p0 = a0 + a1, p1 = c0 + c1;
-            const float mine = part ? p1 : p0, other = part ? p0 : p1;
-            x[g] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) s[u][g] = 0ull;
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const unsigned long long hxy = pack2(hv[q].x, hv[q].y), hzw = pack2(hv[q].z, hv[q].w);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) s[u][g] = fma2(w[u][g][2 * q], hxy, s[u][g]);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) s[u][g] = fma2(w[u][g][2 * q + 1], hzw, s[u][g]);
+            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                float a0, a1, c0, c1;
+                unpack2(s[0][g], a0, a1); unpack2(s[1][g], c0, c1);
+                const float p0 = a0 + a1, p1 = c0 + c1;
+                const float mine = part ? p1 : p0, other = part ? p0 : p1;
+                x[g] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+            }
+        } else {
+            // plain FFMA: 192 single FMAs over six accumulators (an FFMA2 with three 64-bit register operands issued every
+            // ~4 cycles from a lone warp in this kernel; FFMA issues every ~1.1, tools/ffma_probe.cu)
+            float sa[2][3];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) sa[u][g] = 0.0f;
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const float hh[4] = {hv[q].x, hv[q].y, hv[q].z, hv[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) {
+                            float wl, wh;
+                            unpack2(w[u][g][2 * q + (e >> 1)], wl, wh);
+                            sa[u][g] = fmaf((e & 1) ? wh : wl, hh[e], sa[u][g]);
+                        }
+            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const float mine = part ? sa[1][g] : sa[0][g], other = part ? sa[0][g] : sa[1][g];
+                x[g] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+            }
         }
         const float xr = x[0] + (g_r + b_r), xz = x[1] + (g_z + b_z), ghn = x[2] + b_n;
         const float rr = sigmoid_mufu(xr), zz = sigmoid_mufu(xz);

@@ -826,7 +826,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             const int64_t tiles = ceil_div64(a.m_end - a.m_begin, TC_M);
             int64_t per = sms / 2; if (per < 1) per = 1;
             dim3 grid((unsigned)(tiles < per ? tiles : per), 2);
-            { ProfScope _ps("k_agent_in_tc", s_); k_agent_in_tc<<<grid, TC_THREADS, ai_smem, s_>>>(a); }
+            { ProfScope _ps("k_agent_in_tc", s_); k_agent_in_tc<<<grid, AI_THREADS, ai_smem, s_>>>(a); }
             MAL_LAUNCH_CHECK("k_agent_in_tc");
             return 0;
         };
