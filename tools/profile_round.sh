@@ -1,15 +1,16 @@
 #!/bin/bash
 # ncu recipe of /opt/skills/guides/B200_PROFILING.md for one round (run under gpurun; writes gpurun_out/).
-#   tools/profile_round.sh [workload] [steps] [full-capture launch count] [kernel regex of the source-page export]
+#   tools/profile_round.sh [workload] [steps] [full-capture launch count (19 = one step; ~5 s per launch)] [kernel regex of the source-page export] [replay buffer episodes]
 #   1. the bench command without ncu (must exit 0)
 #   2. launch list with device times (cold-cache, serialised)
 #   3. --set full captures of the learner step's kernels; the report stays on the box (gpurun_out/ is capped at 64 MiB):
 #      its raw page (all metrics per captured launch) and the source page of the kernels named in $4 come back as CSV
 WL=${1:-qmix_5v5_b32}
 STEPS=${2:-4}
-NFULL=${3:-40}
+NFULL=${3:-19}
 SRC=${4:-k_gru_}
-CMD="python bench.py --workload $WL --steps $STEPS --warmup 3 --no-cpu-baseline --learner-only"
+BUF=${5:-96}
+CMD="python bench.py --workload $WL --steps $STEPS --warmup 3 --no-cpu-baseline --learner-only --buffer-size $BUF"
 $CMD > gpurun_out/prof_plain_$WL.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/prof_plain_$WL.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|k_linear|k_reduce|k_gru|k_agent' -c 900 --csv \
     --log-file gpurun_out/launches_$WL.csv $CMD > gpurun_out/ncu_launches_$WL.log 2>&1

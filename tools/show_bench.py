@@ -7,8 +7,8 @@ for path in sys.argv[1:]:
     j = json.loads(open(path).read().strip().splitlines()[-1])
     print("== %s  %s" % (path, j["config"]["workload"][:60]))
     print("value %.3f M/s  %.3f ms/step  wall %.3f  e2e %.3f M/s (%.3f ms)  launches/step %s  clocks %s" % (
-        j["value"] / 1e6, j["ms_per_step"], j.get("wall_ms_per_step", 0), j["e2e"]["value"] / 1e6,
-        j["e2e"].get("ms_per_step", 0), j.get("launches_per_step"), j.get("clocks")))
+        j["value"] / 1e6, j["ms_per_step"], j.get("wall_ms_per_step", 0), j.get("e2e", {}).get("value", 0) / 1e6,
+        j.get("e2e", {}).get("ms_per_step", 0), j.get("launches_per_step"), j.get("clocks")))
     if "cpu_baseline" in j:
         print("cpu", j["cpu_baseline"])
     print("roofline", {k: v for k, v in j["roofline"].items() if k != "note"})
