@@ -39,6 +39,7 @@ struct AgentInArgs {
     int64_t M1;
     int64_t m_begin, m_end;    // row range of this launch (time-chunked forward: rows of t in [t0, t1))
     int d_in, n_actions;
+    int gi_tiled;              // 1: gi leaves as gi_tiled[m / 32][chunk 0..47][m % 32][4] for k_gru_fwd_tc (R % 32 == 0)
     BatchView bv;
 };
 
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(AI_THREADS, 1) k_agent_in_tc(const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < HID) b1_s[tid] = __ldg(P + L.fc1_b + tid);
-    if (tid < G3) bih_s[tid] = __ldg(P + L.b_ih + tid);
+    // tiled mode (tensor-core recurrence): the r / z halves of b_hh ride along, only b_hh_n is applied inside the recurrence
+    if (tid < G3) bih_s[tid] = __ldg(P + L.b_ih + tid) + ((a.gi_tiled && tid < 2 * HID) ? __ldg(P + L.b_hh + tid) : 0.0f);
     const int c4 = tid & 15, rbase = tid >> 4;          // staging map: float4 column c4 of a 64-wide chunk, rows rbase + AI_RSTEP i
     const uint32_t a_slab = (uint32_t)(c4 >> 3) * AI_SLAB_A;
     // W_ih [192 x 64], resident for the whole kernel (all twelve loads of a thread in flight before the first split)
@@ -277,8 +279,33 @@ __global__ void __launch_bounds__(AI_THREADS, 1) k_agent_in_tc(const __grid_cons
             umma_commit(&mma_bar);
         }
         wait_mma();
-        // ---------------------------------------------------------------- epilogue 2: gi = . + b_ih, transposed coalesced stores
-        {
+        // ---------------------------------------------------------------- epilogue 2: gi = . + b_ih
+        if (a.gi_tiled) {
+            // tiled layout for the tensor-core recurrence: TMEM lane = row = position inside the 32-row group, so every
+            // float4 chunk of the warp is one contiguous 512-byte store -- no transposition
+            const int q = warp & 3;
+            const int64_t m = m0 + q * 32 + lane;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+            float4 *gt = reinterpret_cast<float4 *>(a.gi[net]) + (m >> 5) * (int64_t)(G3 / 4) * 32 + (m & 31);
+#pragma unroll 1
+            for (int c0 = (warp >> 2) * 16; c0 < G3; c0 += 64) {
+                uint32_t d1[32], d2[32];
+                tmem_ld16_nowait(tlane + (uint32_t)(AI_COL_G1 + c0), d1);
+                tmem_ld16_nowait(tlane + (uint32_t)(AI_COL_G2 + c0), d2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < M) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&bih_s[c0 + 4 * c]);
+                        gt[((c0 >> 2) + c) * 32] =
+                            make_float4((__uint_as_float(d1[4 * c]) + __uint_as_float(d2[4 * c])) + b4.x,
+                                        (__uint_as_float(d1[4 * c + 1]) + __uint_as_float(d2[4 * c + 1])) + b4.y,
+                                        (__uint_as_float(d1[4 * c + 2]) + __uint_as_float(d2[4 * c + 2])) + b4.z,
+                                        (__uint_as_float(d1[4 * c + 3]) + __uint_as_float(d2[4 * c + 3])) + b4.w);
+                    }
+                }
+            }
+        } else {
             const int q = warp & 3;
             const int64_t mw = m0 + q * 32;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);

@@ -9,6 +9,7 @@
 #include "learner.cuh"
 #include "gru_rec.cuh"
 #include "tc_gemm.cuh"
+#include "gru_rec_tc.cuh"
 #include "agent_in_gemm.cuh"
 #include "tc_reduce.cuh"
 
@@ -613,6 +614,9 @@ static thread_local int g_reduce_tc = 1;       // weight-gradient reductions on 
 static thread_local int g_time_chunks = 1;     // 2: time-chunked forward (input projection of the 2nd half beside the recurrence of the 1st): measured 0.406 vs 0.400 ms at B=32, off by default
 static thread_local int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc); 0: two grouped GEMM launches
 static thread_local int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
+static thread_local int g_rec_tc = 1;         // tensor-core recurrence k_gru_fwd_tc: 0 off, 1 when both nets have >= REC_TC_MIN_ROWS chains, 2 whenever R % 32 == 0
+#define REC_TC_MIN_ROWS 8192                  // chains (both nets) from which a 128-chain MMA tile per SM beats one FFMA CTA per chain
+static uint64_t g_stat_rec_tc = 0;
 
 // Launch counters per kernel flavour since process start (tests check which variant the heuristics picked).
 extern "C" uint64_t mal_stat(const char *name) {
@@ -623,6 +627,7 @@ extern "C" uint64_t mal_stat(const char *name) {
     if (strcmp(name, "reduce_tc_swap") == 0) return g_stat_reduce_tc_swap;
     if (strcmp(name, "reduce_ffma") == 0) return g_stat_reduce_ffma;
     if (strcmp(name, "agent_in_fused") == 0) return g_stat_agent_in_fused;
+    if (strcmp(name, "rec_tc") == 0) return g_stat_rec_tc;
     return 0;
 }
 extern "C" int mal_set_option(const char *name, int value) {
@@ -638,6 +643,7 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
     if (strcmp(name, "actsel_lat") == 0) { g_actsel_lat = value ? 1 : 0; return 0; }
     if (strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return 0; }
+    if (strcmp(name, "rec_tc") == 0) { g_rec_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
 }
@@ -766,6 +772,24 @@ static int launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool p
     else launch_k(k_gru_fwd8<0>, dim3(a.R, nets), dim3(128), 0, st, pdl, a);
     return 0;
 }
+// Tensor-core forward recurrence: tiles of g 32-chain groups (g <= 4), g chosen for the fewest waves of CTAs over the SMs
+// (ties: the smaller tile -- fewer idle MMA rows, the per-step time of a tile does not depend on g).
+static int launch_gru_fwd_tc(const GruFwdArgs &a, int nets, int sms, cudaStream_t st, bool pdl) {
+    static size_t attr[MAL_MAX_DEV];
+    if (int rc = ensure_dyn_smem(k_gru_fwd_tc, (size_t)GT_SMEM_BYTES, attr)) return rc;
+    const int G = a.R / 32;
+    int best_g = 4; int64_t best_w = -1;
+    for (int g = 1; g <= 4; ++g) {
+        const int64_t w = ceil_div64(ceil_div64(G, g) * nets, sms);
+        if (best_w < 0 || w < best_w) { best_w = w; best_g = g; }
+    }
+    GruFwdTcArgs ta;
+    ta.g = a; ta.groups_per_tile = best_g;
+    ++g_stat_rec_tc;
+    ProfScope _ps("k_gru_fwd", st);
+    launch_k(k_gru_fwd_tc, dim3((unsigned)ceil_div64(G, best_g), nets), dim3(GT_THREADS), (size_t)GT_SMEM_BYTES, st, pdl, ta);
+    return 0;
+}
 static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
     ProfScope _ps("k_gru_bwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
@@ -813,6 +837,8 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     // second half is still being computed on a side stream (the recurrence is latency-bound and leaves the tensor
     // cores and most issue slots idle)
     const int t_split = (fused_in && g_time_chunks > 1 && g_overlap && d.TT >= 32) ? d.TT / 2 : d.TT;
+    // tensor-core recurrence (k_gru_fwd_tc) for large row counts: gi then leaves k_agent_in_tc in the tiled layout
+    const bool rec_tc = fused_in && (d.R % 32) == 0 && (g_rec_tc == 2 || (g_rec_tc == 1 && 2 * (int64_t)d.R >= REC_TC_MIN_ROWS));
     if (fused_in) {
         const size_t ai_smem = ai_smem_bytes(bv.OBS + bv.A);
         static size_t attr[MAL_MAX_DEV];
@@ -821,7 +847,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         auto launch_in = [&](int tb, int te, cudaStream_t s_) -> int {
             AgentInArgs a;
             for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.x[net] = x[net]; a.gi[net] = gi[net]; }
-            a.M1 = d.M1; a.d_in = d.d_in; a.n_actions = d.A; a.bv = bv;
+            a.M1 = d.M1; a.d_in = d.d_in; a.n_actions = d.A; a.bv = bv; a.gi_tiled = rec_tc ? 1 : 0;
             a.m_begin = (int64_t)tb * d.R; a.m_end = (int64_t)te * d.R;
             const int64_t tiles = ceil_div64(a.m_end - a.m_begin, TC_M);
             int64_t per = sms / 2; if (per < 1) per = 1;
@@ -881,12 +907,12 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         a.t0 = 0; a.t1 = t_split;
-        if (launch_gru_fwd(a, 2, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
+        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
         MAL_LAUNCH_CHECK("k_gru_fwd");
         if (t_split < d.TT) {
             if (join_from(st, ss->s[1], ss->join_ev[1])) return 2;    // second half of gi is ready
             a.t0 = t_split; a.t1 = d.TT;
-            if (launch_gru_fwd(a, 2, st, false)) return 2;
+            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, st, false)) return 2;
             MAL_LAUNCH_CHECK("k_gru_fwd");
         }
     }
