@@ -122,15 +122,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gru_fwd_tc(const __grid_const
 
     for (int t = t0; t < t1; ++t) {
         if (t + PDL_LEAD_STEPS == t1) pdl_trigger();
-        // this step's gi: requested before the MMA wait
-        float4 gv[3][4];
-        if (active) {
-            const float4 *gp = gi4 + (int64_t)t * gi_tstride;
-#pragma unroll
-            for (int g = 0; g < 3; ++g)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) gv[g][c] = __ldg(gp + (g * 16 + c) * 32);
-        }
         if (tid == 0) {
             const uint64_t dA_hi = umma_desc_sw128(smem_u32(A_hi)), dA_lo = umma_desc_sw128(smem_u32(A_lo));
             const uint64_t dW_hi = umma_desc_sw128(smem_u32(W_hi)), dW_lo = umma_desc_sw128(smem_u32(W_lo));
@@ -148,6 +139,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gru_fwd_tc(const __grid_const
                 umma_tf32(tmem_base, dA_hi + ao, dW_hi + wo, idesc, 1u);
             }
             umma_commit(&mma_bar);
+        }
+        // this step's gi: requested right behind the MMA issue: the HBM latency hides under the tensor core
+        float4 gv[3][4];
+        if (active) {
+            const float4 *gp = gi4 + (int64_t)t * gi_tstride;
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) gv[g][c] = __ldg(gp + (g * 16 + c) * 32);
         }
         mbar_wait(&mma_bar, bar_phase);
         bar_phase ^= 1u;
