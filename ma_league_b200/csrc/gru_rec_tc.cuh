@@ -34,6 +34,7 @@
 struct GruFwdTcArgs {
     GruFwdArgs g;
     int groups_per_tile;       // 32-chain groups per CTA tile (1..4)
+    int gates_tiled;           // 1: saved gates as [m / 32][unit][m % 32] float4 (read by k_gru_bwd_tc); 0: [m][unit] float4 (k_gru_bwd9)
 };
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gru_fwd_tc(const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (active) {
             const int64_t mw = (int64_t)t * a.R + row0 + q * 32;           // first global row of this warp's group
+            float4 *gt4 = gates4 ? gates4 + ((mw >> 5) * HID + cg * 16) * 32 + lane : nullptr;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t ar[8], az[8], an[8];
@@ -192,11 +194,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gru_fwd_tc(const __grid_const
                         hprev[u] = nn[j] + zz[j] * (hprev[u] - nn[j]);
                     }
                     if (gates4) {
+                        if (ta.gates_tiled) {                             // [m / 32][unit][m % 32] float4: one 512-byte store per unit
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) stg[lane * 8 + ((4 * qt + j) ^ (lane & 7))] = make_float4(rr[j], zz[j], nn[j], ghn[j]);
+                            for (int j = 0; j < 4; ++j) gt4[(4 * c + j) * 32] = make_float4(rr[j], zz[j], nn[j], ghn[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) stg[lane * 8 + ((4 * qt + j) ^ (lane & 7))] = make_float4(rr[j], zz[j], nn[j], ghn[j]);
+                        }
                     }
                 }
-                if (gates4) {                                             // [m][unit] float4: 128-byte row segments
+                if (gates4 && !ta.gates_tiled) {                          // [m][unit] float4 through the transposition tile: 128-byte row segments
                     __syncwarp();
                     const int ch = lane & 7, rsub = lane >> 3;
 #pragma unroll
@@ -233,4 +240,227 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gru_fwd_tc(const __grid_const
     }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)GT_TMEM_COLS));
+}
+
+// =====================================================================================================================
+// Tensor-core BPTT.  Per timestep (t = TT-1 .. 0) and tile of up to 128 chains:
+//     dh[128 x 64] = [d r' | d z' | d gh_n](t+1)[128 x 192] . W_hh[192 x 64]  + carry + head seed
+// as ONE 3xTF32 tcgen05 GEMM whose A operand lives in TENSOR MEMORY (tools/ta_probe.cu: lane = row, one 32-bit column
+// per k): the epilogue threads (lane = chain) write the hi / lo halves of their d(gates) straight into TMEM columns with
+// tcgen05.st -- no shared-memory operand tile, no swizzle arithmetic -- and only B = W_hh^T (hi + lo, K-major
+// SWIZZLE_128B, 96 KB) sits in shared memory.   TMEM: D at 0 | A hi at 64 | A lo at 256 (448 of 512 columns).
+//   thread 0 : 48 correction MMAs (lo.hi, hi.lo) then 24 hi.hi MMAs (M = 128, N = 64, K = 8), tcgen05.commit;
+//   16 warps : warp w owns TMEM lane quarter w & 3 and hidden units 16 (w >> 2) .. +16.  The saved gates of its 32
+//              chains x 16 units (tiled layout of k_gru_fwd_tc: its own 8 KB per step) arrive through a per-warp
+//              cp.async slot requested at the end of the previous step's epilogue; h_{t-1} and the head seed are
+//              requested into registers behind the MMA issue.  d_g keeps its row-major [m][256] layout (the dx GEMM
+//              and k_reduce_gru read it): the four gate blocks of a half (8 units) go through the half's consumed gate
+//              slot as a transposition tile and leave as 32-byte row pieces.
+// =====================================================================================================================
+#define GB_SLAB_B (HID * 128)                      // 8 KB: [64 rows x 32 floats]
+#define GB_OFF_SLOT (12 * GB_SLAB_B)               // W_hh^T hi (6 slabs) | lo (6 slabs): 96 KB
+#define GB_SLOT 8192                               // per warp: 16 units x 32 chains x float4
+#define GB_SMEM_BYTES (GB_OFF_SLOT + (GT_THREADS / 32) * GB_SLOT)   // 224 KB
+#define GB_COL_AHI 64
+#define GB_COL_ALO 256
+
+struct GruBwdTcArgs {
+    GruBwdArgs g;
+    int groups_per_tile;
+};
+
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// the four values of a quarter as a TF32 hi / exact-remainder lo pair of TMEM column groups
+__device__ __forceinline__ void tmem_st_split4(uint32_t t_hi, uint32_t t_lo, const float (&v)[4]) {
+    uint32_t h[4];
+    float l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = tf32_rna_fast(v[j]); l[j] = v[j] - __uint_as_float(h[j]); }
+    tmem_st4(t_hi, h[0], h[1], h[2], h[3]);
+    tmem_st4(t_lo, __float_as_uint(l[0]), __float_as_uint(l[1]), __float_as_uint(l[2]), __float_as_uint(l[3]));
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) k_gru_bwd_tc(const __grid_constant__ GruBwdTcArgs ta) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    const GruBwdArgs &a = ta.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2;
+    const int G = a.R >> 5;
+    const int g0 = (int)blockIdx.x * ta.groups_per_tile;
+    if (g0 >= G) return;
+    const int ng = (G - g0 < ta.groups_per_tile) ? G - g0 : ta.groups_per_tile;
+    const bool active = q < ng;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const int T = a.TT - 1;
+    uint8_t *B_hi = tc_smem, *B_lo = tc_smem + 6 * GB_SLAB_B;
+    float4 *slot4 = reinterpret_cast<float4 *>(tc_smem + GB_OFF_SLOT + warp * GB_SLOT);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // B[n][k] = W_hh[k][n] (n = hidden column, k = gate row): coalesced float4 reads along n, scattered 4-byte stores
+#pragma unroll
+    for (int i = 0; i < G3 * (HID / 4) / GT_THREADS; ++i) {
+        const int idx = tid + GT_THREADS * i;
+        const int k = idx >> 4, n4 = idx & 15;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(a.params + L.w_hh + (int64_t)k * HID + 4 * n4));
+        const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t off = (uint32_t)(k >> 5) * GB_SLAB_B + sw128_off(4 * n4 + e, k & 31);
+            const uint32_t h = tf32_rna_fast(ve[e]);
+            *reinterpret_cast<uint32_t *>(B_hi + off) = h;
+            *reinterpret_cast<float *>(B_lo + off) = ve[e] - __uint_as_float(h);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    // A = 0: nothing flows into the last timestep from the future
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {                          // this warp's 16 columns of the six 64-column blocks (3 gates x hi / lo)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tmem_st4(tl + (uint32_t)(GB_COL_AHI + c * HID + cg * 16 + 4 * e), 0u, 0u, 0u, 0u);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    pdl_wait();                                            // gates / h / head seeds come from the stream predecessors
+
+    const int r = q * 32 + lane;
+    const int64_t row0 = (int64_t)g0 * 32;
+    const float4 *gates4 = reinterpret_cast<const float4 *>(a.gates);
+    auto fetch_gates = [&](int t) {                        // the warp's 8 KB of step t -> its slot (every thread: its own 16 float4)
+        const float4 *src = gates4 + (((int64_t)t * G + g0 + q) * HID + cg * 16) * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cp_async16(&slot4[u * 32 + lane], src + u * 32);
+    };
+    if (active) fetch_gates(a.TT - 1);
+    cp_async_commit();
+    float carry[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) carry[u] = 0.0f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t bar_phase = 0;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    for (int i = 0; i < a.TT; ++i) {
+        const int t = a.TT - 1 - i;
+        if (i + PDL_LEAD_STEPS == a.TT) pdl_trigger();
+        if (tid == 0) {
+            const uint64_t dB_hi = umma_desc_sw128(smem_u32(B_hi)), dB_lo = umma_desc_sw128(smem_u32(B_lo));
+#pragma unroll
+            for (int ks = 0; ks < G3 / 8; ++ks) {                          // the small correction products first
+                const uint64_t wo = (uint64_t)(((ks >> 2) * GB_SLAB_B + (ks & 3) * 32) >> 4);
+                umma_tf32_ta(tmem_base, tmem_base + (uint32_t)(GB_COL_ALO + 8 * ks), dB_hi + wo, idesc, ks == 0 ? 0u : 1u);
+                umma_tf32_ta(tmem_base, tmem_base + (uint32_t)(GB_COL_AHI + 8 * ks), dB_lo + wo, idesc, 1u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < G3 / 8; ++ks) {
+                const uint64_t wo = (uint64_t)(((ks >> 2) * GB_SLAB_B + (ks & 3) * 32) >> 4);
+                umma_tf32_ta(tmem_base, tmem_base + (uint32_t)(GB_COL_AHI + 8 * ks), dB_hi + wo, idesc, 1u);
+            }
+            umma_commit(&mma_bar);
+        }
+        // h_{t-1} and the head seed of this thread's (chain, 16 units): requested behind the MMA issue
+        float4 hp4[4], dh4[4];
+        if (active) {
+            const int64_t m = (int64_t)t * a.R + row0 + r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                hp4[c] = t > 0 ? __ldg(reinterpret_cast<const float4 *>(a.hout + (m - a.R) * HID + cg * 16) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dh4[c] = t < T ? __ldg(reinterpret_cast<const float4 *>(a.dh_head + m * HID + cg * 16) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        mbar_wait(&mma_bar, bar_phase);
+        bar_phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (active) {
+            const int64_t mw = (int64_t)t * a.R + row0 + q * 32;
+            cp_async_wait<0>();                                           // this thread's own gate copies have landed
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t acc[8];
+                tmem_ld8_nowait(tl + (uint32_t)(cg * 16 + half * 8), acc);
+                float4 g4[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g4[e] = slot4[(half * 8 + e) * 32 + lane];
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                __syncwarp();                                             // the half's gate slot is consumed: it becomes the d_g transposition tile
+                float4 *tile = slot4 + half * 256;                        // [gate block 4][chain 32][2 pieces of 16 B], pieces swizzled
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt) {
+                    const int c = half * 2 + qt;
+                    const float hp[4] = {hp4[c].x, hp4[c].y, hp4[c].z, hp4[c].w};
+                    const float dhh[4] = {dh4[c].x, dh4[c].y, dh4[c].z, dh4[c].w};
+                    float drp[4], dzp[4], dnp[4], dghn[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 g = g4[4 * qt + j];                  // (r, z, n, gh_n)
+                        const float dh = __uint_as_float(acc[4 * qt + j]) + (carry[4 * c + j] + dhh[j]);
+                        const float dn = dh * (1.0f - g.y);
+                        const float dz = dh * (hp[j] - g.z);
+                        dnp[j] = dn * (1.0f - g.z * g.z);
+                        dzp[j] = dz * g.y * (1.0f - g.y);
+                        drp[j] = dnp[j] * g.w * g.x * (1.0f - g.x);
+                        dghn[j] = dnp[j] * g.x;
+                        carry[4 * c + j] = dh * g.y;
+                    }
+                    // next step's A operand: [d r' | d z' | d gh_n], hi / lo, this thread's TMEM lane
+                    const uint32_t ca = (uint32_t)(cg * 16 + 4 * c);
+                    tmem_st_split4(tl + GB_COL_AHI + ca, tl + GB_COL_ALO + ca, drp);
+                    tmem_st_split4(tl + GB_COL_AHI + HID + ca, tl + GB_COL_ALO + HID + ca, dzp);
+                    tmem_st_split4(tl + GB_COL_AHI + 2 * HID + ca, tl + GB_COL_ALO + 2 * HID + ca, dghn);
+                    const int sw = qt ^ ((lane >> 2) & 1);
+                    tile[(0 * 32 + lane) * 2 + sw] = make_float4(drp[0], drp[1], drp[2], drp[3]);
+                    tile[(1 * 32 + lane) * 2 + sw] = make_float4(dzp[0], dzp[1], dzp[2], dzp[3]);
+                    tile[(2 * 32 + lane) * 2 + sw] = make_float4(dnp[0], dnp[1], dnp[2], dnp[3]);
+                    tile[(3 * 32 + lane) * 2 + sw] = make_float4(dghn[0], dghn[1], dghn[2], dghn[3]);
+                }
+                __syncwarp();
+                {   // d_g[m][gate block * 64 + unit]: two lanes per 32-byte row piece
+                    const int p = lane & 1, rs = lane >> 1;
+#pragma unroll
+                    for (int gb = 0; gb < 4; ++gb)
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int rr_ = pass * 16 + rs;
+                            *reinterpret_cast<float4 *>(a.d_g + (mw + rr_) * (4 * HID) + gb * HID + cg * 16 + half * 8 + 4 * p) =
+                                tile[(gb * 32 + rr_) * 2 + (p ^ ((rr_ >> 2) & 1))];
+                        }
+                }
+            }
+            __syncwarp();                                                 // every lane is done with the tiles: the slot may be refilled
+            if (t > 0) fetch_gates(t - 1);
+            cp_async_commit();
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }

@@ -616,7 +616,8 @@ static thread_local int g_fuse_agent_in = 1;   // fc1 + W_ih in one tcgen05 kern
 static thread_local int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2 (0: the one-tile-at-a-time k_linear_tc)
 static thread_local int g_rec_tc = 1;         // tensor-core recurrence k_gru_fwd_tc: 0 off, 1 when both nets have >= REC_TC_MIN_ROWS chains, 2 whenever R % 32 == 0
 #define REC_TC_MIN_ROWS 8192                  // chains (both nets) from which a 128-chain MMA tile per SM beats one FFMA CTA per chain
-static uint64_t g_stat_rec_tc = 0;
+static thread_local int g_rec_tc_bwd = 0;     // tensor-core BPTT k_gru_bwd_tc beside k_gru_fwd_tc (A operand in tensor memory): correct, but measured slower than k_gru_bwd9 (4.16 vs 3.08 ms at 20v20); 1: on
+static uint64_t g_stat_rec_tc = 0, g_stat_rec_tc_bwd = 0;
 
 // Launch counters per kernel flavour since process start (tests check which variant the heuristics picked).
 extern "C" uint64_t mal_stat(const char *name) {
@@ -628,6 +629,7 @@ extern "C" uint64_t mal_stat(const char *name) {
     if (strcmp(name, "reduce_ffma") == 0) return g_stat_reduce_ffma;
     if (strcmp(name, "agent_in_fused") == 0) return g_stat_agent_in_fused;
     if (strcmp(name, "rec_tc") == 0) return g_stat_rec_tc;
+    if (strcmp(name, "rec_tc_bwd") == 0) return g_stat_rec_tc_bwd;
     return 0;
 }
 extern "C" int mal_set_option(const char *name, int value) {
@@ -644,6 +646,7 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "actsel_lat") == 0) { g_actsel_lat = value ? 1 : 0; return 0; }
     if (strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return 0; }
     if (strcmp(name, "rec_tc") == 0) { g_rec_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
+    if (strcmp(name, "rec_tc_bwd") == 0) { g_rec_tc_bwd = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
 }
@@ -772,19 +775,44 @@ static int launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool p
     else launch_k(k_gru_fwd8<0>, dim3(a.R, nets), dim3(128), 0, st, pdl, a);
     return 0;
 }
+// fc1 + W_ih in one tcgen05 kernel (k_agent_in_tc)
+static bool fused_in_selected(const Dims &d, const BatchView &bv) {
+    return d.kind != MAL_AGENT_DQN && g_use_tc && g_fuse_agent_in && d.M1 < (1 << 24) && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 &&
+           (bv.obs.st & 3) == 0 && aligned16(bv.obs.ptr);
+}
+// Tensor-core recurrences (k_gru_fwd_tc / k_gru_bwd_tc; gi and the saved gates then use their tiled layouts).  The forward
+// and the backward call must agree: both evaluate this on the same dims with the calling thread's option value.
+static bool rec_tc_selected(const Dims &d, const BatchView &bv) {
+    return fused_in_selected(d, bv) && (d.R % 32) == 0 && (g_rec_tc == 2 || (g_rec_tc == 1 && 2 * (int64_t)d.R >= REC_TC_MIN_ROWS));
+}
+static int rec_tc_groups(int G, int nets, int sms) {   // 32-chain groups per tile: fewest waves of CTAs, ties -> the smaller tile
+    int best_g = 4; int64_t best_w = -1;
+    for (int g = 1; g <= 4; ++g) {
+        const int64_t w = ceil_div64(ceil_div64(G, g) * nets, sms);
+        if (best_w < 0 || w < best_w) { best_w = w; best_g = g; }
+    }
+    return best_g;
+}
+static int launch_gru_bwd_tc(const GruBwdArgs &a, int sms, cudaStream_t st, bool pdl) {
+    static size_t attr[MAL_MAX_DEV];
+    if (int rc = ensure_dyn_smem(k_gru_bwd_tc, (size_t)GB_SMEM_BYTES, attr)) return rc;
+    const int G = a.R / 32;
+    GruBwdTcArgs ta;
+    ta.g = a; ta.groups_per_tile = rec_tc_groups(G, 1, sms);
+    ++g_stat_rec_tc_bwd;
+    ProfScope _ps("k_gru_bwd", st);
+    launch_k(k_gru_bwd_tc, dim3((unsigned)ceil_div64(G, ta.groups_per_tile)), dim3(GT_THREADS), (size_t)GB_SMEM_BYTES, st, pdl, ta);
+    return 0;
+}
 // Tensor-core forward recurrence: tiles of g 32-chain groups (g <= 4), g chosen for the fewest waves of CTAs over the SMs
 // (ties: the smaller tile -- fewer idle MMA rows, the per-step time of a tile does not depend on g).
 static int launch_gru_fwd_tc(const GruFwdArgs &a, int nets, int sms, cudaStream_t st, bool pdl) {
     static size_t attr[MAL_MAX_DEV];
     if (int rc = ensure_dyn_smem(k_gru_fwd_tc, (size_t)GT_SMEM_BYTES, attr)) return rc;
     const int G = a.R / 32;
-    int best_g = 4; int64_t best_w = -1;
-    for (int g = 1; g <= 4; ++g) {
-        const int64_t w = ceil_div64(ceil_div64(G, g) * nets, sms);
-        if (best_w < 0 || w < best_w) { best_w = w; best_g = g; }
-    }
+    const int best_g = rec_tc_groups(G, nets, sms);
     GruFwdTcArgs ta;
-    ta.g = a; ta.groups_per_tile = best_g;
+    ta.g = a; ta.groups_per_tile = best_g; ta.gates_tiled = g_rec_tc_bwd;
     ++g_stat_rec_tc;
     ProfScope _ps("k_gru_fwd", st);
     launch_k(k_gru_fwd_tc, dim3((unsigned)ceil_div64(G, best_g), nets), dim3(GT_THREADS), (size_t)GT_SMEM_BYTES, st, pdl, ta);
@@ -831,14 +859,13 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
 
     // x = relu(fc1([obs | last action | agent id])) and gi = W_ih x + b_ih for every (t,b,n), both nets
     //                                                  basic_controller.py:80-92, drqn_agent.py:30-31, GRUCell input half
-    const bool fused_in = !dqn && g_use_tc && g_fuse_agent_in && d.M1 < (1 << 24) && (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 &&
-                          (bv.obs.st & 3) == 0 && aligned16(bv.obs.ptr);
+    const bool fused_in = fused_in_selected(d, bv);
     // time-chunked forward: the recurrence over the first half of the timesteps runs while the input projection of the
     // second half is still being computed on a side stream (the recurrence is latency-bound and leaves the tensor
     // cores and most issue slots idle)
     const int t_split = (fused_in && g_time_chunks > 1 && g_overlap && d.TT >= 32) ? d.TT / 2 : d.TT;
     // tensor-core recurrence (k_gru_fwd_tc) for large row counts: gi then leaves k_agent_in_tc in the tiled layout
-    const bool rec_tc = fused_in && (d.R % 32) == 0 && (g_rec_tc == 2 || (g_rec_tc == 1 && 2 * (int64_t)d.R >= REC_TC_MIN_ROWS));
+    const bool rec_tc = rec_tc_selected(d, bv);
     if (fused_in) {
         const size_t ai_smem = ai_smem_bytes(bv.OBS + bv.A);
         static size_t attr[MAL_MAX_DEV];
@@ -1213,7 +1240,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         GruBwdArgs a;
         a.params = agent; a.hout = F(plan->h_on); a.gates = F(plan->gates); a.dh_head = F(plan->dh_head);
         a.d_g = d_g; a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
-        if (launch_gru_bwd(a, st, g_in_step)) return 2;        // inside a step the stream predecessor is k_mix_td
+        if ((rec_tc_selected(d, bv) && g_rec_tc_bwd) ? launch_gru_bwd_tc(a, sms, st, g_in_step) : launch_gru_bwd(a, st, g_in_step)) return 2;        // inside a step the stream predecessor is k_mix_td
         MAL_LAUNCH_CHECK("k_gru_bwd");
     }
     // ---- side stream 2 (after the recurrence): W_ih / W_hh gradients, beside  d x = (d gi . W_ih) * (x > 0)  + fc1 grads

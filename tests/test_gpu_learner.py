@@ -287,7 +287,7 @@ def test_checkpoint_roundtrip(tmp_path):
 # lines of these workloads actually take (k_linear_tc2, k_reduce_tc incl. SWAP, pipelined k_agent_in_tc at d_in > 64)
 # are held to the fp64 oracle, and the test asserts which flavours ran (mal_stat counters).
 # ------------------------------------------------------------------------------------------------------------------
-_FLAVOURS = ("linear_tc2", "linear_tc", "reduce_tc", "reduce_tc_swap", "reduce_ffma", "agent_in_fused", "rec_tc")
+_FLAVOURS = ("linear_tc2", "linear_tc", "reduce_tc", "reduce_tc_swap", "reduce_ffma", "agent_in_fused", "rec_tc", "rec_tc_bwd")
 
 
 def _discrete_choices(it, ref, mixer, E=32, HE=64, tol=1e-5):
@@ -380,8 +380,9 @@ def _check_against_oracle_full(s, mixer, gap_tol=1e-5):
     return ran
 
 
+@pytest.mark.parametrize("bwd_tc", [0, 1])
 @pytest.mark.parametrize("N,B,TT,mixer", [(5, 32, 201, "qmix"), (20, 8, 12, "qmix"), (3, 96, 7, "vdn"), (5, 64, 40, "qmix")])
-def test_tensor_core_recurrence_forced(N, B, TT, mixer):
+def test_tensor_core_recurrence_forced(N, B, TT, mixer, bwd_tc):
     """k_gru_fwd_tc (one tcgen05 GEMM per timestep for a tile of up to 128 chains, gi in the tiled layout written by
     k_agent_in_tc) is what the heuristics pick from 8 192 chains on (20v20 / B=1024); force it on shapes the numpy
     oracle affords -- R = 160 (5 groups: tiles of 1), 160, 288 (9 groups), 320 (10 groups) -- and hold hidden states,
@@ -389,11 +390,13 @@ def test_tensor_core_recurrence_forced(N, B, TT, mixer):
     from ma_league_b200 import _native as nat
     assert (N * B) % 32 == 0
     nat.check(nat.lib().mal_set_option(b"rec_tc", 2), "mal_set_option")
+    nat.check(nat.lib().mal_set_option(b"rec_tc_bwd", bwd_tc), "mal_set_option")     # 1: BPTT on the tensor cores too (A operand in tensor memory, tiled gates)
     try:
         ran = _check_against_oracle_full(seeded_system(N, B, TT, mixer, True, seed=50 + N), mixer)
     finally:
         nat.check(nat.lib().mal_set_option(b"rec_tc", 1), "mal_set_option")
-    assert ran["rec_tc"] >= 1, ran
+        nat.check(nat.lib().mal_set_option(b"rec_tc_bwd", 0), "mal_set_option")
+    assert ran["rec_tc"] >= 1 and (ran["rec_tc_bwd"] >= 1) == bool(bwd_tc), ran
 
 
 def test_config1_qmix_3v3_b32_full_shape():
