@@ -516,7 +516,8 @@ static PartLayout part_layout(const Dims &d, int sms) {
     // dense agent reductions: the fused k_reduce_gru handles a whole row chunk on one CTA -> one chunk per SM once every
     // chunk is long (>= 1024 rows), half as many below that (fewer partials for k_grad_reduce to gather at B = 32)
     chunking(d.M1, d.M1 >= (int64_t)sms * 1024 ? 1 : 2, sms, &p.nc_a, &p.rpc_a);
-    chunking(d.M1, tiles_of(HID, d.d_in), sms, &p.nc_f1, &p.rpc_f1);
+    // fc1: k_reduce_fc1 covers the full input width (<= 256 columns) on one CTA per chunk -> one chunk per SM
+    chunking(d.M1, d.d_in <= 256 ? 1 : tiles_of(HID, d.d_in), sms, &p.nc_f1, &p.rpc_f1);
     {   // k_fc2_grad: one partial per CTA, 8 warps x >= 32 rows each; the kernel is HBM-bound on the h rows, so large batches
         // fill every SM with as many CTAs as their [8][A*64+32]-float accumulators allow (<= 4)
         const int64_t smem = (int64_t)sizeof(float) * 8 * ((int64_t)d.A * HID + 32);
@@ -617,7 +618,8 @@ static thread_local int g_tc_pipelined = 1;   // software-pipelined k_linear_tc2
 static thread_local int g_rec_tc = 1;         // tensor-core recurrence k_gru_fwd_tc: 0 off, 1 when both nets have >= REC_TC_MIN_ROWS chains, 2 whenever R % 32 == 0
 #define REC_TC_MIN_ROWS 8192                  // chains (both nets) from which a 128-chain MMA tile per SM beats one FFMA CTA per chain
 static thread_local int g_rec_tc_bwd = 0;     // tensor-core BPTT k_gru_bwd_tc beside k_gru_fwd_tc (A operand in tensor memory): correct, but measured slower than k_gru_bwd9 (4.16 vs 3.08 ms at 20v20); 1: on
-static uint64_t g_stat_rec_tc = 0, g_stat_rec_tc_bwd = 0;
+static uint64_t g_stat_rec_tc = 0, g_stat_rec_tc_bwd = 0, g_stat_reduce_fc1 = 0;
+static thread_local int g_fc1_fused = 1;      // fc1 weight gradient over the full input width on one CTA per row chunk (k_reduce_fc1); 0: 128-column tiles of k_reduce_tc3
 
 // Launch counters per kernel flavour since process start (tests check which variant the heuristics picked).
 extern "C" uint64_t mal_stat(const char *name) {
@@ -630,6 +632,7 @@ extern "C" uint64_t mal_stat(const char *name) {
     if (strcmp(name, "agent_in_fused") == 0) return g_stat_agent_in_fused;
     if (strcmp(name, "rec_tc") == 0) return g_stat_rec_tc;
     if (strcmp(name, "rec_tc_bwd") == 0) return g_stat_rec_tc_bwd;
+    if (strcmp(name, "reduce_fc1") == 0) return g_stat_reduce_fc1;
     return 0;
 }
 extern "C" int mal_set_option(const char *name, int value) {
@@ -647,6 +650,7 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return 0; }
     if (strcmp(name, "rec_tc") == 0) { g_rec_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "rec_tc_bwd") == 0) { g_rec_tc_bwd = value ? 1 : 0; return 0; }
+    if (strcmp(name, "fc1_fused") == 0) { g_fc1_fused = value ? 1 : 0; return 0; }
     mal_set_error("mal_set_option: unknown option %s", name);
     return 1;
 }
@@ -1281,12 +1285,27 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         int rc = launch_linear(g, d.M1, G3, st, "k_linear_group:dx");
         g_next_pdl = false;
         if (rc) return rc;
-        RedGroup r; r.n = 1; r.bv = bv;
-        r.p[0] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
-        g_next_pdl = g_use_tc != 0;              // stream predecessor: the dx GEMM (the tcgen05 kernels trigger at their last tile)
-        rc = launch_reduce(r, st, "k_reduce_group:agent");
-        g_next_pdl = false;
-        if (rc) return rc;
+        // inputs wider than one 128-column tile (20v20: d_in = 214): one CTA per row chunk over the full width instead of one
+        // k_reduce_tc3 CTA per 128-column tile (4.02 -> 2.53 ms at 20v20 / B = 1024); a single tile (10v10) is a wash (144 vs 138 us)
+        const bool fused_fc1 = g_use_tc && g_reduce_tc && g_reduce_mn >= 3 && g_fc1_fused && d.d_in <= 256 && d.M1 < 2147483647LL &&
+                               (g_reduce_tc == 2 || (pl.rpc_f1 >= 256 && d.d_in > 128));
+        if (fused_fc1) {
+            ReduceFc1Args fa;
+            fa.d_x = d_x; fa.partW = parts + pl.fc1_w; fa.partB = parts + pl.fc1_b;
+            fa.M = d.M1; fa.rows_per_chunk = pl.rpc_f1; fa.n_chunks = pl.nc_f1; fa.d_in = d.d_in; fa.bv = bv;
+            static size_t attr[MAL_MAX_DEV];
+            if (int rc2 = ensure_dyn_smem(k_reduce_fc1, RF_SMEM_BYTES, attr)) return rc2;
+            ++g_stat_reduce_fc1;
+            { ProfScope _ps("k_reduce_tc:agent_fc1", st); launch_k(k_reduce_fc1, dim3(pl.nc_f1), dim3(RT3_THREADS), RF_SMEM_BYTES, st, g_use_tc != 0, fa); }   // stream predecessor: the dx GEMM
+            MAL_LAUNCH_CHECK("k_reduce_fc1");
+        } else {
+            RedGroup r; r.n = 1; r.bv = bv;
+            r.p[0] = red(d.M1, d.d_in, HID, d_x, HID, A_AGENT_IN, 0, nullptr, 0, parts + pl.fc1_w, parts + pl.fc1_b, pl.nc_f1, pl.rpc_f1);
+            g_next_pdl = g_use_tc != 0;              // stream predecessor: the dx GEMM (the tcgen05 kernels trigger at their last tile)
+            rc = launch_reduce(r, st, "k_reduce_group:agent");
+            g_next_pdl = false;
+            if (rc) return rc;
+        }
     }
     if (join_from(st, s1, ss->join_ev[0])) return 2;
     if (join_from(st, s2, ss->join_ev[1])) return 2;

@@ -919,3 +919,226 @@ __global__ void __launch_bounds__(RT3_THREADS, 1) k_reduce_gru(const __grid_cons
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
+
+// =====================================================================================================================
+// k_reduce_fc1: the fc1 weight / bias gradient  dW1[n][k] = sum_m d_x[m][n] in[m][k]  (in = [obs | last-action one-hot |
+// agent-id one-hot], never materialised) as ONE split-M GEMM per 16-row block and row chunk, built like k_reduce_gru:
+//     D[256 x 64] += in^T [16 x 256]  .  d_x [16 x 64]            (two M = 128 halves when d_in > 128, N = 64)
+// k_reduce_tc3 runs this problem as 128-column tiles on separate CTAs (d_x re-read per tile, 32-row blocks of 24 KB with
+// three pieces per thread and two divisions per piece): 4.0 ms at 20v20 / B = 1024 = 16 % of the HBM peak.  Here one CTA
+// owns a row chunk over the FULL input width: warp = row of the block, its (t, b, n) advance incrementally, a lane copies
+// pieces `lane` and `lane + 32` of the input row (16-byte cp.async inside the obs part, 4-byte copies / computed values
+// for the one-hot tail) and, lanes 0-15, one piece of the d_x row.  hi = the raw fp32 bits where they land, lo = v - trunc(v).
+// TMEM: D1 halves at 0 | 64, D2 halves at 128 | 192.   smem: five hi + two lo stages of 20 KB.
+// =====================================================================================================================
+#define RF_STAGE (10 * RG_SLAB)                          // 20 KB: input (8 slabs of 32 columns) | d_x (2 slabs)
+#define RF_SMEM_BYTES ((RG_NHI + RG_NLO) * RF_STAGE)     // 140 KB
+struct ReduceFc1Args {
+    const float *d_x;                 // [M, 64]
+    float *partW, *partB;             // [n_chunks][64][d_in], [n_chunks][64]
+    int64_t M, rows_per_chunk;
+    int n_chunks, d_in;
+    BatchView bv;
+};
+
+__global__ void __launch_bounds__(RT3_THREADS, 1) k_reduce_fc1(const __grid_constant__ ReduceFc1Args a) {
+    extern __shared__ __align__(1024) uint8_t rt_smem[];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    const BatchView &bv = a.bv;
+    const int chunk = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t mb = (int64_t)chunk * a.rows_per_chunk;
+    int64_t me = mb + a.rows_per_chunk;
+    if (me > a.M) me = a.M;
+    const int nblk = me > mb ? (int)((me - mb + RG_BM - 1) / RG_BM) : 0;
+    const int halves = a.d_in > 128 ? 2 : 1;
+    uint8_t *lo_base = rt_smem + RG_NHI * RF_STAGE;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    // ---- this thread's pieces of a block: row `warp`; input pieces `lane` and `lane + 32`, d_x piece `lane` (lanes 0-15)
+    const int KA = bv.OBS + bv.A;                        // first agent-id column
+    const bool obs_vec = (bv.OBS & 3) == 0 && (bv.obs.sb & 3) == 0 && (bv.obs.st & 3) == 0 && ((reinterpret_cast<uintptr_t>(bv.obs.ptr) & 15) == 0);
+    uint32_t off_in[2];
+    int col_in[2], cls_in[2];                            // class 0: zero, 1: one 16-byte copy from the obs row, 2: element-wise
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int pc = lane + 32 * h;
+        off_in[h] = (uint32_t)(pc >> 3) * RG_SLAB + mn_off(warp, pc & 7);
+        col_in[h] = 4 * pc;
+        cls_in[h] = col_in[h] >= a.d_in ? 0 : ((obs_vec && col_in[h] + 4 <= bv.OBS) ? 1 : 2);
+    }
+    const uint32_t off_dx = (uint32_t)(8 + ((lane & 15) >> 3)) * RG_SLAB + mn_off(warp, lane & 7);
+    const bool has_dx = lane < 16;
+    // row bookkeeping: m = mb + warp + 16 j  ->  (t, b, n), advanced incrementally
+    int64_t m_next = mb + warp;
+    int t_, b_, n_, rr_;
+    {
+        const int64_t mc = m_next < a.M ? m_next : 0;
+        t_ = (int)(mc / bv.R); rr_ = (int)(mc - (int64_t)t_ * bv.R); b_ = rr_ / bv.N; n_ = rr_ - b_ * bv.N;
+    }
+    const int q16 = RG_BM / bv.N, r16 = RG_BM - q16 * bv.N;
+    const float *src_dx = a.d_x + (mb + warp) * HID + 4 * (lane & 15);
+    auto zero16 = [&](uint8_t *dst) { *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f); };
+    auto issue_block = [&](int j) {
+        uint8_t *hi = rt_smem + (size_t)(j % RG_NHI) * RF_STAGE;
+        const bool ok = m_next < me;
+        const float *obs = field_ptr<float>(bv.obs, b_, t_) + (int64_t)n_ * bv.OBS;
+        const float *oh = t_ > 0 ? field_ptr<float>(bv.onehot, b_, t_ - 1) + (int64_t)n_ * bv.A : nullptr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint8_t *dst = hi + off_in[h];
+            if (h >= halves) break;
+            if (!ok || cls_in[h] == 0) zero16(dst);
+            else if (cls_in[h] == 1) cp_async16_plain(dst, obs + col_in[h]);
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int kk = col_in[h] + e;
+                    float *d = reinterpret_cast<float *>(dst + 4 * e);
+                    if (kk < bv.OBS) cp_async4_plain(d, obs + kk);
+                    else if (kk < KA) { if (oh) cp_async4_plain(d, oh + (kk - bv.OBS)); else *d = 0.0f; }
+                    else *d = (kk < a.d_in && kk - KA == n_) ? 1.0f : 0.0f;      // agent-id one-hot: computed, not loaded
+                }
+            }
+        }
+        if (has_dx) { if (ok) cp_async16_plain(hi + off_dx, src_dx); else zero16(hi + off_dx); }
+        // next block: row + 16
+        m_next += RG_BM; src_dx += RG_BM * HID;
+        rr_ += RG_BM; b_ += q16; n_ += r16;
+        if (n_ >= bv.N) { n_ -= bv.N; ++b_; }
+        if (rr_ >= bv.R) {
+            do { rr_ -= bv.R; ++t_; } while (rr_ >= bv.R);
+            b_ = rr_ / bv.N; n_ = rr_ - b_ * bv.N;
+        }
+    };
+
+    const int q = warp & 3, cg = warp >> 2;              // TMEM lane quarter q (input column 32 q + lane of a half), d_x columns 16 cg .. +16
+    float acc[2][16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[h][c] = 0.0f;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    bool fresh = true;
+    auto wait_block = [&](int j) {
+        mbar_wait(&mma_bar[j & 1], (uint32_t)((j >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    auto fold = [&]() {
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h >= halves) break;
+            uint32_t d1[32], d2[32];
+            tmem_ld16_nowait(tl + 64 * h, d1);
+            tmem_ld16_nowait(tl + 128 + 64 * h, d2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[h][c] += __uint_as_float(d1[c]) + __uint_as_float(d2[c]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);         // column sums of d_x: columns 4 lane .. +3 (lanes 0-15)
+    auto lo_of = [&](const float4 &v) {
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        return l;
+    };
+
+    pdl_wait();                                          // d_x comes from the stream predecessor (the dx GEMM)
+#pragma unroll
+    for (int jj = 0; jj < RG_AHEAD; ++jj) {
+        if (jj < nblk) issue_block(jj);
+        cp_async_commit();
+    }
+    for (int j = 0; j < nblk; ++j) {
+        uint8_t *hi = rt_smem + (size_t)(j % RG_NHI) * RF_STAGE;
+        uint8_t *lo = lo_base + (size_t)(j & 1) * RF_STAGE;
+        if (j + 1 == nblk) pdl_trigger();                // the gradient gather may start its prologue
+        if (j >= 2) wait_block(j - 2);                   // frees the hi stage block j+3 lands in and this lo stage
+        if (j + RG_AHEAD < nblk) issue_block(j + RG_AHEAD);
+        cp_async_commit();
+        cp_async_wait<RG_AHEAD>();                       // this thread's pieces of block j have landed
+        {
+            const float4 v0 = *reinterpret_cast<const float4 *>(hi + off_in[0]);
+            *reinterpret_cast<float4 *>(lo + off_in[0]) = lo_of(v0);
+            if (halves > 1) {
+                const float4 v1 = *reinterpret_cast<const float4 *>(hi + off_in[1]);
+                *reinterpret_cast<float4 *>(lo + off_in[1]) = lo_of(v1);
+            }
+            if (has_dx) {
+                const float4 g = *reinterpret_cast<const float4 *>(hi + off_dx);
+                bs.x += g.x; bs.y += g.y; bs.z += g.z; bs.w += g.w;
+                *reinterpret_cast<float4 *>(lo + off_dx) = lo_of(g);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const uint64_t dBh = umma_desc_mn_sw128(smem_u32(hi + 8 * RG_SLAB), RG_SLAB), dBl = umma_desc_mn_sw128(smem_u32(lo + 8 * RG_SLAB), RG_SLAB);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h >= halves) break;
+                const uint64_t dAh = umma_desc_mn_sw128(smem_u32(hi + h * 4 * RG_SLAB), RG_SLAB), dAl = umma_desc_mn_sw128(smem_u32(lo + h * 4 * RG_SLAB), RG_SLAB);
+#pragma unroll
+                for (int ks = 0; ks < RG_BM / 8; ++ks) {
+                    const uint64_t o = (uint64_t)((ks * 1024) >> 4);
+                    const uint32_t first = (fresh && ks == 0) ? 0u : 1u;
+                    umma_tf32(tmem_base + 64 * h, dAh + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + 128 + 64 * h, dAl + o, dBh + o, idesc, first);
+                    umma_tf32(tmem_base + 128 + 64 * h, dAh + o, dBl + o, idesc, 1u);
+                }
+            }
+            umma_commit(&mma_bar[j & 1]);
+        }
+        fresh = false;
+        if ((j % RG_FLUSH) == RG_FLUSH - 1 && j + 1 < nblk) {   // the accumulation so far leaves the tensor core's truncating adder
+            wait_block(j);
+            fold();
+            fresh = true;
+        }
+    }
+    if (nblk > 0) { wait_block(nblk - 1); fold(); }
+    // ---- partials: partW[chunk][n][k]; TMEM lane = input column k of a half, accumulator column = n
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = 128 * h + q * 32 + lane;
+        if (h < halves && k < a.d_in) {
+            float *dst = a.partW + ((int64_t)chunk * HID + cg * 16) * a.d_in + k;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dst[(int64_t)c * a.d_in] = acc[h][c];
+        }
+    }
+    // ---- bias partials: column sums of d_x over the chunk
+    __syncthreads();
+    float *bsum = reinterpret_cast<float *>(rt_smem);    // [16 warps][64]
+    if (has_dx) *reinterpret_cast<float4 *>(bsum + warp * HID + 4 * lane) = bs;
+    __syncthreads();
+    if (tid < HID) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < RT3_WARPS; ++w) s += bsum[w * HID + tid];
+        a.partB[(int64_t)chunk * HID + tid] = s;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+}

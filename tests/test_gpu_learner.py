@@ -143,8 +143,9 @@ def test_both_tensor_core_gemm_kernels_inside_the_learner(mode):
         assert_close(grads["mixer." + k], v, TOL, "grad mixer " + k)
 
 
+@pytest.mark.parametrize("fc1_fused", [1, 0])
 @pytest.mark.parametrize("N,B,TT", [(10, 4, 9), (20, 3, 6), (26, 2, 4)])
-def test_tensor_core_reductions_forced_on_small_wide_problems(N, B, TT):
+def test_tensor_core_reductions_forced_on_small_wide_problems(N, B, TT, fc1_fused):
     """fc1 weight gradients with d_in > 64 take the transposed (SWAP) orientation of k_reduce_tc, which the launch
     heuristic only selects for long row chunks: force the tensor-core reductions and the pipelined GEMM on small
     batches of the wide configs and hold every gradient to the oracle."""
@@ -153,11 +154,16 @@ def test_tensor_core_reductions_forced_on_small_wide_problems(N, B, TT):
     ref = _oracle_run(s, "qmix", True, dtype=np.float64)
     nat.check(nat.lib().mal_set_option(b"reduce_tc", 2), "mal_set_option")
     nat.check(nat.lib().mal_set_option(b"tc_pipelined", 2), "mal_set_option")
+    nat.check(nat.lib().mal_set_option(b"fc1_fused", fc1_fused), "mal_set_option")   # 1: k_reduce_fc1 (full input width per CTA), 0: SWAP tiles of k_reduce_tc3
+    n_fc1 = nat.lib().mal_stat(b"reduce_fc1")
     try:
         grads = split_grad(s.learner.forward_backward(s.batch), s.learner)
     finally:
         nat.check(nat.lib().mal_set_option(b"reduce_tc", 1), "mal_set_option")
         nat.check(nat.lib().mal_set_option(b"tc_pipelined", 1), "mal_set_option")
+        nat.check(nat.lib().mal_set_option(b"fc1_fused", 1), "mal_set_option")
+    d_in = s.mac.agent.fc1.weight.shape[1]
+    assert (nat.lib().mal_stat(b"reduce_fc1") - n_fc1 >= 1) == bool(fc1_fused and d_in <= 256), d_in
     for k, v in ref["agent_grads"].items():
         assert_close(grads["agent." + k], v, TOL, "grad " + k)
     for k, v in ref["mixer_grads"].items():
@@ -287,7 +293,7 @@ def test_checkpoint_roundtrip(tmp_path):
 # lines of these workloads actually take (k_linear_tc2, k_reduce_tc incl. SWAP, pipelined k_agent_in_tc at d_in > 64)
 # are held to the fp64 oracle, and the test asserts which flavours ran (mal_stat counters).
 # ------------------------------------------------------------------------------------------------------------------
-_FLAVOURS = ("linear_tc2", "linear_tc", "reduce_tc", "reduce_tc_swap", "reduce_ffma", "agent_in_fused", "rec_tc", "rec_tc_bwd")
+_FLAVOURS = ("linear_tc2", "linear_tc", "reduce_tc", "reduce_tc_swap", "reduce_ffma", "agent_in_fused", "rec_tc", "rec_tc_bwd", "reduce_fc1")
 
 
 def _discrete_choices(it, ref, mixer, E=32, HE=64, tol=1e-5):
@@ -426,7 +432,7 @@ def test_config5_dims_qmix_20v20_b64_default_heuristics():
     the launch heuristics to pick exactly the kernels of the B=1024 bench line)."""
     ran = _check_against_oracle_full(seeded_system(20, 64, 201, "qmix", True, seed=44), "qmix")
     assert ran["agent_in_fused"] == 1 and ran["linear_tc2"] >= 2, ran
-    assert ran["reduce_tc"] >= 3 and ran["reduce_tc_swap"] >= 1 and ran["reduce_ffma"] == 0, ran
+    assert ran["reduce_tc"] >= 3 and ran["reduce_fc1"] >= 1 and ran["reduce_ffma"] == 0, ran
 
 
 def test_nan_in_target_max_propagates_like_torch():
