@@ -117,6 +117,23 @@ struct TcEpi {
 template <int EK>
 __device__ __forceinline__ void tc_epilogue_group(const TcEpi &e, float4 *stg, const uint32_t (&d1)[32], const uint32_t (&d2)[32],
                                                   int gw, int c0, int64_t mw, int lane, const float *bias_s, bool skip) {
+    // ReLU-mask operand (x of the rows this lane will store): all eight float4 are requested up front, UNCONDITIONALLY
+    // (row / column clamped into range instead of guarded) and in one basic block, so that their latencies overlap each
+    // other and the shared-memory round trip.  The r2 profile of the dx GEMM had 36 % of all stall samples on eight serial
+    // load -> compare pairs per group: each load sat in its own guarded block and its result was turned into predicate
+    // bits right away, one DRAM latency after the other (mal_debug_linear M=1M K=64 N=64: 657 us masked vs 147 us plain).
+    float4 avs[8];
+    const bool mask_vec = EK == TCE_MASKPOS && e.vec_ok && e.Nout >= 4 && e.M > 0;
+    if (mask_vec) {
+        const int cpr_ = gw >> 2, ch_ = lane & (cpr_ - 1), rsub_ = lane / cpr_, rpp_ = 32 / cpr_;
+        const int col_ = (c0 + 4 * ch_ + 4 <= e.Nout) ? c0 + 4 * ch_ : 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int64_t m_ = mw + (k * rpp_ + rsub_ < 32 ? k * rpp_ + rsub_ : 31);
+            if (m_ > (int64_t)e.M - 1) m_ = (int64_t)e.M - 1;
+            avs[k] = __ldg(reinterpret_cast<const float4 *>(e.aux + m_ * e.ld_aux + col_));
+        }
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         if (c < (gw >> 2))
@@ -162,7 +179,7 @@ __device__ __forceinline__ void tc_epilogue_group(const TcEpi &e, float4 *stg, c
                 float *y = yp + (int64_t)(k * rpp) * e.ldy;
                 if (vec) {
                     if (EK == TCE_MASKPOS) {
-                        const float4 av = __ldg(reinterpret_cast<const float4 *>(ap + (int64_t)(k * rpp) * e.ld_aux));
+                        const float4 av = mask_vec ? avs[k] : __ldg(reinterpret_cast<const float4 *>(ap + (int64_t)(k * rpp) * e.ld_aux));
                         x.x = av.x > 0.0f ? x.x : 0.0f; x.y = av.y > 0.0f ? x.y : 0.0f;
                         x.z = av.z > 0.0f ? x.z : 0.0f; x.w = av.w > 0.0f ? x.w : 0.0f;
                     }
