@@ -27,6 +27,7 @@ __host__ __device__ inline size_t ai_smem_bytes(int K1) { return AI_OFF_W1 + (si
 #define AI_THREADS 512                    // 16 warps: four per sub-partition hide the load / TMEM / shared-memory latencies of the staging and epilogue phases (r2: 256 threads left ~20 K of a tile's 23 K cycles to those phases)
 #define AI_RSTEP (AI_THREADS / 16)        // rows between two staging pieces of a thread (32)
 #define AI_RPT (TC_M / AI_RSTEP)          // staging rows per thread (4)
+#define AI_REM_MAX 4                      // widest K remainder handled in the epilogue instead of an extra k-chunk
 #define AI_COL_X1 0
 #define AI_COL_X2 64
 #define AI_COL_G1 128
@@ -55,9 +56,14 @@ __global__ void __launch_bounds__(AI_THREADS, 1) k_agent_in_tc(const __grid_cons
     const int n_mtiles = (int)((a.m_end - a.m_begin + TC_M - 1) / TC_M);
     if ((int)blockIdx.x >= n_mtiles) return;
     const BatchView &bv = a.bv;
-    const int K1 = bv.OBS + bv.A;                       // the agent-id columns are a bias gather in the epilogue
+    const int K1f = bv.OBS + bv.A;                      // the agent-id columns are a bias gather in the epilogue
+    // A short remainder past the last full 64-column chunk (20v20: 194 = 3 x 64 + 2) would cost a whole extra load / stage /
+    // MMA / wait round for a handful of columns: those columns (of the one-hot part) join the agent-id term as rank-1
+    // updates in epilogue 1 instead, and the MMA runs over K1 = the full chunks only
+    const int rem1 = (K1f > TC_KC && (K1f % TC_KC) != 0 && (K1f % TC_KC) <= AI_REM_MAX && K1f - (K1f % TC_KC) >= bv.OBS) ? K1f % TC_KC : 0;
+    const int K1 = K1f - rem1;
     const int nkc1 = (K1 + TC_KC - 1) / TC_KC;
-    const bool two_slots = ai_w1_slots(K1) == 2;
+    const bool two_slots = ai_w1_slots(K1f) == 2;
     uint8_t *A_hi = tc_smem, *A_lo = tc_smem + 2 * AI_SLAB_A;
     uint8_t *W1_base = tc_smem + AI_OFF_W1;             // slot s: hi at + s * AI_W1_SLOT, lo 2 slabs further
     uint8_t *W2_hi = W1_base + (two_slots ? 2 : 1) * AI_W1_SLOT, *W2_lo = W2_hi + 2 * AI_SLAB_W2;
@@ -236,12 +242,24 @@ __global__ void __launch_bounds__(AI_THREADS, 1) k_agent_in_tc(const __grid_cons
             const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cgp * 16);
             tmem_ld16_nowait(tl + AI_COL_X1, d1);
             tmem_ld16_nowait(tl + AI_COL_X2, d2);
-            int agent = 0;
-            if (m < M) { int t, rr, b; fast_divmod((int)m, bv.R, invR, t, rr); fast_divmod(rr, bv.N, invN, b, agent); }
-            const float *wid = P + L.fc1_w + K1 + agent;          // fc1.weight[n, K1 + agent]
+            int agent = 0, t_r = 0, b_r = 0;
+            if (m < M) { int rr; fast_divmod((int)m, bv.R, invR, t_r, rr); fast_divmod(rr, bv.N, invN, b_r, agent); }
+            const float *wid = P + L.fc1_w + K1f + agent;         // fc1.weight[n, K1f + agent]
             float wa[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) wa[e] = __ldg(wid + (int64_t)(cgp * 16 + e) * a.d_in);   // in flight under the TMEM load
+            if (rem1 > 0) {                                       // remainder columns K1 .. K1f-1 (one-hot part): x += in[k] W1[n, k]
+                const float *oh = (m < M && t_r > 0) ? field_ptr<float>(bv.onehot, b_r, t_r - 1) + (int64_t)agent * bv.A + (K1 - bv.OBS) : nullptr;
+#pragma unroll
+                for (int j = 0; j < AI_REM_MAX; ++j) {
+                    if (j < rem1) {
+                        const float v = oh ? __ldg(oh + j) : 0.0f;
+                        const float *wr = P + L.fc1_w + K1 + j;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) wa[e] = fmaf(v, __ldg(wr + (int64_t)(cgp * 16 + e) * a.d_in), wa[e]);
+                    }
+                }
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float *xrow = a.x[net] + m * HID + cgp * 16;
 #pragma unroll
