@@ -117,7 +117,7 @@ struct LinProb {
     const float *aux; int64_t ld_aux;             // EPI_MASKPOS: multiply by (aux[m,n] > 0)
     float *Y; int64_t ldy;
 };
-#define LIN_MAX_PROBS 12
+#define LIN_MAX_PROBS 20   // 20v20 hypernet layer 2: 2 nets x (8 + 1) column pieces of <= 80 (kernel parameter block: 20 x 112 B + view < 4 KB)
 struct LinGroup {
     int n;
     int dbg;   // probe switches of k_linear_tc2 (0 in production): 1 no epilogue stores, 2 no A loads, 4 no A split/STS, 8 no MMAs
