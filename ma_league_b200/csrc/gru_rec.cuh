@@ -480,51 +480,38 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd9(GruFwdArgs a) {
     __shared__ __align__(16) float h_s[2][HROW];
     __shared__ float st_s[PF][3][HID];
     __shared__ float pdl_anchor_s[HID];
-    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
+    const int i = threadIdx.x;
     const int ug = i >> 1, part = i & 1;
     const AgentLayout L = agent_layout(a.d_in, a.n_actions);
-    const float *P = net ? a.params[1] : a.params[0];
-    const float *gi = net ? a.gi[1] : a.gi[0];
-    float *hout = net ? a.hout[1] : a.hout[0];
-    const bool save_gates = net == 0;
-    const int t0 = a.t0, n = a.t1 - a.t0;
-
-    float anchor = 0.0f;
-    unsigned long long w[2][3][KC / 2];    // packed pairs of W_hh[g*64 + 2*ug + u][part*32 + 2j, +1]
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + 2 * ug + u) * HID + part * KC);
-#pragma unroll
-            for (int q = 0; q < KC / 4; ++q) {
-                const float4 v = __ldg(wr + q);
-                w[u][g][2 * q] = pack2(v.x, v.y); w[u][g][2 * q + 1] = pack2(v.z, v.w);
-                anchor += v.x;
-            }
-        }
-    const float b_r = __ldg(P + L.b_hh + i), b_z = __ldg(P + L.b_hh + HID + i), b_n = __ldg(P + L.b_hh + 2 * HID + i);
-    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;   // pins the loads above the wait (see k_gru_fwd7)
-    pdl_wait();
-    const int64_t hstride = (int64_t)a.R * HID, tstride = (int64_t)a.R * G3;
-    float *hdst = hout + ((int64_t)t0 * a.R + row) * HID + i;                 // h of the current step
-    float4 *gdst = reinterpret_cast<float4 *>(a.gates) + ((int64_t)t0 * a.R + row) * HID + i;
-    float hprev = t0 > 0 ? *(hdst - hstride) : 0.0f;                           // init_hidden: zeros
-    const int hpos = i + (i >= KC ? GT_PAD : 0);
-    h_s[0][hpos] = hprev; h_s[1][hpos] = 0.0f;
-    const float *gsrc = gi + ((int64_t)t0 * a.R + row) * G3 + i;              // gi row of the next step to request
-#pragma unroll
-    for (int p = 0; p < PF; ++p) {
-        if (p < n) {
-#pragma unroll
-            for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], gsrc + g * HID);
-        }
-        cp_async_commit();
-        gsrc += tstride;
+    // Work of this CTA as a range [lo, hi) of the chain-major step sequence (chain c = net * R + row owns [c TT, (c + 1) TT)).
+    // Plain launches (grid R x nets): the CTA's chain, steps [t0, t1).  Balanced launches (grid workers x 1): bal_D steps that
+    // may straddle chains -- 2 R chains on 2 SMs-worth of two-warp CTAs run a step in ~560 cycles with every warp alone on its
+    // sub-partition, but ~850 once a third chain lands on an SM (measured: tools/gru_bench.cu), so 320 chains are run as 296
+    // equal workers instead of leaving 24 SMs with three chains.
+    int lo, hi;
+    if (a.bal_D > 0) {
+        lo = a.bal_D * (int)blockIdx.x;
+        hi = min(lo + a.bal_D, a.bal_chains * a.TT);
+        if (lo >= hi) return;
+    } else {
+        lo = ((int)blockIdx.y * a.R + (int)blockIdx.x) * a.TT + a.t0;
+        hi = lo + (a.t1 - a.t0);
     }
-    __syncthreads();
+    int cur_net = -1;
+    const float *gi = nullptr;
+    float *hout = nullptr;
+    bool save_gates = false;
+    unsigned long long w[2][3][KC / 2];    // packed pairs of W_hh[g*64 + 2*ug + u][part*32 + 2j, +1]
+    float b_r = 0.f, b_z = 0.f, b_n = 0.f;
+    const int64_t hstride = (int64_t)a.R * HID, tstride = (int64_t)a.R * G3;
+    const int hpos = i + (i >= KC ? GT_PAD : 0);
     const float4 *hp0 = reinterpret_cast<const float4 *>(h_s[0] + part * (KC + GT_PAD));
     const float4 *hp1 = reinterpret_cast<const float4 *>(h_s[1] + part * (KC + GT_PAD));
+    float *hdst = nullptr;                 // h of the current step
+    float4 *gdst = nullptr;
+    const float *gsrc = nullptr;           // gi row of the next step to request
+    float hprev = 0.0f;
+    int n = 0;
 
     // one timestep; SLOT / BUF are compile-time, `more` = the step PF ahead exists (always true in the steady-state loop)
     auto step = [&](auto slot_c, auto buf_c, bool more) {
@@ -610,6 +597,194 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd9(GruFwdArgs a) {
         __syncthreads();
     };
     using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+#pragma unroll 1
+    for (int pend = hi; pend > lo;) {                 // pieces of [lo, hi), last first
+        const int chain = (pend - 1) / a.TT;
+        const int pbeg = max(lo, chain * a.TT);
+        const int tb = pbeg - chain * a.TT, te = pend - chain * a.TT;
+        const int net = chain >= a.R ? 1 : 0, row = chain - net * a.R;
+        const bool last_piece = pbeg == lo;
+        pend = pbeg;
+        if (net != cur_net) {                             // W_hh / b_hh of this net into registers
+            cur_net = net;
+            const float *P = net ? a.params[1] : a.params[0];
+            gi = net ? a.gi[1] : a.gi[0];
+            hout = net ? a.hout[1] : a.hout[0];
+            save_gates = net == 0;
+            float anchor = 0.0f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + 2 * ug + u) * HID + part * KC);
+#pragma unroll
+                    for (int q = 0; q < KC / 4; ++q) {
+                        const float4 v = __ldg(wr + q);
+                        w[u][g][2 * q] = pack2(v.x, v.y); w[u][g][2 * q + 1] = pack2(v.z, v.w);
+                        anchor += v.x;
+                    }
+                }
+            b_r = __ldg(P + L.b_hh + i); b_z = __ldg(P + L.b_hh + HID + i); b_n = __ldg(P + L.b_hh + 2 * HID + i);
+            *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;   // pins the loads above the wait (see k_gru_fwd7)
+            pdl_wait();                                   // (returns at once after the first time)
+        }
+        n = te - tb;
+        hdst = hout + ((int64_t)tb * a.R + row) * HID + i;
+        gdst = reinterpret_cast<float4 *>(a.gates) + ((int64_t)tb * a.R + row) * HID + i;
+        gsrc = gi + ((int64_t)tb * a.R + row) * G3 + i;
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {                    // the ring does not depend on the chain's head: request it before the wait
+            if (p < n) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g) cp_async4(&st_s[p][g][i], gsrc + g * HID);
+            }
+            cp_async_commit();
+            gsrc += tstride;
+        }
+        if (a.bal_D > 0 && tb > 0) {                      // the head of this chain belongs to the next worker: wait for it
+            if (i == 0) {
+                volatile int *f = a.chain_flags + chain;
+                while (*f == 0) { }
+                *f = 0;                                   // single consumer: leave the flag clear for the next launch
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        hprev = tb > 0 ? __ldcg(hdst - hstride) : 0.0f;   // init_hidden: zeros; (written by another SM in balanced mode: L2)
+        h_s[0][hpos] = hprev; h_s[1][hpos] = 0.0f;
+        __syncthreads();
+        int sdone = 0;
+        for (; sdone + 2 * PF <= n; sdone += PF) {       // steady state: every prefetch target exists
+            step(std::integral_constant<int, 0>{}, I0{}, true); step(std::integral_constant<int, 1>{}, I1{}, true);
+            step(std::integral_constant<int, 2>{}, I0{}, true); step(std::integral_constant<int, 3>{}, I1{}, true);
+            step(std::integral_constant<int, 4>{}, I0{}, true); step(std::integral_constant<int, 5>{}, I1{}, true);
+            step(std::integral_constant<int, 6>{}, I0{}, true); step(std::integral_constant<int, 7>{}, I1{}, true);
+        }
+        if (last_piece) pdl_trigger();                   // at most 2 PF - 1 steps left: the dependent kernel may start its prologue
+        // guarded tail (sdone is a multiple of PF, so slots and buffers line up with the unrolled order)
+#define GRU9_TAIL(S, B) if (sdone + S < n) step(std::integral_constant<int, S>{}, B{}, sdone + S + PF < n)
+        for (; sdone < n; sdone += PF) {
+            GRU9_TAIL(0, I0); GRU9_TAIL(1, I1); GRU9_TAIL(2, I0); GRU9_TAIL(3, I1);
+            GRU9_TAIL(4, I0); GRU9_TAIL(5, I1); GRU9_TAIL(6, I0); GRU9_TAIL(7, I1);
+        }
+#undef GRU9_TAIL
+        cp_async_wait<0>();                               // (empty groups of the tail steps)
+        if (a.bal_D > 0 && te < a.TT) {                   // head piece done: its last h row is what the tail's worker starts from
+            __syncthreads();                              // (every thread's stores of this piece precede thread 0's fence)
+            if (i == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile int *>(a.chain_flags + chain) = 1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 11 (forward, small row counts): ONE chain per 256-thread CTA, thread = (unit, quarter of K).  At B = 32 an SM
+// hosts two or three chains and the 64-thread layouts leave every sub-partition with one or two warps that each issue 96
+// half-rate FFMA2 and then walk the serial gate tail alone (~870 cycles per step, the same whether one or two such warps
+// share a sub-partition).  Here a thread issues 24 FFMA2 (3 gates x 16 columns), the four partial sums of a unit meet in
+// a two-stage xor butterfly (all four lanes end with the same bits and do the gate math redundantly), and an SM runs 16
+// to 24 warps whose FMA phases and tails interleave.  Ring / barrier protocol of variant 8 (CTA-wide cp.async ring of
+// 16-byte pieces, step s + PF - 1 requested at step s into the slot step s - 1 used), time loop unrolled over the ring
+// slots like variant 9.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DBG = 0>
+__global__ void __launch_bounds__(256, 3) k_gru_fwd11(GruFwdArgs a) {
+    constexpr int PF = 8;
+    constexpr int KC = HID / 4;            // columns per lane
+    constexpr int SEG = KC + GT_PAD;       // 80-byte pitch: the four quarters of one LDS.128 fall into disjoint banks
+    __shared__ __align__(16) float h_s[2][4 * SEG];
+    __shared__ __align__(16) float st_s[PF][G3];
+    __shared__ float pdl_anchor_s[256];
+    const int i = threadIdx.x, net = blockIdx.y, row = blockIdx.x;
+    const int unit = i >> 2, part = i & 3;
+    const AgentLayout L = agent_layout(a.d_in, a.n_actions);
+    const float *P = net ? a.params[1] : a.params[0];
+    const float *gi = net ? a.gi[1] : a.gi[0];
+    float *hout = net ? a.hout[1] : a.hout[0];
+    const bool h_owner = part == 0, g_owner = part == 1 && net == 0;
+    const int t0 = a.t0, n = a.t1 - a.t0;
+
+    float anchor = 0.0f;
+    unsigned long long w[3][KC / 2];       // packed pairs of W_hh[g*64 + unit][part*16 + 2j, +1]
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const float4 *wr = reinterpret_cast<const float4 *>(P + L.w_hh + (int64_t)(g * HID + unit) * HID + part * KC);
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) {
+            const float4 v = __ldg(wr + q);
+            w[g][2 * q] = pack2(v.x, v.y); w[g][2 * q + 1] = pack2(v.z, v.w);
+            anchor += v.x;
+        }
+    }
+    const float b_r = __ldg(P + L.b_hh + unit), b_z = __ldg(P + L.b_hh + HID + unit), b_n = __ldg(P + L.b_hh + 2 * HID + unit);
+    *reinterpret_cast<volatile float *>(&pdl_anchor_s[i]) = anchor + b_r + b_z + b_n;   // pins the loads above the wait (see k_gru_fwd7)
+    pdl_wait();
+    const int64_t hstride = (int64_t)a.R * HID, tstride = (int64_t)a.R * G3;
+    float *hdst = hout + ((int64_t)t0 * a.R + row) * HID + unit;              // h of the current step
+    float4 *gdst = reinterpret_cast<float4 *>(a.gates) + ((int64_t)t0 * a.R + row) * HID + unit;
+    float hprev = t0 > 0 ? *(hdst - hstride) : 0.0f;                           // init_hidden: zeros
+    const int hpos = unit + (unit / KC) * GT_PAD;
+    if (h_owner) { h_s[0][hpos] = hprev; h_s[1][hpos] = 0.0f; }
+    const bool loader = i < G3 / 4;                                            // 48 16-byte pieces of a 768-byte gi row
+    const float *gsrc = gi + ((int64_t)t0 * a.R + row) * G3 + 4 * (loader ? i : 0);
+#pragma unroll
+    for (int p = 0; p < PF - 1; ++p) {
+        if (loader && p < n) cp_async16(&st_s[p][4 * i], gsrc);
+        cp_async_commit();
+        gsrc += tstride;
+    }
+    cp_async_wait<PF - 2>();
+    __syncthreads();
+    const float4 *hp0 = reinterpret_cast<const float4 *>(h_s[0] + part * SEG);
+    const float4 *hp1 = reinterpret_cast<const float4 *>(h_s[1] + part * SEG);
+
+    // one timestep; SLOT / BUF are compile-time, `more` = step s + PF - 1 exists (always true in the steady-state loop)
+    auto step = [&](auto slot_c, auto buf_c, bool more) {
+        constexpr int SLOT = decltype(slot_c)::value, BUF = decltype(buf_c)::value;
+        const float g_r = st_s[SLOT][unit], g_z = st_s[SLOT][HID + unit], g_n = st_s[SLOT][2 * HID + unit];
+        if (loader && more) cp_async16(&st_s[(SLOT + PF - 1) % PF][4 * i], gsrc);
+        cp_async_commit();
+        gsrc += tstride;
+        const float4 *hp = BUF ? hp1 : hp0;
+        float4 hv[KC / 4];
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) hv[q] = hp[q];
+        unsigned long long s[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) {
+            const unsigned long long hxy = pack2(hv[q].x, hv[q].y), hzw = pack2(hv[q].z, hv[q].w);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) s[g] = fma2(w[g][2 * q], hxy, s[g]);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) s[g] = fma2(w[g][2 * q + 1], hzw, s[g]);
+        }
+        float x[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float a0, a1;
+            unpack2(s[g], a0, a1);
+            float y = a0 + a1;
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            x[g] = y;
+        }
+        const float xr = x[0] + (g_r + b_r), xz = x[1] + (g_z + b_z), ghn = x[2] + b_n;
+        const float rr = sigmoid_mufu(xr), zz = sigmoid_mufu(xz);
+        const float nn = tanh_mufu(g_n + rr * ghn);
+        const float hn = nn + zz * (hprev - nn);
+        hprev = hn;
+        if (h_owner) {
+            h_s[BUF ^ 1][hpos] = hn;
+            if (!(DBG & 1)) *hdst = hn;
+        }
+        if (g_owner && !(DBG & 1)) *gdst = make_float4(rr, zz, nn, ghn);
+        hdst += hstride; gdst += hstride;
+        cp_async_wait<PF - 2>();             // step s + 1's operands have landed (issuing threads); the barrier publishes them
+        __syncthreads();
+    };
+    using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
     int sdone = 0;
     for (; sdone + 2 * PF <= n; sdone += PF) {       // steady state: every prefetch target exists
         step(std::integral_constant<int, 0>{}, I0{}, true); step(std::integral_constant<int, 1>{}, I1{}, true);
@@ -618,13 +793,12 @@ __global__ void __launch_bounds__(64, 4) k_gru_fwd9(GruFwdArgs a) {
         step(std::integral_constant<int, 6>{}, I0{}, true); step(std::integral_constant<int, 7>{}, I1{}, true);
     }
     pdl_trigger();                                   // at most 2 PF - 1 steps left: the dependent kernel may start its prologue
-    // guarded tail (sdone is a multiple of PF, so slots and buffers line up with the unrolled order)
-#define GRU9_TAIL(S, B) if (sdone + S < n) step(std::integral_constant<int, S>{}, B{}, sdone + S + PF < n)
+#define GRU11_TAIL(S, B) if (sdone + S < n) step(std::integral_constant<int, S>{}, B{}, sdone + S + PF - 1 < n)
     for (; sdone < n; sdone += PF) {
-        GRU9_TAIL(0, I0); GRU9_TAIL(1, I1); GRU9_TAIL(2, I0); GRU9_TAIL(3, I1);
-        GRU9_TAIL(4, I0); GRU9_TAIL(5, I1); GRU9_TAIL(6, I0); GRU9_TAIL(7, I1);
+        GRU11_TAIL(0, I0); GRU11_TAIL(1, I1); GRU11_TAIL(2, I0); GRU11_TAIL(3, I1);
+        GRU11_TAIL(4, I0); GRU11_TAIL(5, I1); GRU11_TAIL(6, I0); GRU11_TAIL(7, I1);
     }
-#undef GRU9_TAIL
+#undef GRU11_TAIL
 }
 
 __global__ void __launch_bounds__(64, 4) k_gru_bwd9(GruBwdArgs a) {

@@ -378,6 +378,11 @@ struct GruFwdArgs {
     float *gates;              // [TT*R,64,4] online only: (r, z, n, gh_n) per unit
     int TT, R, d_in, n_actions;
     int t0, t1;                // timesteps of this launch: [t0, t1); h_{t0-1} comes from hout (zeros for t0 = 0)
+    // balanced mode of k_gru_fwd9 (bal_D > 0; grid = workers x 1, t0 = 0, t1 = TT): the nets * R chains of TT steps each are
+    // laid end to end and worker w runs steps [w bal_D, (w + 1) bal_D) of that sequence, LAST piece first, so the head of a
+    // chain that is split between two workers is finished (chain_flags) before the neighbour reaches its tail
+    int bal_D = 0, bal_chains = 0;
+    int *chain_flags = nullptr;   // [bal_chains] zero between launches (the consumer resets what the producer sets)
 };
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }

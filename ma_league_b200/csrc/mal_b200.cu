@@ -141,6 +141,20 @@ static int ensure_dyn_smem(K kernel, size_t bytes, size_t *cache) {
     return 0;
 }
 
+// The L1 / shared-memory split of an SM is fixed while CTAs are resident: a kernel that is happy with the small default
+// carve-out keeps every big-shared-memory kernel (the tcgen05 GEMMs of the side streams: 104+ KB per CTA) off its SMs until
+// it has drained.  The recurrences ask for the largest carve-out so that the hypernet / gradient GEMMs can move in beside them.
+template <typename K>
+static int ensure_max_carveout(K kernel, bool *cache) {
+    int dev = 0;
+    MAL_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < MAL_MAX_DEV && cache[dev]) return 0;
+    MAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    if (dev >= 0 && dev < MAL_MAX_DEV) cache[dev] = true;
+    return 0;
+}
+static thread_local int g_rec_carveout = 1;    // 1: recurrences prefer the largest shared-memory carve-out (side-stream GEMMs co-reside)
+
 // kernel-flavour counters (tests assert which variant the launch heuristics picked): see mal_stat()
 static uint64_t g_stat_tc2 = 0, g_stat_tc1 = 0, g_stat_reduce_tc = 0, g_stat_reduce_tc_swap = 0, g_stat_reduce_ffma = 0,
                 g_stat_agent_in_fused = 0;
@@ -167,7 +181,10 @@ struct SideStreams {
     bool ready = false;
     cudaStream_t s[2];
     cudaEvent_t fork_ev[4], join_ev[2];
+    cudaEvent_t aux_fork_ev, aux_join_ev;   // forward: the weight transposes on s[1], beside the hypernet GEMMs on s[0]
+    int *chain_flags = nullptr;   // k_gru_fwd9 balanced mode: hand-over flags of split chains (zero between launches)
 };
+#define MAL_CHAIN_FLAGS 1024
 static thread_local SideStreams g_side[MAL_MAX_DEV];   // one set per (thread, device)
 // mal_set_option switches are PER CALLING THREAD (like the side streams): two learners driven by two threads of one
 // process do not see each other's settings
@@ -201,6 +218,10 @@ static int side_streams(SideStreams **out) {
         for (int i = 0; i < 2; ++i) MAL_CUDA(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
         for (int i = 0; i < 4; ++i) MAL_CUDA(cudaEventCreateWithFlags(&ss.fork_ev[i], cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) MAL_CUDA(cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming));
+        MAL_CUDA(cudaEventCreateWithFlags(&ss.aux_fork_ev, cudaEventDisableTiming));
+        MAL_CUDA(cudaEventCreateWithFlags(&ss.aux_join_ev, cudaEventDisableTiming));
+        MAL_CUDA(cudaMalloc(&ss.chain_flags, MAL_CHAIN_FLAGS * sizeof(int)));
+        MAL_CUDA(cudaMemset(ss.chain_flags, 0, MAL_CHAIN_FLAGS * sizeof(int)));
         ss.ready = true;
     }
     *out = &ss;
@@ -609,6 +630,11 @@ static BatchView make_view(const mal_batch_t *b, const Dims &d) {
 
 static thread_local int g_use_tc = 1;   // tcgen05 3xTF32 panel GEMM (0: fp32 FFMA panel GEMM)
 static thread_local int g_tc_dbg = 0;
+// k_gru_fwd9 may run a chain count between 2 and 3 per SM as 2 * SMs equal workers (GruFwdArgs.bal_D): 87 -> 66 us alone at
+// 5v5 / B = 32.  Every worker is then on the critical path, so GEMMs that move in beside it (the mixer hypernets) cost more
+// than the balance gains (0.322 vs 0.313 ms per step): 1 (default) balances only when nothing runs beside the forward
+// recurrence (VDN), 2 always, 0 never.
+static thread_local int g_gru_balance = 1;
 static thread_local int g_gru_variant = 9;     // recurrences: 9 = 64-thread CTAs, time loop unrolled over the ring slots; 7 = the same before the trimming; 8 = one chain per 128-thread CTA
 static thread_local int g_reduce_mn = 3;       // k_reduce_tc operands MN-major straight from the loads (0: round-1 transposition into K-major tiles)
 static thread_local int g_reduce_tc = 1;       // weight-gradient reductions on tcgen05 (k_reduce_tc); 0: fp32 FFMA k_reduce_group
@@ -643,6 +669,8 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "reduce_mn") == 0) { g_reduce_mn = value < 0 ? 0 : (value > 3 ? 3 : value); return 0; }   // 0 K-major transposition, 1 MN-major from registers, 2 MN-major cp.async pipeline, 3 the same with 512 threads
     if (strcmp(name, "reduce_tc") == 0) { g_reduce_tc = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "time_chunks") == 0) { g_time_chunks = value; return 0; }
+    if (strcmp(name, "gru_balance") == 0) { g_gru_balance = value; return 0; }
+    if (strcmp(name, "rec_carveout") == 0) { g_rec_carveout = value; return 0; }
     if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
@@ -772,8 +800,22 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
     return p;
 }
 
-static int launch_gru_fwd(const GruFwdArgs &a, int nets, cudaStream_t st, bool pdl) {
+static int launch_gru_fwd(const GruFwdArgs &a_in, int nets, int sms, int *chain_flags, bool alone, cudaStream_t st, bool pdl) {
+    if (g_rec_carveout && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_fwd9<0>, cv)) return rc; }
     ProfScope _ps("k_gru_fwd", st);
+    GruFwdArgs a = a_in;
+    const int chains = nets * a.R, workers = 2 * sms;
+    // Two-warp CTAs: up to two chains per SM every warp has a sub-partition to itself (~560 cycles per step); a third chain
+    // on an SM puts two warps on two of its sub-partitions (~850, and the whole launch waits for those SMs).  In that window
+    // the chains x TT steps are dealt out to 2 * SMs workers of equal length instead (a chain then changes workers once).
+    if (g_gru_variant == 9 && (g_gru_balance == 2 || (g_gru_balance == 1 && alone)) && chain_flags && a.t0 == 0 && a.t1 == a.TT && a.TT >= 32 && chains > workers &&
+        chains <= 3 * sms && chains <= MAL_CHAIN_FLAGS) {
+        a.bal_chains = chains;
+        a.bal_D = (int)ceil_div64((int64_t)chains * a.TT, workers);
+        a.chain_flags = chain_flags;
+        launch_k(k_gru_fwd9<0>, dim3(workers, 1), dim3(HID), 0, st, pdl, a);
+        return 0;
+    }
     if (g_gru_variant == 7) launch_k(k_gru_fwd7<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);      // one batch row per CTA
     else if (g_gru_variant == 9) launch_k(k_gru_fwd9<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);
     else launch_k(k_gru_fwd8<0>, dim3(a.R, nets), dim3(128), 0, st, pdl, a);
@@ -823,6 +865,7 @@ static int launch_gru_fwd_tc(const GruFwdArgs &a, int nets, int sms, cudaStream_
     return 0;
 }
 static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
+    if (g_rec_carveout && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv)) return rc; }
     ProfScope _ps("k_gru_bwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
     else if (g_gru_variant == 9) launch_k(k_gru_bwd9, dim3(a.R), dim3(HID), 0, st, pdl, a);
@@ -913,7 +956,11 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     // they would compete with for shared memory and tensor cores
     if (fork_to(st, sm, ss->fork_ev[0])) return 2;
     // transposed weight copies for the backward GEMMs (d x = d gi . W_ih, mixer d h = d a . W_2): the tensor-core
-    // kernels stage W row-wise with float4 loads; a transposed read would be element-wise.  Off the critical path.
+    // kernels stage W row-wise with float4 loads; a transposed read would be element-wise.  Off the critical path, and on
+    // the OTHER side stream: ahead of the hypernet GEMMs it held them back by its ~10 us, which put mixer_l2 behind the
+    // Q head once the balanced recurrence had shortened the main chain.
+    cudaStream_t sx = g_overlap ? ss->s[1] : st;
+    if (fork_to(st, sx, ss->aux_fork_ev)) return 2;
     {
         TransArgs ta;
         memset(&ta, 0, sizeof(ta));
@@ -929,7 +976,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             const int tl = ((ta.rows[i] + 31) / 32) * ((ta.cols[i] + 31) / 32);
             if (tl > max_tiles) max_tiles = tl;
         }
-        { ProfScope _ps("k_transpose_w", sm); k_transpose_w<<<dim3(max_tiles, ta.n), dim3(32, 8), 0, sm>>>(ta); }
+        { ProfScope _ps("k_transpose_w", sx); k_transpose_w<<<dim3(max_tiles, ta.n), dim3(32, 8), 0, sx>>>(ta); }
         MAL_LAUNCH_CHECK("k_transpose_w");
     }
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
@@ -938,12 +985,12 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         a.t0 = 0; a.t1 = t_split;
-        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
+        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, sms, ss->chain_flags, d.mixer == MAL_MIXER_VDN, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
         MAL_LAUNCH_CHECK("k_gru_fwd");
         if (t_split < d.TT) {
             if (join_from(st, ss->s[1], ss->join_ev[1])) return 2;    // second half of gi is ready
             a.t0 = t_split; a.t1 = d.TT;
-            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, st, false)) return 2;
+            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, sms, ss->chain_flags, d.mixer == MAL_MIXER_VDN, st, false)) return 2;
             MAL_LAUNCH_CHECK("k_gru_fwd");
         }
     }
@@ -995,6 +1042,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         if (int rc = launch_linear(g, d.BT, d.S, sm, "k_linear_group:mixer_l1")) return rc;
     }
     if (join_from(st, sm, ss->join_ev[0])) return 2;
+    if (join_from(st, sx, ss->aux_join_ev)) return 2;
     // mixing + TD error + masked loss + element-wise mixer backward          q_learner.py:81-98
     {
         MixArgs a;

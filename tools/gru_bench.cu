@@ -43,8 +43,11 @@ int main(int argc, char **argv) {
     ba.d_in = d_in; ba.n_actions = A;
 
     const int variant = argc > 4 ? atoi(argv[4]) : 8;
-    auto fwd = [&] { if (variant == 7) k_gru_fwd7<0><<<dim3(R, 2), HID>>>(fa); else if (variant == 9) k_gru_fwd9<0><<<dim3(R, 2), HID>>>(fa); else if (variant == 10) k_gru_fwd9<0, 0><<<dim3(R, 2), HID>>>(fa); else k_gru_fwd8<0><<<dim3(R, 2), 128>>>(fa); };
-    auto bwd = [&] { if (variant == 7) k_gru_bwd7<<<R, HID>>>(ba); else if (variant == 9 || variant == 10) k_gru_bwd9<<<R, HID>>>(ba); else k_gru_bwd8<<<R, 128>>>(ba); };
+    // variant 12 = k_gru_fwd9 in balanced mode: 2 * 148 workers of equal length
+    int *flags; cudaMalloc(&flags, 4096); cudaMemset(flags, 0, 4096);
+    GruFwdArgs fb = fa; fb.bal_chains = 2 * R; fb.bal_D = (int)(((long long)2 * R * TT + 295) / 296); fb.chain_flags = flags;
+    auto fwd = [&] { if (variant == 7) k_gru_fwd7<0><<<dim3(R, 2), HID>>>(fa); else if (variant == 9) k_gru_fwd9<0><<<dim3(R, 2), HID>>>(fa); else if (variant == 10) k_gru_fwd9<0, 0><<<dim3(R, 2), HID>>>(fa); else if (variant == 11) k_gru_fwd11<0><<<dim3(R, 2), 256>>>(fa); else if (variant == 12) k_gru_fwd9<0><<<dim3(296, 1), HID>>>(fb); else k_gru_fwd8<0><<<dim3(R, 2), 128>>>(fa); };
+    auto bwd = [&] { if (variant == 7) k_gru_bwd7<<<R, HID>>>(ba); else if (variant == 9 || variant == 10 || variant == 11 || variant == 12) k_gru_bwd9<<<R, HID>>>(ba); else k_gru_bwd8<<<R, 128>>>(ba); };
     const float fus = time_us(fwd);
     const float bus = time_us(bwd);
     printf("variant %d  fwd grid %dx2: %7.1f us  %5.0f cycles/step    bwd grid %d: %7.1f us  %5.0f cycles/step   (%s)\n", variant, R, fus,
