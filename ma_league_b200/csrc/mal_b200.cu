@@ -635,6 +635,7 @@ static thread_local int g_tc_dbg = 0;
 // than the balance gains (0.322 vs 0.313 ms per step): 1 (default) balances only when nothing runs beside the forward
 // recurrence (VDN), 2 always, 0 never.
 static thread_local int g_gru_balance = 1;
+static thread_local int g_gru_balance_pdl = 0;
 static thread_local int g_gru_variant = 9;     // recurrences: 9 = 64-thread CTAs, time loop unrolled over the ring slots; 7 = the same before the trimming; 8 = one chain per 128-thread CTA
 static thread_local int g_reduce_mn = 3;       // k_reduce_tc operands MN-major straight from the loads (0: round-1 transposition into K-major tiles)
 static thread_local int g_reduce_tc = 1;       // weight-gradient reductions on tcgen05 (k_reduce_tc); 0: fp32 FFMA k_reduce_group
@@ -671,6 +672,7 @@ extern "C" int mal_set_option(const char *name, int value) {
     if (strcmp(name, "time_chunks") == 0) { g_time_chunks = value; return 0; }
     if (strcmp(name, "gru_balance") == 0) { g_gru_balance = value; return 0; }
     if (strcmp(name, "rec_carveout") == 0) { g_rec_carveout = value; return 0; }
+    if (strcmp(name, "gru_balance_pdl") == 0) { g_gru_balance_pdl = value; return 0; }
     if (strcmp(name, "fuse_agent_in") == 0) { g_fuse_agent_in = value ? 1 : 0; return 0; }
     if (strcmp(name, "tc_pipelined") == 0) { g_tc_pipelined = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }   // 0 off, 1 heuristic, 2 always
     if (strcmp(name, "overlap") == 0) { g_overlap = value ? 1 : 0; return 0; }
@@ -813,7 +815,10 @@ static int launch_gru_fwd(const GruFwdArgs &a_in, int nets, int sms, int *chain_
         a.bal_chains = chains;
         a.bal_D = (int)ceil_div64((int64_t)chains * a.TT, workers);
         a.chain_flags = chain_flags;
-        launch_k(k_gru_fwd9<0>, dim3(workers, 1), dim3(HID), 0, st, pdl, a);
+        // NOT as a programmatic dependent launch: the workers must find all SMs free.  Launched early they are packed three
+        // and four deep onto the SMs that the predecessor (k_agent_in_tc: one CTA per SM, ragged last round) vacates first,
+        // and the point of the balance -- two workers per SM -- is lost (graph replay: 0.322 vs 0.313 ms per step)
+        launch_k(k_gru_fwd9<0>, dim3(workers, 1), dim3(HID), 0, st, pdl && g_gru_balance_pdl, a);
         return 0;
     }
     if (g_gru_variant == 7) launch_k(k_gru_fwd7<0>, dim3(a.R, nets), dim3(HID), 0, st, pdl, a);      // one batch row per CTA
@@ -959,9 +964,13 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
     // kernels stage W row-wise with float4 loads; a transposed read would be element-wise.  Off the critical path, and on
     // the OTHER side stream: ahead of the hypernet GEMMs it held them back by its ~10 us, which put mixer_l2 behind the
     // Q head once the balanced recurrence had shortened the main chain.
+    // When the forward recurrence may run balanced (nothing else beside it: VDN) the transposes start AFTER it: a dozen
+    // CTAs that hold SMs (or just their default carve-out) when the 2 x SMs workers are placed push a third worker onto
+    // some SMs, and the whole balanced schedule then runs at the three-per-SM pace (graph replay: 0.300 vs 0.285 ms).
     cudaStream_t sx = g_overlap ? ss->s[1] : st;
-    if (fork_to(st, sx, ss->aux_fork_ev)) return 2;
-    {
+    const bool rec_alone = d.mixer == MAL_MIXER_VDN;
+    auto launch_transposes = [&]() -> int {
+        if (fork_to(st, sx, ss->aux_fork_ev)) return 2;
         TransArgs ta;
         memset(&ta, 0, sizeof(ta));
         float *wt = F(plan->w_t);
@@ -976,21 +985,24 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             const int tl = ((ta.rows[i] + 31) / 32) * ((ta.cols[i] + 31) / 32);
             if (tl > max_tiles) max_tiles = tl;
         }
+        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_transpose_w, cv)) return rc; }
         { ProfScope _ps("k_transpose_w", sx); k_transpose_w<<<dim3(max_tiles, ta.n), dim3(32, 8), 0, sx>>>(ta); }
         MAL_LAUNCH_CHECK("k_transpose_w");
-    }
+        return 0;
+    };
+    if (!rec_alone || dqn) { if (int rc = launch_transposes()) return rc; }
     // the recurrence (online + target concurrently)                         q_learner.py:46-51, 58-62
     if (!dqn) {
         GruFwdArgs a;
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         a.t0 = 0; a.t1 = t_split;
-        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, sms, ss->chain_flags, d.mixer == MAL_MIXER_VDN, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
+        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, sms, ss->chain_flags, rec_alone, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
         MAL_LAUNCH_CHECK("k_gru_fwd");
         if (t_split < d.TT) {
             if (join_from(st, ss->s[1], ss->join_ev[1])) return 2;    // second half of gi is ready
             a.t0 = t_split; a.t1 = d.TT;
-            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, sms, ss->chain_flags, d.mixer == MAL_MIXER_VDN, st, false)) return 2;
+            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, sms, ss->chain_flags, rec_alone, st, false)) return 2;
             MAL_LAUNCH_CHECK("k_gru_fwd");
         }
     }
@@ -1009,9 +1021,11 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         const int64_t qh_grid = ceil_div64(qh_tiles, ceil_div64(qh_tiles, qh_slots));    // number of tiles (+-1), in one wave
         static size_t attr[MAL_MAX_DEV];
         if (int rc = ensure_dyn_smem(k_q_head, smem, attr)) return rc;
+        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_q_head, cv)) return rc; }
         { ProfScope _ps("k_q_head", st); launch_k(k_q_head, dim3((unsigned)qh_grid), dim3(128), smem, st, true, a); }   // predecessor: k_gru_fwd7
         MAL_LAUNCH_CHECK("k_q_head");
     }
+    if (rec_alone && !dqn) { if (int rc = launch_transposes()) return rc; }   // beside the mixing kernel; the backward reads them
     // mixer hypernetworks                                                   qmix.py:41-59
     if (d.mixer == MAL_MIXER_QMIX2) {
         LinGroup g; g.n = 8; g.bv = bv;
@@ -1057,6 +1071,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.q_tot = F(plan->q_tot); a.target_q_tot = F(plan->target_q_tot); a.targets = F(plan->targets); a.td = F(plan->td);
         a.d_a2 = F(plan->d_a2); a.d_y1 = F(plan->d_y1); a.d_chosen = F(plan->d_chosen);
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
+        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_mix_td, cv)) return rc; }
         { ProfScope _ps("k_mix_td", st); launch_k(k_mix_td, dim3(pl.nblk_mix), dim3(256), 0, st, true, a); }   // stream predecessor: k_q_head
         MAL_LAUNCH_CHECK("k_mix_td");
         // nothing before the gradient gather reads the scalars: inside mal_learner_step the finalize runs on the side
@@ -1199,6 +1214,7 @@ static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, con
         return 0;
     }
     ++g_stat_reduce_ffma;
+    if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout((k_reduce_group<AK, DK>), cv)) return rc; }
     { ProfScope _ps(tag, st); launch_k(k_reduce_group<AK, DK>, grid, dim3(256), 0, st, g_next_pdl, g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
     return 0;
@@ -1283,6 +1299,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         const size_t smem = sizeof(float) * 8 * ((size_t)d.A * HID + 32);
         static size_t attr[MAL_MAX_DEV];
         if (int rc = ensure_dyn_smem(k_fc2_grad, smem, attr)) return rc;
+        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_fc2_grad, cv)) return rc; }
         { ProfScope _ps("k_fc2_grad", s2); k_fc2_grad<<<pl.nc_f2, 256, smem, s2>>>(a); }
         MAL_LAUNCH_CHECK("k_fc2_grad");
     }
