@@ -250,8 +250,9 @@ uint64_t mal_stat(const char *name);
  *   "time_chunks"   1 (default) / 2: time-chunked forward (input projection of the 2nd half beside the 1st half's recurrence)
  *   "gru_balance"   a forward recurrence of more than 2 and at most 3 chains per SM can run as 2 x SMs equal workers (a chain
  *                   may change workers once): 1 (default) when nothing runs beside it (VDN), 2 always, 0 never
- *   "rec_carveout"  1 (default): the recurrence kernels prefer the largest shared-memory carve-out, so that the tcgen05 GEMMs
- *                   of the side streams can be resident beside them; 0: default carve-out
+ *   "rec_carveout"  bit 0 / bit 1 (default 2 = backward only): the forward / backward recurrence kernel prefers the largest shared-memory
+ *                   carve-out, so that the tcgen05 GEMMs of the side streams can be resident beside it (an SM keeps its L1 /
+ *                   shared split while CTAs are resident); bit 2: the small kernels of the step too; 0: default carve-outs
  * Returns non-zero (and sets mal_last_error) for an unknown name. */
 int mal_set_option(const char *name, int value);
 

@@ -153,7 +153,12 @@ static int ensure_max_carveout(K kernel, bool *cache) {
     if (dev >= 0 && dev < MAL_MAX_DEV) cache[dev] = true;
     return 0;
 }
-static thread_local int g_rec_carveout = 1;    // 1: recurrences prefer the largest shared-memory carve-out (side-stream GEMMs co-reside)
+// bit 0 / 1: the forward / backward recurrence prefers the largest shared-memory carve-out (the side-stream GEMMs can then be
+// resident beside it); bit 2: the small kernels of the step too.  5v5 / B = 32, ms per step: 0 -> 0.3235, 1 -> 0.3225,
+// 2 -> 0.3111, 3 -> 0.3130, 7 -> 0.3152: the gain is the mixer's backward chain moving in beside the BPTT instead of queueing
+// behind it; beside the forward recurrence the hypernet GEMMs already find free SMs (its CTAs pile up on the SMs that
+// k_agent_in_tc vacates first) and co-residence only slows the chains down.
+static thread_local int g_rec_carveout = 2;
 
 // kernel-flavour counters (tests assert which variant the launch heuristics picked): see mal_stat()
 static uint64_t g_stat_tc2 = 0, g_stat_tc1 = 0, g_stat_reduce_tc = 0, g_stat_reduce_tc_swap = 0, g_stat_reduce_ffma = 0,
@@ -803,7 +808,7 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
 }
 
 static int launch_gru_fwd(const GruFwdArgs &a_in, int nets, int sms, int *chain_flags, bool alone, cudaStream_t st, bool pdl) {
-    if (g_rec_carveout && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_fwd9<0>, cv)) return rc; }
+    if ((g_rec_carveout & 1) && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_fwd9<0>, cv)) return rc; }
     ProfScope _ps("k_gru_fwd", st);
     GruFwdArgs a = a_in;
     const int chains = nets * a.R, workers = 2 * sms;
@@ -870,7 +875,7 @@ static int launch_gru_fwd_tc(const GruFwdArgs &a, int nets, int sms, cudaStream_
     return 0;
 }
 static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
-    if (g_rec_carveout && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv)) return rc; }
+    if ((g_rec_carveout & 2) && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv)) return rc; }
     ProfScope _ps("k_gru_bwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
     else if (g_gru_variant == 9) launch_k(k_gru_bwd9, dim3(a.R), dim3(HID), 0, st, pdl, a);
@@ -985,7 +990,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
             const int tl = ((ta.rows[i] + 31) / 32) * ((ta.cols[i] + 31) / 32);
             if (tl > max_tiles) max_tiles = tl;
         }
-        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_transpose_w, cv)) return rc; }
+        if (g_rec_carveout & 4) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_transpose_w, cv)) return rc; }
         { ProfScope _ps("k_transpose_w", sx); k_transpose_w<<<dim3(max_tiles, ta.n), dim3(32, 8), 0, sx>>>(ta); }
         MAL_LAUNCH_CHECK("k_transpose_w");
         return 0;
@@ -1021,7 +1026,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         const int64_t qh_grid = ceil_div64(qh_tiles, ceil_div64(qh_tiles, qh_slots));    // number of tiles (+-1), in one wave
         static size_t attr[MAL_MAX_DEV];
         if (int rc = ensure_dyn_smem(k_q_head, smem, attr)) return rc;
-        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_q_head, cv)) return rc; }
+        if (g_rec_carveout & 4) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_q_head, cv)) return rc; }
         { ProfScope _ps("k_q_head", st); launch_k(k_q_head, dim3((unsigned)qh_grid), dim3(128), smem, st, true, a); }   // predecessor: k_gru_fwd7
         MAL_LAUNCH_CHECK("k_q_head");
     }
@@ -1071,7 +1076,7 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         a.q_tot = F(plan->q_tot); a.target_q_tot = F(plan->target_q_tot); a.targets = F(plan->targets); a.td = F(plan->td);
         a.d_a2 = F(plan->d_a2); a.d_y1 = F(plan->d_y1); a.d_chosen = F(plan->d_chosen);
         a.part_stats = parts + pl.mix_stats; a.part_v2 = parts + pl.mix_v2;
-        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_mix_td, cv)) return rc; }
+        if (g_rec_carveout & 4) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_mix_td, cv)) return rc; }
         { ProfScope _ps("k_mix_td", st); launch_k(k_mix_td, dim3(pl.nblk_mix), dim3(256), 0, st, true, a); }   // stream predecessor: k_q_head
         MAL_LAUNCH_CHECK("k_mix_td");
         // nothing before the gradient gather reads the scalars: inside mal_learner_step the finalize runs on the side
@@ -1214,7 +1219,7 @@ static int launch_reduce_inst(RedGroup &g, cudaStream_t st, const char *tag, con
         return 0;
     }
     ++g_stat_reduce_ffma;
-    if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout((k_reduce_group<AK, DK>), cv)) return rc; }
+    if (g_rec_carveout & 4) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout((k_reduce_group<AK, DK>), cv)) return rc; }
     { ProfScope _ps(tag, st); launch_k(k_reduce_group<AK, DK>, grid, dim3(256), 0, st, g_next_pdl, g); }
     MAL_LAUNCH_CHECK("k_reduce_group");
     return 0;
@@ -1299,7 +1304,7 @@ extern "C" int mal_learner_backward(const mal_batch_t *batch, const mal_learner_
         const size_t smem = sizeof(float) * 8 * ((size_t)d.A * HID + 32);
         static size_t attr[MAL_MAX_DEV];
         if (int rc = ensure_dyn_smem(k_fc2_grad, smem, attr)) return rc;
-        if (g_rec_carveout >= 2) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_fc2_grad, cv)) return rc; }
+        if (g_rec_carveout & 4) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_fc2_grad, cv)) return rc; }
         { ProfScope _ps("k_fc2_grad", s2); k_fc2_grad<<<pl.nc_f2, 256, smem, s2>>>(a); }
         MAL_LAUNCH_CHECK("k_fc2_grad");
     }

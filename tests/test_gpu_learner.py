@@ -501,3 +501,33 @@ def test_dqn_agent_learner_against_oracle(N, B, TT, mixer):
     _check_against_oracle_full(s, mixer)
     s.learner.train(s.batch, 0, 0)                       # the full step (clip + RMSprop) runs on this agent too
     th.cuda.synchronize()
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+@pytest.mark.parametrize("mixer", ["qmix", "vdn"])
+def test_balanced_forward_recurrence_is_bit_identical(mixer, graphs):
+    """k_gru_fwd9's balanced mode (2 x SMs equal workers over the chain-major step sequence; a chain changes workers once and
+    hands its hidden state over through global memory + a flag) runs every chain's steps in the same order with the same
+    arithmetic: at the metric's size (320 chains > 296 workers) parameters, optimiser state and statistics must be
+    bit-identical to one chain per CTA, eagerly and through the captured graph, over several steps (the hand-over flags are
+    left clear by their consumers)."""
+    from ma_league_b200 import _native as nat
+
+    def run(balance):
+        nat.check(nat.lib().mal_set_option(b"gru_balance", balance), "mal_set_option")
+        try:
+            s = seeded_system(5, 32, 201, mixer, True, seed=37, learner_log_interval=0)
+            s.learner.use_graphs = graphs
+            for i in range(5):
+                s.learner.train(s.batch, t_env=i, episode_num=i)
+            th.cuda.synchronize()
+            return np_params(s.mac.agent), np_params(s.learner.mixer) if s.learner.mixer is not None else {}, \
+                s.learner.optimiser.flat_sq.cpu().numpy(), {k: v[0] for k, v in s.logger.stats.items()}
+        finally:
+            nat.check(nat.lib().mal_set_option(b"gru_balance", 1), "mal_set_option")
+    a, b = run(2), run(0)
+    for x, y in zip(a[:2], b[:2]):
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3]
