@@ -145,12 +145,14 @@ static int ensure_dyn_smem(K kernel, size_t bytes, size_t *cache) {
 // carve-out keeps every big-shared-memory kernel (the tcgen05 GEMMs of the side streams: 104+ KB per CTA) off its SMs until
 // it has drained.  The recurrences ask for the largest carve-out so that the hypernet / gradient GEMMs can move in beside them.
 template <typename K>
-static int ensure_max_carveout(K kernel, bool *cache) {
+static int ensure_max_carveout(K kernel, bool *cache, bool want = true) {   // cache[dev]: the preference currently set on this device
     int dev = 0;
     MAL_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < MAL_MAX_DEV && cache[dev]) return 0;
-    MAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    if (dev >= 0 && dev < MAL_MAX_DEV) cache[dev] = true;
+    const bool cached = dev >= 0 && dev < MAL_MAX_DEV;
+    if (cached && cache[dev] == want) return 0;
+    MAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  want ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault));
+    if (cached) cache[dev] = want;
     return 0;
 }
 // bit 0 / 1: the forward / backward recurrence prefers the largest shared-memory carve-out (the side-stream GEMMs can then be
@@ -808,7 +810,7 @@ static LinProb lin(int64_t M, int K, int Nout, int a_kind, int shift, const floa
 }
 
 static int launch_gru_fwd(const GruFwdArgs &a_in, int nets, int sms, int *chain_flags, bool alone, cudaStream_t st, bool pdl) {
-    if ((g_rec_carveout & 1) && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_fwd9<0>, cv)) return rc; }
+    if (g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_fwd9<0>, cv, (g_rec_carveout & 1) != 0)) return rc; }
     ProfScope _ps("k_gru_fwd", st);
     GruFwdArgs a = a_in;
     const int chains = nets * a.R, workers = 2 * sms;
@@ -875,7 +877,8 @@ static int launch_gru_fwd_tc(const GruFwdArgs &a, int nets, int sms, cudaStream_
     return 0;
 }
 static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
-    if ((g_rec_carveout & 2) && g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv)) return rc; }
+    // (only in the latency regime -- a few chains per SM: with many waves of chains the smaller L1 costs more than the co-residence gains: 20v20 3.08 -> 3.15 ms)
+    if (g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv, (g_rec_carveout & 2) && a.R <= 4 * 148)) return rc; }
     ProfScope _ps("k_gru_bwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
     else if (g_gru_variant == 9) launch_k(k_gru_bwd9, dim3(a.R), dim3(HID), 0, st, pdl, a);
