@@ -189,9 +189,14 @@ struct SideStreams {
     cudaStream_t s[2];
     cudaEvent_t fork_ev[4], join_ev[2];
     cudaEvent_t aux_fork_ev, aux_join_ev;   // forward: the weight transposes on s[1], beside the hypernet GEMMs on s[0]
-    int *chain_flags = nullptr;   // k_gru_fwd9 balanced mode: hand-over flags of split chains (zero between launches)
+    // k_gru_fwd9 balanced mode: hand-over flags of split chains (zero between launches).  MAL_FLAG_SLOTS sets, handed out
+    // round-robin per launch (a captured launch keeps its set), so that two learners driven by one thread on two streams do
+    // not share flags when their recurrences overlap on the device
+    int *chain_flags = nullptr;
+    unsigned flag_slot = 0;
 };
 #define MAL_CHAIN_FLAGS 1024
+#define MAL_FLAG_SLOTS 16
 static thread_local SideStreams g_side[MAL_MAX_DEV];   // one set per (thread, device)
 // mal_set_option switches are PER CALLING THREAD (like the side streams): two learners driven by two threads of one
 // process do not see each other's settings
@@ -227,8 +232,8 @@ static int side_streams(SideStreams **out) {
         for (int i = 0; i < 2; ++i) MAL_CUDA(cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming));
         MAL_CUDA(cudaEventCreateWithFlags(&ss.aux_fork_ev, cudaEventDisableTiming));
         MAL_CUDA(cudaEventCreateWithFlags(&ss.aux_join_ev, cudaEventDisableTiming));
-        MAL_CUDA(cudaMalloc(&ss.chain_flags, MAL_CHAIN_FLAGS * sizeof(int)));
-        MAL_CUDA(cudaMemset(ss.chain_flags, 0, MAL_CHAIN_FLAGS * sizeof(int)));
+        MAL_CUDA(cudaMalloc(&ss.chain_flags, MAL_FLAG_SLOTS * MAL_CHAIN_FLAGS * sizeof(int)));
+        MAL_CUDA(cudaMemset(ss.chain_flags, 0, MAL_FLAG_SLOTS * MAL_CHAIN_FLAGS * sizeof(int)));
         ss.ready = true;
     }
     *out = &ss;
@@ -1005,12 +1010,12 @@ extern "C" int mal_learner_forward(const mal_batch_t *batch, const mal_learner_c
         for (int net = 0; net < 2; ++net) { a.params[net] = ap[net]; a.gi[net] = gi[net]; a.hout[net] = hh[net]; }
         a.gates = F(plan->gates); a.TT = d.TT; a.R = d.R; a.d_in = d.d_in; a.n_actions = d.A;
         a.t0 = 0; a.t1 = t_split;
-        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, sms, ss->chain_flags, rec_alone, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
+        if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, t_split == d.TT) : launch_gru_fwd(a, 2, sms, ss->chain_flags + (size_t)(ss->flag_slot++ % MAL_FLAG_SLOTS) * MAL_CHAIN_FLAGS, rec_alone, st, fused_in && t_split == d.TT)) return 2;   // stream predecessor: k_agent_in_tc
         MAL_LAUNCH_CHECK("k_gru_fwd");
         if (t_split < d.TT) {
             if (join_from(st, ss->s[1], ss->join_ev[1])) return 2;    // second half of gi is ready
             a.t0 = t_split; a.t1 = d.TT;
-            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, sms, ss->chain_flags, rec_alone, st, false)) return 2;
+            if (rec_tc ? launch_gru_fwd_tc(a, 2, sms, st, false) : launch_gru_fwd(a, 2, sms, nullptr, rec_alone, st, false)) return 2;
             MAL_LAUNCH_CHECK("k_gru_fwd");
         }
     }
