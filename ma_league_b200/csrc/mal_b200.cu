@@ -882,8 +882,9 @@ static int launch_gru_fwd_tc(const GruFwdArgs &a, int nets, int sms, cudaStream_
     return 0;
 }
 static int launch_gru_bwd(const GruBwdArgs &a, cudaStream_t st, bool pdl) {
-    // (only in the latency regime -- a few chains per SM: with many waves of chains the smaller L1 costs more than the co-residence gains: 20v20 3.08 -> 3.15 ms)
-    if (g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv, (g_rec_carveout & 2) && a.R <= 4 * 148)) return rc; }
+    // (up to ~32 chains per SM: 10v10 / B = 128 gains 1.711 -> 1.671 ms per step; with many more waves of chains the smaller L1 costs
+    // the kernel more than the co-residence gains -- 20v20 / B = 1024: k_gru_bwd 3.09 -> 3.15 ms, step unchanged)
+    if (g_gru_variant == 9) { static bool cv[MAL_MAX_DEV]; if (int rc = ensure_max_carveout(k_gru_bwd9, cv, (g_rec_carveout & 2) && a.R <= 32 * 148)) return rc; }
     ProfScope _ps("k_gru_bwd", st);
     if (g_gru_variant == 7) launch_k(k_gru_bwd7, dim3(a.R), dim3(HID), 0, st, pdl, a);
     else if (g_gru_variant == 9) launch_k(k_gru_bwd9, dim3(a.R), dim3(HID), 0, st, pdl, a);
