@@ -18,6 +18,13 @@
 // complete sum of ITS unit / column.  The S sub-ranges of the shared operand are shifted by 16 bytes against each other
 // so that the S addresses of one LDS.128 fall into different banks.  fp32 throughout (FFMA2 = two fp32 FMAs per
 // instruction; it issues at half rate, i.e. the same FMA-pipe time as FFMA in half the issue slots).
+//
+// What an SM hosts sets the pace at league batch sizes (tools/gru_bench.cu, cycles per timestep of k_gru_fwd9 against the
+// chains per SM): 527 / 562 / 851 / 878 for 1 / 2 / 3 / 4 -- up to two chains every warp has a sub-partition to itself, a
+// third chain costs the FMA-pipe time of one warp-step.  k_gru_fwd9 therefore has a BALANCED mode (GruFwdArgs.bal_D): the
+// chains x TT steps are laid end to end and dealt out to 2 x SMs workers of equal length, a chain changes workers at most
+// once and hands its hidden state over through global memory and a flag (DESIGN.md section 4 has the schedule, the
+// measurements and when the launcher picks it).
 #pragma once
 #include <type_traits>
 #include "learner.cuh"
