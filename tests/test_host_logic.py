@@ -183,3 +183,54 @@ def test_no_cpu_fallback():
         learner.train(buf, 0, 0)
     with pytest.raises(nat.MalError):
         mac.action_selector.select(th.zeros(1, 3, 9), th.ones(1, 3, 9, dtype=th.int32), 0)
+
+
+def _balanced_pieces(worker, D, chains, TT):
+    """The pieces of one worker of k_gru_fwd9's balanced mode, in the order the kernel runs them (csrc/gru_rec.cuh: the
+    `for (int pend = hi; pend > lo;)` loop): (chain, t_begin, t_end)."""
+    lo = D * worker
+    hi = min(lo + D, chains * TT)
+    out, pend = [], hi
+    while pend > lo:
+        chain = (pend - 1) // TT
+        pbeg = max(lo, chain * TT)
+        out.append((chain, pbeg - chain * TT, pend - chain * TT))
+        pend = pbeg
+    return out
+
+
+@pytest.mark.parametrize("R,TT,sms", [(160, 201, 148), (160, 61, 148), (149, 201, 148), (222, 201, 148), (200, 33, 148),
+                                      (160, 201, 132), (75, 40, 66)])
+def test_balanced_recurrence_schedule_properties(R, TT, sms):
+    """Host restatement of the balanced forward-recurrence schedule (launch_gru_fwd in csrc/mal_b200.cu picks it for
+    2 * SMs < chains <= 3 * SMs): every chain-step is run exactly once, a chain is split between at most two workers, the
+    head piece (the one that signals) is the FIRST thing its worker runs and the tail piece (the one that waits) the LAST
+    thing its worker runs, and a worker with a full share never reaches its tail before the head has ended -- so, when all
+    workers advance at the same pace, the hand-over flag is set before it is polled and nobody idles; the makespan is D."""
+    chains, workers = 2 * R, 2 * sms
+    assert workers < chains <= 3 * sms                      # the launcher's window
+    D = -(-chains * TT // workers)
+    assert D >= TT                                          # a chain cannot span three workers
+    covered = np.zeros((chains, TT), np.int32)
+    head_end, tails = {}, {}
+    for w in range(workers):
+        pieces = _balanced_pieces(w, D, chains, TT)
+        clock = 0
+        for k, (c, tb, te) in enumerate(pieces):
+            assert 0 <= tb < te <= TT
+            covered[c, tb:te] += 1
+            if te < TT:                                     # head of a split chain: signals when done
+                assert tb == 0 and k == 0                   # ... and is the first piece of its worker (starts at time 0)
+                head_end[c] = te
+            if tb > 0:                                      # tail of a split chain: waits for the head
+                assert te == TT and k == len(pieces) - 1    # ... and is the last piece of its worker
+                tails[c] = (w, clock, te - tb, sum(e - b for _, b, e in pieces))
+            clock += te - tb
+        assert clock <= D
+    assert (covered == 1).all()
+    assert set(head_end) == set(tails)                      # every split chain has exactly one producer and one consumer
+    for c, (w, start, length, total) in tails.items():
+        if total == D:                                      # a full worker never waits: the head ended before it gets there
+            assert start >= head_end[c], (c, w, head_end[c], start)
+        # a short worker (the clipped end of the sequence) may poll its flag, but still ends within the makespan
+        assert max(start, head_end[c]) + length <= D
